@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- SV particle-steps/s of the bootstrap particle-filter likelihood (BASELINE.json configs[1]).
+
+A "step" is one pass of the hot path over one batch: P = 4096 proposals x N = 1024 particles x
+T = 4096 observations of a synthetic stochastic-volatility series, one filter per CTA (R = 1
+replicate per proposal), multinomial resampling at every time step.  With --gpus N every rank
+processes its own 4096 proposals (independent units, no data-path collective): weak scaling.
+
+  value  particle-steps/s with proposals already resident in HBM (device-pointer C-ABI entry)
+  e2e    the same metric through the host-buffer C-ABI call the reference would bind
+         (thread_pool::work shape): pinned host theta -> H2D -> kernels -> D2H log-likelihoods
+  roofline / cpu_baseline  as DESIGN.md section "Measurement" defines them
+
+`--impl reference` times the reference's CPU path (oracle/_ref: the reference's own thread_pool.h
+dispatching the restated pf filter) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_PROPOSALS, N_PARTICLES, T_STEPS, R_REPL = 4096, 1024, 4096, 1
+SEED_SERIES, SEED_THETA, SEED_FILTER = 20260101, 20260102, 20260103
+# algorithmic FP64-pipe work per particle-step of the canonical SV / multinomial / rs=1 step at L = 4
+# (DESIGN.md "Roofline"): fused multiply-adds, other adds/muls/converts, compares (binary search, max).
+FP64_FMA, FP64_OTHER, FP64_CMP = 31.0, 13.0, 12.0
+
+
+def synthetic_sv_series(T, seed=SEED_SERIES, beta=1.0, phi=0.95, sigma=0.25):
+    rng = np.random.default_rng(seed)
+    x = np.empty(T)
+    x[0] = rng.standard_normal() * sigma / np.sqrt(1 - phi * phi)
+    for t in range(1, T):
+        x[t] = phi * x[t - 1] + sigma * rng.standard_normal()
+    return beta * np.exp(0.5 * x) * rng.standard_normal(T)
+
+
+def proposals(P, seed=SEED_THETA, beta=1.0, phi=0.95, sigma=0.25):
+    """theta_p = theta* + 0.05 N(0, I) on the transformed scale {null, twice_fisher, log} (estimate_univ_svol.h:155)."""
+    rng = np.random.default_rng(seed)
+    star = np.array([beta, np.log(1 + phi) - np.log(1 - phi), np.log(sigma * sigma)])
+    tr = star + 0.05 * rng.standard_normal((P, 3))
+    th = np.empty_like(tr)
+    th[:, 0] = tr[:, 0]
+    th[:, 1] = 2.0 / (1.0 + np.exp(-tr[:, 1])) - 1.0
+    th[:, 2] = np.exp(tr[:, 2])
+    return np.ascontiguousarray(th)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_refcpu():
+    path = os.path.join(ROOT, "oracle", "_ref", "libssme_refcpu.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, capture_output=True)
+    L = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    L.ssme_refcpu_loglike_batch.argtypes = [C.c_int, C.c_int, dp, C.c_int64, dp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint64,
+                                            dp, dp, C.POINTER(C.c_uint)]
+    return L
+
+
+def cpu_reference_sample(y, theta, n_proposals, threads):
+    """Time thread_pool::work on n_proposals proposals of the bench workload (R replicates each)."""
+    L = load_refcpu()
+    dp = C.POINTER(C.c_double)
+    th = np.ascontiguousarray(theta[:n_proposals])
+    out = np.zeros(n_proposals)
+    sec, used = C.c_double(), C.c_uint()
+    rc = L.ssme_refcpu_loglike_batch(0, N_PARTICLES, y.ctypes.data_as(dp), y.size, th.ctypes.data_as(dp), 3, n_proposals, R_REPL,
+                                     threads, SEED_FILTER, out.ctypes.data_as(dp), C.byref(sec), C.byref(used))
+    if rc != 0:
+        raise RuntimeError("reference CPU path failed")
+    steps = n_proposals * R_REPL * N_PARTICLES * y.size
+    return steps / sec.value, sec.value, used.value, bool(L.ssme_refcpu_pool_kind()), out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    y = synthetic_sv_series(T_STEPS)
+    theta = proposals(P_PROPOSALS)
+    # one proposal = one thread_pool::work call with R = 1 filter, which a pool cannot parallelise; the
+    # reference parallelises over the R replicates of ONE proposal.  To let it use every host core on this
+    # workload, each step hands the pool a sample of `cores` proposals as R = cores replicates would be:
+    # we time `cores` independent work() calls worth of filters via R = cores on one theta.
+    L = load_refcpu()
+    cores = L.ssme_refcpu_hardware_threads()
+    dp = C.POINTER(C.c_double)
+    sample_filters = max(2, cores)
+    times = []
+    for it in range(args.warmup + args.steps):
+        th = np.ascontiguousarray(theta[it % P_PROPOSALS: it % P_PROPOSALS + 1])
+        out = np.zeros(1)
+        sec, used = C.c_double(), C.c_uint()
+        rc = L.ssme_refcpu_loglike_batch(0, N_PARTICLES, y.ctypes.data_as(dp), y.size, th.ctypes.data_as(dp), 3, 1, sample_filters,
+                                         0 if cores > 1 else 1, SEED_FILTER + it, out.ctypes.data_as(dp), C.byref(sec), C.byref(used))
+        if rc != 0:
+            raise RuntimeError("reference CPU path failed")
+        if it >= args.warmup:
+            times.append(sec.value)
+    steps_per_sample = sample_filters * N_PARTICLES * T_STEPS
+    value = steps_per_sample * len(times) / sum(times)
+    sample = "%d filters (one thread_pool::work call, R=%d) of %d particles x %d steps per timed step" % (
+        sample_filters, sample_filters, N_PARTICLES, T_STEPS)
+    line = {
+        "impl": "reference", "metric": "sv_particle_steps_per_sec", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": int(used.value),
+                         "kind": "port", "sample": sample,
+                         "dispatcher": "reference include/ssme/thread_pool.h" if L.ssme_refcpu_pool_kind() else "local API-identical pool"},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "batched SV bootstrap-filter log-likelihood: %d proposals x %d particles x T=%d per GPU, "
+                        "multinomial resampling every step, R=%d (BASELINE.json configs[1])" % (P_PROPOSALS, N_PARTICLES, T_STEPS, R_REPL),
+            "proposals_per_gpu": P_PROPOSALS, "particles": N_PARTICLES, "T": T_STEPS, "replicates": R_REPL,
+            "parallelism": "proposals sharded across %d GPU(s), no data-path collective" % n_gpus,
+            "l2": "flushed between timed steps (256 MiB memset, outside the per-step events); the resident kernel's HBM inputs are 128 KiB"}
+
+
+def run_ours(args):
+    import torch
+    import ssme_b200 as sb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    y = synthetic_sv_series(T_STEPS)
+    theta_all = proposals(P_PROPOSALS * world)
+    theta = np.ascontiguousarray(theta_all[rank * P_PROPOSALS:(rank + 1) * P_PROPOSALS])
+    be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=N_PARTICLES, seed=SEED_FILTER, device=local_rank,
+                                                  scan_items_per_lane=args.L, threads_per_filter=args.threads))
+    be.add_observed_data(y)
+    layout = be.layout
+    stream = torch.cuda.ExternalStream(be.stream, device=dev)
+    d_theta = torch.from_numpy(theta).to(dev)
+    d_out = torch.empty(P_PROPOSALS, dtype=torch.float64, device=dev)
+    d_pf = torch.empty(P_PROPOSALS * R_REPL, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    launches0 = sb.launch_count()
+    F_base = rank * P_PROPOSALS * R_REPL
+
+    def step(i):
+        be.work_batch_device(d_theta.data_ptr(), P_PROPOSALS, R_REPL, F_base + i * world * P_PROPOSALS * R_REPL,
+                             d_out.data_ptr(), d_pf.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`) -------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches_before = sb.launch_count()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step(args.warmup + i)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    gpu_launches = sb.launch_count() - launches_before
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    steps_per_pass = P_PROPOSALS * R_REPL * N_PARTICLES * T_STEPS
+    value = world * steps_per_pass * args.steps / (total_ms * 1e-3)
+    checksum = float(d_out.sum().item())
+
+    # ---- end to end through the host-buffer C-ABI call (`e2e`) ----------------------------------
+    h_theta = torch.from_numpy(theta).pin_memory().numpy()
+    be.work_batch(h_theta, R=R_REPL, stream_base=F_base)  # warm the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out_host = be.work_batch(h_theta, R=R_REPL, stream_base=F_base + (1000 + i) * world * P_PROPOSALS * R_REPL)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * steps_per_pass * args.steps / e2e_s
+    assert np.all(np.isfinite(out_host))
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (bootstrap_filter_kernel): FP64 pipe ----------------
+        fma_rate = sb.measure_fp64_fma_rate(local_rank, 1 << 15)  # thread-level FMA instructions / s, measured now
+        per_gpu = value / world
+        pipe_instr = FP64_FMA + FP64_OTHER + FP64_CMP
+        achieved_tflops = per_gpu * (2 * FP64_FMA + FP64_OTHER + FP64_CMP) / 1e12
+        peak_tflops = 2 * fma_rate / 1e12
+        roofline = {
+            "bound": "fp64", "kernel": "bootstrap_filter_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": per_gpu * pipe_instr / fma_rate,
+            "frac_definition": "FP64-pipe issue slots: (31 FMA + 13 add/mul/cvt + 12 compare) per particle-step x particle-steps/s "
+                               "/ measured FP64 FMA instruction rate (micro-benchmark in this run)",
+            "frac_flops": achieved_tflops / peak_tflops, "peak_source": "measured in-run (ssme_b200_measure_fp64_fma_rate); "
+            "MEASURED_PEAKS.json has no FP64 entry", "traffic": None,
+            "hbm_note": "resident kernel: HBM traffic per launch is the observation stream + theta + outputs (~0.2 MB); not HBM-bound",
+        }
+        # ---- CPU baseline: the reference's thread_pool path on this box's host cores -------------
+        try:
+            L = load_refcpu()
+            cores = L.ssme_refcpu_hardware_threads()
+            nfil = max(2, cores)
+            dp = C.POINTER(C.c_double)
+            out = np.zeros(1)
+            sec, used = C.c_double(), C.c_uint()
+            th1 = np.ascontiguousarray(theta[:1])
+            L.ssme_refcpu_loglike_batch(0, N_PARTICLES, y.ctypes.data_as(dp), y.size, th1.ctypes.data_as(dp), 3, 1, nfil,
+                                        0 if cores > 1 else 1, 1, out.ctypes.data_as(dp), C.byref(sec), C.byref(used))
+            cpu = {"value": nfil * N_PARTICLES * T_STEPS / sec.value, "unit": "particle-steps/s", "cores": int(used.value), "kind": "port",
+                   "sample": "%d filters of the bench workload (one thread_pool::work call, R=%d), %.1f s" % (nfil, nfil, sec.value),
+                   "dispatcher": "reference include/ssme/thread_pool.h" if L.ssme_refcpu_pool_kind() else "local API-identical pool"}
+        except Exception as ex:  # the baseline is a reported extra; never let it sink the GPU line
+            cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        line = {
+            "metric": "sv_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(theta.nbytes),
+                    "d2h_bytes_per_step": int(P_PROPOSALS * 8)},
+            "gpu_launches": int(gpu_launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "layout": layout, "wall_s_timed_region": t_wall, "checksum": checksum,
+            "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-10); all filter arithmetic f64",
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    be.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=0, help="scan items per lane (0 = library default)")
+    ap.add_argument("--threads", type=int, default=0, help="threads per filter (0 = library default)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/*
+ * ssme_b200.h -- C ABI of the B200 (sm_100a) particle-filter likelihood backend for SSME.
+ *
+ * This is the drop-in boundary for SSME's one hot path: the bootstrap particle-filter
+ * log-likelihood estimate that every PMMH proposal evaluates.  Each entry point cites the
+ * reference interface (paths relative to the tbrown122387/ssme tree) it replaces.  Plain C
+ * types only; theta always crosses the boundary UNTRANSFORMED (what param::pack::
+ * get_untrans_params returns, include/ssme/parameters.h:587-595).
+ *
+ * Error convention (reference: C++ exceptions, thread_pool.h:142-145,169,192;
+ * parameters.h:483,498,521,582; estimate_univ_svol.h:112-113): every function returns an
+ * int status; ssme_b200_last_error() gives the thread-local message.  The C++ shim
+ * (include/ssme_b200/gpu_pool.hpp) re-throws the matching std exception.  NaN / -inf
+ * log-likelihoods are returned, never trapped (ada_pmmh_mvn.h:349,357 treats NaN as reject).
+ *
+ * Threading (reference: thread_pool::work is not re-entrant, thread_pool.h:87,199): calls on
+ * one handle must be serialised by the caller; different handles are independent.
+ */
+#ifndef SSME_B200_H
+#define SSME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSME_B200_VERSION 1
+
+/* status codes; the C++ shim maps them to the exception types the reference throws */
+#define SSME_B200_OK 0
+#define SSME_B200_EINVAL 1      /* std::invalid_argument */
+#define SSME_B200_ERUNTIME 2    /* std::runtime_error    */
+#define SSME_B200_ELENGTH 3     /* std::length_error     */
+#define SSME_B200_ECUDA 4       /* CUDA runtime failure (std::runtime_error) */
+#define SSME_B200_EUNSUPPORTED 5 /* configuration not built into this library */
+
+/* state-space models (device functors; the reference's models are C++ virtuals on Eigen vectors) */
+#define SSME_B200_MODEL_SV 0          /* example/univ_svol_bootstrap_filter.h:17-103; theta = (beta, phi, sigma^2) */
+#define SSME_B200_MODEL_SV_LEVERAGE 1 /* test/test_liu_west.cpp:83-157; theta = (phi, mu, sigma, rho); z_t = y_{t-1} */
+
+/* resamplers */
+#define SSME_B200_RESAMP_MULTINOMIAL 0        /* pf::resamplers::mn_resampler (estimate_univ_svol.h:119) */
+#define SSME_B200_RESAMP_SORTED_MULTINOMIAL 1 /* mn_resamp_states_and_params, liu_west_filter.h:91-145 (= pf mn_resamp_fast1) */
+#define SSME_B200_RESAMP_SYSTEMATIC 2         /* u_j = (j+u0)/N */
+
+#define SSME_B200_DTYPE_F64 0
+#define SSME_B200_DTYPE_F32 1
+
+#define SSME_B200_RNG_PHILOX 0   /* on-device Philox4x32-10, counter = (block, t, filter, tag) */
+#define SSME_B200_RNG_INJECTED 1 /* caller supplies the N(0,1) and U[0,1) streams (parity runs) */
+
+typedef struct ssme_b200_filter_s* ssme_b200_handle;
+
+typedef struct {
+    int32_t struct_size;         /* sizeof(ssme_b200_config), for ABI growth */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t model;               /* SSME_B200_MODEL_*   */
+    int32_t num_particles;       /* N: template parameter nparts of svol_bs / BSFilter */
+    int32_t resampler;           /* SSME_B200_RESAMP_*  */
+    int32_t resample_every;      /* rs: resample when (t+1) % rs == 0 (pf BSFilter ctor arg; liu_west_filter.h:1686) */
+    int32_t dtype;               /* SSME_B200_DTYPE_*   */
+    int32_t rng_mode;            /* SSME_B200_RNG_*     */
+    uint64_t seed;               /* Philox key; the reference seeds mt19937 from the clock (liu_west_filter.h:75-76) */
+    int32_t scan_items_per_lane; /* L of the canonical scan order; 0 = library default */
+    int32_t threads_per_filter;  /* CTA size; 0 = library default */
+    int32_t filters_per_sm;      /* resident CTAs per SM; 0 = library default */
+    int32_t reserved;
+} ssme_b200_config;
+
+typedef struct {
+    int32_t scan_items_per_lane; /* L actually used: the oracle must be given the same L */
+    int32_t threads_per_filter;
+    int32_t filters_per_sm;
+    int32_t smem_bytes_per_filter;
+    int32_t num_sms;
+    int32_t registers_per_thread;
+} ssme_b200_layout;
+
+/* Replaces: constructing svol_bs<nparts,...> (estimate_univ_svol.h:119) + thread_pool ctor
+ * (thread_pool.h:118-159).  Creates the handle, its CUDA stream and device scratch. */
+int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out);
+
+/* Replaces: ~thread_pool (thread_pool.h:179-181). */
+int ssme_b200_destroy(ssme_b200_handle h);
+
+/* Replaces: thread_pool::add_observed_data (thread_pool.h:166-173) fed by utils::read_data
+ * (utils.h:25-64).  y_host is row-major [T][dimy]; dimy = 1, or 2 = (y_t, covariate z_t) for the
+ * leverage model.  Copied to the device once; may be called once per handle (as the reference:
+ * a second call fails with SSME_B200_ERUNTIME). */
+int ssme_b200_set_observations(ssme_b200_handle h, const double* y_host, size_t T, size_t dimy);
+
+/* The launch layout chosen for this handle (valid after create). */
+int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out);
+
+/* Replaces: thread_pool::work(theta) (thread_pool.h:189-215) for a BATCH of P proposals:
+ * P x R independent filters (R = num_pfilters, ada_pmmh_mvn.h:57,193) followed by the per-proposal
+ * log-mean-exp (thread_pool.h:263-268).  HOST buffers; the call copies theta in, runs, copies out
+ * and synchronises.
+ *   theta_host      [P][numparams] row-major, untransformed
+ *   stream_base     first Philox filter id; filter (p, r) uses stream_base + p*R + r
+ *   out_host        [P] log-mean-exp over the R replicates
+ *   per_filter_host [P*R] individual filter log-likelihoods, or NULL */
+int ssme_b200_loglike_batch(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R,
+                            uint64_t stream_base, double* out_host, double* per_filter_host);
+
+/* Same computation with DEVICE pointers, asynchronous on the handle's stream (or on
+ * cuda_stream if non-NULL): for callers that keep proposals resident in HBM.
+ * per_filter_dev must hold P*R doubles. */
+int ssme_b200_loglike_batch_device(ssme_b200_handle h, const double* theta_dev, size_t P, uint32_t R,
+                                   uint64_t stream_base, double* out_dev, double* per_filter_dev,
+                                   void* cuda_stream);
+
+/* Parity / diagnostics: run F filters and return everything the reference's filter object
+ * exposes per step (getLogCondLike, liu_west_filter.h:1595-1599) plus resampling ancestors.
+ *   theta_host [F][numparams];  filter f uses Philox id stream_base + f
+ *   z_inj_host [F][T][N], u_inj_host [F][T][stride_u]   (rng_mode INJECTED; else NULL);
+ *               stride_u = N (multinomial), N+1 (sorted multinomial), 1 (systematic)
+ *   loglik_host [F]; cond_like_host [F][T]; ancestors_host [F][T][N]; x_host [F][T][N]
+ *   (any output may be NULL) */
+int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t F, uint64_t stream_base,
+                           const double* z_inj_host, const double* u_inj_host, double* loglik_host,
+                           double* cond_like_host, int32_t* ancestors_host, double* x_host);
+
+/* Blocks until all work queued on the handle's stream has finished. */
+int ssme_b200_synchronize(ssme_b200_handle h);
+
+/* The CUDA stream owned by the handle (a cudaStream_t), for event timing by the caller. */
+void* ssme_b200_stream(ssme_b200_handle h);
+
+/* Kernel launches issued through this library in this process (bench.py's gpu_launches). */
+uint64_t ssme_b200_launch_count(void);
+
+/* Thread-local message of the last failing call on this thread. */
+const char* ssme_b200_last_error(void);
+
+/* Library / build identification, e.g. "ssme_b200 v1 sm_100a cuda-12.9". */
+const char* ssme_b200_build_info(void);
+
+/* Micro-benchmark used for the roofline denominator: sustained FP64 FMA issue rate of the
+ * device, in FMA instructions (thread-level) per second.  iters = inner-loop length. */
+int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSME_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes binding of the CPU oracle (oracle/pf_oracle.h).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssme_oracle.so")
+
+ARITH_CANONICAL, ARITH_FAITHFUL = 0, 1
+RNG_PHILOX, RNG_INJECTED = 0, 1
+
+
+class _Cfg(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("num_particles", C.c_int32), ("resampler", C.c_int32), ("resample_every", C.c_int32),
+        ("arithmetic", C.c_int32), ("scan_items_per_lane", C.c_int32), ("rng_mode", C.c_int32), ("scan_threads", C.c_int32),
+        ("seed", C.c_uint64), ("filter_id", C.c_uint64),
+    ]
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("pf_oracle.c", "pf_oracle.h", "det_math.h", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.ssme_oracle_filter.argtypes = [C.POINTER(_Cfg), dp, dp, C.c_int64, dp, dp, dp, dp, dp, ip, dp, dp]
+        L.ssme_oracle_log_mean_exp.argtypes = [dp, C.c_int64, C.c_int32]
+        L.ssme_oracle_log_mean_exp.restype = C.c_double
+        for name in ("dexp", "dlog"):
+            f = getattr(L, "ssme_oracle_" + name)
+            f.argtypes, f.restype = [C.c_double], C.c_double
+        L.ssme_oracle_box_muller.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ssme_oracle_uniform53.argtypes, L.ssme_oracle_uniform53.restype = [C.c_uint32, C.c_uint32], C.c_double
+        L.ssme_oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.ssme_oracle_draw_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ssme_oracle_draw_normal.restype = C.c_double
+        L.ssme_oracle_draw_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.ssme_oracle_draw_uniform.restype = C.c_double
+        L.ssme_oracle_canonical_scan.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, dp, dp]
+        for name in ("trans", "inv_trans", "log_jacobian"):
+            f = getattr(L, "ssme_oracle_" + name)
+            f.argtypes, f.restype = [C.c_int32, C.c_double], C.c_double
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONICAL, L=4, rng_mode=RNG_PHILOX,
+               seed=20260101, filter_id=0, z=None, u=None, cov=None, trace=True, NT=0):
+    """Run one oracle filter; returns dict(loglik, cond_like, ancestors, x, margin)."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+    T = y.shape[0]
+    cfg = _Cfg(model, N, resampler, rs, arithmetic, L, rng_mode, NT, seed, filter_id)
+    z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+    u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+    cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
+    ll, mg = C.c_double(0), C.c_double(0)
+    cl = np.empty(T) if trace else None
+    anc = np.empty((T, N), dtype=np.int32) if trace else None
+    xs = np.empty((T, N)) if trace else None
+    rc = lib().ssme_oracle_filter(C.byref(cfg), _dp(theta), _dp(y), T, _dp(cov), _dp(z), _dp(u), C.byref(ll), _dp(cl),
+                                  anc.ctypes.data_as(C.POINTER(C.c_int32)) if trace else None, _dp(xs), C.byref(mg))
+    if rc != 0:
+        raise ValueError("ssme_oracle_filter failed with %d" % rc)
+    return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs, "margin": mg.value}
+
+
+def log_mean_exp(v, arithmetic=ARITH_CANONICAL):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    return float(lib().ssme_oracle_log_mean_exp(_dp(v), v.size, arithmetic))
+
+
+def canonical_scan(w, L, NP=None):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    NP = w.size if NP is None else NP
+    out = np.empty(NP)
+    lib().ssme_oracle_canonical_scan(_dp(w), w.size, L, NP, _dp(out), None)
+    return out

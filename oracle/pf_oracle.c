@@ -1,0 +1,439 @@
+/*
+ * oracle/pf_oracle.c -- TEST INFRASTRUCTURE (see pf_oracle.h for the parity status).
+ *
+ * CPU restatement of the bootstrap particle-filter log-likelihood that SSME evaluates once
+ * per PMMH proposal.  Reference call stack restated:
+ *   univ_svol_estimator::log_like_eval        example/estimate_univ_svol.h:107-131   (T loop)
+ *   pf::filters::BSFilter::filter  [external] twin: include/ssme/liu_west_filter.h:1608-1761
+ *   svol_bs model hooks                       example/univ_svol_bootstrap_filter.h:54-103
+ *   pf::resamplers::mn_resampler   [external] libstdc++ discrete_distribution semantics
+ *   mn_resamp_states_and_params::resampLogWts include/ssme/liu_west_filter.h:91-145
+ *   thread_pool log-mean-exp                  include/ssme/thread_pool.h:263-268
+ *   svol_leverage / svol_lw_* models          test/test_pswarm.cpp:81-134, test/test_liu_west.cpp:83-157
+ *
+ * Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/Makefile).  -ffp-contract=off is part
+ * of the spec: every fused multiply-add below is an explicit fma().
+ */
+#include "pf_oracle.h"
+#include "det_math.h"
+
+#include <stdlib.h>
+
+/* ---------------------------------------------------------------- exported raw pieces ------- */
+double ssme_oracle_dexp(double x) { return dm_exp(x); }
+double ssme_oracle_dlog(double x) { return dm_log(x); }
+void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1) { dm_box_muller(a, b, z0, z1); }
+double ssme_oracle_uniform53(uint32_t hi, uint32_t lo) { return dm_uniform53(hi, lo); }
+void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    dm_philox4x32_10(ctr, key, out);
+}
+
+/* Philox counter layout (the RNG spec shared with the kernel):
+ *   key = (seed_lo, seed_hi);  ctr = (block, t, filter_lo, filter_hi << 4 | tag)
+ *   tag 0: state normals   -- block q = i >> 2 serves particles 4q..4q+3:
+ *                             BoxMuller(w0,w1) -> z[4q], z[4q+1];  BoxMuller(w2,w3) -> z[4q+2], z[4q+3]
+ *   tag 1: multinomial uniforms, tag 2: sorted-multinomial uniforms, tag 3: systematic offset
+ *                          -- block h = j >> 1 serves slots 2h, 2h+1: u53(w0,w1), u53(w2,w3)
+ */
+static void philox_block(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t block, uint32_t tag, uint32_t out[4])
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {block, t, (uint32_t)filter_id, ((uint32_t)(filter_id >> 32) << 4) | tag};
+    dm_philox4x32_10(ctr, key, out);
+}
+
+double ssme_oracle_draw_normal(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t i)
+{
+    uint32_t w[4];
+    float z0, z1;
+    philox_block(seed, filter_id, t, i >> 2, 0u, w);
+    if (i & 2u) dm_box_muller(w[2], w[3], &z0, &z1);
+    else dm_box_muller(w[0], w[1], &z0, &z1);
+    return (double)((i & 1u) ? z1 : z0);
+}
+
+double ssme_oracle_draw_uniform(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t j, uint32_t tag)
+{
+    uint32_t w[4];
+    philox_block(seed, filter_id, t, j >> 1, tag, w);
+    return (j & 1u) ? dm_uniform53(w[2], w[3]) : dm_uniform53(w[0], w[1]);
+}
+
+/* ---------------------------------------------------------------- canonical scan order ------ */
+/*
+ * Inclusive prefix sums in the order the kernel produces them:
+ *   1. lane-local sequential scan over L consecutive items            (lane l owns items lL..lL+L-1)
+ *   2. Kogge-Stone inclusive scan of the 32 lane totals of each warp  (d = 1,2,4,8,16)
+ *   3. Kogge-Stone inclusive scan of the (<=32) warp totals
+ *   4. C[i] = (warp_exclusive + lane_exclusive) + local_inclusive;  total = last entry of step 3
+ * Items n..np-1 are padding with weight +0.0; np = threads_per_filter * L is a power of two
+ * (the kernel's CTA covers np slots) and C receives all np entries.
+ */
+void ssme_oracle_canonical_scan(const double* w, int32_t n, int32_t L, int32_t np, double* C, double* total)
+{
+    int32_t lanes = (np + L - 1) / L;
+    int32_t warps = (lanes + 31) / 32;
+    int32_t lanes_pad = warps * 32;
+    double* tot = (double*)calloc((size_t)lanes_pad, sizeof(double));
+    double* tmp = (double*)calloc((size_t)lanes_pad, sizeof(double));
+    double* loc = (double*)calloc((size_t)lanes_pad * (size_t)L, sizeof(double));
+    for (int32_t l = 0; l < lanes_pad; ++l) {
+        double s = 0.0;
+        for (int32_t k = 0; k < L; ++k) {
+            int64_t i = (int64_t)l * L + k;
+            double v = (i < n) ? w[i] : 0.0;
+            s = (k == 0) ? v : s + v;
+            loc[i] = s;
+        }
+        tot[l] = s;
+    }
+    for (int32_t d = 1; d < 32; d <<= 1) {
+        for (int32_t l = 0; l < lanes_pad; ++l) tmp[l] = ((l & 31) >= d) ? tot[l - d] + tot[l] : tot[l];
+        for (int32_t l = 0; l < lanes_pad; ++l) tot[l] = tmp[l];
+    }
+    double wt[32], wtmp[32];
+    for (int32_t g = 0; g < 32; ++g) wt[g] = (g < warps) ? tot[g * 32 + 31] : 0.0;
+    for (int32_t d = 1; d < 32; d <<= 1) {
+        for (int32_t g = 0; g < 32; ++g) wtmp[g] = (g >= d) ? wt[g - d] + wt[g] : wt[g];
+        for (int32_t g = 0; g < 32; ++g) wt[g] = wtmp[g];
+    }
+    for (int32_t l = 0; l < lanes_pad; ++l) {
+        int32_t g = l >> 5;
+        double wex = (g > 0) ? wt[g - 1] : 0.0;
+        double lex = ((l & 31) > 0) ? tot[l - 1] : 0.0;
+        double base = wex + lex;
+        for (int32_t k = 0; k < L; ++k) {
+            int64_t i = (int64_t)l * L + k;
+            if (i < np) C[i] = base + loc[i];
+        }
+    }
+    /* the block total is the last entry of the warp-total scan (NOT C[np-1], which is associated differently) */
+    if (total) *total = wt[warps - 1];
+    free(tot); free(tmp); free(loc);
+}
+
+/* The kernel's search: branch-free descent over the padded power-of-two CDF, then clamp to n-1.
+ * Equals lower_bound when C is sorted.  A parallel scan is only sorted up to rounding (an entry can sit
+ * one ulp below its predecessor when a weight is far smaller than the running sum), so the probing
+ * sequence is part of the canonical spec and restated here step for step. */
+static int32_t descent_search(const double* C, int32_t np, int32_t n, double tau)
+{
+    int32_t idx = 0;
+    for (int32_t s = np / 2; s >= 1; s >>= 1)
+        if (C[idx + s - 1] < tau) idx += s;
+    return idx < n - 1 ? idx : n - 1;
+}
+
+/* ---------------------------------------------------------------- densities ------------------ */
+/* pf::rveval::evalUnivNorm(x, mu, sigma, log=true) as restated in SURVEY.md a8 / Appendix B */
+static double faithful_log_norm(double x, double mu, double sigma)
+{
+    double exponent = -.5 * (x - mu) * (x - mu) / (sigma * sigma);
+    if (sigma > 0.0) return -log(sigma) - .5 * log(2.0 * M_PI) + exponent;
+    return -INFINITY;
+}
+
+typedef struct {
+    int model;
+    /* SV: beta, phi, sigma ; leverage: phi, mu, sigma, rho */
+    double beta, phi, sigma, mu, rho;
+    /* canonical per-filter constants */
+    double sd0;     /* sigma / sqrt(1 - phi^2) */
+    double c0;      /* -log(beta) - 0.5 log(2 pi) */
+    double inv2b2;  /* 0.5 / beta^2 */
+    double rho_sigma, sdv; /* leverage: rho*sigma, sigma*sqrt(1-rho^2) */
+} model_t;
+
+static void model_init(model_t* m, int model, const double* theta)
+{
+    m->model = model;
+    if (model == SSME_OR_MODEL_SV) {
+        /* svol_bs(const pack&): beta = theta0, phi = theta1, sigma = sqrt(theta2) (:54-61) */
+        m->beta = theta[0]; m->phi = theta[1]; m->sigma = sqrt(theta[2]);
+        m->mu = 0.0; m->rho = 0.0;
+    } else {
+        /* phi, mu, sigma, rho (test_liu_west.cpp:70 transform order logit,null,log,twice_fisher) */
+        m->beta = 1.0; m->phi = theta[0]; m->mu = theta[1]; m->sigma = theta[2]; m->rho = theta[3];
+    }
+    m->sd0 = m->sigma / sqrt(1.0 - m->phi * m->phi);
+    m->c0 = -dm_log(m->beta) - DM_HALF_LOG_2PI;
+    m->inv2b2 = 0.5 / (m->beta * m->beta);
+    m->rho_sigma = m->rho * m->sigma;
+    m->sdv = m->sigma * sqrt(1.0 - m->rho * m->rho);
+}
+
+/* canonical: time-1 draw, transition and log-observation density */
+static double can_q1(const model_t* m, double z) { return z * m->sd0; }
+static double can_f(const model_t* m, double xa, double z, double cov)
+{
+    if (m->model == SSME_OR_MODEL_SV) return fma(m->phi, xa, m->sigma * z);
+    double e2 = dm_exp(-0.5 * xa);
+    double cz = m->rho_sigma * cov;
+    double mean = fma(m->phi, xa - m->mu, m->mu);
+    mean = fma(cz, e2, mean);
+    return fma(m->sdv, z, mean);
+}
+static double can_logg(const model_t* m, double y, double x)
+{
+    double h = (y * y) * m->inv2b2;
+    double e = dm_exp(-x);
+    return fma(-h, e, fma(-0.5, x, m->c0));
+}
+
+/* faithful: the reference's expressions, operand order preserved */
+static double fai_q1(const model_t* m, double z) { return z * m->sigma / sqrt(1. - m->phi * m->phi); }
+static double fai_f(const model_t* m, double xa, double z, double cov)
+{
+    if (m->model == SSME_OR_MODEL_SV) return m->phi * xa + z * m->sigma; /* univ_svol_bootstrap_filter.h:77 */
+    double xt = m->mu + m->phi * (xa - m->mu) + cov * m->rho * m->sigma * exp(-.5 * xa); /* test_liu_west.cpp:116 */
+    xt += z * m->sigma * sqrt(1.0 - m->rho * m->rho);                                  /* :118 */
+    return xt;
+}
+static double fai_logg(const model_t* m, double y, double x)
+{
+    return faithful_log_norm(y, 0.0, m->beta * exp(.5 * x)); /* :85 ; leverage: beta = 1 */
+}
+static double fai_logmu(const model_t* m, double x)
+{
+    return faithful_log_norm(x, 0.0, m->sigma / sqrt(1.0 - m->phi * m->phi)); /* :92-95 == :102 */
+}
+
+/* first i in [0,n) with !(C[i] < tau); n-1 if none (the reference pins cp[n-1] = 1.0 instead) */
+static int32_t lower_bound_idx(const double* C, int32_t n, double tau)
+{
+    int32_t lo = 0, hi = n;
+    while (lo < hi) {
+        int32_t mid = lo + (hi - lo) / 2;
+        if (C[mid] < tau) lo = mid + 1; else hi = mid;
+    }
+    return lo < n ? lo : n - 1;
+}
+
+static void upd_margin(double* margin, const double* C, int32_t a, double tau, double total)
+{
+    double m = fabs(C[a] - tau);
+    if (a > 0) { double m2 = fabs(tau - C[a - 1]); if (m2 < m) m = m2; }
+    m = m / total;
+    if (m < *margin) *margin = m;
+}
+
+int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
+                       const double* cov, const double* z_inj, const double* u_inj,
+                       double* loglik_out, double* cond_like, int32_t* ancestors, double* x_trace,
+                       double* tie_margin)
+{
+    if (!cfg || !theta || !y || T < 0) return -1;
+    const int32_t N = cfg->num_particles;
+    const int canonical = (cfg->arithmetic == SSME_OR_ARITH_CANONICAL);
+    const int32_t L = cfg->scan_items_per_lane;
+    const int32_t rs = cfg->resample_every;
+    if (N < 1 || rs < 1 || (canonical && L < 1)) return -2;
+    /* padded slot count of the kernel's CTA: threads * L, threads a power of two >= 32 */
+    int32_t NP = N;
+    if (canonical) {
+        int32_t nt = cfg->scan_threads;
+        if (nt == 0) { nt = 32; while ((int64_t)nt * L < N) nt <<= 1; }
+        if ((nt & (nt - 1)) != 0 || (L & (L - 1)) != 0 || (int64_t)nt * L < N) return -7;
+        NP = nt * L;
+    }
+    if (cfg->model != SSME_OR_MODEL_SV && cfg->model != SSME_OR_MODEL_SV_LEVERAGE) return -3;
+    if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
+    const int injected = (cfg->rng_mode == SSME_OR_RNG_INJECTED);
+    if (injected && !z_inj) return -5;
+    const int64_t stride_u = cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL ? N
+                             : cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL ? N + 1 : 1;
+    const uint32_t utag = 1u + (uint32_t)cfg->resampler;
+
+    model_t mod;
+    model_init(&mod, cfg->model, theta);
+
+    double* x = (double*)malloc(sizeof(double) * (size_t)N);
+    double* xn = (double*)malloc(sizeof(double) * (size_t)N);
+    double* lw = (double*)calloc((size_t)N, sizeof(double));
+    double* w = (double*)malloc(sizeof(double) * (size_t)N);
+    double* C = (double*)malloc(sizeof(double) * (size_t)NP);
+    double* E = (double*)malloc(sizeof(double) * (size_t)(N + 1));
+    double* PE = (double*)malloc(sizeof(double) * (size_t)NP);
+    int32_t* anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+
+    double loglik = 0.0, margin = INFINITY;
+    int prev_resampled = 1;
+    double M_prev = 0.0, S_prev = 0.0;
+    const double logN = canonical ? dm_log((double)N) : log((double)N);
+
+    for (int64_t t = 0; t < T; ++t) {
+        const double yt = y[t];
+        const double ct = (cfg->model == SSME_OR_MODEL_SV_LEVERAGE && t > 0) ? (cov ? cov[t] : y[t - 1]) : 0.0;
+        /* propagate + log-weights (particle order; one normal per particle per step) */
+        for (int32_t i = 0; i < N; ++i) {
+            double z = injected ? z_inj[t * N + i]
+                                : ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
+            if (t == 0) {
+                if (canonical) {
+                    x[i] = can_q1(&mod, z);
+                    lw[i] = can_logg(&mod, yt, x[i]); /* logMu - logQ1 cancels analytically */
+                } else {
+                    x[i] = fai_q1(&mod, z);
+                    double v = fai_logmu(&mod, x[i]);  /* liu_west_filter.h:1703-1705 order */
+                    v += fai_logg(&mod, yt, x[i]);
+                    v -= fai_logmu(&mod, x[i]);
+                    lw[i] = v;
+                }
+            } else {
+                if (canonical) {
+                    x[i] = can_f(&mod, x[i], z, ct);
+                    lw[i] = lw[i] + can_logg(&mod, yt, x[i]);
+                } else {
+                    x[i] = fai_f(&mod, x[i], z, ct);
+                    lw[i] += fai_logg(&mod, yt, x[i]);
+                }
+            }
+            if (x_trace) x_trace[t * N + i] = x[i];
+        }
+        /* log p(y_t | y_{1:t-1}) by log-sum-exp (liu_west_filter.h:1651-1659, :1722-1727) */
+        double M = -INFINITY;
+        for (int32_t i = 0; i < N; ++i) if (lw[i] > M) M = lw[i];
+        double S;
+        if (canonical) {
+            for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lw[i] - M);
+            ssme_oracle_canonical_scan(w, N, L, NP, C, &S);
+        } else {
+            S = 0.0;
+            for (int32_t i = 0; i < N; ++i) { w[i] = exp(lw[i] - M); S += w[i]; }
+        }
+        double cl;
+        const double logS = canonical ? dm_log(S) : log(S);
+        if (t == 0) {
+            cl = -logN + M + logS;
+        } else {
+            double Mo = prev_resampled ? 0.0 : M_prev;
+            double logS2 = prev_resampled ? logN : (canonical ? dm_log(S_prev) : log(S_prev));
+            cl = M + logS - Mo - logS2;
+        }
+        if (cond_like) cond_like[t] = cl;
+        loglik += cl; /* estimate_univ_svol.h:125 */
+
+        if ((t + 1) % rs == 0) {
+            const double* ut = injected ? (u_inj ? u_inj + t * stride_u : NULL) : NULL;
+            if (injected && !ut) { free(x); free(xn); free(lw); free(w); free(C); free(E); free(PE); free(anc); return -6; }
+            if (!canonical) {
+                /* libstdc++ discrete_distribution::param_type::_M_initialize: normalise by the
+                 * sequential sum, sequential partial_sum, last entry forced to 1.0 */
+                double sum = 0.0;
+                for (int32_t i = 0; i < N; ++i) sum += w[i];
+                double acc = 0.0;
+                for (int32_t i = 0; i < N; ++i) { acc += w[i] / sum; C[i] = acc; }
+                C[N - 1] = 1.0;
+            }
+            const double total = canonical ? S : 1.0;
+            if (cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL) {
+                for (int32_t j = 0; j < N; ++j) {
+                    double u = injected ? ut[j]
+                                        : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                    double tau = canonical ? u * S : u;
+                    anc[j] = canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
+                    upd_margin(&margin, C, anc[j], tau, total);
+                }
+            } else if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL) {
+                /* liu_west_filter.h:104-139: N+1 exponential spacings -> uniform order statistics */
+                for (int32_t j = 0; j <= N; ++j) {
+                    double u = injected ? ut[j]
+                                        : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                    if (!injected && u == 0.0) u = 0x1p-53;
+                    E[j] = canonical ? -dm_log(u) : -log(u);
+                }
+                if (canonical) {
+                    double G;
+                    ssme_oracle_canonical_scan(E, N, L, NP, PE, &G);
+                    G = G + E[N];
+                    double sg = S / G;
+                    for (int32_t j = 0; j < N; ++j) {
+                        double tau = PE[j] * sg;
+                        anc[j] = descent_search(C, NP, N, tau);
+                        upd_margin(&margin, C, anc[j], tau, total);
+                    }
+                } else {
+                    double G = 0.0;
+                    for (int32_t j = 0; j < N; ++j) G += E[j];
+                    G += E[N];
+                    double ustat = 0.0;
+                    int32_t idx = 0; /* monotone walk; equals lower_bound on the running CDF */
+                    for (int32_t j = 0; j < N; ++j) {
+                        ustat += E[j] / G;
+                        while (idx < N - 1 && C[idx] < ustat) idx++; /* bound check added: see SURVEY A.3 caveat */
+                        anc[j] = idx;
+                        upd_margin(&margin, C, idx, ustat, total);
+                    }
+                }
+            } else { /* systematic: u_j = (j + u0)/N, spec'd by us (not in the reference tree) */
+                double u0 = injected ? ut[0] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
+                double sN = S / (double)N;
+                for (int32_t j = 0; j < N; ++j) {
+                    double tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
+                    anc[j] = canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
+                    upd_margin(&margin, C, anc[j], tau, total);
+                }
+            }
+            for (int32_t j = 0; j < N; ++j) xn[j] = x[anc[j]];
+            for (int32_t j = 0; j < N; ++j) { x[j] = xn[j]; lw[j] = 0.0; } /* liu_west_filter.h:144 */
+            prev_resampled = 1;
+        } else {
+            for (int32_t j = 0; j < N; ++j) anc[j] = j;
+            prev_resampled = 0;
+            M_prev = M; S_prev = S;
+        }
+        if (ancestors) for (int32_t j = 0; j < N; ++j) ancestors[t * N + j] = anc[j];
+    }
+    if (loglik_out) *loglik_out = loglik;
+    if (tie_margin) *tie_margin = margin;
+    free(x); free(xn); free(lw); free(w); free(C); free(E); free(PE); free(anc);
+    return 0;
+}
+
+/* thread_pool.h:263-268 */
+double ssme_oracle_log_mean_exp(const double* v, int64_t n, int32_t arithmetic)
+{
+    double m = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) if (v[i] > m) m = v[i];
+    double sum_exp = 0.0;
+    if (arithmetic == SSME_OR_ARITH_CANONICAL) {
+        for (int64_t i = 0; i < n; ++i) sum_exp += dm_exp(v[i] - m);
+        return m + dm_log(sum_exp) - dm_log((double)n);
+    }
+    for (int64_t i = 0; i < n; ++i) sum_exp += exp(v[i] - m);
+    return m + log(sum_exp) - log((double)n);
+}
+
+/* ---------------------------------------------------------------- param::pack transforms ---- */
+/* include/ssme/parameters.h:317-449 */
+double ssme_oracle_trans(int32_t type, double p)
+{
+    switch (type) {
+    case 0: return p;
+    case 1: return (p <= -1.0 || p >= 1.0) ? NAN : log(1.0 + p) - log(1.0 - p);
+    case 2: return (p < 0.0 || p > 1.0) ? NAN : log(p) - log(1.0 - p);
+    case 3: return (p < 0.0) ? NAN : log(p);
+    default: return NAN;
+    }
+}
+double ssme_oracle_inv_trans(int32_t type, double tp)
+{
+    switch (type) {
+    case 0: return tp;
+    case 1: return tp >= 0.0 ? 2 / (1.0 + exp(-tp)) - 1.0 : 1.0 - 2.0 / (1.0 + exp(tp));
+    case 2: return tp >= 0.0 ? 1.0 / (1.0 + exp(-tp)) : exp(tp) / (1.0 + exp(tp));
+    case 3: return exp(tp);
+    default: return NAN;
+    }
+}
+double ssme_oracle_log_jacobian(int32_t type, double tp)
+{
+    switch (type) {
+    case 0: return 0.0;
+    case 1: return log(2.0) + tp - 2.0 * log(1.0 + exp(tp));
+    case 2: return -tp - 2.0 * log(1.0 + exp(-tp));
+    case 3: return tp;
+    default: return NAN;
+    }
+}

@@ -1,0 +1,96 @@
+/*
+ * oracle/pf_oracle.h -- TEST INFRASTRUCTURE.  CPU restatement of SSME's particle-filter
+ * log-likelihood hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may call this; the product (ssme_b200/) never does.
+ *
+ * Parity status: **parity unpinned at the pf boundary** -- the arithmetic of the path lives
+ * in the external, unpinned library tbrown122387/pf (find_package(pf), reference
+ * CMakeLists.txt:12), absent from /root/reference and from this image, and the reference's
+ * own tests assert nothing about filter outputs (test/test_liu_west.cpp:172,199;
+ * test/test_ada_pmmh_mvn.cpp:6-9 is empty).  What IS pinned against the reference's own
+ * known answers: param::pack transforms / log-Jacobian (test/test_parameters.cpp:114,145),
+ * thread_pool log-mean-exp (test/test_thread_pool.cpp:40), split pool (:184), CSV reader
+ * (test/test_utils.cpp:15-18) -- see tests/test_reference_known_answers.py.
+ *
+ * Two arithmetics are restated here:
+ *   FAITHFUL   the reference's formulas with libm, sequential sums, normalised CDF
+ *              (structure: liu_west_filter.h:1608-1761 SISR twin; model:
+ *              example/univ_svol_bootstrap_filter.h:54-103; multinomial resampling:
+ *              libstdc++ discrete_distribution semantics, bits/random.tcc:2660-2714).
+ *   CANONICAL  the algebraically equal form the sm_100a kernel evaluates (det_math.h
+ *              functions, fused multiply-adds, two-level Kogge-Stone scan order,
+ *              unnormalised CDF).  GPU == CANONICAL bit for bit; CANONICAL vs FAITHFUL is
+ *              checked to <=1e-12 relative on log-likelihoods with identical ancestors on
+ *              tie-margin-screened vectors (tests/test_oracle.py).
+ */
+#ifndef SSME_PF_ORACLE_H
+#define SSME_PF_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1 };
+enum { SSME_OR_RESAMP_MULTINOMIAL = 0, SSME_OR_RESAMP_SORTED_MULTINOMIAL = 1, SSME_OR_RESAMP_SYSTEMATIC = 2 };
+enum { SSME_OR_ARITH_CANONICAL = 0, SSME_OR_ARITH_FAITHFUL = 1 };
+enum { SSME_OR_RNG_PHILOX = 0, SSME_OR_RNG_INJECTED = 1 };
+
+typedef struct {
+    int32_t model;               /* SSME_OR_MODEL_* */
+    int32_t num_particles;       /* N */
+    int32_t resampler;           /* SSME_OR_RESAMP_* */
+    int32_t resample_every;      /* rs: resample when (t+1) % rs == 0 (liu_west_filter.h:1686) */
+    int32_t arithmetic;          /* SSME_OR_ARITH_* */
+    int32_t scan_items_per_lane; /* L of the canonical scan order (ignored when FAITHFUL) */
+    int32_t rng_mode;            /* SSME_OR_RNG_* */
+    int32_t scan_threads;        /* threads per filter NT of the kernel layout (power of two; NT*L slots); 0 = smallest that fits */
+    uint64_t seed;               /* Philox key */
+    uint64_t filter_id;          /* Philox counter words 2,3 */
+} ssme_oracle_cfg;
+
+/*
+ * Run one bootstrap filter over y[0..T).
+ *   theta      untransformed parameters: SV (beta, phi, sigma^2)  [svol_bs ctor, :54-61];
+ *              SV_LEVERAGE (phi, mu, sigma, rho)                  [test/test_liu_west.cpp:83-157]
+ *   cov        covariate series z_t (leverage only); NULL means z_t = y_{t-1}, z_0 unused
+ *   z_inj      injected N(0,1) stream [T][N]              (rng_mode INJECTED)
+ *   u_inj      injected U[0,1) stream [T][stride_u]       (rng_mode INJECTED); stride_u = N
+ *              (multinomial), N+1 (sorted multinomial) or 1 (systematic)
+ * Outputs (each may be NULL): loglik (scalar), cond_like[T], ancestors[T][N] (identity when a
+ * step does not resample), x_trace[T][N] (post-propagation states), tie_margin (scalar: the
+ * smallest distance, relative to the CDF total, between any resampling target and the CDF
+ * entries that bracket it).
+ * Returns 0 on success, <0 on bad arguments.
+ */
+int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
+                       const double* cov, const double* z_inj, const double* u_inj,
+                       double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
+                       double* tie_margin);
+
+/* thread_pool's reduction (reference include/ssme/thread_pool.h:263-268): m + log(sum exp(v-m)) - log(n).
+ * arithmetic CANONICAL uses det_math, index-order sum; FAITHFUL uses libm. */
+double ssme_oracle_log_mean_exp(const double* v, int64_t n, int32_t arithmetic);
+
+/* raw pieces, exported so tests can pin them */
+double ssme_oracle_dexp(double x);
+double ssme_oracle_dlog(double x);
+void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1);
+double ssme_oracle_uniform53(uint32_t hi, uint32_t lo);
+void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* the N(0,1) draw of particle i at time t, and the U[0,1) draw of slot j (Philox mode) */
+double ssme_oracle_draw_normal(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t i);
+double ssme_oracle_draw_uniform(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t j, uint32_t tag);
+/* canonical inclusive scan of w[0..n) padded with zeros to np slots, L items per lane; C has room for np entries */
+void ssme_oracle_canonical_scan(const double* w, int32_t n, int32_t L, int32_t np, double* C, double* total);
+
+/* parameter transforms (reference include/ssme/parameters.h:317-449); type: 0 null, 1 twice_fisher, 2 logit, 3 log */
+double ssme_oracle_trans(int32_t type, double p);
+double ssme_oracle_inv_trans(int32_t type, double tp);
+double ssme_oracle_log_jacobian(int32_t type, double tp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

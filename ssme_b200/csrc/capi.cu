@@ -1,0 +1,462 @@
+// ssme_b200/csrc/capi.cu -- the C ABI declared in include/ssme_b200.h: handle management,
+// kernel dispatch, host<->device staging.  No torch types, no CPU fallback: every entry point
+// either launches the sm_100a kernels or returns an error.
+#include "../../include/ssme_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "det_math.cuh"
+#include "pf_dispatch.h"
+#include "pf_kernel.cuh"
+
+#define SSME_STR2(x) #x
+#define SSME_STR(x) SSME_STR2(x)
+
+namespace ssme {
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SSME_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(SSME_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// K6: per-proposal log-mean-exp over R replicate filters (reference thread_pool.h:263-268),
+// index-order sum (the reference's order is thread-completion order, i.e. unspecified).
+__global__ void log_mean_exp_kernel(const double* __restrict__ per_filter, unsigned R, size_t P, double* __restrict__ out)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double* v = per_filter + p * R;
+    double m = __longlong_as_double(0xfff0000000000000ll);
+    for (unsigned i = 0; i < R; ++i) m = (v[i] > m) ? v[i] : m;
+    double sum_exp = 0.0;
+    for (unsigned i = 0; i < R; ++i) sum_exp = __dadd_rn(sum_exp, dexp(__dsub_rn(v[i], m)));
+    out[p] = __dsub_rn(__dadd_rn(m, dlog(sum_exp)), dlog((double)R));
+}
+
+// Roofline denominator: 8 independent FMA chains per thread keep the FP64 pipe saturated.
+__global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
+{
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        v0 = __fma_rn(v0, a, b); v1 = __fma_rn(v1, a, b); v2 = __fma_rn(v2, a, b); v3 = __fma_rn(v3, a, b);
+        v4 = __fma_rn(v4, a, b); v5 = __fma_rn(v5, a, b); v6 = __fma_rn(v6, a, b); v7 = __fma_rn(v7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+static const KernelEntry* find_kernel(int L, int NT, int model, int resamp, int debug)
+{
+    typedef const KernelEntry* (*table_fn)(int*);
+    static const table_fn tables[] = {kernel_table_nt32,  kernel_table_nt64,  kernel_table_nt128,
+                                      kernel_table_nt256, kernel_table_nt512, kernel_table_nt1024};
+    for (table_fn tf : tables) {
+        int n = 0;
+        const KernelEntry* t = tf(&n);
+        for (int i = 0; i < n; ++i)
+            if (t[i].L == L && t[i].NT == NT && t[i].model == model && t[i].resamp == resamp && t[i].debug == debug)
+                return &t[i];
+    }
+    return nullptr;
+}
+
+}  // namespace ssme
+
+using namespace ssme;
+
+struct ssme_b200_filter_s {
+    ssme_b200_config cfg;
+    int L = 0, NT = 0;
+    int num_params = 0;
+    int num_sms = 0;
+    int filters_per_sm = 0;
+    const KernelEntry* fast = nullptr;
+    const KernelEntry* debug = nullptr;
+    cudaStream_t stream = nullptr;
+    double* d_obs = nullptr;
+    size_t T = 0;
+    bool have_obs = false;
+    // staging for the host-buffer entry point
+    double* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    double* d_theta = nullptr;
+    double* d_out = nullptr;
+    double* d_per_filter = nullptr;
+    size_t cap_theta = 0, cap_out = 0, cap_pf = 0;
+};
+
+namespace {
+
+int set_device(ssme_b200_handle h)
+{
+    SSME_CUDA(cudaSetDevice(h->cfg.device));
+    return SSME_B200_OK;
+}
+
+int ensure_dev(double** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return SSME_B200_OK;
+    if (*p) SSME_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    SSME_CUDA(cudaMalloc(p, need * sizeof(double)));
+    *cap = need;
+    return SSME_B200_OK;
+}
+
+int ensure_pinned(ssme_b200_handle h, size_t bytes)
+{
+    if (h->h_pinned_bytes >= bytes) return SSME_B200_OK;
+    if (h->h_pinned) SSME_CUDA(cudaFreeHost(h->h_pinned));
+    h->h_pinned = nullptr;
+    h->h_pinned_bytes = 0;
+    SSME_CUDA(cudaMallocHost(&h->h_pinned, bytes));
+    h->h_pinned_bytes = bytes;
+    return SSME_B200_OK;
+}
+
+int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Launch the filter kernel for F = P*R filters.
+int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& args, size_t F, cudaStream_t st)
+{
+    if (F == 0) return SSME_B200_OK;
+    if (F > 0x7fffffffull) return fail(SSME_B200_EINVAL, "too many filters in one launch: %zu", F);
+    FilterArgs a = args;
+    void* params[] = {&a};
+    SSME_CUDA(cudaLaunchKernel(ke->fn, dim3((unsigned)F), dim3((unsigned)ke->NT), params, ke->smem_bytes, st));
+    g_launches.fetch_add(1);
+    return SSME_B200_OK;
+}
+
+int prepare_kernel(const KernelEntry* ke)
+{
+    SSME_CUDA(cudaFuncSetAttribute(ke->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke->smem_bytes));
+    return SSME_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ssme_b200_last_error(void) { return g_last_error.c_str(); }
+
+const char* ssme_b200_build_info(void) { return "ssme_b200 v1 sm_100a cuda-" SSME_STR(CUDART_VERSION); }
+
+uint64_t ssme_b200_launch_count(void) { return g_launches.load(); }
+
+int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
+{
+    if (!cfg || !out) return fail(SSME_B200_EINVAL, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(ssme_b200_config))
+        return fail(SSME_B200_EINVAL, "ssme_b200_config size mismatch: got %d, library expects %zu", cfg->struct_size,
+                    sizeof(ssme_b200_config));
+    if (cfg->model != SSME_B200_MODEL_SV && cfg->model != SSME_B200_MODEL_SV_LEVERAGE)
+        return fail(SSME_B200_EINVAL, "unknown model id %d", cfg->model);
+    if (cfg->num_particles < 1) return fail(SSME_B200_EINVAL, "num_particles must be >= 1");
+    if (cfg->resample_every < 1) return fail(SSME_B200_EINVAL, "resample_every must be >= 1");
+    if (cfg->resampler != SSME_B200_RESAMP_MULTINOMIAL && cfg->resampler != SSME_B200_RESAMP_SYSTEMATIC)
+        return fail(SSME_B200_EUNSUPPORTED, "resampler %d is not built into this library yet", cfg->resampler);
+    if (cfg->dtype != SSME_B200_DTYPE_F64) return fail(SSME_B200_EUNSUPPORTED, "only the fp64 path is built");
+    if (cfg->rng_mode != SSME_B200_RNG_PHILOX && cfg->rng_mode != SSME_B200_RNG_INJECTED)
+        return fail(SSME_B200_EINVAL, "unknown rng_mode %d", cfg->rng_mode);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SSME_B200_ECUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SSME_B200_EINVAL, "device %d out of range [0,%d)", cfg->device, ndev);
+    SSME_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    SSME_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(SSME_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
+                    prop.minor);
+
+    // layout: L items per lane, NT threads per filter (NT*L = padded particle count, a power of two)
+    int L = cfg->scan_items_per_lane;
+    if (L == 0) L = (cfg->num_particles > 4096) ? 8 : 4;
+    if (L != 4 && L != 8) return fail(SSME_B200_EUNSUPPORTED, "scan_items_per_lane must be 4 or 8 (got %d)", L);
+    int NT = cfg->threads_per_filter;
+    const int need = (cfg->num_particles + L - 1) / L;
+    if (NT == 0) NT = next_pow2(need < 32 ? 32 : need);
+    if (NT < need || NT > 1024 || (NT & (NT - 1)) != 0 || NT < 32)
+        return fail(SSME_B200_EUNSUPPORTED,
+                    "num_particles %d needs %d threads at L=%d; the resident kernel supports power-of-two CTAs of 32..1024 threads",
+                    cfg->num_particles, need, L);
+    const KernelEntry* fast = find_kernel(L, NT, cfg->model, cfg->resampler, 0);
+    const KernelEntry* dbg = find_kernel(L, NT, cfg->model, cfg->resampler, 1);
+    if (!fast || !dbg) return fail(SSME_B200_EUNSUPPORTED, "no kernel built for L=%d NT=%d model=%d resampler=%d", L, NT, cfg->model, cfg->resampler);
+    int rc;
+    if ((rc = prepare_kernel(fast)) != SSME_B200_OK) return rc;
+    if ((rc = prepare_kernel(dbg)) != SSME_B200_OK) return rc;
+
+    ssme_b200_handle h = new ssme_b200_filter_s();
+    h->cfg = *cfg;
+    h->L = L;
+    h->NT = NT;
+    h->num_params = (cfg->model == SSME_B200_MODEL_SV) ? 3 : 4;
+    h->num_sms = prop.multiProcessorCount;
+    h->fast = fast;
+    h->debug = dbg;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
+    if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
+    h->filters_per_sm = occ;
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_destroy(ssme_b200_handle h)
+{
+    if (!h) return SSME_B200_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->d_obs) cudaFree(h->d_obs);
+    if (h->d_theta) cudaFree(h->d_theta);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->d_per_filter) cudaFree(h->d_per_filter);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    delete h;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out)
+{
+    if (!h || !out) return fail(SSME_B200_EINVAL, "null argument");
+    out->scan_items_per_lane = h->L;
+    out->threads_per_filter = h->NT;
+    out->filters_per_sm = h->filters_per_sm;
+    out->smem_bytes_per_filter = (int32_t)h->fast->smem_bytes;
+    out->num_sms = h->num_sms;
+    cudaFuncAttributes fa;
+    SSME_CUDA(cudaFuncGetAttributes(&fa, h->fast->fn));
+    out->registers_per_thread = fa.numRegs;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_set_observations(ssme_b200_handle h, const double* y_host, size_t T, size_t dimy)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (h->have_obs) return fail(SSME_B200_ERUNTIME, "you already called add_observed_data once before!");
+    if (!y_host || T == 0) return fail(SSME_B200_ELENGTH, "can't read in data");
+    if (dimy != 1 && dimy != 2) return fail(SSME_B200_EINVAL, "dimy must be 1 (y) or 2 (y, covariate)");
+    if (T > 0x7fffffffull) return fail(SSME_B200_EINVAL, "series too long");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const int OS = obs_stride(h->cfg.model);
+    const size_t Tpad = ((T + kYChunk - 1) / kYChunk) * kYChunk;
+    std::vector<double> rows(Tpad * OS, 0.0);
+    for (size_t t = 0; t < T; ++t) {
+        rows[t * OS] = y_host[t * dimy];
+        if (OS == 2) rows[t * OS + 1] = (dimy == 2) ? y_host[t * dimy + 1] : (t > 0 ? y_host[(t - 1) * dimy] : 0.0);
+    }
+    SSME_CUDA(cudaMalloc(&h->d_obs, rows.size() * sizeof(double)));
+    SSME_CUDA(cudaMemcpy(h->d_obs, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->T = T;
+    h->have_obs = true;
+    return SSME_B200_OK;
+}
+
+static FilterArgs base_args(ssme_b200_handle h, const double* theta_dev, unsigned R, uint64_t stream_base, double* loglik_dev)
+{
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.theta = theta_dev;
+    a.theta_stride = h->num_params;
+    a.obs = h->d_obs;
+    a.T = (int)h->T;
+    a.N = h->cfg.num_particles;
+    a.R = R;
+    a.rs = h->cfg.resample_every;
+    a.seed = h->cfg.seed;
+    a.filter_base = stream_base;
+    a.loglik = loglik_dev;
+    return a;
+}
+
+int ssme_b200_loglike_batch_device(ssme_b200_handle h, const double* theta_dev, size_t P, uint32_t R, uint64_t stream_base,
+                                   double* out_dev, double* per_filter_dev, void* cuda_stream)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (R == 0) return fail(SSME_B200_EINVAL, "R (num_pfilters) must be >= 1");
+    if (P == 0) return SSME_B200_OK;
+    if (!theta_dev || !per_filter_dev) return fail(SSME_B200_EINVAL, "null device buffer");
+    if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX)
+        return fail(SSME_B200_EINVAL, "batch evaluation needs rng_mode PHILOX; injected streams go through ssme_b200_filter_trace");
+    int rc = set_device(h);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const bool fast_ok = (h->cfg.resample_every == 1);
+    FilterArgs a = base_args(h, theta_dev, R, stream_base, per_filter_dev);
+    if ((rc = launch_filters(h, fast_ok ? h->fast : h->debug, a, P * (size_t)R, st)) != SSME_B200_OK) return rc;
+    if (out_dev) {
+        const unsigned nb = (unsigned)((P + 127) / 128);
+        log_mean_exp_kernel<<<nb, 128, 0, st>>>(per_filter_dev, R, P, out_dev);
+        SSME_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1);
+    }
+    return SSME_B200_OK;
+}
+
+int ssme_b200_loglike_batch(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R, uint64_t stream_base,
+                            double* out_host, double* per_filter_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (R == 0) return fail(SSME_B200_EINVAL, "R (num_pfilters) must be >= 1");
+    if (P == 0) return SSME_B200_OK;
+    if (!theta_host || !out_host) return fail(SSME_B200_EINVAL, "null host buffer");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t np = (size_t)h->num_params, F = P * (size_t)R;
+    if ((rc = ensure_dev(&h->d_theta, &h->cap_theta, P * np))) return rc;
+    if ((rc = ensure_dev(&h->d_out, &h->cap_out, P))) return rc;
+    if ((rc = ensure_dev(&h->d_per_filter, &h->cap_pf, F))) return rc;
+    const size_t in_bytes = P * np * sizeof(double);
+    const size_t out_bytes = (P + (per_filter_host ? F : 0)) * sizeof(double);
+    if ((rc = ensure_pinned(h, in_bytes > out_bytes ? in_bytes : out_bytes))) return rc;
+    memcpy(h->h_pinned, theta_host, in_bytes);
+    SSME_CUDA(cudaMemcpyAsync(h->d_theta, h->h_pinned, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ssme_b200_loglike_batch_device(h, h->d_theta, P, R, stream_base, h->d_out, h->d_per_filter, nullptr))) return rc;
+    SSME_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_out, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (per_filter_host)
+        SSME_CUDA(cudaMemcpyAsync(h->h_pinned + P, h->d_per_filter, F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(out_host, h->h_pinned, P * sizeof(double));
+    if (per_filter_host) memcpy(per_filter_host, h->h_pinned + P, F * sizeof(double));
+    return SSME_B200_OK;
+}
+
+int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t F, uint64_t stream_base, const double* z_inj_host,
+                           const double* u_inj_host, double* loglik_host, double* cond_like_host, int32_t* ancestors_host,
+                           double* x_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (F == 0) return SSME_B200_OK;
+    if (!theta_host) return fail(SSME_B200_EINVAL, "null theta");
+    const bool inject = (h->cfg.rng_mode == SSME_B200_RNG_INJECTED);
+    if (inject && (!z_inj_host || !u_inj_host)) return fail(SSME_B200_EINVAL, "rng_mode INJECTED needs z_inj_host and u_inj_host");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t N = (size_t)h->cfg.num_particles, T = h->T, np = (size_t)h->num_params;
+    const size_t stride_u = h->cfg.resampler == SSME_B200_RESAMP_MULTINOMIAL          ? N
+                            : h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? N + 1
+                                                                                       : 1;
+    double *d_theta = nullptr, *d_z = nullptr, *d_u = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_x = nullptr;
+    int* d_anc = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_theta); cudaFree(d_z); cudaFree(d_u); cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_x); cudaFree(d_anc);
+    };
+#define SSME_CUDA_T(expr)                                                                                         \
+    do {                                                                                                          \
+        cudaError_t _e = (expr);                                                                                  \
+        if (_e != cudaSuccess) {                                                                                  \
+            cleanup();                                                                                            \
+            return fail(SSME_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                                         \
+    } while (0)
+    SSME_CUDA_T(cudaMalloc(&d_theta, F * np * sizeof(double)));
+    SSME_CUDA_T(cudaMemcpy(d_theta, theta_host, F * np * sizeof(double), cudaMemcpyHostToDevice));
+    SSME_CUDA_T(cudaMalloc(&d_ll, F * sizeof(double)));
+    if (inject) {
+        SSME_CUDA_T(cudaMalloc(&d_z, F * T * N * sizeof(double)));
+        SSME_CUDA_T(cudaMemcpy(d_z, z_inj_host, F * T * N * sizeof(double), cudaMemcpyHostToDevice));
+        SSME_CUDA_T(cudaMalloc(&d_u, F * T * stride_u * sizeof(double)));
+        SSME_CUDA_T(cudaMemcpy(d_u, u_inj_host, F * T * stride_u * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (cond_like_host) SSME_CUDA_T(cudaMalloc(&d_cl, F * T * sizeof(double)));
+    if (ancestors_host) SSME_CUDA_T(cudaMalloc(&d_anc, F * T * N * sizeof(int)));
+    if (x_host) SSME_CUDA_T(cudaMalloc(&d_x, F * T * N * sizeof(double)));
+    FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
+    a.inject = inject ? 1 : 0;
+    a.stride_u = (int)stride_u;
+    a.z_inj = d_z;
+    a.u_inj = d_u;
+    a.cond_like = d_cl;
+    a.ancestors = d_anc;
+    a.x_trace = d_x;
+    rc = launch_filters(h, h->debug, a, F, h->stream);
+    if (rc) { cleanup(); return rc; }
+    SSME_CUDA_T(cudaStreamSynchronize(h->stream));
+    if (loglik_host) SSME_CUDA_T(cudaMemcpy(loglik_host, d_ll, F * sizeof(double), cudaMemcpyDeviceToHost));
+    if (cond_like_host) SSME_CUDA_T(cudaMemcpy(cond_like_host, d_cl, F * T * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ancestors_host) SSME_CUDA_T(cudaMemcpy(ancestors_host, d_anc, F * T * N * sizeof(int), cudaMemcpyDeviceToHost));
+    if (x_host) SSME_CUDA_T(cudaMemcpy(x_host, d_x, F * T * N * sizeof(double), cudaMemcpyDeviceToHost));
+    cleanup();
+#undef SSME_CUDA_T
+    return SSME_B200_OK;
+}
+
+int ssme_b200_synchronize(ssme_b200_handle h)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    int rc = set_device(h);
+    if (rc) return rc;
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    return SSME_B200_OK;
+}
+
+void* ssme_b200_stream(ssme_b200_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_per_second)
+{
+    if (!fma_per_second || iters < 1) return fail(SSME_B200_EINVAL, "bad argument");
+    SSME_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SSME_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double* d_out = nullptr;
+    SSME_CUDA(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    SSME_CUDA(cudaEventCreate(&e0));
+    SSME_CUDA(cudaEventCreate(&e1));
+    fp64_fma_rate_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);  // warm-up
+    SSME_CUDA(cudaEventRecord(e0));
+    fp64_fma_rate_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+    SSME_CUDA(cudaEventRecord(e1));
+    SSME_CUDA(cudaEventSynchronize(e1));
+    g_launches.fetch_add(2);
+    float ms = 0.f;
+    SSME_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *fma_per_second = (double)blocks * threads * 8.0 * (double)iters / ((double)ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return SSME_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+// ssme_b200/csrc/pf_kernel.cuh -- K1: the resident bootstrap particle filter (one filter per CTA).
+//
+// Replaces, for a whole batch of filters and the whole time loop in one launch:
+//   univ_svol_estimator::log_like_eval            example/estimate_univ_svol.h:107-131
+//   pf::filters::BSFilter::filter (external pf)   twin: include/ssme/liu_west_filter.h:1608-1761
+//   svol_bs hooks q1Samp/fSamp/logGEv             example/univ_svol_bootstrap_filter.h:64-86
+//   pf::resamplers::mn_resampler::resampLogWts    (libstdc++ discrete_distribution semantics)
+//
+// Layout.  CTA f owns filter f.  Thread `tid` owns particles tid*L .. tid*L+L-1 in registers for
+// the whole time loop.  Shared memory holds the gather table X (double-buffered), the inclusive
+// CDF C, a double-buffered ring of observations filled by 1-D bulk TMA copies (cp.async.bulk +
+// mbarrier), and a few reduction slots.  HBM traffic is the observation stream only.
+//
+// Per step: draw N(0,1) (Philox4x32-10 + float Box-Muller) -> propagate -> log-weight ->
+// block max (warp shuffles + one barrier) -> w = exp(lw - max) -> two-level Kogge-Stone scan
+// (one barrier) -> CDF to smem (one barrier) -> draw U[0,1) -> branch-free binary search +
+// gather.  Three block barriers per step.  All arithmetic follows the canonical spec shared
+// with oracle/pf_oracle.c, so outputs are bit-identical to the oracle's CANONICAL mode.
+#pragma once
+#include "det_math.cuh"
+
+namespace ssme {
+
+constexpr int kModelSV = 0;
+constexpr int kModelSVLeverage = 1;
+constexpr int kResampMultinomial = 0;
+constexpr int kResampSortedMultinomial = 1;
+constexpr int kResampSystematic = 2;
+constexpr int kYChunk = 64;  // observations per TMA bulk copy
+
+struct FilterArgs {
+    const double* theta;  // [P][theta_stride], untransformed
+    int theta_stride;
+    const double* obs;  // [Tpad][OS]: y_t (and covariate z_t for the leverage model)
+    int T;
+    int N;
+    unsigned R;  // replicate filters per proposal: filter f uses theta[f / R]
+    int rs;
+    unsigned long long seed;
+    unsigned long long filter_base;
+    double* loglik;  // [F]
+    // diagnostics (DEBUG instantiations only)
+    int inject;
+    int stride_u;
+    const double* z_inj;  // [F][T][N]
+    const double* u_inj;  // [F][T][stride_u]
+    double* cond_like;    // [F][T]
+    int* ancestors;       // [F][T][N]
+    double* x_trace;      // [F][T][N]
+};
+
+__host__ __device__ constexpr int obs_stride(int model) { return model == kModelSVLeverage ? 2 : 1; }
+
+template <int L, int NT, int MODEL>
+__host__ __device__ constexpr size_t filter_smem_bytes()
+{
+    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * obs_stride(MODEL) + 64 + 64) + 16;
+}
+
+// ---- mbarrier / bulk-TMA helpers (PTX ISA: mbarrier, cp.async.bulk) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// per-filter constants of the canonical arithmetic (oracle: model_init)
+struct ModelConst {
+    double phi, sigma, mu;
+    double sd0, c0, inv2b2, rho_sigma, sdv;
+};
+
+template <int MODEL>
+__device__ __forceinline__ ModelConst model_init(const double* th)
+{
+    ModelConst m;
+    double beta;
+    double rho = 0.0;
+    if (MODEL == kModelSV) {
+        beta = th[0];
+        m.phi = th[1];
+        m.sigma = __dsqrt_rn(th[2]);
+        m.mu = 0.0;
+    } else {
+        beta = 1.0;
+        m.phi = th[0];
+        m.mu = th[1];
+        m.sigma = th[2];
+        rho = th[3];
+    }
+    m.sd0 = __ddiv_rn(m.sigma, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(m.phi, m.phi))));
+    m.c0 = __dsub_rn(-dlog(beta), SSME_DM_HALF_LOG_2PI);
+    m.inv2b2 = __ddiv_rn(0.5, __dmul_rn(beta, beta));
+    m.rho_sigma = __dmul_rn(rho, m.sigma);
+    m.sdv = __dmul_rn(m.sigma, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(rho, rho))));
+    return m;
+}
+
+template <int L, int NT, int MODEL, int RESAMP, bool DEBUG>
+__global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a)
+{
+    static_assert(L % 4 == 0, "Philox blocks serve 4 particles");
+    static_assert(NT % 32 == 0 && NT >= 32 && NT <= 1024, "whole warps");
+    constexpr int NP = L * NT;
+    constexpr int NW = NT / 32;
+    constexpr int OS = obs_stride(MODEL);
+    constexpr uint32_t kChunkBytes = kYChunk * OS * sizeof(double);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Xs = reinterpret_cast<double*>(smem_raw);  // [2][NP]
+    double* Cs = Xs + 2 * NP;                          // [NP]
+    double* ybuf = Cs + NP;                            // [2][kYChunk*OS]
+    double* red_max = ybuf + 2 * kYChunk * OS;         // [32]
+    double* red_sum = red_max + 32;                    // [32]
+    double* clM = red_sum + 32;                        // [32]
+    double* clS = clM + 32;                            // [32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(clS + 32);  // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long f = blockIdx.x;
+    const int N = a.N, T = a.T;
+    const int i0 = tid * L;
+    const int nchunks = (T + kYChunk - 1) / kYChunk;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        if (nchunks > 0) {
+            mbar_expect_tx(&bars[0], kChunkBytes);
+            tma_load_1d(ybuf, a.obs, kChunkBytes, &bars[0]);
+        }
+        if (nchunks > 1) {
+            mbar_expect_tx(&bars[1], kChunkBytes);
+            tma_load_1d(ybuf + kYChunk * OS, a.obs + (size_t)kYChunk * OS, kChunkBytes, &bars[1]);
+        }
+    }
+
+    const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
+    const unsigned long long fid = a.filter_base + f;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
+    const double logN = dlog((double)N);
+    const double dN = (double)N;
+
+    double x[L];
+    double lwacc[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) { x[k] = 0.0; lwacc[k] = 0.0; }
+    double loglik = 0.0;
+    bool prev_resampled = true;
+    double M_prev = 0.0, S_prev = 0.0;
+
+    __syncthreads();  // mbarrier init visible to every waiter
+
+    for (int t = 0; t < T; ++t) {
+        const int c = t / kYChunk, o = t % kYChunk;
+        if (o == 0) mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
+        const double* yrow = ybuf + (c & 1) * (kYChunk * OS) + o * OS;
+        const double y = yrow[0];
+        const double cov = (OS == 2) ? yrow[1] : 0.0;
+
+        // ---- N(0,1) draws: one Philox block per 4 particles --------------------------------
+        double z[L];
+        if (DEBUG && a.inject) {
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+                z[k] = (i0 + k < N) ? a.z_inj[((size_t)f * T + t) * N + i0 + k] : 0.0;
+        } else {
+#pragma unroll
+            for (int q = 0; q < L / 4; ++q) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
+                float z0, z1, z2, z3;
+                box_muller(r.x, r.y, z0, z1);
+                box_muller(r.z, r.w, z2, z3);
+                z[4 * q + 0] = (double)z0;
+                z[4 * q + 1] = (double)z1;
+                z[4 * q + 2] = (double)z2;
+                z[4 * q + 3] = (double)z3;
+            }
+        }
+
+        // ---- propagate (q1Samp at t = 0, fSamp afterwards) and log-weight (logGEv) ----------
+        const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
+        double lw[L];
+        double mloc = __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            if (t == 0) {
+                x[k] = __dmul_rn(z[k], mc.sd0);
+            } else if (MODEL == kModelSV) {
+                x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+            } else {
+                const double e2 = dexp(__dmul_rn(-0.5, x[k]));
+                const double cz = __dmul_rn(mc.rho_sigma, cov);
+                double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
+                mean = __fma_rn(cz, e2, mean);
+                x[k] = __fma_rn(mc.sdv, z[k], mean);
+            }
+            const double e = dexp(-x[k]);
+            const double g = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
+            double v = DEBUG ? __dadd_rn(lwacc[k], g) : g;
+            v = (i0 + k < N) ? v : __longlong_as_double(0xfff0000000000000ll);
+            lw[k] = v;
+            mloc = (v > mloc) ? v : mloc;
+        }
+        double* Xcur = Xs + (t & 1) * NP;
+#pragma unroll
+        for (int k = 0; k < L; k += 2)
+            *reinterpret_cast<double2*>(Xcur + i0 + k) = make_double2(x[k], x[k + 1]);
+        if (DEBUG && a.x_trace) {
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+                if (i0 + k < N) a.x_trace[((size_t)f * T + t) * N + i0 + k] = x[k];
+        }
+
+        // ---- block max -----------------------------------------------------------------------
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(mloc, d);
+            mloc = (other > mloc) ? other : mloc;
+        }
+        if (lane == 0) red_max[warp] = mloc;
+        __syncthreads();  // B2
+        if (tid == 0 && o == 0 && c >= 1 && c + 1 < nchunks) {
+            // every thread has now read its first observation of chunk c, so chunk c-1's buffer is free
+            uint64_t* bar = &bars[(c + 1) & 1];
+            mbar_expect_tx(bar, kChunkBytes);
+            tma_load_1d(ybuf + ((c + 1) & 1) * (kYChunk * OS), a.obs + (size_t)(c + 1) * kYChunk * OS, kChunkBytes, bar);
+        }
+        double M;
+        if (NW <= 8) {
+            M = red_max[0];
+#pragma unroll
+            for (int g = 1; g < NW; ++g) {
+                const double other = red_max[g];
+                M = (other > M) ? other : M;
+            }
+        } else {
+            M = (lane < NW) ? red_max[lane] : __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double other = shfl_xor_d(M, d);
+                M = (other > M) ? other : M;
+            }
+        }
+
+        // ---- batched log p(y_t | y_{1:t-1}) for the previous 32 steps (fast path) -----------
+        if (!DEBUG && warp == 0 && (t & 31) == 0 && t > 0) {
+            const int s = t - 32 + lane;
+            const double logS = dlog(clS[lane]);
+            const double cl = (s == 0) ? __dadd_rn(__dadd_rn(-logN, clM[lane]), logS)
+                                       : __dsub_rn(__dsub_rn(__dadd_rn(clM[lane], logS), 0.0), logN);
+            __syncwarp();
+            clM[lane] = cl;
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) loglik = __dadd_rn(loglik, clM[j]);
+            }
+            __syncwarp();
+        }
+
+        // ---- weights and the canonical two-level Kogge-Stone scan ---------------------------
+        double sc[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            const double w = dexp_nonpos(__dsub_rn(lw[k], M));
+            sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
+        }
+        double incl = sc[L - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(incl, d);
+            incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+        }
+        if (lane == 31) red_sum[warp] = incl;
+        __syncthreads();  // B3
+        double wv = (lane < NW) ? red_sum[lane] : 0.0;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            const double other = shfl_up_d(wv, d);
+            wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+        }
+        const double S = shfl_d(wv, NW - 1);
+        double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
+        wex = (warp > 0) ? wex : 0.0;
+        double lex = shfl_up_d(incl, 1);
+        lex = (lane > 0) ? lex : 0.0;
+        const double base = __dadd_rn(wex, lex);
+#pragma unroll
+        for (int k = 0; k < L; k += 2)
+            *reinterpret_cast<double2*>(Cs + i0 + k) = make_double2(__dadd_rn(base, sc[k]), __dadd_rn(base, sc[k + 1]));
+
+        const bool do_resample = DEBUG ? ((t + 1) % a.rs == 0) : true;
+
+        if (DEBUG) {
+            if (tid == 0) {
+                const double logS = dlog(S);
+                double cl;
+                if (t == 0) {
+                    cl = __dadd_rn(__dadd_rn(-logN, M), logS);
+                } else {
+                    const double Mo = prev_resampled ? 0.0 : M_prev;
+                    const double logS2 = prev_resampled ? logN : dlog(S_prev);
+                    cl = __dsub_rn(__dsub_rn(__dadd_rn(M, logS), Mo), logS2);
+                }
+                loglik = __dadd_rn(loglik, cl);
+                if (a.cond_like) a.cond_like[(size_t)f * T + t] = cl;
+            }
+            M_prev = M;
+            S_prev = S;
+            prev_resampled = do_resample;
+        } else if (tid == 0) {
+            clM[t & 31] = M;
+            clS[t & 31] = S;
+        }
+
+        if (!do_resample) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) lwacc[k] = lw[k];
+            if (DEBUG && a.ancestors) {
+#pragma unroll
+                for (int k = 0; k < L; ++k)
+                    if (i0 + k < N) a.ancestors[((size_t)f * T + t) * N + i0 + k] = i0 + k;
+            }
+            continue;  // next step has its own barriers before X / C are touched again
+        }
+        if (!DEBUG && t == T - 1) break;  // the last resampling does not enter the likelihood
+
+        // ---- resampling targets -------------------------------------------------------------
+        double tau[L];
+        if (RESAMP == kResampMultinomial) {
+            if (DEBUG && a.inject) {
+#pragma unroll
+                for (int k = 0; k < L; ++k)
+                    tau[k] = (i0 + k < N) ? __dmul_rn(a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k], S) : 0.0;
+            } else {
+#pragma unroll
+                for (int q = 0; q < L / 2; ++q) {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                    tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
+                    tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
+                }
+            }
+        } else {  // systematic
+            double u0;
+            if (DEBUG && a.inject) {
+                u0 = a.u_inj[((size_t)f * T + t) * a.stride_u];
+            } else {
+                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
+                u0 = uniform53(r.x, r.y);
+            }
+            const double sN = __ddiv_rn(S, dN);
+#pragma unroll
+            for (int k = 0; k < L; ++k) tau[k] = __dmul_rn(__dadd_rn((double)(i0 + k), u0), sN);
+        }
+        __syncthreads();  // B4: CDF and gather table complete
+
+        // ---- branch-free lower_bound over the padded CDF, then gather -------------------------
+        int idx[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) idx[k] = 0;
+#pragma unroll
+        for (int s = NP / 2; s >= 1; s >>= 1) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) idx[k] += (Cs[idx[k] + s - 1] < tau[k]) ? s : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            idx[k] = min(idx[k], N - 1);
+            x[k] = (i0 + k < N) ? Xcur[idx[k]] : 0.0;
+            lwacc[k] = 0.0;
+        }
+        if (DEBUG && a.ancestors) {
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+                if (i0 + k < N) a.ancestors[((size_t)f * T + t) * N + i0 + k] = idx[k];
+        }
+    }
+
+    // ---- epilogue: the cond-likes still buffered (fast path) -----------------------------------
+    if (!DEBUG && T > 0) {
+        __syncthreads();
+        if (warp == 0) {
+            const int t0 = ((T - 1) / 32) * 32;  // first step of the unfinished batch
+            const int cnt = T - t0;
+            double cl = 0.0;
+            if (lane < cnt) {
+                const double logS = dlog(clS[lane]);
+                cl = (t0 + lane == 0) ? __dadd_rn(__dadd_rn(-logN, clM[lane]), logS)
+                                      : __dsub_rn(__dsub_rn(__dadd_rn(clM[lane], logS), 0.0), logN);
+            }
+            __syncwarp();
+            clM[lane] = cl;
+            __syncwarp();
+            if (lane == 0)
+                for (int j = 0; j < cnt; ++j) loglik = __dadd_rn(loglik, clM[j]);
+        }
+    }
+    if (tid == 0) a.loglik[f] = loglik;
+}
+
+}  // namespace ssme

@@ -1,0 +1,128 @@
+"""-m gpu: the sm_100a kernel, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact.  Ancestor indices are integers; log-likelihoods, conditional likelihoods and
+particle states are compared with == because kernel and oracle evaluate the same IEEE-754
+operation sequence (canonical arithmetic).  The faithful (libm, reference-formula) oracle is
+compared at 1e-9 relative, the tolerance BASELINE.json's north_star states for fp64.
+"""
+import numpy as np
+import pytest
+
+import ssme_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+SV_THETA = np.array([1.0, 0.95, 0.0625])
+LEV_THETA = np.array([0.9, 0.0, 0.3, -0.1])  # phi, mu, sigma, rho
+
+
+def _theta(model):
+    return SV_THETA if model == sb.MODEL_SV else LEV_THETA
+
+
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("N,T,rs", [(32, 1, 1), (32, 2, 1), (500, 64, 1), (1024, 130, 1), (100, 65, 2), (500, 40, 5)])
+def test_injected_streams_trace_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, rs):
+    """Identical pre-generated normal and uniform streams -> identical ancestors, states, cond-likes."""
+    rng = np.random.default_rng(N * 1000 + T)
+    y = sv_series(T, seed=3)
+    F = 2
+    stride_u = N if resampler == sb.RESAMP_MULTINOMIAL else 1
+    z = rng.standard_normal((F, T, N))
+    u = rng.random((F, T, stride_u))
+    theta = np.stack([_theta(model), _theta(model) * np.array([1.05, 0.9, 1.2, 1.0][: len(_theta(model))])])
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, resample_every=rs, rng_mode=sb.RNG_INJECTED)
+    be.add_observed_data(y)
+    got = be.trace(theta, z=z, u=u)
+    L, NT = be.layout["scan_items_per_lane"], be.layout["threads_per_filter"]
+    for f in range(F):
+        ref = oracle.filter_run(theta[f], y, N, model=model, resampler=resampler, rs=rs, L=L, NT=NT,
+                                rng_mode=oracle.RNG_INJECTED, z=z[f], u=u[f])
+        assert np.array_equal(got["ancestors"][f], ref["ancestors"])
+        assert np.array_equal(got["x"][f], ref["x"])
+        assert np.array_equal(got["cond_like"][f], ref["cond_like"])
+        assert got["loglik"][f] == ref["loglik"]
+        fai = oracle.filter_run(theta[f], y, N, model=model, resampler=resampler, rs=rs, arithmetic=oracle.ARITH_FAITHFUL,
+                                rng_mode=oracle.RNG_INJECTED, z=z[f], u=u[f])
+        if ref["margin"] > 1e-12:  # no resampling target within rounding distance of a CDF boundary
+            assert np.array_equal(got["ancestors"][f], fai["ancestors"])
+            assert abs(got["loglik"][f] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+
+
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("N,T", [(500, 100), (1024, 257), (37, 33), (2048, 64), (8192, 40)])
+def test_philox_fast_path_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T):
+    """Production path (on-device Philox, no tracing): log-likelihoods equal the oracle's bit for bit."""
+    y = sv_series(T, seed=5)
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=99)
+    be.add_observed_data(y)
+    th = _theta(model)
+    theta = np.stack([th, th * 0.97, th * 1.01])
+    R = 2
+    out, pf = be.work_batch(theta, R=R, stream_base=1000, return_per_filter=True)
+    L, NT = be.layout["scan_items_per_lane"], be.layout["threads_per_filter"]
+    for p in range(theta.shape[0]):
+        ref = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=L, NT=NT, seed=99,
+                                 filter_id=1000 + p * R + r, trace=False)["loglik"] for r in range(R)]
+        assert pf[p].tolist() == ref
+        assert out[p] == oracle.log_mean_exp(np.array(ref))
+    # the tracing instantiation must agree with the fast one
+    tr = be.trace(theta[:1], stream_base=1000, want=("loglik",))
+    assert tr["loglik"][0] == pf[0, 0]
+
+
+def test_resample_schedule_philox(oracle, sv_series, gpu_backend_factory):
+    y = sv_series(90, seed=8)
+    for rs in (2, 3):
+        be = gpu_backend_factory(num_particles=256, resample_every=rs, seed=5)
+        be.add_observed_data(y)
+        out, pf = be.work_batch(SV_THETA[None, :], R=3, stream_base=7, return_per_filter=True)
+        L, NT = be.layout["scan_items_per_lane"], be.layout["threads_per_filter"]
+        ref = [oracle.filter_run(SV_THETA, y, 256, rs=rs, L=L, NT=NT, seed=5, filter_id=7 + r, trace=False)["loglik"] for r in range(3)]
+        assert pf[0].tolist() == ref
+
+
+def test_error_conventions(gpu_backend_factory):
+    be = gpu_backend_factory(num_particles=64)
+    with pytest.raises(sb.SsmeB200Error):  # thread_pool.h:192 "must add observed data before calculating anything"
+        be.work(SV_THETA)
+    be.add_observed_data(np.ones(10))
+    with pytest.raises(sb.SsmeB200Error):  # thread_pool.h:169 second add_observed_data throws
+        be.add_observed_data(np.ones(10))
+    with pytest.raises(ValueError):
+        sb.ParticleFilterBackend(sb.FilterConfig(num_particles=0))
+    # invalid parameters give NaN, not a trap (ada_pmmh_mvn.h:349 treats NaN as reject)
+    assert np.isnan(be.work(np.array([1.0, 1.5, 0.1])))
+
+
+def test_spy_example_config(gpu_backend_factory):
+    """Config 1: the reference's SPY series (T = 3084), N = 500, the example's start theta; expected values are
+    the committed golden log-likelihoods (tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spy_config1.npz"))
+    be = gpu_backend_factory(num_particles=500, seed=int(g["seed"][0]), scan_items_per_lane=4)
+    be.add_observed_data(g["y"])
+    got = be.work_batch(g["theta"][None, :], R=8, stream_base=0, return_per_filter=True)[1][0]
+    assert got.tolist() == g["loglik_canonical_L4"].tolist()
+    assert np.all(np.abs(got - g["loglik_faithful"]) <= 1e-9 * np.abs(g["loglik_faithful"]))
+
+
+def test_golden_vectors(gpu_backend_factory):
+    """Kernel against the committed golden vectors (inputs and expected outputs both from the fixture)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "filter_vectors.npz"))
+    for name in g["cases"]:
+        model, res, N, T, rs = (int(v) for v in g[name + "/cfg"])
+        if res == sb.RESAMP_SORTED_MULTINOMIAL:
+            continue  # not built into the kernel yet
+        be = gpu_backend_factory(model=model, num_particles=N, resampler=res, resample_every=rs, rng_mode=sb.RNG_INJECTED,
+                                 scan_items_per_lane=4)
+        be.add_observed_data(g[name + "/y"])
+        got = be.trace(g[name + "/theta"][None, :], z=g[name + "/z"][None], u=g[name + "/u"][None])
+        assert np.array_equal(got["ancestors"][0], g[name + "/ancestors"]), name
+        assert np.array_equal(got["cond_like"][0], g[name + "/cond_like"]), name
+        assert np.array_equal(got["x"][0][-1], g[name + "/x_last"]), name
+        assert got["loglik"][0] == g[name + "/loglik"][0], name
+        assert abs(got["loglik"][0] - g[name + "/loglik"][1]) <= 1e-9 * abs(g[name + "/loglik"][1]), name

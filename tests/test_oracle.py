@@ -1,0 +1,157 @@
+"""CPU tests of the oracle itself (no GPU): pins the RNG against published vectors, the
+deterministic math against libm, the canonical arithmetic against the faithful (reference-formula)
+arithmetic, and the whole thing against the committed golden vectors."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_philox_known_answers(oracle):
+    """Random123 known-answer vectors for philox4x32-10 (Salmon et al., SC'11; kat_vectors)."""
+    L = oracle.lib()
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    out = (C.c_uint32 * 4)()
+    for ctr, key, want in kat:
+        L.ssme_oracle_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want
+
+
+def test_det_exp_log_within_ulps_of_libm(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-708, 709, 20000), rng.uniform(-2, 2, 20000), rng.uniform(-60, 0, 20000)])
+    for x in xs:
+        a, b = L.ssme_oracle_dexp(x), math.exp(x)
+        assert abs(a - b) <= 1.0 * math.ulp(b)
+    for x in np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0.5, 2, 20000)]):
+        a, b = L.ssme_oracle_dlog(x), math.log(x)
+        assert abs(a - b) <= 2.0 * max(math.ulp(b), 1e-300)
+    assert L.ssme_oracle_dexp(-708.0) == 0.0 and L.ssme_oracle_dexp(-1e9) == 0.0
+    assert L.ssme_oracle_dexp(-float("inf")) == 0.0
+    assert L.ssme_oracle_dexp(709.5) == float("inf")
+    assert math.isnan(L.ssme_oracle_dexp(float("nan")))
+    assert L.ssme_oracle_dexp(0.0) == 1.0
+    assert L.ssme_oracle_dlog(1.0) == 0.0
+    assert L.ssme_oracle_dlog(0.0) == -float("inf")
+    assert math.isnan(L.ssme_oracle_dlog(-1.0))
+
+
+def test_box_muller_is_standard_normal(oracle):
+    """The float Box-Muller transform: moments, tails and the polynomial pieces against libm."""
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    words = rng.integers(0, 2 ** 32, size=(200000, 2), dtype=np.uint64)
+    z0, z1 = C.c_float(), C.c_float()
+    zs = np.empty((words.shape[0], 2))
+    for i, (a, b) in enumerate(words):
+        L.ssme_oracle_box_muller(int(a), int(b), C.byref(z0), C.byref(z1))
+        zs[i] = (z0.value, z1.value)
+        if i < 2000:  # exact transform evaluated in double
+            u = ((int(a) >> 8) + 1) * 2.0 ** -24
+            r = math.sqrt(-2 * math.log(u))
+            ang = 2 * math.pi * ((int(b) >> 6) * 2.0 ** -26)
+            assert abs(z0.value - r * math.cos(ang)) < 3e-6 * max(1.0, r)
+            assert abs(z1.value - r * math.sin(ang)) < 3e-6 * max(1.0, r)
+    z = zs.ravel()
+    n = z.size
+    assert abs(z.mean()) < 4 / math.sqrt(n)
+    assert abs(z.var() - 1) < 4 * math.sqrt(2 / n)
+    assert abs((z ** 4).mean() - 3) < 0.1
+    assert abs(np.corrcoef(zs[:, 0], zs[:, 1])[0, 1]) < 0.01
+    assert abs((np.abs(z) > 1.959964).mean() - 0.05) < 0.002
+    # extreme words
+    for a, b in [(0, 0), (0xffffffff, 0xffffffff), (0xffffff00, 0x40000000), (0x100, 0x80000000)]:
+        L.ssme_oracle_box_muller(a, b, C.byref(z0), C.byref(z1))
+        assert math.isfinite(z0.value) and math.isfinite(z1.value) and abs(z0.value) < 6.7 and abs(z1.value) < 6.7
+
+
+def test_uniform53(oracle):
+    L = oracle.lib()
+    assert L.ssme_oracle_uniform53(0, 0) == 0.0
+    assert L.ssme_oracle_uniform53(0xffffffff, 0xffffffff) == 1.0 - 2.0 ** -53
+    assert L.ssme_oracle_uniform53(0x80000000, 0) == 0.5
+
+
+@pytest.mark.parametrize("n,L", [(1, 4), (5, 4), (128, 4), (500, 4), (1024, 4), (1024, 8), (4097, 8), (8192, 8)])
+def test_canonical_scan_matches_sequential_to_rounding(oracle, n, L):
+    rng = np.random.default_rng(n)
+    w = rng.random(n) ** 8
+    c = oracle.canonical_scan(w, L)
+    ref = np.cumsum(w)
+    # a parallel scan is sorted only up to rounding: an entry may sit an ulp below its predecessor
+    assert np.all(np.diff(c) >= -4e-16 * c[-1])
+    assert np.allclose(c, ref, rtol=1e-13, atol=0)
+    # exactness on integers: any summation order gives the same result
+    wi = rng.integers(0, 1000, n).astype(float)
+    assert np.array_equal(oracle.canonical_scan(wi, L), np.cumsum(wi))
+
+
+@pytest.mark.parametrize("model,theta", [(0, [1.0, 0.95, 0.0625]), (1, [0.9, 0.0, 0.3, -0.1])])
+@pytest.mark.parametrize("resampler", [0, 1, 2])
+@pytest.mark.parametrize("N,T,rs", [(32, 40, 1), (500, 60, 1), (100, 50, 3)])
+def test_canonical_agrees_with_faithful(oracle, sv_series, model, theta, resampler, N, T, rs):
+    """CANONICAL (what the kernel computes) vs FAITHFUL (the reference's formulas, libm, sequential sums,
+    normalised CDF): identical ancestors whenever no target is within rounding distance of a CDF boundary,
+    log-likelihood within 1e-12 relative (the north_star bar is 1e-9)."""
+    y = sv_series(T, seed=N + T + resampler)
+    for L in (4, 8):
+        a = oracle.filter_run(theta, y, N, model=model, resampler=resampler, rs=rs, L=L, seed=3, filter_id=9)
+        b = oracle.filter_run(theta, y, N, model=model, resampler=resampler, rs=rs, arithmetic=oracle.ARITH_FAITHFUL, seed=3, filter_id=9)
+        assert a["margin"] > 1e-12, "vector too close to a tie to be a parity vector"
+        assert np.array_equal(a["ancestors"], b["ancestors"])
+        assert abs(a["loglik"] - b["loglik"]) <= 1e-12 * abs(b["loglik"])
+        assert np.allclose(a["cond_like"], b["cond_like"], rtol=0, atol=1e-11)
+
+
+def test_golden_vectors(oracle):
+    g = np.load(os.path.join(GOLDEN, "filter_vectors.npz"))
+    for name in g["cases"]:
+        model, res, N, T, rs = (int(v) for v in g[name + "/cfg"])
+        r = oracle.filter_run(g[name + "/theta"], g[name + "/y"], N, model=model, resampler=res, rs=rs, L=4,
+                              rng_mode=oracle.RNG_INJECTED, z=g[name + "/z"], u=g[name + "/u"])
+        assert r["loglik"] == g[name + "/loglik"][0], name
+        assert np.array_equal(r["ancestors"], g[name + "/ancestors"]), name
+        assert np.array_equal(r["cond_like"], g[name + "/cond_like"]), name
+    s = np.load(os.path.join(GOLDEN, "spy_config1.npz"))
+    ll = oracle.filter_run(s["theta"], s["y"], 500, L=4, seed=int(s["seed"][0]), filter_id=2, trace=False)["loglik"]
+    assert ll == s["loglik_canonical_L4"][2]
+
+
+def test_edge_cases(oracle, sv_series):
+    y = sv_series(8)
+    # single particle: every ancestor is 0, cond-likes are the single weight
+    r = oracle.filter_run([1.0, 0.9, 0.04], y, 1, L=4)
+    assert np.all(r["ancestors"] == 0) and np.isfinite(r["loglik"])
+    # empty series
+    e = oracle.filter_run([1.0, 0.9, 0.04], np.zeros(0), 16, L=4, trace=False)
+    assert e["loglik"] == 0.0
+    # non-stationary phi -> NaN log-likelihood (sqrt of a negative number), never a crash
+    assert math.isnan(oracle.filter_run([1.0, 1.5, 0.04], y, 16, L=4)["loglik"])
+    # an exact zero observation (spy_returns.csv contains one) is fine
+    y0 = y.copy()
+    y0[3] = 0.0
+    assert np.isfinite(oracle.filter_run([1.0, 0.9, 0.04], y0, 64, L=4)["loglik"])
+    # outlier: weights collapse on few particles but the estimate stays finite
+    y0[4] = 60.0
+    r = oracle.filter_run([1.0, 0.9, 0.04], y0, 64, L=4)
+    assert np.isfinite(r["loglik"]) and r["ancestors"].min() >= 0 and r["ancestors"].max() < 64
+
+
+def test_loglik_estimator_is_sane(oracle, sv_series):
+    """More particles -> lower variance, same mean level (unbiased likelihood estimator)."""
+    y = sv_series(100, seed=4)
+    th = [1.0, 0.95, 0.0625]
+    small = [oracle.filter_run(th, y, 64, seed=1, filter_id=i, trace=False)["loglik"] for i in range(30)]
+    big = [oracle.filter_run(th, y, 1024, seed=1, filter_id=i, trace=False)["loglik"] for i in range(30)]
+    assert np.std(big) < np.std(small)
+    assert abs(np.mean(big) - np.mean(small)) < 4 * np.std(small)
