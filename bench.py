@@ -280,6 +280,8 @@ def run_ours(args):
         }
         # ---- CPU baseline: the reference's thread_pool path on this box's host cores -------------
         try:
+            if args.no_cpu:
+                raise RuntimeError("skipped (--no-cpu)")
             L = load_refcpu()
             cores = L.ssme_refcpu_hardware_threads()
             nfil = max(2, cores)
@@ -314,6 +316,7 @@ def run_ours(args):
 
 
 def main():
+    global P_PROPOSALS, T_STEPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -321,7 +324,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=0, help="scan items per lane (0 = library default)")
     ap.add_argument("--threads", type=int, default=0, help="threads per filter (0 = library default)")
+    ap.add_argument("--proposals", type=int, default=4096, help="experiments only: proposals per GPU")
+    ap.add_argument("--T", type=int, default=4096, help="experiments only: series length")
+    ap.add_argument("--no-cpu", action="store_true", help="experiments only: skip the CPU baseline leg")
     args = ap.parse_args()
+    P_PROPOSALS, T_STEPS = args.proposals, args.T
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -13,8 +13,10 @@
 //
 // Per step: draw N(0,1) (Philox4x32-10 + float Box-Muller) -> propagate -> log-weight ->
 // block max (warp shuffles + one barrier) -> w = exp(lw - max) -> two-level Kogge-Stone scan
-// (one barrier) -> CDF to smem (one barrier) -> draw U[0,1) -> branch-free binary search +
-// gather.  Three block barriers per step.  All arithmetic follows the canonical spec shared
+// (one barrier) -> CDF to smem in Eytzinger (breadth-first) order (one barrier) -> draw U[0,1) ->
+// branch-free descent + gather.  Three block barriers per step.  The breadth-first layout keeps the
+// nodes of one tree level contiguous, so the 32 probes of a warp spread over the banks; in sorted
+// order all probes of a level share one bank (ncu round 1: 13.5 wavefronts per LDS.64).  All arithmetic follows the canonical spec shared
 // with oracle/pf_oracle.c, so outputs are bit-identical to the oracle's CANONICAL mode.
 #pragma once
 #include "det_math.cuh"
@@ -149,6 +151,20 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     const int N = a.N, T = a.T;
     const int i0 = tid * L;
     const int nchunks = (T + kYChunk - 1) / kYChunk;
+
+    // Eytzinger slot (byte offset) of each of this thread's CDF entries: sorted index i is probed by
+    // the descent at tree level K-1-ctz(i+1), position (i+1) >> (ctz(i+1)+1); entry NP-1 is never
+    // probed and parks in the spare slot NP-1.
+    constexpr int K = (NP <= 1) ? 0 : (31 - __builtin_clz((unsigned)NP));
+    static_assert((1 << K) == NP, "padded particle count must be a power of two");
+    uint32_t eoff[L];
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+        const uint32_t v = (uint32_t)(i0 + k + 1);
+        const int tz = __ffs((int)v) - 1;
+        const uint32_t node = (v == (uint32_t)NP) ? (uint32_t)(NP - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
+        eoff[k] = node * 8u;
+    }
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -316,9 +332,9 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
+        unsigned char* Cb = reinterpret_cast<unsigned char*>(Cs);
 #pragma unroll
-        for (int k = 0; k < L; k += 2)
-            *reinterpret_cast<double2*>(Cs + i0 + k) = make_double2(__dadd_rn(base, sc[k]), __dadd_rn(base, sc[k + 1]));
+        for (int k = 0; k < L; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
 
         const bool do_resample = DEBUG ? ((t + 1) % a.rs == 0) : true;
 
@@ -385,18 +401,23 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         }
         __syncthreads();  // B4: CDF and gather table complete
 
-        // ---- branch-free lower_bound over the padded CDF, then gather -------------------------
+        // ---- branch-free descent over the breadth-first CDF, then gather -------------------------
+        // Probe sequence identical to "for (s = NP/2; s >= 1; s >>= 1) if (C[idx+s-1] < tau) idx += s".
+        uint32_t nb[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) nb[k] = 0u;
+#pragma unroll
+        for (int lvl = 0; lvl < K; ++lvl) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                const double v = *reinterpret_cast<const double*>(Cb + nb[k]);
+                nb[k] = 2u * nb[k] + ((v < tau[k]) ? 16u : 8u);
+            }
+        }
         int idx[L];
 #pragma unroll
-        for (int k = 0; k < L; ++k) idx[k] = 0;
-#pragma unroll
-        for (int s = NP / 2; s >= 1; s >>= 1) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) idx[k] += (Cs[idx[k] + s - 1] < tau[k]) ? s : 0;
-        }
-#pragma unroll
         for (int k = 0; k < L; ++k) {
-            idx[k] = min(idx[k], N - 1);
+            idx[k] = min((int)(nb[k] >> 3) - (NP - 1), N - 1);
             x[k] = (i0 + k < N) ? Xcur[idx[k]] : 0.0;
             lwacc[k] = 0.0;
         }
