@@ -46,6 +46,14 @@ def _run(cmd):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LIB, OBJDIR
+    extra = os.environ.get("SSME_NVCC_EXTRA", "").split()  # experiments only, e.g. -DSSME_STAGGER_NS=400
+    if extra:
+        tag = "_".join(e.replace("-D", "").replace("=", "") for e in extra)
+        LIB = os.path.join(LIBDIR, "libssme_b200_%s.so" % tag)
+        OBJDIR = os.path.join(HERE, "build", tag)
+        NVCC_FLAGS.extend(extra)
+        force = True
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     newest = _sources()

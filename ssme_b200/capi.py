@@ -46,7 +46,8 @@ class _Layout(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libssme_b200.so")
+    # SSME_B200_LIB: experiments only (A/B-testing alternative builds of the same sources)
+    return os.environ.get("SSME_B200_LIB") or os.path.join(_HERE, "lib", "libssme_b200.so")
 
 
 _lib = None
