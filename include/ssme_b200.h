@@ -123,6 +123,10 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
                            const double* z_inj_host, const double* u_inj_host, double* loglik_host,
                            double* cond_like_host, int32_t* ancestors_host, double* x_host);
 
+/* Replaces: the reduction at the end of thread_pool::worker_thread (thread_pool.h:263-268) on its own:
+ * out[p] = log-mean-exp of values[p*R .. p*R+R).  HOST buffers; runs kernel K6 on `device`. */
+int ssme_b200_log_mean_exp(int32_t device, const double* values_host, size_t P, uint32_t R, double* out_host);
+
 /* Blocks until all work queued on the handle's stream has finished. */
 int ssme_b200_synchronize(ssme_b200_handle h);
 

@@ -12,6 +12,7 @@ from .capi import (  # noqa: F401
     library_path,
     launch_count,
     measure_fp64_fma_rate,
+    log_mean_exp,
     MODEL_SV,
     MODEL_SV_LEVERAGE,
     RESAMP_MULTINOMIAL,

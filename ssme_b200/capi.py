@@ -77,6 +77,7 @@ def load_library():
     lib.ssme_b200_loglike_batch_device.argtypes = [H, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_void_p,
                                                    C.c_void_p, C.c_void_p]
     lib.ssme_b200_filter_trace.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp, dp, dp, ip, dp]
+    lib.ssme_b200_log_mean_exp.argtypes = [C.c_int32, dp, C.c_size_t, C.c_uint32, dp]
     lib.ssme_b200_synchronize.argtypes = [H]
     lib.ssme_b200_stream.argtypes = [H]
     lib.ssme_b200_stream.restype = C.c_void_p
@@ -102,6 +103,15 @@ def measure_fp64_fma_rate(device: int = 0, iters: int = 1 << 16) -> float:
     out = C.c_double(0.0)
     _check(load_library().ssme_b200_measure_fp64_fma_rate(device, iters, C.byref(out)))
     return out.value
+
+
+def log_mean_exp(values, device: int = 0):
+    """[P][R] -> [P]: thread_pool's reduction (thread_pool.h:263-268) on the GPU."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    v = v.reshape(1, -1) if v.ndim == 1 else v
+    out = np.empty(v.shape[0])
+    _check(load_library().ssme_b200_log_mean_exp(device, _dptr(v), v.shape[0], v.shape[1], _dptr(out)))
+    return out
 
 
 @dataclass

@@ -423,6 +423,28 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     return SSME_B200_OK;
 }
 
+int ssme_b200_log_mean_exp(int32_t device, const double* values_host, size_t P, uint32_t R, double* out_host)
+{
+    if (!values_host || !out_host) return fail(SSME_B200_EINVAL, "null buffer");
+    if (R == 0) return fail(SSME_B200_EINVAL, "R must be >= 1");
+    if (P == 0) return SSME_B200_OK;
+    SSME_CUDA(cudaSetDevice(device));
+    double *d_in = nullptr, *d_out = nullptr;
+    SSME_CUDA(cudaMalloc(&d_in, P * (size_t)R * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_out, P * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, values_host, P * (size_t)R * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        log_mean_exp_kernel<<<(unsigned)((P + 127) / 128), 128>>>(d_in, R, P, d_out);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d_out, P * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "log_mean_exp failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_synchronize(ssme_b200_handle h)
 {
     if (!h) return fail(SSME_B200_EINVAL, "null handle");

@@ -1,0 +1,113 @@
+// tests/cpp/test_gpu_host.cpp -- GPU tests of the C++ host layer (gpu_pool, ada_pmmh_mvn) through the C ABI.
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <ssme_b200/ada_pmmh_mvn.hpp>
+#include <ssme_b200/gpu_pool.hpp>
+#include <ssme_b200/rv_eval.hpp>
+
+#include "../../examples/estimate_univ_svol.hpp"
+#include "check.hpp"
+
+static std::vector<double> sv_series(size_t T, unsigned seed)
+{
+    std::mt19937 g(seed);
+    std::normal_distribution<double> n(0, 1);
+    std::vector<double> y(T);
+    double x = n(g) * 0.25 / std::sqrt(1 - 0.95 * 0.95);
+    for (size_t t = 0; t < T; ++t) {
+        if (t) x = 0.95 * x + 0.25 * n(g);
+        y[t] = std::exp(0.5 * x) * n(g);
+    }
+    return y;
+}
+
+int main(int argc, char** argv)
+{
+    const std::string tmpdir = argc > 1 ? argv[1] : "/tmp";
+    using pool_t = ssme_b200::gpu_pool<3, 1, double>;
+    using pack3 = param::pack<double, 3>;
+    const std::vector<std::string> tts{"null", "twice_fisher", "log"};
+    const auto y = sv_series(300, 5);
+    std::vector<ssme_b200::vec<double, 1>> data(y.size());
+    for (size_t t = 0; t < y.size(); ++t) data[t](0) = y[t];
+
+    TEST_CASE("test thread pool [thread_pool] -- log-mean-exp known answer")  // test_thread_pool.cpp:36-47
+    {
+        std::vector<double> vals(10000, 3.0);  // NUMCALCS 1e4 evaluations of d({1,1,1}) = 3
+        double out = 0;
+        for (int i = 0; i < 100; ++i) {
+            ssme_b200::throw_on_error(ssme_b200_log_mean_exp(0, vals.data(), 1, 10000, &out));
+            REQUIRE(std::abs(out - 3.0) < .001);
+        }
+    }
+    TEST_CASE("gpu_pool: thread_pool error conventions")
+    {
+        pool_t pool(4, 500);
+        pack3 theta(ssme_b200::vec<double, 3>{1.0, ssme_b200::rveval::twiceFisher(.95), std::log(0.0625)}, tts);
+        REQUIRE_THROWS_AS(pool.work(theta), std::runtime_error);  // thread_pool.h:192
+        REQUIRE_THROWS_AS(pool.add_observed_data({}), std::length_error);  // estimate_univ_svol.h:112-113
+        pool.add_observed_data(data);
+        REQUIRE_THROWS_AS(pool.add_observed_data(data), std::runtime_error);  // thread_pool.h:169
+        const double a = pool.work(theta), b = pool.work(theta);
+        REQUIRE(std::isfinite(a) && std::isfinite(b));
+        REQUIRE(a != b);                  // fresh random streams on every call, like the clock-seeded reference
+        REQUIRE(std::abs(a - b) < 5.0);   // but the same likelihood
+        pool.set_next_stream(0);
+        const double a2 = pool.work(theta);
+        REQUIRE(a2 == a);                 // and reproducible when the stream ids are pinned
+        std::vector<pack3> batch{theta, theta};
+        pool.set_next_stream(0);
+        auto v = pool.work_batch(batch);
+        REQUIRE(v.size() == 2 && v[0] == a && v[1] == b);
+    }
+    TEST_CASE("ada_pmmh_mvn on the GPU backend: file formats and chain behaviour")
+    {
+        const std::string f = tmpdir + "/ssme_b200_pmmh_data.csv";
+        { std::ofstream o(f); o.precision(17); for (double v : y) o << v << "\n"; }
+        using est = univ_svol_estimator<3, 1, 1, 200, double>;
+        est::psv start{1.0, ssme_b200::rveval::twiceFisher(.9), std::log(0.05)};
+        est::psm C0 = est::psm::Identity() * .01;
+        const unsigned iters = 60;
+        std::string samples_file, messages_file;
+        {
+            est m(start, tts, iters, 2, f, tmpdir + "/ssme_b200_samples", tmpdir + "/ssme_b200_messages", false, 20, 1000, C0, false, 1, 0,
+                  ssme_b200::gpu_options(), 12345);
+            m.commence_sampling();
+            REQUIRE(m.iterations_done() == iters);
+            REQUIRE(m.accept_rate() > 0.0 && m.accept_rate() < 1.0);
+            REQUIRE(std::isfinite(m.current_log_like()));
+            // adaptation happened inside the window (t0 = 20): C_t is no longer the diagonal C0
+            REQUIRE(std::abs(m.get_ct()(0, 1)) > 0.0);
+            REQUIRE(std::isfinite(m.log_like_eval(m.current_theta(), data)));
+        }
+        // locate the two time-stamped files
+        FILE* p = popen(("ls " + tmpdir + "/ssme_b200_samples_* " + tmpdir + "/ssme_b200_messages_* 2>/dev/null").c_str(), "r");
+        char line[512];
+        while (p && fgets(line, sizeof(line), p)) {
+            std::string s(line);
+            s.erase(s.find_last_not_of("\n") + 1);
+            if (s.find("samples") != std::string::npos) samples_file = s; else messages_file = s;
+        }
+        if (p) pclose(p);
+        std::ifstream sf(samples_file), mf(messages_file);
+        std::string l;
+        unsigned nrows = 0;
+        while (std::getline(sf, l)) {
+            ++nrows;
+            REQUIRE(std::count(l.begin(), l.end(), ',') == 2);  // numparams - 1 commas, no header
+        }
+        REQUIRE(nrows == iters);
+        std::getline(mf, l);
+        REQUIRE(l == "iter number, accept rate, old_ll, new_ll, old_lprior, new_lprior, accept prob, outcome");  // ada_pmmh_mvn.h:308
+        unsigned mrows = 0;
+        while (std::getline(mf, l)) { ++mrows; REQUIRE(std::count(l.begin(), l.end(), ',') == 7); }
+        REQUIRE(mrows == iters);
+        std::remove(samples_file.c_str());
+        std::remove(messages_file.c_str());
+    }
+    return finish();
+}
