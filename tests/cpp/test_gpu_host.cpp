@@ -1,4 +1,5 @@
 // tests/cpp/test_gpu_host.cpp -- GPU tests of the C++ host layer (gpu_pool, ada_pmmh_mvn) through the C ABI.
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
