@@ -123,6 +123,66 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
                            const double* z_inj_host, const double* u_inj_host, double* loglik_host,
                            double* cond_like_host, int32_t* ancestors_host, double* x_host);
 
+/* ---- multi-GPU: proposals / chains / replicates sharded over ranks (one process per GPU) ----------
+ * The reference fans the num_pfilters filters of a proposal out over std::threads that share memory
+ * (thread_pool.h:235-254); across GPUs the same bag of independent filters is split into contiguous
+ * ranges, one per rank, and the per-filter log-likelihoods are all-gathered (NCCL over NVLink) so that
+ * every rank takes the same Metropolis-Hastings decision.  NCCL is loaded with dlopen at comm_init;
+ * single-GPU users never need it. */
+
+/* Filter range [first, first+count) of `rank` out of `world` for F filters, and the padded per-rank
+ * chunk length used by the all-gather (chunk * world >= F).  Pure function, no device needed. */
+int ssme_b200_shard_range(uint64_t F, int32_t world, int32_t rank, uint64_t* first, uint64_t* count, uint64_t* chunk);
+
+/* ncclGetUniqueId: rank 0 calls this and hands the 128 bytes to every rank (any out-of-band channel). */
+int ssme_b200_comm_unique_id(uint8_t id_out[128]);
+
+/* ncclCommInitRank on the handle's device; collective over all ranks. */
+int ssme_b200_comm_init(ssme_b200_handle h, const uint8_t id[128], int32_t rank, int32_t world);
+
+/* Sharded thread_pool::work for P proposals x R replicates: this rank runs its range of the P*R filters,
+ * the ranks all-gather, and EVERY rank receives all P*R per-filter log-likelihoods (host buffer, filter
+ * (p, r) at index p*R + r) plus, if out_host is non-NULL, the P log-mean-exp values.  Without a prior
+ * ssme_b200_comm_init the call evaluates everything locally (world = 1). */
+int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R,
+                                    uint64_t stream_base, double* out_host, double* per_filter_host);
+
+/* ---- the PMMH host loop, in C++ behind the C ABI (for hosts that cannot include the C++ headers) -------
+ * Replaces: do_ada_pmmh_univ_svol + ada_pmmh_mvn::commence_sampling (example/estimate_univ_svol.h:139-178,
+ * ada_pmmh_mvn.h:325-372) for `num_chains` chains advanced in lock step (include/ssme_b200/pmmh_multichain.hpp).
+ * Transforms and priors per model: SV -> {null, twice_fisher, log}, beta ~ N(1,1), phi ~ U(0,1),
+ * sigma^2 ~ InvGamma(.001,.001) (estimate_univ_svol.h:95-101,155); SV_LEVERAGE -> {logit, null, log, twice_fisher}
+ * (test_liu_west.cpp:70), phi ~ U(0,1), mu ~ N(0,1), sigma ~ U(0,5), rho ~ U(-1,1).
+ * With a communicator on the handle the C*R filters of every iteration are sharded over the ranks and
+ * all-gathered; all ranks return identical results. */
+typedef struct {
+    int32_t struct_size;
+    int32_t num_chains;    /* C */
+    int32_t num_pfilters;  /* R: filters per proposal (ada_pmmh_mvn ctor arg) */
+    int32_t iterations;    /* num_mcmc_iters, counting iteration 0 (which evaluates without proposing) */
+    int32_t t0, t1;        /* adaptation window (ada_pmmh_mvn.h:247) */
+    int32_t reserved0, reserved1;
+    double c0_diag;        /* C0 = c0_diag * I (estimate_univ_svol.h:158: 0.15) */
+    uint64_t proposal_seed;
+} ssme_b200_pmmh_config;
+
+/* start_theta [C][numparams] untransformed.  Outputs (each may be NULL): final_theta [C][numparams],
+ * mean_theta [C][numparams] (average of the untransformed chain over all iterations), accept_rate [C],
+ * last_loglik [C], seconds (wall time of the sampling loop). */
+int ssme_b200_pmmh_run(ssme_b200_handle h, const ssme_b200_pmmh_config* cfg, const double* start_theta, double* final_theta,
+                       double* mean_theta, double* accept_rate, double* last_loglik, double* seconds);
+
+/* The same host loop with a caller-supplied likelihood evaluator instead of a device handle (no GPU
+ * needed): evaluator fills per_filter[C*R] for the C untransformed thetas and returns 0; it must return
+ * the same numbers on every rank.  Used by the multi-rank CPU tests and by hosts with their own backend. */
+typedef int (*ssme_b200_evaluator_fn)(void* user, const double* theta, size_t C, uint32_t R, uint64_t stream_base, double* per_filter);
+int ssme_b200_pmmh_run_custom(int32_t model, const ssme_b200_pmmh_config* cfg, ssme_b200_evaluator_fn evaluator, void* user,
+                              const double* start_theta, double* final_theta, double* mean_theta, double* accept_rate,
+                              double* last_loglik, double* seconds);
+
+/* model id the handle was created with */
+int32_t ssme_b200_model(ssme_b200_handle h);
+
 /* Replaces: the reduction at the end of thread_pool::worker_thread (thread_pool.h:263-268) on its own:
  * out[p] = log-mean-exp of values[p*R .. p*R+R).  HOST buffers; runs kernel K6 on `device`. */
 int ssme_b200_log_mean_exp(int32_t device, const double* values_host, size_t P, uint32_t R, double* out_host);

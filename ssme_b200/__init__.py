@@ -13,6 +13,9 @@ from .capi import (  # noqa: F401
     launch_count,
     measure_fp64_fma_rate,
     log_mean_exp,
+    shard_range,
+    comm_unique_id,
+    pmmh_run_custom,
     MODEL_SV,
     MODEL_SV_LEVERAGE,
     RESAMP_MULTINOMIAL,

@@ -34,7 +34,9 @@ def _nvcc() -> str:
 
 
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ssme_b200.h"), __file__]
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, "ssme_b200.h"), __file__]
+    deps += [os.path.join(inc, "ssme_b200", f) for f in os.listdir(os.path.join(inc, "ssme_b200"))]
     return max(os.path.getmtime(d) for d in deps)
 
 
@@ -66,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         jobs.append((obj, [nvcc, *NVCC_FLAGS, "-DSSME_NT=%d" % nt, "-c", os.path.join(CSRC, "pf_inst.cu"), "-o", obj]))
     obj = os.path.join(OBJDIR, "capi.o")
     jobs.append((obj, [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "capi.cu"), "-o", obj]))
+    obj = os.path.join(OBJDIR, "pmmh_capi.o")  # host-only C++ (the PMMH loop above the C ABI)
+    jobs.append((obj, [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, "pmmh_capi.cpp"), "-o", obj]))
     todo = [(o, c) for o, c in jobs if force or not os.path.exists(o) or os.path.getmtime(o) < newest]
     if verbose:
         for _, c in todo:

@@ -38,6 +38,17 @@ class _Config(C.Structure):
     ]
 
 
+class _PmmhConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("num_chains", C.c_int32), ("num_pfilters", C.c_int32), ("iterations", C.c_int32),
+        ("t0", C.c_int32), ("t1", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("c0_diag", C.c_double), ("proposal_seed", C.c_uint64),
+    ]
+
+
+EVALUATOR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.c_uint32, C.c_uint64, C.POINTER(C.c_double))
+
+
 class _Layout(C.Structure):
     _fields_ = [
         ("scan_items_per_lane", C.c_int32), ("threads_per_filter", C.c_int32), ("filters_per_sm", C.c_int32),
@@ -78,6 +89,15 @@ def load_library():
                                                    C.c_void_p, C.c_void_p]
     lib.ssme_b200_filter_trace.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp, dp, dp, ip, dp]
     lib.ssme_b200_log_mean_exp.argtypes = [C.c_int32, dp, C.c_size_t, C.c_uint32, dp]
+    u64p = C.POINTER(C.c_uint64)
+    lib.ssme_b200_shard_range.argtypes = [C.c_uint64, C.c_int32, C.c_int32, u64p, u64p, u64p]
+    lib.ssme_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    lib.ssme_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
+    lib.ssme_b200_loglike_batch_sharded.argtypes = [H, dp, C.c_size_t, C.c_uint32, C.c_uint64, dp, dp]
+    lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
+    lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
+    lib.ssme_b200_model.argtypes = [H]
+    lib.ssme_b200_model.restype = C.c_int32
     lib.ssme_b200_synchronize.argtypes = [H]
     lib.ssme_b200_stream.argtypes = [H]
     lib.ssme_b200_stream.restype = C.c_void_p
@@ -112,6 +132,48 @@ def log_mean_exp(values, device: int = 0):
     out = np.empty(v.shape[0])
     _check(load_library().ssme_b200_log_mean_exp(device, _dptr(v), v.shape[0], v.shape[1], _dptr(out)))
     return out
+
+
+def shard_range(F: int, world: int, rank: int):
+    """(first, count, chunk): the contiguous filter range of `rank` and the padded all-gather chunk length."""
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _check(load_library().ssme_b200_shard_range(F, world, rank, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().ssme_b200_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def _pmmh_outputs(C_, npar):
+    return np.empty((C_, npar)), np.empty((C_, npar)), np.empty(C_), np.empty(C_)
+
+
+def pmmh_run_custom(model, evaluator, start_theta, num_pfilters, iterations, t0=150, t1=1000, c0_diag=0.15, proposal_seed=1):
+    """The C++ multi-chain PMMH host loop with a Python likelihood evaluator
+    evaluator(theta[C, np], R, stream_base) -> per_filter[C*R]  (tests; no GPU involved)."""
+    start = np.ascontiguousarray(start_theta, dtype=np.float64)
+    C_, npar = start.shape
+    cfg = _PmmhConfig(C.sizeof(_PmmhConfig), C_, num_pfilters, iterations, t0, t1, 0, 0, c0_diag, proposal_seed)
+    final, mean, acc, ll = _pmmh_outputs(C_, npar)
+    sec = C.c_double()
+
+    def trampoline(user, theta, n, R, base, out):
+        try:
+            th = np.ctypeslib.as_array(theta, shape=(n, npar)).copy()
+            res = np.asarray(evaluator(th, int(R), int(base)), dtype=np.float64).ravel()
+            np.ctypeslib.as_array(out, shape=(n * R,))[:] = res
+            return 0
+        except Exception:  # pragma: no cover - reported through the C ABI
+            import traceback
+            traceback.print_exc()
+            return 1
+    cb = EVALUATOR_FN(trampoline)
+    _check(load_library().ssme_b200_pmmh_run_custom(model, C.byref(cfg), cb, None, _dptr(start), _dptr(final), _dptr(mean), _dptr(acc),
+                                                    _dptr(ll), C.byref(sec)))
+    return {"final_theta": final, "mean_theta": mean, "accept_rate": acc, "last_loglik": ll, "seconds": sec.value}
 
 
 @dataclass
@@ -196,6 +258,30 @@ class ParticleFilterBackend:
 
     def synchronize(self):
         _check(self._lib.ssme_b200_synchronize(self._h))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the NCCL communicator (collective).  unique_id comes from comm_unique_id() on rank 0."""
+        buf = (C.c_uint8 * 128)(*unique_id)
+        _check(self._lib.ssme_b200_comm_init(self._h, buf, rank, world))
+
+    def work_batch_sharded(self, theta, R: int = 1, stream_base: int = 0):
+        """Multi-rank thread_pool::work: returns (lme[P], per_filter[P, R]), identical on every rank."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
+        P = theta.shape[0]
+        out, pf = np.empty(P), np.empty(P * R)
+        _check(self._lib.ssme_b200_loglike_batch_sharded(self._h, _dptr(theta), P, R, stream_base, _dptr(out), _dptr(pf)))
+        return out, pf.reshape(P, R)
+
+    def pmmh_run(self, start_theta, num_pfilters, iterations, t0=150, t1=1000, c0_diag=0.15, proposal_seed=1):
+        """ada_pmmh_mvn::commence_sampling for C chains in lock step (C++ host loop behind the C ABI)."""
+        start = np.ascontiguousarray(start_theta, dtype=np.float64).reshape(-1, self.num_params)
+        C_ = start.shape[0]
+        cfg = _PmmhConfig(C.sizeof(_PmmhConfig), C_, num_pfilters, iterations, t0, t1, 0, 0, c0_diag, proposal_seed)
+        final, mean, acc, ll = _pmmh_outputs(C_, self.num_params)
+        sec = C.c_double()
+        _check(self._lib.ssme_b200_pmmh_run(self._h, C.byref(cfg), _dptr(start), _dptr(final), _dptr(mean), _dptr(acc), _dptr(ll),
+                                            C.byref(sec)))
+        return {"final_theta": final, "mean_theta": mean, "accept_rate": acc, "last_loglik": ll, "seconds": sec.value}
 
     def trace(self, theta, stream_base: int = 0, z=None, u=None, want=("loglik", "cond_like", "ancestors", "x")):
         """Per-step outputs of F filters (parity / diagnostics)."""

@@ -4,6 +4,7 @@
 #include "../../include/ssme_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cmath>
@@ -33,6 +34,13 @@ static int fail(int code, const char* fmt, ...)
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_last_error = buf;
+    return code;
+}
+
+// for the host-only translation units of the library (pmmh_capi.cpp)
+int set_last_error(int code, const char* msg)
+{
+    g_last_error = msg ? msg : "";
     return code;
 }
 
@@ -67,6 +75,37 @@ __global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
 }
+
+// ---- NCCL, loaded lazily so that the library has no link-time dependency on it --------------------
+struct NcclApi {
+    typedef struct { char internal[128]; } unique_id;
+    int (*GetUniqueId)(unique_id*) = nullptr;
+    int (*CommInitRank)(void**, int, unique_id, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib) {
+            api.GetUniqueId = (int (*)(NcclApi::unique_id*))dlsym(lib, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, NcclApi::unique_id, int))dlsym(lib, "ncclCommInitRank");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+            api.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+            api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+        }
+    }
+    return &api;
+}
+constexpr int kNcclFloat64 = 8;  // ncclDataType_t ncclFloat64 (nccl.h)
 
 static const KernelEntry* find_kernel(int L, int NT, int model, int resamp, int debug)
 {
@@ -106,6 +145,9 @@ struct ssme_b200_filter_s {
     double* d_out = nullptr;
     double* d_per_filter = nullptr;
     size_t cap_theta = 0, cap_out = 0, cap_pf = 0;
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
 };
 
 namespace {
@@ -244,7 +286,9 @@ int ssme_b200_destroy(ssme_b200_handle h)
 {
     if (!h) return SSME_B200_OK;
     cudaSetDevice(h->cfg.device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && nccl_api()->ok) nccl_api()->CommDestroy(h->nccl_comm);
+    if (h->stream) cudaStreamDestroy(h->stream);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_theta) cudaFree(h->d_theta);
     if (h->d_out) cudaFree(h->d_out);
@@ -423,6 +467,93 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     return SSME_B200_OK;
 }
 
+int ssme_b200_shard_range(uint64_t F, int32_t world, int32_t rank, uint64_t* first, uint64_t* count, uint64_t* chunk)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(SSME_B200_EINVAL, "bad rank %d of %d", rank, world);
+    const uint64_t c = (F + (uint64_t)world - 1) / (uint64_t)world;  // contiguous, equal-sized chunks; the last may be short
+    const uint64_t f0 = c * (uint64_t)rank < F ? c * (uint64_t)rank : F;
+    const uint64_t f1 = f0 + c < F ? f0 + c : F;
+    if (first) *first = f0;
+    if (count) *count = f1 - f0;
+    if (chunk) *chunk = c;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_comm_unique_id(uint8_t id_out[128])
+{
+    if (!id_out) return fail(SSME_B200_EINVAL, "null argument");
+    NcclApi* n = nccl_api();
+    if (!n->ok) return fail(SSME_B200_ERUNTIME, "NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbols missing");
+    NcclApi::unique_id id;
+    int rc = n->GetUniqueId(&id);
+    if (rc != 0) return fail(SSME_B200_ERUNTIME, "ncclGetUniqueId failed: %s", n->GetErrorString(rc));
+    memcpy(id_out, id.internal, 128);
+    return SSME_B200_OK;
+}
+
+int ssme_b200_comm_init(ssme_b200_handle h, const uint8_t id[128], int32_t rank, int32_t world)
+{
+    if (!h || !id) return fail(SSME_B200_EINVAL, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(SSME_B200_EINVAL, "bad rank %d of %d", rank, world);
+    if (h->nccl_comm) return fail(SSME_B200_ERUNTIME, "communicator already initialised on this handle");
+    NcclApi* n = nccl_api();
+    if (!n->ok) return fail(SSME_B200_ERUNTIME, "NCCL (libnccl.so.2) could not be loaded");
+    int rc = set_device(h);
+    if (rc) return rc;
+    NcclApi::unique_id uid;
+    memcpy(uid.internal, id, 128);
+    int nrc = n->CommInitRank(&h->nccl_comm, world, uid, rank);
+    if (nrc != 0) { h->nccl_comm = nullptr; return fail(SSME_B200_ERUNTIME, "ncclCommInitRank failed: %s", n->GetErrorString(nrc)); }
+    h->rank = rank;
+    h->world = world;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R, uint64_t stream_base,
+                                    double* out_host, double* per_filter_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (R == 0) return fail(SSME_B200_EINVAL, "R (num_pfilters) must be >= 1");
+    if (P == 0) return SSME_B200_OK;
+    if (!theta_host || !per_filter_host) return fail(SSME_B200_EINVAL, "null host buffer");
+    if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "batch evaluation needs rng_mode PHILOX");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t np = (size_t)h->num_params, F = P * (size_t)R;
+    uint64_t f0 = 0, cnt = 0, chunk = 0;
+    if ((rc = ssme_b200_shard_range(F, h->world, h->rank, &f0, &cnt, &chunk))) return rc;
+    const size_t Fpad = (size_t)chunk * (size_t)h->world;
+    if ((rc = ensure_dev(&h->d_theta, &h->cap_theta, P * np))) return rc;
+    if ((rc = ensure_dev(&h->d_out, &h->cap_out, P))) return rc;
+    if ((rc = ensure_dev(&h->d_per_filter, &h->cap_pf, Fpad))) return rc;
+    const size_t in_bytes = P * np * sizeof(double), out_bytes = (P + Fpad) * sizeof(double);
+    if ((rc = ensure_pinned(h, in_bytes > out_bytes ? in_bytes : out_bytes))) return rc;
+    memcpy(h->h_pinned, theta_host, in_bytes);
+    SSME_CUDA(cudaMemcpyAsync(h->d_theta, h->h_pinned, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    FilterArgs a = base_args(h, h->d_theta, R, stream_base, h->d_per_filter);
+    a.filter_offset = f0;
+    const bool fast_ok = (h->cfg.resample_every == 1);
+    if ((rc = launch_filters(h, fast_ok ? h->fast : h->debug, a, (size_t)cnt, h->stream)) != SSME_B200_OK) return rc;
+    if (h->world > 1) {
+        // in-place all-gather: this rank's chunk already sits at d_per_filter + rank * chunk
+        NcclApi* n = nccl_api();
+        int nrc = n->AllGather(h->d_per_filter + (size_t)h->rank * chunk, h->d_per_filter, (size_t)chunk, kNcclFloat64, h->nccl_comm, h->stream);
+        if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", n->GetErrorString(nrc));
+    }
+    if (out_host) {
+        log_mean_exp_kernel<<<(unsigned)((P + 127) / 128), 128, 0, h->stream>>>(h->d_per_filter, R, P, h->d_out);
+        SSME_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1);
+        SSME_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_out, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    SSME_CUDA(cudaMemcpyAsync(h->h_pinned + P, h->d_per_filter, F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    if (out_host) memcpy(out_host, h->h_pinned, P * sizeof(double));
+    memcpy(per_filter_host, h->h_pinned + P, F * sizeof(double));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_log_mean_exp(int32_t device, const double* values_host, size_t P, uint32_t R, double* out_host)
 {
     if (!values_host || !out_host) return fail(SSME_B200_EINVAL, "null buffer");
@@ -455,6 +586,8 @@ int ssme_b200_synchronize(ssme_b200_handle h)
 }
 
 void* ssme_b200_stream(ssme_b200_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int32_t ssme_b200_model(ssme_b200_handle h) { return h ? h->cfg.model : -1; }
 
 int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_per_second)
 {

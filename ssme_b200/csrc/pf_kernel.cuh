@@ -40,7 +40,8 @@ struct FilterArgs {
     int rs;
     unsigned long long seed;
     unsigned long long filter_base;
-    double* loglik;  // [F]
+    unsigned long long filter_offset;  // CTA b evaluates filter filter_offset + b (a rank's shard of the batch)
+    double* loglik;                    // [F_total]: written at the filter's global index
     // diagnostics (DEBUG instantiations only)
     int inject;
     int stride_u;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     uint64_t* bars = reinterpret_cast<uint64_t*>(clS + 32);  // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long f = blockIdx.x;
+    const unsigned long long f = a.filter_offset + blockIdx.x;
     const int N = a.N, T = a.T;
     const int i0 = tid * L;
     const int nchunks = (T + kYChunk - 1) / kYChunk;
