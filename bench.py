@@ -175,6 +175,68 @@ def workload_config(n_gpus):
             "l2": "flushed between timed steps (256 MiB memset, outside the per-step events); the resident kernel's HBM inputs are 128 KiB"}
 
 
+def run_pmmh_legs(sb, dist, rank, world, local_rank):
+    """PMMH iterations/s = Metropolis-Hastings proposals decided across all chains / wall time, host accept/adapt and
+    (N > 1) the NCCL all-gather of the per-filter log-likelihoods included.
+      config 3: 64 chains x 8192 particles, SV with leverage, chains x replicates sharded over the ranks
+      config 1: the README example: SPY returns (T = 3084), 500 particles, 100 filters per proposal, one chain"""
+    out = {}
+
+    def comm(be):
+        if world > 1:
+            uid = [sb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            be.comm_init(uid[0], rank, world)
+
+    # config 3
+    C3_CHAINS, C3_N, C3_T, C3_R, C3_ITERS = 64, 8192, 1024, 1, 12
+    rng = np.random.default_rng(SEED_SERIES + 3)
+    phi, mu, sigma, rho = 0.9, 0.0, 0.3, -0.1
+    x = np.empty(C3_T); yv = np.empty(C3_T)
+    x[0] = rng.standard_normal() * sigma / np.sqrt(1 - phi * phi)
+    yv[0] = np.exp(0.5 * x[0]) * rng.standard_normal()
+    for t in range(1, C3_T):
+        x[t] = mu + phi * (x[t - 1] - mu) + rho * sigma * yv[t - 1] * np.exp(-0.5 * x[t - 1]) + sigma * np.sqrt(1 - rho * rho) * rng.standard_normal()
+        yv[t] = np.exp(0.5 * x[t]) * rng.standard_normal()
+    be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV_LEVERAGE, num_particles=C3_N, seed=SEED_FILTER + 3, device=local_rank))
+    be.add_observed_data(yv)
+    comm(be)
+    start = np.tile(np.array([phi, mu, sigma, rho]), (C3_CHAINS, 1)) * (1 + 0.01 * np.random.default_rng(5).standard_normal((C3_CHAINS, 4)))
+    start[:, 1] = 0.01 * np.random.default_rng(6).standard_normal(C3_CHAINS)
+    be.pmmh_run(start, C3_R, 3, t0=2, t1=1000, c0_diag=1e-3, proposal_seed=1)  # warm-up
+    if dist is not None:
+        dist.barrier()
+    r = be.pmmh_run(start, C3_R, C3_ITERS, t0=2, t1=1000, c0_diag=1e-3, proposal_seed=2)
+    out["config3"] = {"iters_per_sec": C3_CHAINS * (C3_ITERS - 1) / r["seconds"], "chains": C3_CHAINS, "particles": C3_N, "T": C3_T,
+                      "filters_per_proposal": C3_R, "model": "sv_leverage", "iterations_timed": C3_ITERS, "seconds": r["seconds"],
+                      "mean_accept_rate": float(r["accept_rate"].mean()),
+                      "particle_steps_per_sec": C3_CHAINS * C3_R * C3_N * C3_T * C3_ITERS / r["seconds"],
+                      "sharding": "chains x replicates over %d rank(s), NCCL all-gather of %d log-likelihoods per iteration" % (world, C3_CHAINS * C3_R)}
+    be.close()
+    # config 1 (one chain: the replicates are what is sharded)
+    spy = os.path.join(ROOT, "tests", "golden", "spy_config1.npz")
+    if os.path.exists(spy):
+        g = np.load(spy)
+        C1_N, C1_R, C1_ITERS = 500, 100, 12
+        # 100 filters do not fill 148 SMs, so the step latency of one CTA sets the pace: 4 particles per thread
+        # (128 threads per filter) measured 1.58 us/step against 2.69 us/step for the throughput layout (8 per thread)
+        be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=C1_N, seed=SEED_FILTER + 1, device=local_rank,
+                                                      scan_items_per_lane=4))
+        be.add_observed_data(g["y"])
+        comm(be)
+        be.pmmh_run(g["theta"][None, :], C1_R, 3, proposal_seed=1)
+        if dist is not None:
+            dist.barrier()
+        r = be.pmmh_run(g["theta"][None, :], C1_R, C1_ITERS, proposal_seed=2)
+        out["config1"] = {"iters_per_sec": (C1_ITERS - 1) / r["seconds"], "chains": 1, "particles": C1_N, "T": int(g["y"].size),
+                          "filters_per_proposal": C1_R, "model": "sv", "iterations_timed": C1_ITERS, "seconds": r["seconds"],
+                          "particle_steps_per_sec": C1_R * C1_N * int(g["y"].size) * C1_ITERS / r["seconds"],
+                          "last_loglik": float(r["last_loglik"][0]),
+                          "note": "README example shape (example/main.cpp: 500 particles, 100 filters per proposal, SPY returns)"}
+        be.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import ssme_b200 as sb
@@ -262,6 +324,11 @@ def run_ours(args):
     e2e_value = world * steps_per_pass * args.steps / e2e_s
     assert np.all(np.isfinite(out_host))
 
+    # ---- PMMH iterations/s (second half of BASELINE.json's metric): the C++ host loop behind the C ABI -----
+    pmmh = None
+    if not args.no_pmmh:
+        pmmh = run_pmmh_legs(sb, dist, rank, world, local_rank)
+
     if rank == 0:
         # ---- roofline of the dominant kernel (bootstrap_filter_kernel): FP64 pipe ----------------
         fma_rate = sb.measure_fp64_fma_rate(local_rank, 1 << 15)  # thread-level FMA instructions / s, measured now
@@ -284,7 +351,7 @@ def run_ours(args):
                 raise RuntimeError("skipped (--no-cpu)")
             L = load_refcpu()
             cores = L.ssme_refcpu_hardware_threads()
-            nfil = max(2, cores)
+            nfil = max(2, 3 * cores)
             dp = C.POINTER(C.c_double)
             out = np.zeros(1)
             sec, used = C.c_double(), C.c_uint()
@@ -305,6 +372,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(P_PROPOSALS * 8)},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu,
+            "pmmh": pmmh,
             "layout": layout, "wall_s_timed_region": t_wall, "checksum": checksum,
             "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-10); all filter arithmetic f64",
         }
@@ -327,6 +395,7 @@ def main():
     ap.add_argument("--proposals", type=int, default=4096, help="experiments only: proposals per GPU")
     ap.add_argument("--T", type=int, default=4096, help="experiments only: series length")
     ap.add_argument("--no-cpu", action="store_true", help="experiments only: skip the CPU baseline leg")
+    ap.add_argument("--no-pmmh", action="store_true", help="experiments only: skip the PMMH iterations/s legs")
     args = ap.parse_args()
     P_PROPOSALS, T_STEPS = args.proposals, args.T
     if args.impl == "reference":
