@@ -147,6 +147,16 @@ int ssme_b200_comm_init(ssme_b200_handle h, const uint8_t id[128], int32_t rank,
 int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R,
                                     uint64_t stream_base, double* out_host, double* per_filter_host);
 
+/* Replaces: Swarm::update / SwarmWithCovs::update over a whole series (pswarm_filter.h:223-239, 520-539):
+ * P independent bootstrap filters, one per parameter draw theta_j (the reference draws them once in
+ * finish_construction, :280-304), advanced over all T observations; per observation the swarm's
+ * log p(y_t | y_{1:t-1}) is the arithmetic MEAN over j of the filters' log conditional likelihoods
+ * (comp_func :86-92 and the aggregation functions :96-160 average logs, not likelihoods).
+ *   theta_host [P][numparams]; log_cond_like_host [T]; per_filter_host [P][T] or NULL.
+ * Filter j uses Philox stream stream_base + j. */
+int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
+                           double* log_cond_like_host, double* per_filter_host);
+
 /* ---- the PMMH host loop, in C++ behind the C ABI (for hosts that cannot include the C++ headers) -------
  * Replaces: do_ada_pmmh_univ_svol + ada_pmmh_mvn::commence_sampling (example/estimate_univ_svol.h:139-178,
  * ada_pmmh_mvn.h:325-372) for `num_chains` chains advanced in lock step (include/ssme_b200/pmmh_multichain.hpp).

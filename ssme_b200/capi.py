@@ -94,6 +94,7 @@ def load_library():
     lib.ssme_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.ssme_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
     lib.ssme_b200_loglike_batch_sharded.argtypes = [H, dp, C.c_size_t, C.c_uint32, C.c_uint64, dp, dp]
+    lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_model.argtypes = [H]
@@ -271,6 +272,15 @@ class ParticleFilterBackend:
         out, pf = np.empty(P), np.empty(P * R)
         _check(self._lib.ssme_b200_loglike_batch_sharded(self._h, _dptr(theta), P, R, stream_base, _dptr(out), _dptr(pf)))
         return out, pf.reshape(P, R)
+
+    def swarm_filter(self, theta, stream_base: int = 0, return_per_filter: bool = False):
+        """Swarm::update over the whole series: [T] mean over the P filters of log p(y_t | y_{1:t-1})."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
+        P = theta.shape[0]
+        out = np.empty(self.T)
+        pf = np.empty((P, self.T)) if return_per_filter else None
+        _check(self._lib.ssme_b200_swarm_filter(self._h, _dptr(theta), P, stream_base, _dptr(out), _dptr(pf)))
+        return (out, pf) if return_per_filter else out
 
     def pmmh_run(self, start_theta, num_pfilters, iterations, t0=150, t1=1000, c0_diag=0.15, proposal_seed=1):
         """ada_pmmh_mvn::commence_sampling for C chains in lock step (C++ host loop behind the C ABI)."""

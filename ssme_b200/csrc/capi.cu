@@ -65,6 +65,17 @@ __global__ void log_mean_exp_kernel(const double* __restrict__ per_filter, unsig
     out[p] = __dsub_rn(__dadd_rn(m, dlog(sum_exp)), dlog((double)R));
 }
 
+// Swarm aggregation (reference pswarm_filter.h:96-160): per time step the mean over the P filters of
+// their log conditional likelihoods, summed in filter order.
+__global__ void swarm_mean_kernel(const double* __restrict__ cond_like, size_t P, int T, double* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double s = 0.0;
+    for (size_t j = 0; j < P; ++j) s = __dadd_rn(s, cond_like[j * (size_t)T + t]);
+    out[t] = __ddiv_rn(s, (double)P);
+}
+
 // Roofline denominator: 8 independent FMA chains per thread keep the FP64 pipe saturated.
 __global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
 {
@@ -464,6 +475,40 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     if (x_host) SSME_CUDA_T(cudaMemcpy(x_host, d_x, F * T * N * sizeof(double), cudaMemcpyDeviceToHost));
     cleanup();
 #undef SSME_CUDA_T
+    return SSME_B200_OK;
+}
+
+int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base, double* log_cond_like_host,
+                           double* per_filter_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (P == 0) return fail(SSME_B200_EINVAL, "the swarm needs at least one parameter particle");
+    if (!theta_host || !log_cond_like_host) return fail(SSME_B200_EINVAL, "null host buffer");
+    if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t np = (size_t)h->num_params, T = h->T;
+    double *d_theta = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_mean = nullptr;
+    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_mean); };
+    cudaError_t e = cudaMalloc(&d_theta, P * np * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ll, P * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cl, P * T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mean, T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_theta, theta_host, P * np * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "swarm setup failed: %s", cudaGetErrorString(e)); }
+    FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
+    a.cond_like = d_cl;
+    rc = launch_filters(h, (h->cfg.resample_every == 1) ? h->fast : h->debug, a, P, h->stream);
+    if (rc) { cleanup(); return rc; }
+    swarm_mean_kernel<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(d_cl, P, (int)T, d_mean);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(log_cond_like_host, d_mean, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && per_filter_host) e = cudaMemcpyAsync(per_filter_host, d_cl, P * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "swarm filter failed: %s", cudaGetErrorString(e));
     return SSME_B200_OK;
 }
 

@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             const double logS = dlog(clS[lane]);
             const double cl = (s == 0) ? __dadd_rn(__dadd_rn(-logN, clM[lane]), logS)
                                        : __dsub_rn(__dsub_rn(__dadd_rn(clM[lane], logS), 0.0), logN);
+            if (a.cond_like) a.cond_like[(size_t)f * T + s] = cl;  // per-step output for the swarm (pswarm_filter.h:86-92)
             __syncwarp();
             clM[lane] = cl;
             __syncwarp();
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                 const double logS = dlog(clS[lane]);
                 cl = (t0 + lane == 0) ? __dadd_rn(__dadd_rn(-logN, clM[lane]), logS)
                                       : __dsub_rn(__dsub_rn(__dadd_rn(clM[lane], logS), 0.0), logN);
+                if (a.cond_like) a.cond_like[(size_t)f * T + t0 + lane] = cl;
             }
             __syncwarp();
             clM[lane] = cl;

@@ -126,3 +126,32 @@ def test_golden_vectors(gpu_backend_factory):
         assert np.array_equal(got["x"][0][-1], g[name + "/x_last"]), name
         assert got["loglik"][0] == g[name + "/loglik"][0], name
         assert abs(got["loglik"][0] - g[name + "/loglik"][1]) <= 1e-9 * abs(g[name + "/loglik"][1]), name
+
+
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("T", [31, 32, 33, 100])
+def test_swarm_per_step_cond_likes(oracle, sv_series, gpu_backend_factory, model, T):
+    """Swarm::update over a series (pswarm_filter.h:223-239): per-step log cond-likes of every filter equal the
+    oracle's, and the swarm value is their mean over the parameter particles (mean of logs, summed in filter order).
+    Prior box of the reference's swarm test for the leverage model (test_pswarm.cpp:244)."""
+    y = sv_series(T, seed=21)
+    rng = np.random.default_rng(2)
+    P = 5
+    if model == sb.MODEL_SV_LEVERAGE:
+        theta = np.column_stack([rng.uniform(.8, .99, P), rng.uniform(-.1, .1, P), rng.uniform(.01, .1, P), rng.uniform(-.5, -.01, P)])
+    else:
+        theta = np.column_stack([rng.uniform(.8, 1.2, P), rng.uniform(.8, .99, P), rng.uniform(.01, .1, P)])
+    be = gpu_backend_factory(model=model, num_particles=100, seed=4)
+    be.add_observed_data(y)
+    mean, pf = be.swarm_filter(theta, stream_base=50, return_per_filter=True)
+    L, NT = be.layout["scan_items_per_lane"], be.layout["threads_per_filter"]
+    want = np.empty((P, T))
+    for j in range(P):
+        want[j] = oracle.filter_run(theta[j], y, 100, model=model, L=L, NT=NT, seed=4, filter_id=50 + j)["cond_like"]
+    assert np.array_equal(pf, want)
+    acc = np.zeros(T)
+    for j in range(P):
+        acc = acc + want[j]
+    assert np.array_equal(mean, acc / P)
+    # the likelihood entry point is unchanged by the extra output
+    assert be.work_batch(theta, R=1, stream_base=50).tolist() == [oracle.filter_run(theta[j], y, 100, model=model, L=L, NT=NT, seed=4, filter_id=50 + j, trace=False)["loglik"] for j in range(P)]
