@@ -66,7 +66,8 @@ typedef struct {
     int32_t scan_items_per_lane; /* L of the canonical scan order; 0 = library default */
     int32_t threads_per_filter;  /* CTA size; 0 = library default */
     int32_t filters_per_sm;      /* resident CTAs per SM; 0 = library default */
-    int32_t reserved;
+    int32_t force_global_memory; /* 1 = use the global-memory ("spilled") kernels even when N fits one CTA (parity runs);
+                                    they are selected automatically for N > 8192 */
 } ssme_b200_config;
 
 typedef struct {
@@ -192,6 +193,18 @@ int ssme_b200_pmmh_run_custom(int32_t model, const ssme_b200_pmmh_config* cfg, s
 
 /* model id the handle was created with */
 int32_t ssme_b200_model(ssme_b200_handle h);
+
+/* ---- one filter sharded by particles over the ranks (N > 8192, "spilled" mode) --------------------------
+ * The reference keeps a filter's particles in std::array members of one object on one thread
+ * (univ_svol_bootstrap_filter.h:18 -> pf BSFilter); nothing there shards a filter.  Here rank r owns a
+ * contiguous range of 4096-particle tiles; per time step the ranks all-reduce the weight maximum and
+ * all-gather the tile weight sums (NCCL), and read ancestors' states from each other's HBM over NVLink.
+ * After ssme_b200_comm_init, every rank exports four CUDA-IPC handles (256 bytes), the launcher gathers
+ * them ([world][256], rank order) and every rank imports the lot.  All ranks then call the same
+ * ssme_b200_loglike_batch / ssme_b200_filter_trace with the same arguments and get the same results,
+ * which are bit-identical to the single-GPU run. */
+int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t handles_out[256]);
+int ssme_b200_spill_ipc_import(ssme_b200_handle h, const uint8_t* all_handles);
 
 /* Replaces: the reduction at the end of thread_pool::worker_thread (thread_pool.h:263-268) on its own:
  * out[p] = log-mean-exp of values[p*R .. p*R+R).  HOST buffers; runs kernel K6 on `device`. */

@@ -19,7 +19,7 @@ class _Cfg(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("num_particles", C.c_int32), ("resampler", C.c_int32), ("resample_every", C.c_int32),
         ("arithmetic", C.c_int32), ("scan_items_per_lane", C.c_int32), ("rng_mode", C.c_int32), ("scan_threads", C.c_int32),
-        ("seed", C.c_uint64), ("filter_id", C.c_uint64),
+        ("seed", C.c_uint64), ("filter_id", C.c_uint64), ("tiled", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -65,12 +65,12 @@ def _dp(a):
 
 
 def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONICAL, L=4, rng_mode=RNG_PHILOX,
-               seed=20260101, filter_id=0, z=None, u=None, cov=None, trace=True, NT=0):
+               seed=20260101, filter_id=0, z=None, u=None, cov=None, trace=True, NT=0, tiled=False):
     """Run one oracle filter; returns dict(loglik, cond_like, ancestors, x, margin)."""
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
     T = y.shape[0]
-    cfg = _Cfg(model, N, resampler, rs, arithmetic, L, rng_mode, NT, seed, filter_id)
+    cfg = _Cfg(model, N, resampler, rs, arithmetic, L, rng_mode, NT, seed, filter_id, 1 if tiled else 0, 0)
     z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
     cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)

@@ -125,6 +125,63 @@ static int32_t descent_search(const double* C, int32_t np, int32_t n, double tau
     return idx < n - 1 ? idx : n - 1;
 }
 
+/* ---- tiled order (global-memory kernels, N beyond one CTA) ---------------------------------------
+ * Tile b holds particles b*TS .. b*TS+TS-1 (TS = NT*L).  Inside a tile the scan is the CTA scan above
+ * (local prefixes cl, tile total Tt_b).  The tile totals are scanned by ONE CTA of 1024 lanes with
+ * Lp = next_pow2(ceil(nb/1024)) items per lane -> inclusive tile ends E_b and the grand total S.
+ * C_i = O_b + cl_i with O_b = E_{b-1} (O_0 = +0).  A target tau is located by the descent over E
+ * (padded to 1024*Lp entries), clamped to the last tile, then by the descent over the tile's C values. */
+typedef struct {
+    int32_t N, TS, L, nb, Lp, NBP;
+    double* cl;  /* [nb*TS] tile-local inclusive prefixes */
+    double* E;   /* [NBP] inclusive tile ends (padded) */
+    double S;
+} tiled_cdf_t;
+
+static void tiled_alloc(tiled_cdf_t* c, int32_t N, int32_t TS, int32_t L)
+{
+    c->N = N; c->TS = TS; c->L = L;
+    c->nb = (N + TS - 1) / TS;
+    int32_t per = (c->nb + 1023) / 1024, Lp = 1;
+    while (Lp < per) Lp <<= 1;
+    c->Lp = Lp; c->NBP = 1024 * Lp;
+    c->cl = (double*)malloc(sizeof(double) * (size_t)c->nb * (size_t)TS);
+    c->E = (double*)malloc(sizeof(double) * (size_t)c->NBP);
+}
+static void tiled_free(tiled_cdf_t* c) { free(c->cl); free(c->E); }
+
+static void tiled_build(tiled_cdf_t* c, const double* w)
+{
+    double* tt = (double*)calloc((size_t)c->nb, sizeof(double));
+    for (int32_t b = 0; b < c->nb; ++b) {
+        int32_t n_b = c->N - b * c->TS < c->TS ? c->N - b * c->TS : c->TS;
+        ssme_oracle_canonical_scan(w + (size_t)b * c->TS, n_b, c->L, c->TS, c->cl + (size_t)b * c->TS, &tt[b]);
+    }
+    ssme_oracle_canonical_scan(tt, c->nb, c->Lp, c->NBP, c->E, &c->S);
+    free(tt);
+}
+
+static int32_t tiled_search(const tiled_cdf_t* c, double tau)
+{
+    int32_t b = 0;
+    for (int32_t s = c->NBP / 2; s >= 1; s >>= 1)
+        if (c->E[b + s - 1] < tau) b += s;
+    if (b > c->nb - 1) b = c->nb - 1;
+    const double O = (b > 0) ? c->E[b - 1] : 0.0;
+    const double* cl = c->cl + (size_t)b * c->TS;
+    int32_t idx = 0;
+    for (int32_t s = c->TS / 2; s >= 1; s >>= 1)
+        if (O + cl[idx + s - 1] < tau) idx += s;
+    int64_t i = (int64_t)b * c->TS + idx;
+    return (int32_t)(i < c->N - 1 ? i : c->N - 1);
+}
+
+static double tiled_value(const tiled_cdf_t* c, int32_t i)
+{
+    int32_t b = i / c->TS;
+    return ((b > 0) ? c->E[b - 1] : 0.0) + c->cl[i];
+}
+
 /* ---------------------------------------------------------------- densities ------------------ */
 /* pf::rveval::evalUnivNorm(x, mu, sigma, log=true) as restated in SURVEY.md a8 / Appendix B */
 static double faithful_log_norm(double x, double mu, double sigma)
@@ -231,11 +288,20 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
     if (N < 1 || rs < 1 || (canonical && L < 1)) return -2;
     /* padded slot count of the kernel's CTA: threads * L, threads a power of two >= 32 */
     int32_t NP = N;
-    if (canonical) {
+    if (canonical && !cfg->tiled) {
         int32_t nt = cfg->scan_threads;
         if (nt == 0) { nt = 32; while ((int64_t)nt * L < N) nt <<= 1; }
         if ((nt & (nt - 1)) != 0 || (L & (L - 1)) != 0 || (int64_t)nt * L < N) return -7;
         NP = nt * L;
+    }
+    const int tiled = canonical && cfg->tiled;
+    tiled_cdf_t tc;
+    if (tiled) {
+        if (cfg->resampler != SSME_OR_RESAMP_SYSTEMATIC && cfg->resampler != SSME_OR_RESAMP_MULTINOMIAL) return -8;
+        int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
+        if ((nt & (nt - 1)) != 0) return -7;
+        tiled_alloc(&tc, N, nt * L, L);
+        NP = N; /* C below holds the global values O_b + cl_i, for the margin report only */
     }
     if (cfg->model != SSME_OR_MODEL_SV && cfg->model != SSME_OR_MODEL_SV_LEVERAGE) return -3;
     if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
@@ -297,7 +363,13 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
         double S;
         if (canonical) {
             for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lw[i] - M);
-            ssme_oracle_canonical_scan(w, N, L, NP, C, &S);
+            if (tiled) {
+                tiled_build(&tc, w);
+                S = tc.S;
+                for (int32_t i = 0; i < N; ++i) C[i] = tiled_value(&tc, i);
+            } else {
+                ssme_oracle_canonical_scan(w, N, L, NP, C, &S);
+            }
         } else {
             S = 0.0;
             for (int32_t i = 0; i < N; ++i) { w[i] = exp(lw[i] - M); S += w[i]; }
@@ -332,7 +404,7 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
                     double u = injected ? ut[j]
                                         : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
                     double tau = canonical ? u * S : u;
-                    anc[j] = canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
+                    anc[j] = tiled ? tiled_search(&tc, tau) : canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
                     upd_margin(&margin, C, anc[j], tau, total);
                 }
             } else if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL) {
@@ -371,7 +443,7 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
                 double sN = S / (double)N;
                 for (int32_t j = 0; j < N; ++j) {
                     double tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
-                    anc[j] = canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
+                    anc[j] = tiled ? tiled_search(&tc, tau) : canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
                     upd_margin(&margin, C, anc[j], tau, total);
                 }
             }
@@ -385,6 +457,7 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
         }
         if (ancestors) for (int32_t j = 0; j < N; ++j) ancestors[t * N + j] = anc[j];
     }
+    if (tiled) tiled_free(&tc);
     if (loglik_out) *loglik_out = loglik;
     if (tie_margin) *tie_margin = margin;
     free(x); free(xn); free(lw); free(w); free(C); free(E); free(PE); free(anc);

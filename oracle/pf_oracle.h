@@ -48,6 +48,9 @@ typedef struct {
     int32_t scan_threads;        /* threads per filter NT of the kernel layout (power of two; NT*L slots); 0 = smallest that fits */
     uint64_t seed;               /* Philox key */
     uint64_t filter_id;          /* Philox counter words 2,3 */
+    int32_t tiled;               /* 1 = the order of the global-memory ("spilled") kernels: tiles of NT*L particles scanned
+                                    as above, tile totals scanned by one CTA of 1024 lanes, two-level search (CANONICAL only) */
+    int32_t reserved2;
 } ssme_oracle_cfg;
 
 /*

@@ -68,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         jobs.append((obj, [nvcc, *NVCC_FLAGS, "-DSSME_NT=%d" % nt, "-c", os.path.join(CSRC, "pf_inst.cu"), "-o", obj]))
     obj = os.path.join(OBJDIR, "capi.o")
     jobs.append((obj, [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "capi.cu"), "-o", obj]))
+    obj = os.path.join(OBJDIR, "spill_capi.o")
+    jobs.append((obj, [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "spill_capi.cu"), "-o", obj]))
     obj = os.path.join(OBJDIR, "pmmh_capi.o")  # host-only C++ (the PMMH loop above the C ABI)
     jobs.append((obj, [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, "pmmh_capi.cpp"), "-o", obj]))
     todo = [(o, c) for o, c in jobs if force or not os.path.exists(o) or os.path.getmtime(o) < newest]

@@ -34,7 +34,7 @@ class _Config(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("num_particles", C.c_int32),
         ("resampler", C.c_int32), ("resample_every", C.c_int32), ("dtype", C.c_int32), ("rng_mode", C.c_int32),
         ("seed", C.c_uint64), ("scan_items_per_lane", C.c_int32), ("threads_per_filter", C.c_int32),
-        ("filters_per_sm", C.c_int32), ("reserved", C.c_int32),
+        ("filters_per_sm", C.c_int32), ("force_global_memory", C.c_int32),
     ]
 
 
@@ -94,6 +94,8 @@ def load_library():
     lib.ssme_b200_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.ssme_b200_comm_init.argtypes = [H, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
     lib.ssme_b200_loglike_batch_sharded.argtypes = [H, dp, C.c_size_t, C.c_uint32, C.c_uint64, dp, dp]
+    lib.ssme_b200_spill_ipc_export.argtypes = [H, C.POINTER(C.c_uint8)]
+    lib.ssme_b200_spill_ipc_import.argtypes = [H, C.POINTER(C.c_uint8)]
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
@@ -190,6 +192,7 @@ class FilterConfig:
     scan_items_per_lane: int = 0
     threads_per_filter: int = 0
     filters_per_sm: int = 0
+    force_global_memory: int = 0
 
 
 def _dptr(a):
@@ -204,7 +207,7 @@ class ParticleFilterBackend:
         self.cfg = cfg
         c = _Config(C.sizeof(_Config), cfg.device, cfg.model, cfg.num_particles, cfg.resampler, cfg.resample_every,
                     cfg.dtype, cfg.rng_mode, cfg.seed, cfg.scan_items_per_lane, cfg.threads_per_filter,
-                    cfg.filters_per_sm, 0)
+                    cfg.filters_per_sm, cfg.force_global_memory)
         self._h = C.c_void_p()
         _check(self._lib.ssme_b200_create(C.byref(c), C.byref(self._h)))
         self.num_params = 3 if cfg.model == MODEL_SV else 4
@@ -264,6 +267,15 @@ class ParticleFilterBackend:
         """Join the NCCL communicator (collective).  unique_id comes from comm_unique_id() on rank 0."""
         buf = (C.c_uint8 * 128)(*unique_id)
         _check(self._lib.ssme_b200_comm_init(self._h, buf, rank, world))
+
+    def spill_ipc_export(self) -> bytes:
+        buf = (C.c_uint8 * 256)()
+        _check(self._lib.ssme_b200_spill_ipc_export(self._h, buf))
+        return bytes(buf)
+
+    def spill_ipc_import(self, all_handles: bytes):
+        buf = (C.c_uint8 * len(all_handles))(*all_handles)
+        _check(self._lib.ssme_b200_spill_ipc_import(self._h, buf))
 
     def work_batch_sharded(self, theta, R: int = 1, stream_base: int = 0):
         """Multi-rank thread_pool::work: returns (lme[P], per_filter[P, R]), identical on every rank."""

@@ -1,9 +1,8 @@
 // ssme_b200/csrc/capi.cu -- the C ABI declared in include/ssme_b200.h: handle management,
 // kernel dispatch, host<->device staging.  No torch types, no CPU fallback: every entry point
 // either launches the sm_100a kernels or returns an error.
-#include "../../include/ssme_b200.h"
+#include "capi_internal.h"
 
-#include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <atomic>
@@ -26,7 +25,7 @@ namespace ssme {
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 
-static int fail(int code, const char* fmt, ...)
+int fail(int code, const char* fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -44,12 +43,6 @@ int set_last_error(int code, const char* msg)
     return code;
 }
 
-#define SSME_CUDA(expr)                                                                              \
-    do {                                                                                             \
-        cudaError_t _e = (expr);                                                                     \
-        if (_e != cudaSuccess)                                                                       \
-            return fail(SSME_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
 
 // K6: per-proposal log-mean-exp over R replicate filters (reference thread_pool.h:263-268),
 // index-order sum (the reference's order is thread-completion order, i.e. unspecified).
@@ -87,17 +80,9 @@ __global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
 }
 
-// ---- NCCL, loaded lazily so that the library has no link-time dependency on it --------------------
-struct NcclApi {
-    typedef struct { char internal[128]; } unique_id;
-    int (*GetUniqueId)(unique_id*) = nullptr;
-    int (*CommInitRank)(void**, int, unique_id, int) = nullptr;
-    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
-    int (*CommDestroy)(void*) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
-    bool ok = false;
-};
-static NcclApi* nccl_api()
+void count_launch(unsigned n) { g_launches.fetch_add(n); }
+
+NcclApi* nccl_api()
 {
     static NcclApi api;
     static bool tried = false;
@@ -109,14 +94,14 @@ static NcclApi* nccl_api()
             api.GetUniqueId = (int (*)(NcclApi::unique_id*))dlsym(lib, "ncclGetUniqueId");
             api.CommInitRank = (int (*)(void**, int, NcclApi::unique_id, int))dlsym(lib, "ncclCommInitRank");
             api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
             api.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
             api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-            api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy && api.GetErrorString;
         }
     }
     return &api;
 }
-constexpr int kNcclFloat64 = 8;  // ncclDataType_t ncclFloat64 (nccl.h)
 
 static const KernelEntry* find_kernel(int L, int NT, int model, int resamp, int debug)
 {
@@ -137,31 +122,8 @@ static const KernelEntry* find_kernel(int L, int NT, int model, int resamp, int 
 
 using namespace ssme;
 
-struct ssme_b200_filter_s {
-    ssme_b200_config cfg;
-    int L = 0, NT = 0;
-    int num_params = 0;
-    int num_sms = 0;
-    int filters_per_sm = 0;
-    const KernelEntry* fast = nullptr;
-    const KernelEntry* debug = nullptr;
-    cudaStream_t stream = nullptr;
-    double* d_obs = nullptr;
-    size_t T = 0;
-    bool have_obs = false;
-    // staging for the host-buffer entry point
-    double* h_pinned = nullptr;
-    size_t h_pinned_bytes = 0;
-    double* d_theta = nullptr;
-    double* d_out = nullptr;
-    double* d_per_filter = nullptr;
-    size_t cap_theta = 0, cap_out = 0, cap_pf = 0;
-    // multi-GPU
-    void* nccl_comm = nullptr;
-    int rank = 0, world = 1;
-};
 
-namespace {
+namespace ssme {
 
 int set_device(ssme_b200_handle h)
 {
@@ -190,6 +152,10 @@ int ensure_pinned(ssme_b200_handle h, size_t bytes)
     h->h_pinned_bytes = bytes;
     return SSME_B200_OK;
 }
+
+}  // namespace ssme
+
+namespace {
 
 int next_pow2(int v)
 {
@@ -255,25 +221,36 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         return fail(SSME_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
                     prop.minor);
 
+    const bool spill = cfg->force_global_memory != 0 || cfg->num_particles > 8192;
+    int L = 0, NT = 0;
+    const KernelEntry *fast = nullptr, *dbg = nullptr;
+    if (spill) {
+        // K3: particles in HBM, tiles of 4096 (spill_kernel.cuh)
+        if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels resample at every step (resample_every = 1)");
+        if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels use the on-device Philox streams");
+        L = 8;
+        NT = 512;
+    } else {
     // layout: L items per lane, NT threads per filter (NT*L = padded particle count, a power of two)
-    int L = cfg->scan_items_per_lane;
+    L = cfg->scan_items_per_lane;
     // default: 8 particles per thread once that still fills a warp (measured on B200, configs[1]:
     // L=8/NT=128 1.06e11 particle-steps/s vs L=4/NT=256 0.95e11), else 4
     if (L == 0) L = (cfg->num_particles > 8 * 24) ? 8 : 4;
     if (L != 4 && L != 8) return fail(SSME_B200_EUNSUPPORTED, "scan_items_per_lane must be 4 or 8 (got %d)", L);
-    int NT = cfg->threads_per_filter;
+    NT = cfg->threads_per_filter;
     const int need = (cfg->num_particles + L - 1) / L;
     if (NT == 0) NT = next_pow2(need < 32 ? 32 : need);
     if (NT < need || NT > 1024 || (NT & (NT - 1)) != 0 || NT < 32)
         return fail(SSME_B200_EUNSUPPORTED,
                     "num_particles %d needs %d threads at L=%d; the resident kernel supports power-of-two CTAs of 32..1024 threads",
                     cfg->num_particles, need, L);
-    const KernelEntry* fast = find_kernel(L, NT, cfg->model, cfg->resampler, 0);
-    const KernelEntry* dbg = find_kernel(L, NT, cfg->model, cfg->resampler, 1);
+    fast = find_kernel(L, NT, cfg->model, cfg->resampler, 0);
+    dbg = find_kernel(L, NT, cfg->model, cfg->resampler, 1);
     if (!fast || !dbg) return fail(SSME_B200_EUNSUPPORTED, "no kernel built for L=%d NT=%d model=%d resampler=%d", L, NT, cfg->model, cfg->resampler);
     int rc;
     if ((rc = prepare_kernel(fast)) != SSME_B200_OK) return rc;
     if ((rc = prepare_kernel(dbg)) != SSME_B200_OK) return rc;
+    }
 
     ssme_b200_handle h = new ssme_b200_filter_s();
     h->cfg = *cfg;
@@ -283,9 +260,14 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->num_sms = prop.multiProcessorCount;
     h->fast = fast;
     h->debug = dbg;
+    h->spill = spill;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
-    if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
+    if (!spill) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
+        if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
+    } else {
+        spill_create(h);
+    }
     h->filters_per_sm = occ;
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
@@ -298,6 +280,7 @@ int ssme_b200_destroy(ssme_b200_handle h)
     if (!h) return SSME_B200_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->spill) spill_destroy(h);
     if (h->nccl_comm && nccl_api()->ok) nccl_api()->CommDestroy(h->nccl_comm);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->d_obs) cudaFree(h->d_obs);
@@ -315,11 +298,15 @@ int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out)
     out->scan_items_per_lane = h->L;
     out->threads_per_filter = h->NT;
     out->filters_per_sm = h->filters_per_sm;
-    out->smem_bytes_per_filter = (int32_t)h->fast->smem_bytes;
     out->num_sms = h->num_sms;
-    cudaFuncAttributes fa;
-    SSME_CUDA(cudaFuncGetAttributes(&fa, h->fast->fn));
-    out->registers_per_thread = fa.numRegs;
+    out->smem_bytes_per_filter = 0;
+    out->registers_per_thread = 0;
+    if (!h->spill) {
+        out->smem_bytes_per_filter = (int32_t)h->fast->smem_bytes;
+        cudaFuncAttributes fa;
+        SSME_CUDA(cudaFuncGetAttributes(&fa, h->fast->fn));
+        out->registers_per_thread = fa.numRegs;
+    }
     return SSME_B200_OK;
 }
 
@@ -376,9 +363,15 @@ int ssme_b200_loglike_batch_device(ssme_b200_handle h, const double* theta_dev, 
     int rc = set_device(h);
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    const bool fast_ok = (h->cfg.resample_every == 1);
-    FilterArgs a = base_args(h, theta_dev, R, stream_base, per_filter_dev);
-    if ((rc = launch_filters(h, fast_ok ? h->fast : h->debug, a, P * (size_t)R, st)) != SSME_B200_OK) return rc;
+    if (h->spill) {
+        if (cuda_stream && (cudaStream_t)cuda_stream != h->stream)
+            return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels run on the handle's own stream");
+        if ((rc = spill_run_filters(h, theta_dev, P * (size_t)R, R, stream_base, per_filter_dev, nullptr, nullptr))) return rc;
+    } else {
+        const bool fast_ok = (h->cfg.resample_every == 1);
+        FilterArgs a = base_args(h, theta_dev, R, stream_base, per_filter_dev);
+        if ((rc = launch_filters(h, fast_ok ? h->fast : h->debug, a, P * (size_t)R, st)) != SSME_B200_OK) return rc;
+    }
     if (out_dev) {
         const unsigned nb = (unsigned)((P + 127) / 128);
         log_mean_exp_kernel<<<nb, 128, 0, st>>>(per_filter_dev, R, P, out_dev);
@@ -458,15 +451,20 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     if (cond_like_host) SSME_CUDA_T(cudaMalloc(&d_cl, F * T * sizeof(double)));
     if (ancestors_host) SSME_CUDA_T(cudaMalloc(&d_anc, F * T * N * sizeof(int)));
     if (x_host) SSME_CUDA_T(cudaMalloc(&d_x, F * T * N * sizeof(double)));
-    FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
-    a.inject = inject ? 1 : 0;
-    a.stride_u = (int)stride_u;
-    a.z_inj = d_z;
-    a.u_inj = d_u;
-    a.cond_like = d_cl;
-    a.ancestors = d_anc;
-    a.x_trace = d_x;
-    rc = launch_filters(h, h->debug, a, F, h->stream);
+    if (h->spill) {
+        if (x_host) { cleanup(); return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels do not trace states (x_host must be NULL)"); }
+        rc = spill_run_filters(h, d_theta, F, 1u, stream_base, d_ll, d_cl, d_anc);
+    } else {
+        FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
+        a.inject = inject ? 1 : 0;
+        a.stride_u = (int)stride_u;
+        a.z_inj = d_z;
+        a.u_inj = d_u;
+        a.cond_like = d_cl;
+        a.ancestors = d_anc;
+        a.x_trace = d_x;
+        rc = launch_filters(h, h->debug, a, F, h->stream);
+    }
     if (rc) { cleanup(); return rc; }
     SSME_CUDA_T(cudaStreamSynchronize(h->stream));
     if (loglik_host) SSME_CUDA_T(cudaMemcpy(loglik_host, d_ll, F * sizeof(double), cudaMemcpyDeviceToHost));
@@ -486,6 +484,7 @@ int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t 
     if (P == 0) return fail(SSME_B200_EINVAL, "the swarm needs at least one parameter particle");
     if (!theta_host || !log_cond_like_host) return fail(SSME_B200_EINVAL, "null host buffer");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
+    if (h->spill) return fail(SSME_B200_EUNSUPPORTED, "the swarm entry point runs resident filters (num_particles <= 8192)");
     int rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, T = h->T;
@@ -566,6 +565,13 @@ int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host
     int rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, F = P * (size_t)R;
+    if (h->spill) {
+        // every filter is already spread over all ranks by particles; nothing left to shard by filters
+        std::vector<double> lme(P);
+        if ((rc = ssme_b200_loglike_batch(h, theta_host, P, R, stream_base, lme.data(), per_filter_host))) return rc;
+        if (out_host) memcpy(out_host, lme.data(), P * sizeof(double));
+        return SSME_B200_OK;
+    }
     uint64_t f0 = 0, cnt = 0, chunk = 0;
     if ((rc = ssme_b200_shard_range(F, h->world, h->rank, &f0, &cnt, &chunk))) return rc;
     const size_t Fpad = (size_t)chunk * (size_t)h->world;
