@@ -71,6 +71,8 @@ static int prepare(ssme_b200_handle h)
         s->peer_x[i][s->rank] = s->x_cur[i];
         s->peer_lwc[i][s->rank] = s->lwc[i];
     }
+    SSME_CUDA(cudaFuncSetAttribute(spill_resample_kernel<kResampSystematic>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kStageTiles * kTile * sizeof(double))));
     s->peers_ready = (s->world == 1);
     s->prepared = true;
     return SSME_B200_OK;
@@ -149,7 +151,8 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
             spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
             count_launch(4);
             if (t + 1 < T || a.ancestors) {
-                if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_resample_kernel<kResampSystematic><<<tiles, kTileNT, 0, st>>>(a);
+                if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC)
+                    spill_resample_kernel<kResampSystematic><<<tiles, kTileNT, kStageTiles * kTile * sizeof(double), st>>>(a);
                 else spill_resample_kernel<kResampMultinomial><<<tiles, kTileNT, 0, st>>>(a);
                 count_launch(1);
             }

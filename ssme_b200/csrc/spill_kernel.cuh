@@ -241,32 +241,126 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     }
 }
 
-// slot j: target -> tile (descent over E) -> position inside the tile (descent over O_b + cl) -> gather x'
+// State of the branch-free descent "for (s = size/2; s >= 1; s >>= 1) if (O + arr[idx+s-1] < tau) idx += s".
+struct Descent {
+    int base, s;
+};
+// Whether a probe sends a target right is monotone in the target, so while the two extreme targets lo <= hi take
+// the same decision every target in [lo, hi] takes it too -- for ANY array, sorted or not.  advance() walks that
+// shared prefix once for a whole group of targets; finish() walks the remainder for one target.  Together they
+// give exactly the result of an independent descent per target.
+__device__ __forceinline__ void advance(const double* __restrict__ arr, double O, Descent& d, double lo, double hi)
+{
+    while (d.s >= 1) {
+        const double v = __dadd_rn(O, arr[d.base + d.s - 1]);
+        const bool dlo = v < lo, dhi = v < hi;
+        if (dlo != dhi) break;
+        d.base += dlo ? d.s : 0;
+        d.s >>= 1;
+    }
+}
+__device__ __forceinline__ int finish(const double* __restrict__ arr, double O, Descent d, double tau)
+{
+    while (d.s >= 1) {
+        d.base += (__dadd_rn(O, arr[d.base + d.s - 1]) < tau) ? d.s : 0;
+        d.s >>= 1;
+    }
+    return d.base;
+}
+
+constexpr int kStageTiles = 3;  // CDF tiles a CTA stages in shared memory (96 KB)
+
+// slot j: target -> tile (descent over E) -> position inside the tile (descent over O_b + cl) -> gather x'.
+// Systematic targets increase with j, and the descent's result is monotone in the target for any array (at the
+// first probe where two targets differ the smaller goes left), so the 4096 slots of a CTA land in the tile range
+// [tile(first target), tile(last target)] -- usually 1-2 tiles.  Those tiles' CDFs are staged in shared memory with
+// coalesced loads and every slot runs its 12-level descent there; the tile-level descent starts from the prefix
+// common to the whole CTA.  Wider ranges (degenerate weights) fall back to descents in global memory.
+// Multinomial targets are i.i.d.: one full descent in global memory each.
 template <int RESAMP>
 __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs a)
 {
+    extern __shared__ __align__(16) double scl[];  // [kStageTiles][kTile]
+    __shared__ int sh_b[2];
+    __shared__ Descent sh_A;
     const int tid = threadIdx.x;
     const int tile = a.tile0 + blockIdx.x;
     const double S = a.scal[1];
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    double u0 = 0.0, sN = 0.0;
     if (RESAMP == kResampSystematic) {
         const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), key);
-        u0 = uniform53(r.x, r.y);
-        sN = __ddiv_rn(S, (double)a.N);
+        const double u0 = uniform53(r.x, r.y);
+        const double sN = __ddiv_rn(S, (double)a.N);
+        const int jc = tile * kTile;  // first slot of this CTA
+        if (jc >= a.N) return;
+        auto target = [&](int j) { return __dmul_rn(__dadd_rn((double)min(j, a.N - 1), u0), sN); };
+        const bool single = (a.tiles_per_rank == a.nb);  // one rank owns every tile: no owner lookup (integer division)
+        auto tile_cdf = [&](int b) {
+            const int owner = single ? 0 : b / a.tiles_per_rank;
+            return a.peer_lwc[owner] + (size_t)(b - owner * a.tiles_per_rank) * kTile;
+        };
+        auto tile_x = [&](int b) {
+            const int owner = single ? 0 : b / a.tiles_per_rank;
+            return a.peer_x[owner] + (size_t)(b - owner * a.tiles_per_rank) * kTile;
+        };
+        auto tile_off = [&](int b) { return (b > 0) ? a.E[b - 1] : 0.0; };
+        if (tid < 32) {
+            const double lo = target(jc), hi = target(jc + kTile - 1);
+            Descent A{0, a.NBP >> 1};
+            advance(a.E, 0.0, A, lo, hi);
+            if (tid == 0) {
+                sh_A = A;
+                sh_b[0] = min(finish(a.E, 0.0, A, lo), a.nb - 1);
+                sh_b[1] = min(finish(a.E, 0.0, A, hi), a.nb - 1);
+            }
+        }
+        __syncthreads();
+        const Descent A = sh_A;
+        const int b_lo = sh_b[0], b_hi = sh_b[1];
+        const bool staged = (b_hi - b_lo + 1) <= kStageTiles;
+        if (staged) {
+            for (int q = 0; q <= b_hi - b_lo; ++q) {
+                const double* src = tile_cdf(b_lo + q);
+#pragma unroll
+                for (int k = 0; k < kTileL; k += 2)
+                    *reinterpret_cast<double2*>(scl + q * kTile + k * kTileNT + 2 * tid) =
+                        *reinterpret_cast<const double2*>(src + k * kTileNT + 2 * tid);
+            }
+        }
+        __syncthreads();
+        double* dst = a.x_anc + (size_t)blockIdx.x * kTile;
+#pragma unroll 4
+        for (int k = 0; k < kTileL; ++k) {
+            const int j = jc + k * kTileNT + tid;
+            if (j >= a.N) break;
+            const double tau = target(j);
+            const int b = min(finish(a.E, 0.0, A, tau), a.nb - 1);
+            const double O = tile_off(b);
+            int idx = 0;
+            if (staged) {
+                const double* cl = scl + (b - b_lo) * kTile;
+#pragma unroll
+                for (int sstep = kTile / 2; sstep >= 1; sstep >>= 1) idx += (__dadd_rn(O, cl[idx + sstep - 1]) < tau) ? sstep : 0;
+            } else {
+                idx = finish(tile_cdf(b), O, Descent{0, kTile / 2}, tau);
+            }
+            long long i = (long long)b * kTile + idx;
+            if (i > (long long)a.N - 1) {  // clamp to the last real particle (it lives in the last tile)
+                i = (long long)a.N - 1;
+                idx = (int)(i - (long long)b * kTile);
+            }
+            dst[k * kTileNT + tid] = tile_x(b)[idx];
+            if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
+        }
+        return;
     }
 #pragma unroll 2
     for (int k = 0; k < kTileL; ++k) {
         const int j = tile * kTile + k * kTileNT + tid;  // coalesced over the CTA
         if (j >= a.N) continue;
-        double tau;
-        if (RESAMP == kResampSystematic) {
-            tau = __dmul_rn(__dadd_rn((double)j, u0), sN);
-        } else {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), key);
-            tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
-        }
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), key);
+        const double tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
         int b = 0;
         for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;
         b = min(b, a.nb - 1);
