@@ -237,6 +237,40 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
     return out
 
 
+def run_spilled_leg(sb, dist, rank, world, local_rank, hbm_gbs):
+    """BASELINE.json config 5: ONE SV filter with 2^28 particles (global-memory kernels K3), sharded by particles over
+    the ranks (K5: per step one NCCL all-reduce of the weight maximum, one all-gather of the tile weight sums, peer
+    reads of ancestors over NVLink).  Strong scaling: the filter is the same at every N.  Systematic resampling."""
+    N, T = 1 << 28, 8
+    rng = np.random.default_rng(SEED_SERIES + 5)
+    y = np.exp(0.1 * np.cumsum(rng.standard_normal(T))) * rng.standard_normal(T)
+    be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=N, resampler=sb.RESAMP_SYSTEMATIC,
+                                                  seed=SEED_FILTER + 5, device=local_rank))
+    be.add_observed_data(y)
+    if world > 1:
+        uid = [sb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        be.comm_init(uid[0], rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, be.spill_ipc_export())
+        be.spill_ipc_import(b"".join(handles))
+        dist.barrier()
+    theta = np.array([[1.0, 0.95, 0.0625]])
+    be.work_batch(theta, R=1, stream_base=0)  # warm-up (allocations, NCCL channels)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ll = be.work_batch(theta, R=1, stream_base=1)[0]
+    dt = time.perf_counter() - t0
+    be.close()
+    rate = N * T / dt
+    return {"particle_steps_per_sec": rate, "particles": N, "T": T, "seconds": dt, "ms_per_time_step": 1e3 * dt / T, "loglik": float(ll),
+            "resampler": "systematic", "sharding": "particles over %d rank(s)" % world,
+            "roofline": {"bound": "hbm", "achieved": rate * 48 / 1e9 / world, "peak": hbm_gbs, "unit": "GB/s", "frac": rate * 48 / 1e9 / world / hbm_gbs,
+                         "algorithmic_bytes_per_particle_step": 48, "note": "per GPU; SURVEY.md 8d: write x' 8 + write lw 8 + read lw 8 + write cdf 8 "
+                         "+ read cdf 8 + gather x 8; peak = MEASURED_PEAKS.json hbm_gbs (measured) or 6650 (fallback)"}}
+
+
 def run_ours(args):
     import torch
     import ssme_b200 as sb
@@ -329,6 +363,15 @@ def run_ours(args):
     if not args.no_pmmh:
         pmmh = run_pmmh_legs(sb, dist, rank, world, local_rank)
 
+    spilled = None
+    if not args.no_pmmh:
+        hbm = 6650.0
+        try:
+            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        spilled = run_spilled_leg(sb, dist, rank, world, local_rank, hbm)
+
     if rank == 0:
         # ---- roofline of the dominant kernel (bootstrap_filter_kernel): FP64 pipe ----------------
         fma_rate = sb.measure_fp64_fma_rate(local_rank, 1 << 15)  # thread-level FMA instructions / s, measured now
@@ -372,7 +415,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(P_PROPOSALS * 8)},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "pmmh": pmmh,
+            "pmmh": pmmh, "spilled_filter": spilled,
             "layout": layout, "wall_s_timed_region": t_wall, "checksum": checksum,
             "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-10); all filter arithmetic f64",
         }
