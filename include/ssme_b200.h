@@ -158,6 +158,19 @@ int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host
 int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
                            double* log_cond_like_host, double* per_filter_host);
 
+/* Replaces: LWFilter2WithCovs::filter called over a whole series (liu_west_filter.h:2191-2343, with
+ * update_parameter_proposal_components :2346-2360 and mn_resamp_states_and_params :91-145) for the SV-with-leverage
+ * model svol_lw_2_par (test/test_liu_west.cpp:213-358): joint state / parameter learning with kernel shrinkage
+ * a = (3 delta - 1) / (2 delta).  Parameters (phi, mu, sigma, rho), transforms (logit, null, log, twice_fisher),
+ * uniform prior box [prior_lo, prior_hi] on the untransformed scale (paramPriorSamp, :339-349).  The handle must use
+ * the global-memory kernels (force_global_memory = 1 or N > 8192) and MODEL_SV_LEVERAGE; resampling at every step.
+ * Outputs (each may be NULL): loglik; cond_like [T] (getLogCondLike per step); theta_bar [T][4] (mean of the
+ * transformed parameter particles entering step t, row 0 zero); final_mean [4] (mean of the untransformed parameter
+ * particles after the last step); ancestors [T][N]. */
+int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id,
+                        double* loglik_host, double* cond_like_host, double* theta_bar_host, double* final_mean_host,
+                        int32_t* ancestors_host);
+
 /* ---- the PMMH host loop, in C++ behind the C ABI (for hosts that cannot include the C++ headers) -------
  * Replaces: do_ada_pmmh_univ_svol + ada_pmmh_mvn::commence_sampling (example/estimate_univ_svol.h:139-178,
  * ada_pmmh_mvn.h:325-372) for `num_chains` chains advanced in lock step (include/ssme_b200/pmmh_multichain.hpp).

@@ -40,6 +40,9 @@ def lib():
         L = C.CDLL(LIB_PATH)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.ssme_oracle_filter.argtypes = [C.POINTER(_Cfg), dp, dp, C.c_int64, dp, dp, dp, dp, dp, ip, dp, dp]
+        L.ssme_oracle_lw_filter.argtypes = [C.POINTER(_Cfg), dp, dp, C.c_double, dp, C.c_int64, dp, dp, dp, dp, dp, ip, dp]
+        L.ssme_oracle_canonical_sum.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32]
+        L.ssme_oracle_canonical_sum.restype = C.c_double
         L.ssme_oracle_log_mean_exp.argtypes = [dp, C.c_int64, C.c_int32]
         L.ssme_oracle_log_mean_exp.restype = C.c_double
         for name in ("dexp", "dlog"):
@@ -83,6 +86,26 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
     if rc != 0:
         raise ValueError("ssme_oracle_filter failed with %d" % rc)
     return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs, "margin": mg.value}
+
+
+def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
+                  cov=None, trace=True):
+    """Liu-West filter (LWFilter2WithCovs on the SV-with-leverage model); returns dict(loglik, cond_like, theta_bar,
+    final_mean, ancestors, margin)."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
+    hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+    T = y.shape[0]
+    cfg = _Cfg(1, N, resampler, 1, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, 1 if arithmetic == ARITH_CANONICAL else 0, 0)
+    cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
+    ll, mg = C.c_double(0), C.c_double(0)
+    cl, tb, fm = np.empty(T), np.zeros((T, 4)), np.empty(4)
+    anc = np.empty((T, N), dtype=np.int32) if trace else None
+    rc = lib().ssme_oracle_lw_filter(C.byref(cfg), _dp(lo), _dp(hi), delta, _dp(y), T, _dp(cov), C.byref(ll), _dp(cl), _dp(tb), _dp(fm),
+                                     anc.ctypes.data_as(C.POINTER(C.c_int32)) if trace else None, C.byref(mg))
+    if rc != 0:
+        raise ValueError("ssme_oracle_lw_filter failed with %d" % rc)
+    return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "margin": mg.value}
 
 
 def log_mean_exp(v, arithmetic=ARITH_CANONICAL):

@@ -464,6 +464,236 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
     return 0;
 }
 
+/* ---------------------------------------------------------------- Liu-West filter ------------ */
+static double block_sum(const double* v, int32_t n_valid, int32_t L, int32_t lanes)
+{
+    /* lanes is a multiple of 32; lane l owns items lL..lL+L-1 (zero beyond n_valid) */
+    double* t = (double*)calloc((size_t)lanes, sizeof(double));
+    for (int32_t l = 0; l < lanes; ++l) {
+        double s = 0.0;
+        for (int32_t k = 0; k < L; ++k) {
+            int64_t i = (int64_t)l * L + k;
+            double x = (i < n_valid) ? v[i] : 0.0;
+            s = (k == 0) ? x : s + x;
+        }
+        t[l] = s;
+    }
+    double acc = 0.0;
+    for (int32_t g = 0; g < lanes / 32; ++g) {
+        double* w = t + g * 32;
+        for (int32_t d = 16; d >= 1; d >>= 1) {
+            double tmp[32];
+            for (int32_t l = 0; l < 32; ++l) tmp[l] = w[l] + w[l ^ d];
+            for (int32_t l = 0; l < 32; ++l) w[l] = tmp[l];
+        }
+        acc = (g == 0) ? w[0] : acc + w[0];
+    }
+    free(t);
+    return acc;
+}
+
+double ssme_oracle_canonical_sum(const double* v, int32_t n, int32_t L, int32_t nt)
+{
+    const int32_t TS = L * nt, nb = (n + TS - 1) / TS;
+    double* part = (double*)calloc((size_t)nb, sizeof(double));
+    for (int32_t b = 0; b < nb; ++b) {
+        int32_t n_b = n - b * TS < TS ? n - b * TS : TS;
+        part[b] = block_sum(v + (size_t)b * TS, n_b, L, nt);
+    }
+    int32_t per = (nb + 1023) / 1024, Lp = 1;
+    while (Lp < per) Lp <<= 1;
+    double r = block_sum(part, nb, Lp, 1024);
+    free(part);
+    return r;
+}
+
+static double lw_inv_trans(int type, double t, int canonical)
+{
+    /* parameters.h:361-372, 403-413, 441-443 with det_math's exp in CANONICAL */
+    switch (type) {
+    case 0: return t;
+    case 1: return t >= 0.0 ? 2.0 / (1.0 + (canonical ? dm_exp(-t) : exp(-t))) - 1.0 : 1.0 - 2.0 / (1.0 + (canonical ? dm_exp(t) : exp(t)));
+    case 2: {
+        if (t >= 0.0) return 1.0 / (1.0 + (canonical ? dm_exp(-t) : exp(-t)));
+        double e = canonical ? dm_exp(t) : exp(t);
+        return e / (1.0 + e);
+    }
+    default: return canonical ? dm_exp(t) : exp(t);
+    }
+}
+static double lw_trans(int type, double p, int canonical)
+{
+    switch (type) {
+    case 0: return p;
+    case 1: return canonical ? dm_log(1.0 + p) - dm_log(1.0 - p) : log(1.0 + p) - log(1.0 - p);
+    case 2: return canonical ? dm_log(p) - dm_log(1.0 - p) : log(p) - log(1.0 - p);
+    default: return canonical ? dm_log(p) : log(p);
+    }
+}
+
+int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, const double* prior_hi, double delta,
+                          const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
+                          double* theta_bar, double* final_mean, int32_t* ancestors, double* tie_margin)
+{
+    static const int TT[4] = {2, 0, 3, 1}; /* logit, null, log, twice_fisher */
+    if (!cfg || !prior_lo || !prior_hi || !y || T < 0) return -1;
+    const int32_t N = cfg->num_particles, L = cfg->scan_items_per_lane;
+    const int canonical = (cfg->arithmetic == SSME_OR_ARITH_CANONICAL);
+    if (N < 1 || (canonical && (!cfg->tiled || L < 1))) return -2;
+    if (cfg->resampler != SSME_OR_RESAMP_MULTINOMIAL && cfg->resampler != SSME_OR_RESAMP_SYSTEMATIC) return -4;
+    const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
+    const uint32_t utag = 1u + (uint32_t)cfg->resampler;
+    const double a = (3.0 * delta - 1.0) / (2.0 * delta), h2 = 1.0 - a * a, oma = 1.0 - a;
+    tiled_cdf_t tc;
+    if (canonical) tiled_alloc(&tc, N, nt * L, L);
+    double* x = (double*)malloc(sizeof(double) * (size_t)N);
+    double* th = (double*)malloc(sizeof(double) * (size_t)N * 4); /* SoA: th[k*N + i], transformed */
+    double* xn = (double*)malloc(sizeof(double) * (size_t)N * 5);
+    double* lw = (double*)malloc(sizeof(double) * (size_t)N);
+    double* w = (double*)malloc(sizeof(double) * (size_t)N);
+    double* C = (double*)malloc(sizeof(double) * (size_t)N);
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)N);
+    int32_t* anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    double loglik = 0.0, margin = INFINITY;
+    const double logN = canonical ? dm_log((double)N) : log((double)N);
+    const double c0 = -DM_HALF_LOG_2PI;
+
+    for (int64_t t = 0; t < T; ++t) {
+        const double yt = y[t];
+        const double ct = (t > 0) ? (cov ? cov[t] : y[t - 1]) : 0.0;
+        double Lc[4][4] = {{0}}, tb[4] = {0, 0, 0, 0};
+        if (t > 0) {
+            /* update_parameter_proposal_components: thetaBar, V_t, cov = h^2 V_t, factor */
+            double V[4][4];
+            if (canonical) {
+                double s2[4][4];
+                for (int k = 0; k < 4; ++k) tb[k] = ssme_oracle_canonical_sum(th + (size_t)k * N, N, L, nt) / (double)N;
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l <= k; ++l) {
+                        for (int32_t i = 0; i < N; ++i) tmp[i] = th[(size_t)k * N + i] * th[(size_t)l * N + i];
+                        s2[k][l] = ssme_oracle_canonical_sum(tmp, N, L, nt) / (double)N;
+                    }
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l <= k; ++l) V[k][l] = h2 * (s2[k][l] - tb[k] * tb[l]);
+            } else {
+                double s2[4][4] = {{0}};
+                for (int32_t i = 0; i < N; ++i)
+                    for (int k = 0; k < 4; ++k) {
+                        tb[k] += th[(size_t)k * N + i] / N;
+                        for (int l = 0; l <= k; ++l) s2[k][l] += th[(size_t)k * N + i] * th[(size_t)l * N + i] / N;
+                    }
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l <= k; ++l) V[k][l] = h2 * (s2[k][l] - tb[k] * tb[l]);
+            }
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double sacc = V[i][j];
+                    for (int k = 0; k < j; ++k) sacc = sacc - Lc[i][k] * Lc[j][k];
+                    Lc[i][j] = (i == j) ? sqrt(sacc) : sacc / Lc[j][j];
+                }
+            if (theta_bar) for (int k = 0; k < 4; ++k) theta_bar[t * 4 + k] = tb[k];
+        }
+        for (int32_t i = 0; i < N; ++i) {
+            double z = ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
+            double p[4]; /* untransformed phi, mu, sigma, rho used by this step */
+            if (t == 0) {
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t wd[4];
+                    philox_block(cfg->seed, cfg->filter_id, 0u, 2u * (uint32_t)i + (uint32_t)(k >> 1), 5u, wd);
+                    double u = (k & 1) ? dm_uniform53(wd[2], wd[3]) : dm_uniform53(wd[0], wd[1]);
+                    p[k] = canonical ? fma(u, prior_hi[k] - prior_lo[k], prior_lo[k]) : prior_lo[k] + u * (prior_hi[k] - prior_lo[k]);
+                    th[(size_t)k * N + i] = lw_trans(TT[k], p[k], canonical);
+                }
+                x[i] = canonical ? z * (p[2] / sqrt(1.0 - p[0] * p[0])) : z * p[2] / sqrt(1.0 - p[0] * p[0]);
+            } else {
+                uint32_t wd[4];
+                float zf[4];
+                philox_block(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i, 4u, wd);
+                dm_box_muller(wd[0], wd[1], &zf[0], &zf[1]);
+                dm_box_muller(wd[2], wd[3], &zf[2], &zf[3]);
+                double m[4], nth[4];
+                for (int k = 0; k < 4; ++k)
+                    m[k] = canonical ? fma(a, th[(size_t)k * N + i], oma * tb[k]) : a * th[(size_t)k * N + i] + oma * tb[k];
+                for (int k = 0; k < 4; ++k) {
+                    double acc = m[k];
+                    for (int l = 0; l <= k; ++l) acc = canonical ? fma(Lc[k][l], (double)zf[l], acc) : acc + Lc[k][l] * (double)zf[l];
+                    nth[k] = acc;
+                }
+                for (int k = 0; k < 4; ++k) { th[(size_t)k * N + i] = nth[k]; p[k] = lw_inv_trans(TT[k], nth[k], canonical); }
+                if (canonical) {
+                    double e2 = dm_exp(-0.5 * x[i]);
+                    double cz = (p[3] * p[2]) * ct;
+                    double mean = fma(p[0], x[i] - p[1], p[1]);
+                    mean = fma(cz, e2, mean);
+                    x[i] = fma(p[2] * sqrt(1.0 - p[3] * p[3]), z, mean);
+                } else {
+                    double mean = p[1] + p[0] * (x[i] - p[1]) + ct * p[3] * p[2] * exp(-.5 * x[i]);
+                    x[i] = mean + z * p[2] * sqrt(1.0 - p[3] * p[3]);
+                }
+            }
+            if (canonical) {
+                double hh = (yt * yt) * 0.5;
+                lw[i] = fma(-hh, dm_exp(-x[i]), fma(-0.5, x[i], c0));
+            } else {
+                lw[i] = faithful_log_norm(yt, 0.0, exp(.5 * x[i]));
+            }
+        }
+        double M = -INFINITY;
+        for (int32_t i = 0; i < N; ++i) if (lw[i] > M) M = lw[i];
+        double S;
+        if (canonical) {
+            for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lw[i] - M);
+            tiled_build(&tc, w);
+            S = tc.S;
+            for (int32_t i = 0; i < N; ++i) C[i] = tiled_value(&tc, i);
+        } else {
+            S = 0.0;
+            for (int32_t i = 0; i < N; ++i) { w[i] = exp(lw[i] - M); S += w[i]; }
+            double acc = 0.0;
+            for (int32_t i = 0; i < N; ++i) { acc += w[i] / S; C[i] = acc; }
+            C[N - 1] = 1.0;
+        }
+        const double logS = canonical ? dm_log(S) : log(S);
+        const double cl = (t == 0) ? -logN + M + logS : M + logS - 0.0 - logN;
+        if (cond_like) cond_like[t] = cl;
+        loglik += cl;
+        const double total = canonical ? S : 1.0;
+        double u0 = 0.0, sN = S / (double)N;
+        if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) u0 = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
+        for (int32_t j = 0; j < N; ++j) {
+            double tau;
+            if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
+            else {
+                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                tau = canonical ? u * S : u;
+            }
+            anc[j] = canonical ? tiled_search(&tc, tau) : lower_bound_idx(C, N, tau);
+            upd_margin(&margin, C, anc[j], tau, total);
+        }
+        for (int32_t j = 0; j < N; ++j) {
+            xn[j] = x[anc[j]];
+            for (int k = 0; k < 4; ++k) xn[(size_t)(k + 1) * N + j] = th[(size_t)k * N + anc[j]];
+        }
+        for (int32_t j = 0; j < N; ++j) {
+            x[j] = xn[j];
+            for (int k = 0; k < 4; ++k) th[(size_t)k * N + j] = xn[(size_t)(k + 1) * N + j];
+        }
+        if (ancestors) for (int32_t j = 0; j < N; ++j) ancestors[t * N + j] = anc[j];
+    }
+    if (final_mean) {
+        for (int k = 0; k < 4; ++k) {
+            for (int32_t i = 0; i < N; ++i) tmp[i] = lw_inv_trans(TT[k], th[(size_t)k * N + i], canonical);
+            if (canonical) final_mean[k] = ssme_oracle_canonical_sum(tmp, N, L, nt) / (double)N;
+            else { double sacc = 0.0; for (int32_t i = 0; i < N; ++i) sacc += tmp[i]; final_mean[k] = sacc / (double)N; }
+        }
+    }
+    if (canonical) tiled_free(&tc);
+    if (loglik_out) *loglik_out = loglik;
+    if (tie_margin) *tie_margin = margin;
+    free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc);
+    return 0;
+}
+
 /* thread_pool.h:263-268 */
 double ssme_oracle_log_mean_exp(const double* v, int64_t n, int32_t arithmetic)
 {

@@ -72,6 +72,27 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
                        double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
                        double* tie_margin);
 
+/*
+ * Liu-West joint state/parameter filter, SISR form with the bootstrap proposal: LWFilter2WithCovs::filter
+ * (reference include/ssme/liu_west_filter.h:2191-2343, update_parameter_proposal_components :2346-2360, shrinkage
+ * a = (3 delta - 1)/(2 delta) :2176) on the SV-with-leverage model svol_lw_2_par (test/test_liu_west.cpp:213-358;
+ * parameter order phi, mu, sigma, rho; transforms logit, null, log, twice_fisher :263; uniform prior boxes :165).
+ * Resampling every step; cfg->resampler selects multinomial / systematic targets on the tiled CDF.
+ * cfg->arithmetic CANONICAL (tiled order, cfg->tiled must be 1) or FAITHFUL (libm, sequential sums, reference's
+ * moment formulas).  Both draw theta' = m + chol(h^2 V) z (the reference factorises inside pf's MVNSampler).
+ *   prior_lo/hi[4]  uniform prior box of the untransformed parameters
+ * Outputs (may be NULL): loglik, cond_like[T], theta_bar[T][4] (mean of the TRANSFORMED parameter particles entering
+ * step t; row 0 unused), final_mean[4] (mean of the UNTRANSFORMED particles after the last resampling),
+ * ancestors[T][N], tie_margin.
+ */
+int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, const double* prior_hi, double delta,
+                          const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
+                          double* theta_bar, double* final_mean, int32_t* ancestors, double* tie_margin);
+
+/* canonical sum of v[0..n): tile partials (lane-local sequential over L, butterfly over the 32 lanes, sequential
+ * over the warps of the tile), then the tile partials by one CTA of 1024 lanes the same way */
+double ssme_oracle_canonical_sum(const double* v, int32_t n, int32_t L, int32_t nt);
+
 /* thread_pool's reduction (reference include/ssme/thread_pool.h:263-268): m + log(sum exp(v-m)) - log(n).
  * arithmetic CANONICAL uses det_math, index-order sum; FAITHFUL uses libm. */
 double ssme_oracle_log_mean_exp(const double* v, int64_t n, int32_t arithmetic);

@@ -1,0 +1,237 @@
+// ssme_b200/csrc/lw_kernel.cuh -- K4: the Liu-West joint state/parameter filter on the global-memory tiles of K3.
+//
+// Replaces LWFilter2WithCovs::filter (include/ssme/liu_west_filter.h:2191-2343) and
+// update_parameter_proposal_components (:2346-2360) for the SV-with-leverage model svol_lw_2_par
+// (test/test_liu_west.cpp:213-358): per step
+//   lw_moments_kernel + lw_moments_final_kernel   thetaBar, V_t over all particles, chol(h^2 V_t)        (:2346-2360)
+//   lw_propagate_kernel    theta' = a theta + (1-a) thetaBar + L z, untransform, x' ~ f(.|x, theta'), log g  (:2210-2224)
+//   spill_reduce_max / weights_scan / tile_scan   log-sum-exp of :2238-2245 (K3 kernels, unchanged)
+//   spill_resample_kernel  states and the 4 parameters resampled together (mn_resamp_states_and_params, :91-145)
+// The reference builds 2-3 param::pack objects (heap, string-keyed factory) per particle per step (:2214, parameters.h:290-313);
+// here a particle is five doubles in five SoA arrays.  Arithmetic = oracle's ssme_oracle_lw_filter, CANONICAL.
+#pragma once
+#include "spill_kernel.cuh"
+
+namespace ssme {
+
+struct LwArgs {
+    SpillArgs s;
+    const double* th_anc[4];  // transformed parameters entering the step (after resampling)
+    double* th_cur[4];        // jittered parameters of this step
+    double* part;             // [14][nb] tile partial sums
+    double* mom;              // [0..3] thetaBar, [4..19] chol factor row-major, [20..23] scratch means
+    double* theta_bar_out;    // [T][4] or null
+    double lo[4], hi[4];      // uniform prior box (untransformed)
+    double a, oma, h2;
+    int mode;                 // moments kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values
+};
+
+__device__ __forceinline__ double lw_inv_trans(int k, double t)
+{
+    // parameter order phi (logit), mu (null), sigma (log), rho (twice_fisher): parameters.h:403-413, 441-443, 361-372
+    if (k == 1) return t;
+    if (k == 2) return dexp(t);
+    if (k == 0) {
+        if (t >= 0.0) return __ddiv_rn(1.0, __dadd_rn(1.0, dexp(-t)));
+        const double e = dexp(t);
+        return __ddiv_rn(e, __dadd_rn(1.0, e));
+    }
+    return (t >= 0.0) ? __dsub_rn(__ddiv_rn(2.0, __dadd_rn(1.0, dexp(-t))), 1.0) : __dsub_rn(1.0, __ddiv_rn(2.0, __dadd_rn(1.0, dexp(t))));
+}
+__device__ __forceinline__ double lw_trans(int k, double p)
+{
+    if (k == 1) return p;
+    if (k == 2) return dlog(p);
+    if (k == 0) return __dsub_rn(dlog(p), dlog(__dsub_rn(1.0, p)));
+    return __dsub_rn(dlog(__dadd_rn(1.0, p)), dlog(__dsub_rn(1.0, p)));
+}
+
+// canonical block sum: lane-local sequential (done by the caller), butterfly over the lanes, sequential over the warps
+template <int NW>
+__device__ __forceinline__ double block_sum_finish(double v, double* red /*[NW]*/, int lane, int warp)
+{
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = __dadd_rn(v, shfl_xor_d(v, d));
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double acc = red[0];
+    for (int g = 1; g < NW; ++g) acc = __dadd_rn(acc, red[g]);
+    __syncthreads();
+    return acc;
+}
+
+__global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
+{
+    __shared__ double red[kTileNT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
+    double th[4][kTileL];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < kTileL; ++k) {
+            double v = (i0 + k < a.s.N) ? a.th_anc[q][(size_t)i0 + k] : 0.0;
+            if (a.mode == 1 && i0 + k < a.s.N) v = lw_inv_trans(q, v);
+            th[q][k] = v;
+        }
+    int slot = 0;
+    for (int q = 0; q < 4; ++q) {
+        double s = th[q][0];
+#pragma unroll
+        for (int k = 1; k < kTileL; ++k) s = __dadd_rn(s, th[q][k]);
+        const double tot = block_sum_finish<kTileNT / 32>(s, red, lane, warp);
+        if (tid == 0) a.part[(size_t)slot * a.s.nb + tile] = tot;
+        ++slot;
+    }
+    if (a.mode == 1) return;
+    for (int q = 0; q < 4; ++q)
+        for (int l = 0; l <= q; ++l) {
+            double s = __dmul_rn(th[q][0], th[l][0]);
+#pragma unroll
+            for (int k = 1; k < kTileL; ++k) s = __dadd_rn(s, __dmul_rn(th[q][k], th[l][k]));
+            const double tot = block_sum_finish<kTileNT / 32>(s, red, lane, warp);
+            if (tid == 0) a.part[(size_t)slot * a.s.nb + tile] = tot;
+            ++slot;
+        }
+}
+
+// one CTA: totals of the tile partials, thetaBar, V_t, cholesky(h^2 V_t)
+__global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwArgs a)
+{
+    __shared__ double red[32];
+    __shared__ double tot[14];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nq = (a.mode == 1) ? 4 : 14;
+    for (int q = 0; q < nq; ++q) {
+        const double* p = a.part + (size_t)q * a.s.nb;
+        const int b0 = tid * a.s.Lp;
+        double s = 0.0;
+        for (int k = 0; k < a.s.Lp; ++k) {
+            const double v = (b0 + k < a.s.nb) ? p[b0 + k] : 0.0;
+            s = (k == 0) ? v : __dadd_rn(s, v);
+        }
+        const double t = block_sum_finish<32>(s, red, lane, warp);
+        if (tid == 0) tot[q] = t;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const double dN = (double)a.s.N;
+    if (a.mode == 1) {
+        for (int k = 0; k < 4; ++k) a.mom[20 + k] = __ddiv_rn(tot[k], dN);
+        return;
+    }
+    double tb[4], V[4][4], Lc[4][4];
+    for (int k = 0; k < 4; ++k) tb[k] = __ddiv_rn(tot[k], dN);
+    int slot = 4;
+    for (int k = 0; k < 4; ++k)
+        for (int l = 0; l <= k; ++l) {
+            const double s2 = __ddiv_rn(tot[slot++], dN);
+            V[k][l] = __dmul_rn(a.h2, __dsub_rn(s2, __dmul_rn(tb[k], tb[l])));
+        }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) Lc[i][j] = 0.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double sacc = V[i][j];
+            for (int k = 0; k < j; ++k) sacc = __dsub_rn(sacc, __dmul_rn(Lc[i][k], Lc[j][k]));
+            Lc[i][j] = (i == j) ? __dsqrt_rn(sacc) : __ddiv_rn(sacc, Lc[j][j]);
+        }
+    for (int k = 0; k < 4; ++k) a.mom[k] = tb[k];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) a.mom[4 + 4 * i + j] = Lc[i][j];
+    if (a.theta_bar_out)
+        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)a.s.t * 4 + k] = tb[k];
+}
+
+__global__ void __launch_bounds__(kTileNT) lw_propagate_kernel(const LwArgs a)
+{
+    __shared__ double red[kTileNT / 32];
+    __shared__ double smom[20];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
+    const int t = a.s.t;
+    if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
+    __syncthreads();
+    const double y = a.s.obs[(size_t)t * 2];
+    const double cov = a.s.obs[(size_t)t * 2 + 1];
+    const uint2 key = make_uint2((uint32_t)a.s.seed, (uint32_t)(a.s.seed >> 32));
+    const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
+    const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
+    double mloc = __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll 1
+    for (int q = 0; q < kTileL / 4; ++q) {
+        const uint4 rz = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
+        float zs[4];
+        box_muller(rz.x, rz.y, zs[0], zs[1]);
+        box_muller(rz.z, rz.w, zs[2], zs[3]);
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk) {
+            const int i = i0 + 4 * q + kk;
+            const double z = (double)zs[kk];
+            double p[4], nth[4], x;
+            if (t == 0) {
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const uint4 ru = philox4x32_10(make_uint4(2u * (uint32_t)i + (uint32_t)k2, 0u, ctr2, ctr3 | 5u), key);
+                    const double ua = uniform53(ru.x, ru.y), ub = uniform53(ru.z, ru.w);
+                    p[2 * k2] = __fma_rn(ua, __dsub_rn(a.hi[2 * k2], a.lo[2 * k2]), a.lo[2 * k2]);
+                    p[2 * k2 + 1] = __fma_rn(ub, __dsub_rn(a.hi[2 * k2 + 1], a.lo[2 * k2 + 1]), a.lo[2 * k2 + 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nth[k] = lw_trans(k, p[k]);
+                x = __dmul_rn(z, __ddiv_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[0], p[0])))));
+            } else {
+                const uint4 rp = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), key);
+                float zf[4];
+                box_muller(rp.x, rp.y, zf[0], zf[1]);
+                box_muller(rp.z, rp.w, zf[2], zf[3]);
+                const bool valid = i < a.s.N;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double th = valid ? a.th_anc[k][i] : 0.0;
+                    double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[k]));
+#pragma unroll
+                    for (int l = 0; l <= k; ++l) acc = __fma_rn(smom[4 + 4 * k + l], (double)zf[l], acc);
+                    nth[k] = acc;
+                    p[k] = lw_inv_trans(k, acc);
+                }
+                const double xa = valid ? a.s.x_anc[i] : 0.0;
+                const double e2 = dexp(__dmul_rn(-0.5, xa));
+                const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
+                double mean = __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]);
+                mean = __fma_rn(cz, e2, mean);
+                x = __fma_rn(__dmul_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[3], p[3])))), z, mean);
+            }
+            double v = __fma_rn(-hh, dexp(-x), __fma_rn(-0.5, x, -SSME_DM_HALF_LOG_2PI));
+            if (i < a.s.N) {
+                a.s.x_cur[i] = x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a.th_cur[k][i] = nth[k];
+            } else {
+                v = __longlong_as_double(0xfff0000000000000ll);
+            }
+            a.s.lwc[i] = v;
+            mloc = (v > mloc) ? v : mloc;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(mloc, d);
+        mloc = (other > mloc) ? other : mloc;
+    }
+    if (lane == 0) red[warp] = mloc;
+    __syncthreads();
+    if (warp == 0) {
+        double m = (lane < kTileNT / 32) ? red[lane] : __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(m, d);
+            m = (other > m) ? other : m;
+        }
+        if (lane == 0) a.s.tmax[tile] = m;
+    }
+}
+
+}  // namespace ssme

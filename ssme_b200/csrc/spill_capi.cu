@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include "lw_kernel.cuh"
 #include "spill_kernel.cuh"
 
 namespace ssme {
@@ -23,6 +24,10 @@ struct SpillState {
     const double* peer_lwc[2][kMaxPeers] = {};
     void* opened[kMaxPeers][4] = {};
     bool prepared = false, peers_ready = false;
+    // Liu-West extras (allocated on first use)
+    double* th_anc[4] = {};
+    double* th_cur[4] = {};
+    double *part = nullptr, *mom = nullptr;
 };
 
 __global__ void spill_init_kernel(double* scal, int N)
@@ -94,6 +99,8 @@ void spill_destroy(ssme_b200_handle h)
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
     cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->E); cudaFree(s->scal);
+    for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
+    cudaFree(s->part); cudaFree(s->mom);
     delete s;
     h->spill_state = nullptr;
 }
@@ -163,11 +170,126 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
     return SSME_B200_OK;
 }
 
+static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik, double* d_cond_like,
+                  double* d_theta_bar, double* d_final_mean, int* d_ancestors)
+{
+    int rc = prepare(h);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    if (s->world != 1) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter runs on one GPU");
+    if (!s->part) {
+        for (int k = 0; k < 4; ++k) {
+            SSME_CUDA(cudaMalloc(&s->th_anc[k], s->local * sizeof(double)));
+            SSME_CUDA(cudaMalloc(&s->th_cur[k], s->local * sizeof(double)));
+        }
+        SSME_CUDA(cudaMalloc(&s->part, (size_t)14 * s->nb * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&s->mom, 32 * sizeof(double)));
+    }
+    const int T = (int)h->T, tiles = s->nb;
+    cudaStream_t st = h->stream;
+    LwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s.obs = h->d_obs;
+    a.s.N = s->N; a.s.nb = s->nb; a.s.Lp = s->Lp; a.s.NBP = s->NBP;
+    a.s.tile0 = 0; a.s.tile1 = s->nb; a.s.tiles_per_rank = s->nb;
+    a.s.T = T;
+    a.s.seed = h->cfg.seed;
+    a.s.fid = stream_id;
+    a.s.x_anc = s->x_anc;
+    a.s.tmax = s->tmax; a.s.ttot = s->ttot; a.s.E = s->E; a.s.scal = s->scal;
+    a.s.cond_like = d_cond_like;
+    a.s.ancestors = d_ancestors;
+    a.s.nextra = 4;
+    for (int k = 0; k < 4; ++k) {
+        a.th_anc[k] = s->th_anc[k];
+        a.th_cur[k] = s->th_cur[k];
+        a.s.extra_cur[k] = s->th_cur[k];
+        a.s.extra_anc[k] = s->th_anc[k];
+        a.lo[k] = lo[k];
+        a.hi[k] = hi[k];
+    }
+    a.part = s->part;
+    a.mom = s->mom;
+    a.theta_bar_out = d_theta_bar;
+    a.a = (3.0 * delta - 1.0) / (2.0 * delta);
+    a.h2 = 1.0 - a.a * a.a;
+    a.oma = 1.0 - a.a;
+    spill_init_kernel<<<1, 1, 0, st>>>(s->scal, s->N);
+    for (int t = 0; t < T; ++t) {
+        a.s.t = t;
+        a.s.x_cur = s->x_cur[0];
+        a.s.lwc = s->lwc[0];
+        a.s.peer_x[0] = s->x_cur[0];
+        a.s.peer_lwc[0] = s->lwc[0];
+        if (t > 0) {
+            a.mode = 0;
+            lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
+            lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
+            count_launch(2);
+        }
+        lw_propagate_kernel<<<tiles, kTileNT, 0, st>>>(a);
+        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(a.s);
+        spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
+        if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC)
+            spill_resample_kernel<kResampSystematic><<<tiles, kTileNT, kStageTiles * kTile * sizeof(double), st>>>(a.s);
+        else spill_resample_kernel<kResampMultinomial><<<tiles, kTileNT, 0, st>>>(a.s);
+        count_launch(5);
+    }
+    if (T > 0 && d_final_mean) {
+        a.mode = 1;
+        lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
+        lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        SSME_CUDA(cudaMemcpyAsync(d_final_mean, s->mom + 20, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        count_launch(2);
+    }
+    spill_store_kernel<<<1, 1, 0, st>>>(s->scal, d_loglik);
+    SSME_CUDA(cudaGetLastError());
+    return SSME_B200_OK;
+}
+
 }  // namespace ssme
 
 using namespace ssme;
 
 extern "C" {
+
+int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id,
+                        double* loglik_host, double* cond_like_host, double* theta_bar_host, double* final_mean_host, int32_t* ancestors_host)
+{
+    if (!h || !prior_lo || !prior_hi) return fail(SSME_B200_EINVAL, "null argument");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (!h->spill) return fail(SSME_B200_EINVAL, "the Liu-West filter uses the global-memory kernels: create the handle with force_global_memory = 1 (or N > 8192)");
+    if (h->cfg.model != SSME_B200_MODEL_SV_LEVERAGE) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter is built for the SV-with-leverage model");
+    if (!(delta > 1.0 / 3.0 && delta <= 1.0)) return fail(SSME_B200_EINVAL, "delta must lie in (1/3, 1]");
+    for (int k = 0; k < 4; ++k)
+        if (!(prior_hi[k] > prior_lo[k])) return fail(SSME_B200_EINVAL, "prior box %d is empty", k);
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t T = h->T, N = (size_t)h->cfg.num_particles;
+    double *d_sc = nullptr, *d_cl = nullptr, *d_tb = nullptr;
+    int* d_anc = nullptr;
+    auto cleanup = [&]() { cudaFree(d_sc); cudaFree(d_cl); cudaFree(d_tb); cudaFree(d_anc); };
+    cudaError_t e = cudaMalloc(&d_sc, 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cl, T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tb, T * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_tb, 0, T * 4 * sizeof(double), h->stream);
+    if (e == cudaSuccess && ancestors_host) e = cudaMalloc(&d_anc, T * N * sizeof(int));
+    if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "Liu-West setup failed: %s", cudaGetErrorString(e)); }
+    rc = lw_run(h, prior_lo, prior_hi, delta, stream_id, d_sc, d_cl, d_tb, d_sc + 1, d_anc);
+    if (rc) { cleanup(); return rc; }
+    e = cudaStreamSynchronize(h->stream);
+    double sc[5];
+    if (e == cudaSuccess) e = cudaMemcpy(sc, d_sc, 5 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cond_like_host) e = cudaMemcpy(cond_like_host, d_cl, T * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && theta_bar_host) e = cudaMemcpy(theta_bar_host, d_tb, T * 4 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ancestors_host) e = cudaMemcpy(ancestors_host, d_anc, T * N * sizeof(int), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "Liu-West filter failed: %s", cudaGetErrorString(e));
+    if (loglik_host) *loglik_host = sc[0];
+    if (final_mean_host) memcpy(final_mean_host, sc + 1, 4 * sizeof(double));
+    return SSME_B200_OK;
+}
 
 int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[256])
 {

@@ -42,6 +42,10 @@ struct SpillArgs {
     int* ancestors;     // [T][N] or null (parity runs at small N)
     const double* peer_x[kMaxPeers];    // per-rank base pointers of x_cur / lwc (own rank included)
     const double* peer_lwc[kMaxPeers];
+    // extra per-particle fields resampled together with the state (Liu-West: the 4 transformed parameters); single rank
+    int nextra;
+    const double* extra_cur[4];
+    double* extra_anc[4];
 };
 
 template <int MODEL>
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
                 idx = (int)(i - (long long)b * kTile);
             }
             dst[k * kTileNT + tid] = tile_x(b)[idx];
+            for (int e = 0; e < a.nextra; ++e) a.extra_anc[e][(size_t)blockIdx.x * kTile + k * kTileNT + tid] = a.extra_cur[e][i];
             if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
         }
         return;
@@ -377,6 +382,7 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
             idx = (int)(i - (long long)b * kTile);
         }
         a.x_anc[(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid] = a.peer_x[owner][lbase + idx];
+        for (int e = 0; e < a.nextra; ++e) a.extra_anc[e][(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid] = a.extra_cur[e][i];
         if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
     }
 }

@@ -1,0 +1,74 @@
+"""-m gpu: the Liu-West kernels (K4) against the oracle's restatement of LWFilter2WithCovs::filter
+(liu_west_filter.h:2191-2343) on the reference's own test model and prior box (test/test_liu_west.cpp:165,213-358)."""
+import numpy as np
+import pytest
+
+import ssme_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+LO = np.array([.8, -.1, .01, -.5])   # phi, mu, sigma, rho   (svol_lw_2_par mod(.99, .8, .99, -.1, .1, .01, .1, -.5, -.01, 10))
+HI = np.array([.99, .1, .1, -.01])
+
+
+def leverage_series(T, seed, phi=0.9, mu=0.0, sigma=0.3, rho=-0.3):
+    rng = np.random.default_rng(seed)
+    x, y = np.zeros(T), np.zeros(T)
+    x[0] = rng.normal() * sigma / np.sqrt(1 - phi ** 2)
+    y[0] = np.exp(x[0] / 2) * rng.normal()
+    for t in range(1, T):
+        x[t] = mu + phi * (x[t - 1] - mu) + rho * sigma * y[t - 1] * np.exp(-x[t - 1] / 2) + sigma * np.sqrt(1 - rho ** 2) * rng.normal()
+        y[t] = np.exp(x[t] / 2) * rng.normal()
+    return y
+
+
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("N,T", [(10, 1), (10, 5), (5000, 30), (4096 * 2 + 5, 12)])
+def test_liu_west_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
+    y = leverage_series(T, seed=N + T)
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=6, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.lw_filter(LO, HI, delta=0.99, stream_id=2, want_ancestors=True)
+    ref = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, seed=6, filter_id=2)
+    assert np.array_equal(got["ancestors"], ref["ancestors"])
+    assert np.array_equal(got["cond_like"], ref["cond_like"])
+    assert np.array_equal(got["theta_bar"], ref["theta_bar"])
+    assert np.array_equal(got["final_mean"], ref["final_mean"])
+    assert got["loglik"] == ref["loglik"]
+    # the reference's own smoke assertion (test_liu_west.cpp:374): logCondLike^2 > 0
+    assert np.all(got["cond_like"] ** 2 > 0.0)
+    fai = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=6, filter_id=2)
+    if ref["margin"] > 1e-11:
+        assert np.array_equal(got["ancestors"], fai["ancestors"])
+        assert abs(got["loglik"] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+        assert np.allclose(got["final_mean"], fai["final_mean"], rtol=1e-9, atol=1e-12)
+
+
+def test_liu_west_learns_the_parameters(gpu_backend_factory):
+    """2^18 particles, wide prior: the posterior mean moves from the prior centre towards the generating values."""
+    true = dict(phi=0.95, mu=0.0, sigma=0.25, rho=-0.4)
+    y = leverage_series(600, seed=4, **true)
+    lo, hi = np.array([.5, -1., .05, -.9]), np.array([.995, 1., .6, .5])
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=1 << 18, resampler=sb.RESAMP_SYSTEMATIC, seed=3)
+    be.add_observed_data(y)
+    r = be.lw_filter(lo, hi, delta=0.99)
+    centre = 0.5 * (lo + hi)
+    truth = np.array([true["phi"], true["mu"], true["sigma"], true["rho"]])
+    assert np.all(np.isfinite(r["cond_like"])) and np.isfinite(r["loglik"])
+    assert np.all((r["final_mean"] > lo) & (r["final_mean"] < hi))
+    assert abs(r["final_mean"][0] - truth[0]) < abs(centre[0] - truth[0])      # phi
+    assert abs(r["final_mean"][2] - truth[2]) < abs(centre[2] - truth[2])      # sigma
+    assert abs(r["final_mean"][3] - truth[3]) < abs(centre[3] - truth[3]) + 0.1  # rho is weakly identified
+
+
+def test_liu_west_argument_checks(gpu_backend_factory):
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=64)  # resident kernels: not the Liu-West path
+    be.add_observed_data(np.ones(4))
+    with pytest.raises(ValueError):
+        be.lw_filter(LO, HI)
+    be2 = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=64, force_global_memory=1)
+    be2.add_observed_data(np.ones(4))
+    with pytest.raises(ValueError):
+        be2.lw_filter(HI, LO)
+    with pytest.raises(ValueError):
+        be2.lw_filter(LO, HI, delta=0.2)
