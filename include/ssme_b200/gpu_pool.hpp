@@ -38,6 +38,7 @@ struct gpu_options {
     int resample_every = 1;
     std::uint64_t seed = 20260101;  // Philox key of the filters' random streams
     int scan_items_per_lane = 0, threads_per_filter = 0;
+    int use_cluster = 0;  // 1 = one filter per thread-block cluster (fewer filters than SMs: lower step latency)
 };
 
 template <size_t numparams, size_t dimobs, typename float_t, bool debug = false>
@@ -68,6 +69,7 @@ public:
         c.seed = opt.seed;
         c.scan_items_per_lane = opt.scan_items_per_lane;
         c.threads_per_filter = opt.threads_per_filter;
+        c.use_cluster = opt.use_cluster;
         throw_on_error(ssme_b200_create(&c, &m_h));
     }
     ~gpu_pool() { ssme_b200_destroy(m_h); }

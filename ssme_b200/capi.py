@@ -34,7 +34,7 @@ class _Config(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("num_particles", C.c_int32),
         ("resampler", C.c_int32), ("resample_every", C.c_int32), ("dtype", C.c_int32), ("rng_mode", C.c_int32),
         ("seed", C.c_uint64), ("scan_items_per_lane", C.c_int32), ("threads_per_filter", C.c_int32),
-        ("filters_per_sm", C.c_int32), ("force_global_memory", C.c_int32),
+        ("filters_per_sm", C.c_int32), ("force_global_memory", C.c_int32), ("use_cluster", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -194,6 +194,7 @@ class FilterConfig:
     threads_per_filter: int = 0
     filters_per_sm: int = 0
     force_global_memory: int = 0
+    use_cluster: int = 0
 
 
 def _dptr(a):
@@ -208,7 +209,7 @@ class ParticleFilterBackend:
         self.cfg = cfg
         c = _Config(C.sizeof(_Config), cfg.device, cfg.model, cfg.num_particles, cfg.resampler, cfg.resample_every,
                     cfg.dtype, cfg.rng_mode, cfg.seed, cfg.scan_items_per_lane, cfg.threads_per_filter,
-                    cfg.filters_per_sm, cfg.force_global_memory)
+                    cfg.filters_per_sm, cfg.force_global_memory, cfg.use_cluster, 0)
         self._h = C.c_void_p()
         _check(self._lib.ssme_b200_create(C.byref(c), C.byref(self._h)))
         self.num_params = 3 if cfg.model == MODEL_SV else 4

@@ -16,6 +16,7 @@
 #include "det_math.cuh"
 #include "pf_dispatch.h"
 #include "pf_kernel.cuh"
+#include "cluster_kernel.cuh"
 
 #define SSME_STR2(x) #x
 #define SSME_STR(x) SSME_STR2(x)
@@ -169,6 +170,32 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
 {
     if (F == 0) return SSME_B200_OK;
     if (F > 0x7fffffffull) return fail(SSME_B200_EINVAL, "too many filters in one launch: %zu", F);
+    if (h->cluster) {
+        FilterArgs ca = args;
+        const int model = h->cfg.model, res = h->cfg.resampler;
+        const void* fn = model == SSME_B200_MODEL_SV
+                             ? (res == SSME_B200_RESAMP_MULTINOMIAL ? (const void*)&cluster_filter_kernel<kModelSV, kResampMultinomial>
+                                                                    : (const void*)&cluster_filter_kernel<kModelSV, kResampSystematic>)
+                             : (res == SSME_B200_RESAMP_MULTINOMIAL ? (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampMultinomial>
+                                                                    : (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampSystematic>);
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3((unsigned)(F * (size_t)h->cluster_size));
+        lc.blockDim = dim3(kClNT);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)h->cluster_size;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        void* cparams[] = {&ca};
+        SSME_CUDA(cudaLaunchKernelExC(&lc, fn, cparams));
+        g_launches.fetch_add(1);
+        return SSME_B200_OK;
+    }
     FilterArgs a = args;
     void* params[] = {&a};
     SSME_CUDA(cudaLaunchKernel(ke->fn, dim3((unsigned)F), dim3((unsigned)ke->NT), params, ke->smem_bytes, st));
@@ -222,9 +249,17 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
                     prop.minor);
 
     const bool spill = cfg->force_global_memory != 0 || cfg->num_particles > 8192;
+    const bool use_cluster = cfg->use_cluster != 0 && !spill;
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
-    if (spill) {
+    if (use_cluster) {
+        // K2: tiles of 512 particles, one CTA each, cluster of ceil(N/512) CTAs (cluster_kernel.cuh)
+        if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");
+        if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel uses the on-device Philox streams");
+        if (cfg->num_particles <= kClTile) return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", kClTile);
+        L = kClL;
+        NT = kClNT;
+    } else if (spill) {
         // K3: particles in HBM, tiles of 4096 (spill_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels resample at every step (resample_every = 1)");
         if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels use the on-device Philox streams");
@@ -261,8 +296,18 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->fast = fast;
     h->debug = dbg;
     h->spill = spill;
+    h->cluster = use_cluster;
+    h->cluster_size = use_cluster ? (cfg->num_particles + kClTile - 1) / kClTile : 1;
     int occ = 0;
-    if (!spill) {
+    if (use_cluster) {
+        const void* fns[] = {(const void*)&cluster_filter_kernel<kModelSV, kResampMultinomial>, (const void*)&cluster_filter_kernel<kModelSV, kResampSystematic>,
+                             (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampMultinomial>,
+                             (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampSystematic>};
+        for (const void* fn : fns) {
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
+        }
+    } else if (!spill) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
         if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }
     } else {
@@ -301,7 +346,7 @@ int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out)
     out->num_sms = h->num_sms;
     out->smem_bytes_per_filter = 0;
     out->registers_per_thread = 0;
-    if (!h->spill) {
+    if (!h->spill && !h->cluster) {
         out->smem_bytes_per_filter = (int32_t)h->fast->smem_bytes;
         cudaFuncAttributes fa;
         SSME_CUDA(cudaFuncGetAttributes(&fa, h->fast->fn));
@@ -451,6 +496,10 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     if (cond_like_host) SSME_CUDA_T(cudaMalloc(&d_cl, F * T * sizeof(double)));
     if (ancestors_host) SSME_CUDA_T(cudaMalloc(&d_anc, F * T * N * sizeof(int)));
     if (x_host) SSME_CUDA_T(cudaMalloc(&d_x, F * T * N * sizeof(double)));
+    if (h->cluster && (inject || ancestors_host || x_host)) {
+        cleanup();
+        return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel traces log-likelihoods and conditional likelihoods only");
+    }
     if (h->spill) {
         if (x_host) { cleanup(); return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels do not trace states (x_host must be NULL)"); }
         rc = spill_run_filters(h, d_theta, F, 1u, stream_base, d_ll, d_cl, d_anc);
@@ -463,7 +512,7 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
         a.cond_like = d_cl;
         a.ancestors = d_anc;
         a.x_trace = d_x;
-        rc = launch_filters(h, h->debug, a, F, h->stream);
+        rc = launch_filters(h, h->debug, a, F, h->stream);  // (cluster mode ignores the kernel entry)
     }
     if (rc) { cleanup(); return rc; }
     SSME_CUDA_T(cudaStreamSynchronize(h->stream));

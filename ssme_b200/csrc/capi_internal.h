@@ -62,6 +62,9 @@ struct ssme_b200_filter_s {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // one filter per thread-block cluster (K2)
+    bool cluster = false;
+    int cluster_size = 1;
     // N beyond one CTA: particles live in HBM
     bool spill = false;
     ssme::SpillState* spill_state = nullptr;

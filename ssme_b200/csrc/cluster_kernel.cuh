@@ -1,0 +1,279 @@
+// ssme_b200/csrc/cluster_kernel.cuh -- K2: one bootstrap filter per thread-block CLUSTER.
+//
+// K1 keeps a filter inside one CTA, so its time-step latency is what one SM can issue: ~20 us per step at
+// N = 8192, which is what paces PMMH when there are fewer chains than SMs (BASELINE.json config 3:
+// 64 chains x 8192 particles; 8 chains per GPU on 8 GPUs).  K2 spreads one filter over up to 16 SMs:
+// CTA r of the cluster owns the tile of particles r*512 .. r*512+511 (64 threads x 8) in registers / its
+// own shared memory; the three filter-wide quantities per step travel through distributed shared memory:
+//   max of the log-weights   each CTA publishes its tile maximum, cluster barrier, every CTA reads all of them
+//   CDF offsets              each CTA publishes its tile weight sum, cluster barrier, every CTA scans all tile sums
+//   resampling               a slot's target is located among the tile ends (local), then by a 9-level descent in
+//                            the OWNER's shared memory (ld.shared::cluster) and the ancestor's state is read from there
+// Same per-particle arithmetic and Philox streams as K1/K3; scan and search order = the oracle's "tiled" order with
+// tiles of 512 (oracle/pf_oracle.c: tiled_build / tiled_search with L = 8, NT = 64), bit-identical to it, and
+// therefore independent of how the clusters are spread over GPUs.
+// Reference replaced: the same BSFilter::filter step as K1 (liu_west_filter.h:1608-1761 twin).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "pf_kernel.cuh"
+
+namespace ssme {
+
+namespace cg = cooperative_groups;
+
+constexpr int kClL = 8;
+constexpr int kClNT = 64;
+constexpr int kClTile = kClL * kClNT;  // 512 particles per CTA
+constexpr int kClMax = 16;             // CTAs per cluster (non-portable size, opt-in)
+
+struct ClusterShared {
+    double X[2][kClTile];      // this tile's states, double-buffered (peers gather from the previous step's buffer)
+    double C[kClTile];         // tile-local inclusive CDF, breadth-first order
+    double E[kClMax];          // inclusive tile ends (every CTA computes all of them)
+    double red[4];
+    double pub_max, pub_tot;   // published to the cluster
+    double clM[32], clS[32];
+};
+
+template <int MODEL, int RESAMP>
+__global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs a)
+{
+    constexpr int OS = obs_stride(MODEL);
+    constexpr int K = 9;  // log2(kClTile)
+    __shared__ ClusterShared sh;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long f = a.filter_offset + blockIdx.x / CS;
+    const int N = a.N, T = a.T;
+    const int i0 = rank * kClTile + tid * kClL;  // first particle of this thread (global index within the filter)
+    const int l0 = tid * kClL;                   // ... within the tile
+
+    uint32_t eoff[kClL];
+#pragma unroll
+    for (int k = 0; k < kClL; ++k) {
+        const uint32_t v = (uint32_t)(l0 + k + 1);
+        const int tz = __ffs((int)v) - 1;
+        const uint32_t node = (v == (uint32_t)kClTile) ? (uint32_t)(kClTile - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
+        eoff[k] = node * 8u;
+    }
+    const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
+    const unsigned long long fid = a.filter_base + f;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
+    const double logN = dlog((double)N);
+    const double dN = (double)N;
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+
+    // peers' shared-memory blocks
+    const ClusterShared* peer = cluster.map_shared_rank(&sh, (lane < CS) ? lane : 0);
+
+    double x[kClL];
+#pragma unroll
+    for (int k = 0; k < kClL; ++k) x[k] = 0.0;
+    double loglik = 0.0;
+    cluster.sync();
+
+    for (int t = 0; t < T; ++t) {
+        const double y = a.obs[(size_t)t * OS];
+        const double cov = (OS == 2) ? a.obs[(size_t)t * OS + 1] : 0.0;
+        double z[kClL];
+#pragma unroll
+        for (int q = 0; q < kClL / 4; ++q) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
+            float z0, z1, z2, z3;
+            box_muller(r.x, r.y, z0, z1);
+            box_muller(r.z, r.w, z2, z3);
+            z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
+        }
+        const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
+        double lw[kClL];
+        double mloc = ninf;
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
+            if (t == 0) {
+                x[k] = __dmul_rn(z[k], mc.sd0);
+            } else if (MODEL == kModelSV) {
+                x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+            } else {
+                const double e2 = dexp(__dmul_rn(-0.5, x[k]));
+                const double cz = __dmul_rn(mc.rho_sigma, cov);
+                double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
+                mean = __fma_rn(cz, e2, mean);
+                x[k] = __fma_rn(mc.sdv, z[k], mean);
+            }
+            const double e = dexp(-x[k]);
+            double v = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
+            v = (i0 + k < N) ? v : ninf;
+            lw[k] = v;
+            mloc = (v > mloc) ? v : mloc;
+        }
+        double* Xcur = sh.X[t & 1];
+#pragma unroll
+        for (int k = 0; k < kClL; k += 2) *reinterpret_cast<double2*>(Xcur + l0 + k) = make_double2(x[k], x[k + 1]);
+
+        // ---- filter-wide max: tile max -> published -> all tiles' maxima read through DSMEM --------
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(mloc, d);
+            mloc = (other > mloc) ? other : mloc;
+        }
+        if (lane == 0) sh.red[warp] = mloc;
+        __syncthreads();
+        if (tid == 0) sh.pub_max = (sh.red[1] > sh.red[0]) ? sh.red[1] : sh.red[0];
+        cluster.sync();  // C1
+        double M = (lane < CS) ? peer->pub_max : ninf;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(M, d);
+            M = (other > M) ? other : M;
+        }
+
+        // ---- batched log p(y_t | y_{1:t-1}) for the previous 32 steps (rank 0, warp 0) -------------
+        if (rank == 0 && warp == 0 && (t & 31) == 0 && t > 0) {
+            const int s = t - 32 + lane;
+            const double logS = dlog(sh.clS[lane]);
+            const double cl = (s == 0) ? __dadd_rn(__dadd_rn(-logN, sh.clM[lane]), logS)
+                                       : __dsub_rn(__dsub_rn(__dadd_rn(sh.clM[lane], logS), 0.0), logN);
+            if (a.cond_like) a.cond_like[(size_t)f * T + s] = cl;
+            __syncwarp();
+            sh.clM[lane] = cl;
+            __syncwarp();
+            if (lane == 0)
+                for (int j = 0; j < 32; ++j) loglik = __dadd_rn(loglik, sh.clM[j]);
+            __syncwarp();
+        }
+
+        // ---- weights, tile-local scan (lanes, then the tile's two warps) ---------------------------
+        double sc[kClL];
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
+            const double w = dexp_nonpos(__dsub_rn(lw[k], M));
+            sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
+        }
+        double incl = sc[kClL - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(incl, d);
+            incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+        }
+        if (lane == 31) sh.red[2 + warp] = incl;
+        __syncthreads();
+        // Kogge-Stone over the tile's 2 warps: inclusive (w0, w0 + w1)
+        const double w0 = sh.red[2], w1 = sh.red[3];
+        const double tile_total = __dadd_rn(w0, w1);
+        const double wex = (warp > 0) ? w0 : 0.0;
+        double lex = shfl_up_d(incl, 1);
+        lex = (lane > 0) ? lex : 0.0;
+        const double base = __dadd_rn(wex, lex);
+        unsigned char* Cb = reinterpret_cast<unsigned char*>(sh.C);
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
+        if (tid == 0) sh.pub_tot = tile_total;
+        cluster.sync();  // C2: tile sums, tile CDFs and states of this step are visible cluster-wide
+
+        // ---- scan of the tile sums (every warp, redundantly): oracle's 1024-lane scan with one item per lane ----
+        double tt = (lane < CS) ? peer->pub_tot : 0.0;
+        double tincl = tt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(tincl, d);
+            tincl = (lane >= d) ? __dadd_rn(other, tincl) : tincl;
+        }
+        const double S = shfl_d(tincl, 31);
+        double tlex = shfl_up_d(tincl, 1);
+        tlex = (lane > 0) ? tlex : 0.0;
+        const double Eb = __dadd_rn(__dadd_rn(0.0, tlex), tt);  // inclusive end of tile `lane`
+        if (warp == 0 && lane < kClMax) sh.E[lane] = Eb;
+        if (rank == 0 && tid == 0) {
+            sh.clM[t & 31] = M;
+            sh.clS[t & 31] = S;
+        }
+        if (t == T - 1) break;  // the last resampling does not enter the likelihood
+        __syncthreads();        // E visible to both warps
+
+        // ---- resampling targets -----------------------------------------------------------------
+        double tau[kClL];
+        if (RESAMP == kResampMultinomial) {
+#pragma unroll
+            for (int q = 0; q < kClL / 2; ++q) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
+                tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
+            }
+        } else {
+            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
+            const double u0 = uniform53(r.x, r.y);
+            const double sN = __ddiv_rn(S, dN);
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(__dadd_rn((double)(i0 + k), u0), sN);
+        }
+        // ---- tile of each target: the padded 1024-entry descent always goes left above 16 (padding = S >= tau) ----
+        const int nb = (N + kClTile - 1) / kClTile;
+        int b[kClL];
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
+            int bb = 0;
+#pragma unroll
+            for (int s = kClMax / 2; s >= 1; s >>= 1) bb += (sh.E[bb + s - 1] < tau[k]) ? s : 0;
+            b[k] = min(bb, nb - 1);
+        }
+        // ---- descent in the owner's shared memory, then gather its state ---------------------------
+        const unsigned char* pC[kClL];
+        double O[kClL];
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
+            pC[k] = reinterpret_cast<const unsigned char*>(cluster.map_shared_rank(&sh, b[k])->C);
+            O[k] = (b[k] > 0) ? sh.E[b[k] - 1] : 0.0;
+        }
+        uint32_t nbp[kClL];
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) nbp[k] = 0u;
+#pragma unroll
+        for (int lvl = 0; lvl < K; ++lvl) {
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) {
+                const double v = __dadd_rn(O[k], *reinterpret_cast<const double*>(pC[k] + nbp[k]));
+                nbp[k] = 2u * nbp[k] + ((v < tau[k]) ? 16u : 8u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
+            int idx = (int)(nbp[k] >> 3) - (kClTile - 1);
+            long long i = (long long)b[k] * kClTile + idx;
+            if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)b[k] * kClTile);
+            const ClusterShared* owner = cluster.map_shared_rank(&sh, b[k]);
+            x[k] = (i0 + k < N) ? owner->X[t & 1][idx] : 0.0;
+        }
+        cluster.sync();  // C3: every read of this step's CDFs / maxima / sums is done before they are overwritten
+    }
+
+    // ---- epilogue: the cond-likes still buffered -------------------------------------------------
+    if (rank == 0 && T > 0) {
+        __syncthreads();
+        if (warp == 0) {
+            const int t0 = ((T - 1) / 32) * 32;
+            const int cnt = T - t0;
+            double cl = 0.0;
+            if (lane < cnt) {
+                const double logS = dlog(sh.clS[lane]);
+                cl = (t0 + lane == 0) ? __dadd_rn(__dadd_rn(-logN, sh.clM[lane]), logS)
+                                      : __dsub_rn(__dsub_rn(__dadd_rn(sh.clM[lane], logS), 0.0), logN);
+                if (a.cond_like) a.cond_like[(size_t)f * T + t0 + lane] = cl;
+            }
+            __syncwarp();
+            sh.clM[lane] = cl;
+            __syncwarp();
+            if (lane == 0) {
+                for (int j = 0; j < cnt; ++j) loglik = __dadd_rn(loglik, sh.clM[j]);
+                a.loglik[f] = loglik;
+            }
+        }
+    }
+    if (rank == 0 && T == 0 && tid == 0) a.loglik[f] = 0.0;
+    cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
+
+}  // namespace ssme

@@ -1,0 +1,53 @@
+"""-m gpu: K2, one filter per thread-block cluster (distributed shared memory), against the oracle's tiled order
+with tiles of 512 particles (L = 8, NT = 64) -- bit for bit."""
+import numpy as np
+import pytest
+
+import ssme_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+SV_THETA = np.array([1.0, 0.95, 0.0625])
+LEV_THETA = np.array([0.9, 0.0, 0.3, -0.1])
+
+
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("N,T", [(1024, 40), (8192, 33), (5000, 65), (600, 7), (4096, 1)])
+def test_cluster_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T):
+    y = sv_series(T, seed=41)
+    th = SV_THETA if model == sb.MODEL_SV else LEV_THETA
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=12, use_cluster=1)
+    be.add_observed_data(y)
+    theta = np.stack([th, th * 0.98, th * 1.01])
+    out, pf = be.work_batch(theta, R=2, stream_base=30, return_per_filter=True)
+    for p in range(3):
+        ref = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=8, NT=64, tiled=True, seed=12,
+                                 filter_id=30 + 2 * p + r, trace=False)["loglik"] for r in range(2)]
+        assert pf[p].tolist() == ref
+        assert out[p] == oracle.log_mean_exp(np.array(ref))
+    tr = be.trace(theta[:1], stream_base=30, want=("loglik", "cond_like"))
+    ref = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, L=8, NT=64, tiled=True, seed=12, filter_id=30)
+    assert np.array_equal(tr["cond_like"][0], ref["cond_like"]) and tr["loglik"][0] == ref["loglik"]
+    fai = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=12, filter_id=30)
+    assert abs(tr["loglik"][0] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+
+
+def test_cluster_pmmh_matches_oracle_driven_chain(oracle, sv_series, gpu_backend_factory):
+    y = sv_series(50, seed=42)
+    be = gpu_backend_factory(num_particles=2048, seed=13, use_cluster=1)
+    be.add_observed_data(y)
+    start = np.stack([SV_THETA, SV_THETA * 0.97])
+    gpu = be.pmmh_run(start, 2, 8, t0=2, t1=100, c0_diag=0.02, proposal_seed=4)
+
+    def ev(th, R_, base):
+        return np.array([oracle.filter_run(th[f // R_], y, 2048, L=8, NT=64, tiled=True, seed=13, filter_id=base + f, trace=False)["loglik"]
+                         for f in range(th.shape[0] * R_)])
+    cpu = sb.pmmh_run_custom(sb.MODEL_SV, ev, start, 2, 8, t0=2, t1=100, c0_diag=0.02, proposal_seed=4)
+    for k in ("final_theta", "accept_rate", "last_loglik"):
+        assert np.array_equal(gpu[k], cpu[k]), k
+
+
+def test_cluster_argument_checks():
+    with pytest.raises(ValueError):
+        sb.ParticleFilterBackend(sb.FilterConfig(num_particles=256, use_cluster=1))
