@@ -215,11 +215,11 @@ int32_t ssme_b200_model(ssme_b200_handle h);
  * (univ_svol_bootstrap_filter.h:18 -> pf BSFilter); nothing there shards a filter.  Here rank r owns a
  * contiguous range of 4096-particle tiles; per time step the ranks all-reduce the weight maximum and
  * all-gather the tile weight sums (NCCL), and read ancestors' states from each other's HBM over NVLink.
- * After ssme_b200_comm_init, every rank exports four CUDA-IPC handles (256 bytes), the launcher gathers
- * them ([world][256], rank order) and every rank imports the lot.  All ranks then call the same
+ * After ssme_b200_comm_init, every rank exports five CUDA-IPC handles (320 bytes), the launcher gathers
+ * them ([world][320], rank order) and every rank imports the lot.  All ranks then call the same
  * ssme_b200_loglike_batch / ssme_b200_filter_trace with the same arguments and get the same results,
  * which are bit-identical to the single-GPU run. */
-int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t handles_out[256]);
+int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t handles_out[320]);
 int ssme_b200_spill_ipc_import(ssme_b200_handle h, const uint8_t* all_handles);
 
 /* Replaces: the reduction at the end of thread_pool::worker_thread (thread_pool.h:263-268) on its own:

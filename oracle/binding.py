@@ -73,7 +73,7 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
     T = y.shape[0]
-    cfg = _Cfg(model, N, resampler, rs, arithmetic, L, rng_mode, NT, seed, filter_id, 1 if tiled else 0, 0)
+    cfg = _Cfg(model, N, resampler, rs, arithmetic, L, rng_mode, NT, seed, filter_id, int(tiled), 0)
     z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
     cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
@@ -89,14 +89,14 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
 
 
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
-                  cov=None, trace=True):
+                  cov=None, trace=True, tiled=2):
     """Liu-West filter (LWFilter2WithCovs on the SV-with-leverage model); returns dict(loglik, cond_like, theta_bar,
     final_mean, ancestors, margin)."""
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
     hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
     T = y.shape[0]
-    cfg = _Cfg(1, N, resampler, 1, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, 1 if arithmetic == ARITH_CANONICAL else 0, 0)
+    cfg = _Cfg(1, N, resampler, 1, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, int(tiled) if arithmetic == ARITH_CANONICAL else 0, 0)
     cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
     ll, mg = C.c_double(0), C.c_double(0)
     cl, tb, fm = np.empty(T), np.zeros((T, 4)), np.empty(4)

@@ -176,6 +176,36 @@ static int32_t tiled_search(const tiled_cdf_t* c, double tau)
     return (int32_t)(i < c->N - 1 ? i : c->N - 1);
 }
 
+static double tiled_value(const tiled_cdf_t* c, int32_t i);
+
+/* Systematic resampling by offspring counts (tiled == 2).  Ct_i = max_{k<=i} C_k is the running maximum of the
+ * CDF (a parallel scan is sorted only up to rounding; its running maximum is sorted exactly).  With targets
+ * tau_j = fl(fl(j + u0) * sN), non-decreasing in j, A_i = #{j : tau_j <= Ct_i} (A_{N-1} := N) and particle i
+ * fathers the slots A_{i-1} .. A_i - 1.  count_targets() is the O(1) evaluation of A the kernel uses. */
+static int64_t count_targets(double c, double u0, double sN, int64_t N)
+{
+    if (!(c >= (0.0 + u0) * sN)) return 0; /* also when anything is NaN */
+    double q = c / sN - u0;
+    int64_t k = (q >= (double)(N - 1)) ? N - 1 : (q > 0.0 ? (int64_t)q : 0); /* truncation; NaN/inf guarded by the comparisons */
+    while (k + 1 < N && ((double)(k + 1) + u0) * sN <= c) ++k;
+    while (k > 0 && ((double)k + u0) * sN > c) --k;
+    return k + 1;
+}
+
+static void systematic_by_counts(const tiled_cdf_t* c, int32_t N, double u0, double sN, int32_t* anc)
+{
+    double run = -INFINITY;
+    int64_t prev = 0;
+    for (int32_t i = 0; i < N; ++i) {
+        double v = tiled_value(c, i);
+        if (v > run) run = v;
+        int64_t A = (i == N - 1) ? N : count_targets(run, u0, sN, N);
+        if (A < prev) A = prev;
+        for (int64_t j = prev; j < A; ++j) anc[j] = i;
+        prev = A;
+    }
+}
+
 static double tiled_value(const tiled_cdf_t* c, int32_t i)
 {
     int32_t b = i / c->TS;
@@ -441,6 +471,8 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
             } else { /* systematic: u_j = (j + u0)/N, spec'd by us (not in the reference tree) */
                 double u0 = injected ? ut[0] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
                 double sN = S / (double)N;
+                if (tiled && cfg->tiled == 2) systematic_by_counts(&tc, N, u0, sN, anc);
+                else
                 for (int32_t j = 0; j < N; ++j) {
                     double tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
                     anc[j] = tiled ? tiled_search(&tc, tau) : canonical ? descent_search(C, NP, N, tau) : lower_bound_idx(C, N, tau);
@@ -660,6 +692,8 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
         const double total = canonical ? S : 1.0;
         double u0 = 0.0, sN = S / (double)N;
         if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) u0 = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
+        if (canonical && cfg->tiled == 2 && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) systematic_by_counts(&tc, N, u0, sN, anc);
+        else
         for (int32_t j = 0; j < N; ++j) {
             double tau;
             if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;

@@ -49,7 +49,9 @@ typedef struct {
     uint64_t seed;               /* Philox key */
     uint64_t filter_id;          /* Philox counter words 2,3 */
     int32_t tiled;               /* 1 = the order of the global-memory ("spilled") kernels: tiles of NT*L particles scanned
-                                    as above, tile totals scanned by one CTA of 1024 lanes, two-level search (CANONICAL only) */
+                                    as above, tile totals scanned by one CTA of 1024 lanes, two-level search (CANONICAL only);
+                                    2 = the same, and SYSTEMATIC resampling by offspring counts on the running maximum of
+                                    the CDF (no search): what spill_expand_kernel does */
     int32_t reserved2;
 } ssme_oracle_cfg;
 

@@ -271,7 +271,7 @@ class ParticleFilterBackend:
         _check(self._lib.ssme_b200_comm_init(self._h, buf, rank, world))
 
     def spill_ipc_export(self) -> bytes:
-        buf = (C.c_uint8 * 256)()
+        buf = (C.c_uint8 * 320)()
         _check(self._lib.ssme_b200_spill_ipc_export(self._h, buf))
         return bytes(buf)
 

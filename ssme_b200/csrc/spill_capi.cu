@@ -19,10 +19,11 @@ struct SpillState {
     double* x_anc = nullptr;
     double* x_cur[2] = {nullptr, nullptr};
     double* lwc[2] = {nullptr, nullptr};
-    double *tmax = nullptr, *ttot = nullptr, *E = nullptr, *scal = nullptr;
+    double *tmax = nullptr, *ttot = nullptr, *tclmax = nullptr, *carry = nullptr, *E = nullptr, *scal = nullptr, *sync_word = nullptr;
     const double* peer_x[2][kMaxPeers] = {};
     const double* peer_lwc[2][kMaxPeers] = {};
-    void* opened[kMaxPeers][4] = {};
+    double* peer_x_anc[kMaxPeers] = {};
+    void* opened[kMaxPeers][5] = {};
     bool prepared = false, peers_ready = false;
     // Liu-West extras (allocated on first use)
     double* th_anc[4] = {};
@@ -70,14 +71,18 @@ static int prepare(ssme_b200_handle h)
     }
     SSME_CUDA(cudaMalloc(&s->tmax, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->ttot, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->tclmax, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->sync_word, sizeof(double)));
+    SSME_CUDA(cudaMemset(s->sync_word, 0, sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->E, (size_t)s->NBP * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scal, 8 * sizeof(double)));
     for (int i = 0; i < 2; ++i) {
         s->peer_x[i][s->rank] = s->x_cur[i];
         s->peer_lwc[i][s->rank] = s->lwc[i];
     }
-    SSME_CUDA(cudaFuncSetAttribute(spill_resample_kernel<kResampSystematic>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kStageTiles * kTile * sizeof(double))));
+    s->peer_x_anc[s->rank] = s->x_anc;
+    SSME_CUDA(cudaFuncSetAttribute(spill_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandBuf * sizeof(double))));
     s->peers_ready = (s->world == 1);
     s->prepared = true;
     return SSME_B200_OK;
@@ -94,11 +99,11 @@ void spill_destroy(ssme_b200_handle h)
     SpillState* s = h->spill_state;
     if (!s) return;
     for (int r = 0; r < kMaxPeers; ++r)
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 5; ++i)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->E); cudaFree(s->scal);
+    cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom);
     delete s;
@@ -133,7 +138,8 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
         a.seed = h->cfg.seed;
         a.fid = stream_base + f;
         a.x_anc = s->x_anc;
-        a.tmax = s->tmax; a.ttot = s->ttot; a.E = s->E; a.scal = s->scal;
+        a.tmax = s->tmax; a.ttot = s->ttot; a.tclmax = s->tclmax; a.carry = s->carry; a.E = s->E; a.scal = s->scal;
+        for (int r = 0; r < s->world; ++r) a.peer_x_anc[r] = s->peer_x_anc[r];
         a.cond_like = cond_like_dev ? cond_like_dev + f * (size_t)T : nullptr;
         a.ancestors = ancestors_dev ? ancestors_dev + f * (size_t)T * (size_t)s->N : nullptr;
         spill_init_kernel<<<1, 1, 0, st>>>(s->scal, s->N);
@@ -153,14 +159,22 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
             spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a);
             if (s->world > 1) {
                 int nrc = nccl->AllGather(s->ttot + s->tile0, s->ttot, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
+                if (nrc == 0) nrc = nccl->AllGather(s->tclmax + s->tile0, s->tclmax, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
                 if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", nccl->GetErrorString(nrc));
             }
             spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
             count_launch(4);
             if (t + 1 < T || a.ancestors) {
-                if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC)
-                    spill_resample_kernel<kResampSystematic><<<tiles, kTileNT, kStageTiles * kTile * sizeof(double), st>>>(a);
-                else spill_resample_kernel<kResampMultinomial><<<tiles, kTileNT, 0, st>>>(a);
+                if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
+                    spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a);
+                    if (s->world > 1) {
+                        // offspring are written into the slot owners' HBM: nobody may propagate before everybody has expanded
+                        int nrc = nccl->AllReduce(s->sync_word, s->sync_word, 1, kNcclFloat64, kNcclMax, h->nccl_comm, st);
+                        if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllReduce failed: %s", nccl->GetErrorString(nrc));
+                    }
+                } else {
+                    spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a);
+                }
                 count_launch(1);
             }
         }
@@ -196,7 +210,8 @@ static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double
     a.s.seed = h->cfg.seed;
     a.s.fid = stream_id;
     a.s.x_anc = s->x_anc;
-    a.s.tmax = s->tmax; a.s.ttot = s->ttot; a.s.E = s->E; a.s.scal = s->scal;
+    a.s.tmax = s->tmax; a.s.ttot = s->ttot; a.s.tclmax = s->tclmax; a.s.carry = s->carry; a.s.E = s->E; a.s.scal = s->scal;
+    a.s.peer_x_anc[0] = s->x_anc;
     a.s.cond_like = d_cond_like;
     a.s.ancestors = d_ancestors;
     a.s.nextra = 4;
@@ -231,9 +246,8 @@ static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double
         spill_reduce_max_kernel<<<1, 1024, 0, st>>>(a.s);
         spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
         spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
-        if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC)
-            spill_resample_kernel<kResampSystematic><<<tiles, kTileNT, kStageTiles * kTile * sizeof(double), st>>>(a.s);
-        else spill_resample_kernel<kResampMultinomial><<<tiles, kTileNT, 0, st>>>(a.s);
+        if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
+        else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
         count_launch(5);
     }
     if (T > 0 && d_final_mean) {
@@ -291,7 +305,7 @@ int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double
     return SSME_B200_OK;
 }
 
-int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[256])
+int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[320])
 {
     if (!h || !out) return fail(SSME_B200_EINVAL, "null argument");
     if (!h->spill) return fail(SSME_B200_EINVAL, "handle is not in global-memory (spilled) mode");
@@ -300,12 +314,13 @@ int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[256])
     if ((rc = prepare(h))) return rc;
     SpillState* s = h->spill_state;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    cudaIpcMemHandle_t hd[4];
+    cudaIpcMemHandle_t hd[5];
     SSME_CUDA(cudaIpcGetMemHandle(&hd[0], s->x_cur[0]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[1], s->x_cur[1]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[2], s->lwc[0]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[3], s->lwc[1]));
-    memcpy(out, hd, 256);
+    SSME_CUDA(cudaIpcGetMemHandle(&hd[4], s->x_anc));
+    memcpy(out, hd, 320);
     return SSME_B200_OK;
 }
 
@@ -319,9 +334,10 @@ int ssme_b200_spill_ipc_import(ssme_b200_handle h, const uint8_t* all_handles)
     SpillState* s = h->spill_state;
     for (int r = 0; r < s->world; ++r) {
         if (r == s->rank) continue;
-        cudaIpcMemHandle_t hd[4];
-        memcpy(hd, all_handles + (size_t)r * 256, 256);
-        for (int i = 0; i < 4; ++i) SSME_CUDA(cudaIpcOpenMemHandle(&s->opened[r][i], hd[i], cudaIpcMemLazyEnablePeerAccess));
+        cudaIpcMemHandle_t hd[5];
+        memcpy(hd, all_handles + (size_t)r * 320, 320);
+        for (int i = 0; i < 5; ++i) SSME_CUDA(cudaIpcOpenMemHandle(&s->opened[r][i], hd[i], cudaIpcMemLazyEnablePeerAccess));
+        s->peer_x_anc[r] = (double*)s->opened[r][4];
         s->peer_x[0][r] = (const double*)s->opened[r][0];
         s->peer_x[1][r] = (const double*)s->opened[r][1];
         s->peer_lwc[0][r] = (const double*)s->opened[r][2];

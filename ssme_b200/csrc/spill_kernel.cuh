@@ -36,12 +36,15 @@ struct SpillArgs {
     double* lwc;     // [local] log-weights, overwritten by the tile-local CDF
     double* tmax;    // [nb]
     double* ttot;    // [nb]
+    double* tclmax;  // [nb] largest tile-local CDF entry of each tile
+    double* carry;   // [nb] running maximum of the global CDF over all earlier tiles (-inf for tile 0)
     double* E;       // [NBP]
     double* scal;    // [0] M  [1] S  [2] log-likelihood so far  [3] log N
     double* cond_like;  // [T] or null
     int* ancestors;     // [T][N] or null (parity runs at small N)
     const double* peer_x[kMaxPeers];    // per-rank base pointers of x_cur / lwc (own rank included)
     const double* peer_lwc[kMaxPeers];
+    double* peer_x_anc[kMaxPeers];      // per-rank base pointers of x_anc (systematic expansion writes offspring to their slot's owner)
     // extra per-particle fields resampled together with the state (Liu-West: the 4 transformed parameters); single rank
     int nextra;
     const double* extra_cur[4];
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const Spill
 {
     constexpr int NW = kTileNT / 32;
     __shared__ double red_sum[32];
+    __shared__ double red_max[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = a.tile0 + blockIdx.x;
     const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
@@ -193,9 +197,25 @@ __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const Spill
     lex = (lane > 0) ? lex : 0.0;
     const double base = __dadd_rn(wex, lex);
 #pragma unroll
-    for (int k = 0; k < kTileL; k += 2)
-        *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(__dadd_rn(base, sc[k]), __dadd_rn(base, sc[k + 1]));
-    if (tid == 0) a.ttot[tile] = S;
+    for (int k = 0; k < kTileL; ++k) sc[k] = __dadd_rn(base, sc[k]);
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(sc[k], sc[k + 1]);
+    // largest tile-local CDF entry (feeds the running maximum used by the systematic expansion).  Inside a thread the
+    // entries are non-decreasing (floating-point addition of non-negative terms is monotone), so its last one is its largest.
+    double cmax = sc[kTileL - 1];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(cmax, d);
+        cmax = (other > cmax) ? other : cmax;
+    }
+    if (lane == 0) red_max[warp] = cmax;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red_max[0];
+        for (int g = 1; g < NW; ++g) m = (red_max[g] > m) ? red_max[g] : m;
+        a.ttot[tile] = S;
+        a.tclmax[tile] = m;
+    }
 }
 
 // one CTA: canonical scan of the nb tile totals with Lp items per lane; E[b] for all NBP padded entries
@@ -205,6 +225,7 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = tid * a.Lp;
     double tot = 0.0;
+#pragma unroll 8
     for (int k = 0; k < a.Lp; ++k) {
         const double v = (b0 + k < a.nb) ? a.ttot[b0 + k] : 0.0;
         tot = (k == 0) ? v : __dadd_rn(tot, v);
@@ -230,10 +251,50 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     lex = (lane > 0) ? lex : 0.0;
     const double base = __dadd_rn(wex, lex);
     double run = 0.0;
+#pragma unroll 8
     for (int k = 0; k < a.Lp; ++k) {
         const double v = (b0 + k < a.nb) ? a.ttot[b0 + k] : 0.0;
         run = (k == 0) ? v : __dadd_rn(run, v);
         a.E[b0 + k] = __dadd_rn(base, run);
+    }
+    // exclusive running maximum over tiles of (O_b + largest local entry): exact, order-free
+    {
+        __shared__ double red_max[32];
+        const double ninf = __longlong_as_double(0xfff0000000000000ll);
+        double loc = ninf;
+        __syncthreads();  // E complete
+    #pragma unroll 8
+    for (int k = 0; k < a.Lp; ++k) {
+            const int b = b0 + k;
+            if (b < a.nb) {
+                const double O = (b > 0) ? a.E[b - 1] : 0.0;
+                const double v = __dadd_rn(O, a.tclmax[b]);
+                loc = (v > loc) ? v : loc;
+            }
+        }
+        double inc = loc;  // inclusive max over lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(inc, d);
+            inc = (lane >= d && other > inc) ? other : inc;
+        }
+        if (lane == 31) red_max[warp] = inc;
+        __syncthreads();
+        double wprev = ninf;
+        for (int g = 0; g < warp; ++g) wprev = (red_max[g] > wprev) ? red_max[g] : wprev;
+        double excl = shfl_up_d(inc, 1);
+        excl = (lane > 0) ? excl : ninf;
+        double run = (wprev > excl) ? wprev : excl;  // max over all tiles before this lane's first tile
+    #pragma unroll 8
+    for (int k = 0; k < a.Lp; ++k) {
+            const int b = b0 + k;
+            if (b < a.nb) {
+                a.carry[b] = run;
+                const double O = (b > 0) ? a.E[b - 1] : 0.0;
+                const double v = __dadd_rn(O, a.tclmax[b]);
+                run = (v > run) ? v : run;
+            }
+        }
     }
     if (tid == 0) {
         const double M = a.scal[0], logN = a.scal[3];
@@ -245,121 +306,154 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     }
 }
 
-// State of the branch-free descent "for (s = size/2; s >= 1; s >>= 1) if (O + arr[idx+s-1] < tau) idx += s".
-struct Descent {
-    int base, s;
-};
-// Whether a probe sends a target right is monotone in the target, so while the two extreme targets lo <= hi take
-// the same decision every target in [lo, hi] takes it too -- for ANY array, sorted or not.  advance() walks that
-// shared prefix once for a whole group of targets; finish() walks the remainder for one target.  Together they
-// give exactly the result of an independent descent per target.
-__device__ __forceinline__ void advance(const double* __restrict__ arr, double O, Descent& d, double lo, double hi)
+// A = #{ j in [0,N) : tau_j <= c },  tau_j = fl(fl(j + u0) * sN)  (oracle: count_targets).  The estimate q only has to
+// land near the answer: tau_j is non-decreasing in j, so the two fix-up loops end at the largest j with tau_j <= c
+// whatever the starting point -- the oracle starts from c / sN - u0, the kernel from the cheaper c * (1/sN) - u0.
+__device__ __forceinline__ int count_targets(double c, double u0, double sN, double inv_sN, int N)
 {
-    while (d.s >= 1) {
-        const double v = __dadd_rn(O, arr[d.base + d.s - 1]);
-        const bool dlo = v < lo, dhi = v < hi;
-        if (dlo != dhi) break;
-        d.base += dlo ? d.s : 0;
-        d.s >>= 1;
-    }
-}
-__device__ __forceinline__ int finish(const double* __restrict__ arr, double O, Descent d, double tau)
-{
-    while (d.s >= 1) {
-        d.base += (__dadd_rn(O, arr[d.base + d.s - 1]) < tau) ? d.s : 0;
-        d.s >>= 1;
-    }
-    return d.base;
+    if (!(c >= __dmul_rn(__dadd_rn(0.0, u0), sN))) return 0;
+    const double q = __fma_rn(c, inv_sN, -u0);
+    int k = (q >= (double)(N - 1)) ? N - 1 : (q > 0.0 ? (int)q : 0);
+    const double t0 = __dmul_rn(__dadd_rn((double)k, u0), sN);
+    const double t1 = __dmul_rn(__dadd_rn((double)(k + 1), u0), sN);
+    if (t0 <= c && (k + 1 >= N || t1 > c)) return k + 1;  // the estimate was exact (the usual case)
+    while (k + 1 < N && __dmul_rn(__dadd_rn((double)(k + 1), u0), sN) <= c) ++k;
+    while (k > 0 && __dmul_rn(__dadd_rn((double)k, u0), sN) > c) --k;
+    return k + 1;
 }
 
-constexpr int kStageTiles = 3;  // CDF tiles a CTA stages in shared memory (96 KB)
+constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wider slot ranges (degenerate weights) are written directly
 
-// slot j: target -> tile (descent over E) -> position inside the tile (descent over O_b + cl) -> gather x'.
-// Systematic targets increase with j, and the descent's result is monotone in the target for any array (at the
-// first probe where two targets differ the smaller goes left), so the 4096 slots of a CTA land in the tile range
-// [tile(first target), tile(last target)] -- usually 1-2 tiles.  Those tiles' CDFs are staged in shared memory with
-// coalesced loads and every slot runs its 12-level descent there; the tile-level descent starts from the prefix
-// common to the whole CTA.  Wider ranges (degenerate weights) fall back to descents in global memory.
-// Multinomial targets are i.i.d.: one full descent in global memory each.
-template <int RESAMP>
+// Systematic resampling WITHOUT a search (oracle: systematic_by_counts).  Each CTA takes a tile of PARTICLES: it forms
+// the running maximum Ct of the global CDF over its tile (carry-in from earlier tiles in a.carry; a parallel scan is
+// sorted only up to rounding, its running maximum exactly), turns it into cumulative offspring counts
+// A_i = #{targets <= Ct_i} in O(1) per particle; particle i fathers the slots A_{i-1} .. A_i - 1, which are contiguous
+// over the CTA: they are staged in shared memory and written out coalesced (to the slot owner's HBM when the filter is
+// sharded over ranks).  HBM traffic: read CDF 8 + read x' 8 + write 8 B per particle.
+__global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a)
+{
+    extern __shared__ __align__(16) double ebuf[];  // [kExpandBuf]
+    __shared__ double red[kTileNT / 32];
+    __shared__ int sh_range[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = a.tile0 + blockIdx.x;
+    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
+    const int i0 = tile * kTile + tid * kTileL;
+    const int N = a.N;
+    const double S = a.scal[1];
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
+    const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), key);
+    const double u0 = uniform53(r.x, r.y);
+    const double sN = __ddiv_rn(S, (double)a.N);
+    const double inv_sN = __ddiv_rn(1.0, sN);
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    const double O = (tile > 0) ? a.E[tile - 1] : 0.0;
+    double c[kTileL];
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(a.lwc + l0 + k);
+        c[k] = v.x; c[k + 1] = v.y;
+    }
+    double m = ninf;
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) {
+        const double v = __dadd_rn(O, c[k]);
+        m = (v > m) ? v : m;
+        c[k] = m;  // running maximum inside the thread
+    }
+    double inc = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(inc, d);
+        inc = (lane >= d && other > inc) ? other : inc;
+    }
+    if (lane == 31) red[warp] = inc;
+    if (tid == 0) { sh_range[0] = 0; sh_range[1] = 0; }
+    __syncthreads();
+    double prevmax = a.carry[tile];
+    for (int g = 0; g < warp; ++g) prevmax = (red[g] > prevmax) ? red[g] : prevmax;
+    double excl = shfl_up_d(inc, 1);
+    excl = (lane > 0) ? excl : ninf;
+    prevmax = (excl > prevmax) ? excl : prevmax;  // running maximum of the CDF over every particle before this thread's first
+    // cumulative offspring counts of this thread's particles
+    int A[kTileL + 1];
+    A[0] = (i0 == 0 || i0 >= N) ? 0 : count_targets(prevmax, u0, sN, inv_sN, N);
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) {
+        const int i = i0 + k;
+        int Ak = A[k];
+        if (i < N) {
+            const double ct = (c[k] > prevmax) ? c[k] : prevmax;
+            Ak = (i == N - 1) ? N : count_targets(ct, u0, sN, inv_sN, N);
+            Ak = (Ak < A[k]) ? A[k] : Ak;
+        }
+        A[k + 1] = Ak;
+    }
+    const int tile_first = tile * kTile;
+    const int tile_last = min(tile_first + kTile, N) - 1;  // last real particle of this tile
+    if (tid == 0) sh_range[0] = A[0];
+    if (i0 <= tile_last && tile_last < i0 + kTileL) sh_range[1] = A[tile_last - i0 + 1];
+    __syncthreads();
+    const int s_lo = sh_range[0], s_hi = sh_range[1];
+    const bool staged = (s_hi - s_lo) <= kExpandBuf;
+    const bool single = (a.tiles_per_rank == a.nb);
+    const long long per_rank = (long long)a.tiles_per_rank * kTile;
+    const int nfields = 1 + a.nextra;
+    for (int fld = 0; fld < nfields; ++fld) {
+        const double* src = (fld == 0) ? a.x_cur + l0 : a.extra_cur[fld - 1] + i0;  // extras are single-rank: global index
+        double v[kTileL];
+#pragma unroll
+        for (int k = 0; k < kTileL; k += 2) {
+            const double2 w = *reinterpret_cast<const double2*>(src + k);
+            v[k] = w.x; v[k + 1] = w.y;
+        }
+        double* dst_local = (fld == 0) ? a.x_anc : a.extra_anc[fld - 1];
+        if (staged) {
+#pragma unroll
+            for (int k = 0; k < kTileL; ++k)
+                for (int sl = A[k]; sl < A[k + 1]; ++sl) ebuf[sl - s_lo] = v[k];
+            __syncthreads();
+            for (int q = tid; q < s_hi - s_lo; q += kTileNT) {
+                const long long sl = (long long)s_lo + q;
+                if (single || fld > 0) {
+                    dst_local[sl] = ebuf[q];
+                } else {
+                    const int owner = (int)(sl / per_rank);
+                    a.peer_x_anc[owner][sl - (long long)owner * per_rank] = ebuf[q];
+                }
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int k = 0; k < kTileL; ++k)
+                for (long long sl = A[k]; sl < A[k + 1]; ++sl) {
+                    if (single || fld > 0) {
+                        dst_local[sl] = v[k];
+                    } else {
+                        const int owner = (int)(sl / per_rank);
+                        a.peer_x_anc[owner][sl - (long long)owner * per_rank] = v[k];
+                    }
+                }
+        }
+    }
+    if (a.ancestors) {
+#pragma unroll
+        for (int k = 0; k < kTileL; ++k)
+            for (int sl = A[k]; sl < A[k + 1]; ++sl) a.ancestors[(size_t)a.t * a.N + sl] = i0 + k;
+    }
+}
+
+// Multinomial resampling: slot j draws its own target (i.i.d.), finds its tile by the descent over E and its position
+// by the descent over O_b + cl in global memory, and gathers x' (and the extra fields).  Random access: the slow path
+// at large N by nature; systematic resampling uses spill_expand_kernel instead.
 __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs a)
 {
-    extern __shared__ __align__(16) double scl[];  // [kStageTiles][kTile]
-    __shared__ int sh_b[2];
-    __shared__ Descent sh_A;
     const int tid = threadIdx.x;
     const int tile = a.tile0 + blockIdx.x;
     const double S = a.scal[1];
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    if (RESAMP == kResampSystematic) {
-        const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), key);
-        const double u0 = uniform53(r.x, r.y);
-        const double sN = __ddiv_rn(S, (double)a.N);
-        const int jc = tile * kTile;  // first slot of this CTA
-        if (jc >= a.N) return;
-        auto target = [&](int j) { return __dmul_rn(__dadd_rn((double)min(j, a.N - 1), u0), sN); };
-        const bool single = (a.tiles_per_rank == a.nb);  // one rank owns every tile: no owner lookup (integer division)
-        auto tile_cdf = [&](int b) {
-            const int owner = single ? 0 : b / a.tiles_per_rank;
-            return a.peer_lwc[owner] + (size_t)(b - owner * a.tiles_per_rank) * kTile;
-        };
-        auto tile_x = [&](int b) {
-            const int owner = single ? 0 : b / a.tiles_per_rank;
-            return a.peer_x[owner] + (size_t)(b - owner * a.tiles_per_rank) * kTile;
-        };
-        auto tile_off = [&](int b) { return (b > 0) ? a.E[b - 1] : 0.0; };
-        if (tid < 32) {
-            const double lo = target(jc), hi = target(jc + kTile - 1);
-            Descent A{0, a.NBP >> 1};
-            advance(a.E, 0.0, A, lo, hi);
-            if (tid == 0) {
-                sh_A = A;
-                sh_b[0] = min(finish(a.E, 0.0, A, lo), a.nb - 1);
-                sh_b[1] = min(finish(a.E, 0.0, A, hi), a.nb - 1);
-            }
-        }
-        __syncthreads();
-        const Descent A = sh_A;
-        const int b_lo = sh_b[0], b_hi = sh_b[1];
-        const bool staged = (b_hi - b_lo + 1) <= kStageTiles;
-        if (staged) {
-            for (int q = 0; q <= b_hi - b_lo; ++q) {
-                const double* src = tile_cdf(b_lo + q);
-#pragma unroll
-                for (int k = 0; k < kTileL; k += 2)
-                    *reinterpret_cast<double2*>(scl + q * kTile + k * kTileNT + 2 * tid) =
-                        *reinterpret_cast<const double2*>(src + k * kTileNT + 2 * tid);
-            }
-        }
-        __syncthreads();
-        double* dst = a.x_anc + (size_t)blockIdx.x * kTile;
-#pragma unroll 4
-        for (int k = 0; k < kTileL; ++k) {
-            const int j = jc + k * kTileNT + tid;
-            if (j >= a.N) break;
-            const double tau = target(j);
-            const int b = min(finish(a.E, 0.0, A, tau), a.nb - 1);
-            const double O = tile_off(b);
-            int idx = 0;
-            if (staged) {
-                const double* cl = scl + (b - b_lo) * kTile;
-#pragma unroll
-                for (int sstep = kTile / 2; sstep >= 1; sstep >>= 1) idx += (__dadd_rn(O, cl[idx + sstep - 1]) < tau) ? sstep : 0;
-            } else {
-                idx = finish(tile_cdf(b), O, Descent{0, kTile / 2}, tau);
-            }
-            long long i = (long long)b * kTile + idx;
-            if (i > (long long)a.N - 1) {  // clamp to the last real particle (it lives in the last tile)
-                i = (long long)a.N - 1;
-                idx = (int)(i - (long long)b * kTile);
-            }
-            dst[k * kTileNT + tid] = tile_x(b)[idx];
-            for (int e = 0; e < a.nextra; ++e) a.extra_anc[e][(size_t)blockIdx.x * kTile + k * kTileNT + tid] = a.extra_cur[e][i];
-            if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
-        }
-        return;
-    }
 #pragma unroll 2
     for (int k = 0; k < kTileL; ++k) {
         const int j = tile * kTile + k * kTileNT + tid;  // coalesced over the CTA
