@@ -89,8 +89,10 @@ NcclApi* nccl_api()
     static bool tried = false;
     if (!tried) {
         tried = true;
-        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        // prefer the NCCL the host process already loaded (torch ships its own); never export its symbols globally
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (lib) {
             api.GetUniqueId = (int (*)(NcclApi::unique_id*))dlsym(lib, "ncclGetUniqueId");
             api.CommInitRank = (int (*)(void**, int, NcclApi::unique_id, int))dlsym(lib, "ncclCommInitRank");

@@ -123,7 +123,9 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
     if (rc) return rc;
     SpillState* s = h->spill_state;
     if (!s->peers_ready) return fail(SSME_B200_ERUNTIME, "multi-rank spilled filter: exchange the IPC handles first (ssme_b200_spill_ipc_export/import)");
-    NcclApi* nccl = nccl_api();
+    // NCCL is looked up only when there are peers: loading it in a single-GPU process could shadow the NCCL a host
+    // application (e.g. torch) brings along and loads later
+    NcclApi* nccl = (s->world > 1) ? nccl_api() : nullptr;
     const int T = (int)h->T;
     const int tiles = s->tiles_per_rank;
     cudaStream_t st = h->stream;

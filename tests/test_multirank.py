@@ -212,7 +212,14 @@ def test_particle_sharded_filter_matches_single_gpu(resampler):
     got.sort(key=lambda t: t[0])
     assert np.array_equal(got[0][1], one["loglik"]) and np.array_equal(got[1][1], one["loglik"])
     assert np.array_equal(got[0][2], one["cond_like"]) and np.array_equal(got[1][2], one["cond_like"])
-    # each rank traces the ancestors of its own slots (tile range); together they cover the single-GPU trace
     half = N // 2
-    assert np.array_equal(got[0][3][0][:, :half], one["ancestors"][0][:, :half])
-    assert np.array_equal(got[1][3][0][:, half:], one["ancestors"][0][:, half:])
+    ref = one["ancestors"][0]
+    if resampler == 0:
+        # multinomial (slot-side gather): each rank traces the ancestors of its own slots
+        assert np.array_equal(got[0][3][0][:, :half], ref[:, :half])
+        assert np.array_equal(got[1][3][0][:, half:], ref[:, half:])
+    else:
+        # systematic (particle-side expansion): each rank traces the slots fathered by its own particles
+        own0 = ref < half
+        assert np.array_equal(got[0][3][0][own0], ref[own0])
+        assert np.array_equal(got[1][3][0][~own0], ref[~own0])
