@@ -46,23 +46,33 @@ __device__ __forceinline__ double lw_trans(int k, double p)
     return __dsub_rn(dlog(__dadd_rn(1.0, p)), dlog(__dsub_rn(1.0, p)));
 }
 
-// canonical block sum: lane-local sequential (done by the caller), butterfly over the lanes, sequential over the warps
-template <int NW>
-__device__ __forceinline__ double block_sum_finish(double v, double* red /*[NW]*/, int lane, int warp)
+// canonical block sums of NQ quantities at once: lane-local sequential sums come from the caller; butterfly over the
+// 32 lanes of each warp, then a sequential sum over the warps (oracle: block_sum).  One barrier for all NQ.
+template <int NQ, int NW>
+__device__ __forceinline__ void block_sums(double (&v)[NQ], double* red /*[NW][NQ]*/, int nq, int lane, int warp, int tid, double* out /*[NQ] smem*/)
 {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = __dadd_rn(v, shfl_xor_d(v, d));
-    if (lane == 0) red[warp] = v;
+    for (int q = 0; q < NQ; ++q) {
+        if (q < nq) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v[q] = __dadd_rn(v[q], shfl_xor_d(v[q], d));
+            if (lane == 0) red[warp * NQ + q] = v[q];
+        }
+    }
     __syncthreads();
-    double acc = red[0];
-    for (int g = 1; g < NW; ++g) acc = __dadd_rn(acc, red[g]);
+    if (tid < nq) {
+        double acc = red[tid];
+        for (int g = 1; g < NW; ++g) acc = __dadd_rn(acc, red[g * NQ + tid]);
+        out[tid] = acc;
+    }
     __syncthreads();
-    return acc;
 }
 
 __global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
 {
-    __shared__ double red[kTileNT / 32];
+    constexpr int NW = kTileNT / 32;
+    __shared__ double red[NW * 14];
+    __shared__ double tot[14];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
@@ -75,46 +85,49 @@ __global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
             if (a.mode == 1 && i0 + k < a.s.N) v = lw_inv_trans(q, v);
             th[q][k] = v;
         }
-    int slot = 0;
+    double s[14];
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
-        double s = th[q][0];
+        s[q] = th[q][0];
 #pragma unroll
-        for (int k = 1; k < kTileL; ++k) s = __dadd_rn(s, th[q][k]);
-        const double tot = block_sum_finish<kTileNT / 32>(s, red, lane, warp);
-        if (tid == 0) a.part[(size_t)slot * a.s.nb + tile] = tot;
-        ++slot;
+        for (int k = 1; k < kTileL; ++k) s[q] = __dadd_rn(s[q], th[q][k]);
     }
-    if (a.mode == 1) return;
-    for (int q = 0; q < 4; ++q)
-        for (int l = 0; l <= q; ++l) {
-            double s = __dmul_rn(th[q][0], th[l][0]);
+    int slot = 4;
 #pragma unroll
-            for (int k = 1; k < kTileL; ++k) s = __dadd_rn(s, __dmul_rn(th[q][k], th[l][k]));
-            const double tot = block_sum_finish<kTileNT / 32>(s, red, lane, warp);
-            if (tid == 0) a.part[(size_t)slot * a.s.nb + tile] = tot;
-            ++slot;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int l = 0; l <= q; ++l) {
+            double acc = __dmul_rn(th[q][0], th[l][0]);
+#pragma unroll
+            for (int k = 1; k < kTileL; ++k) acc = __dadd_rn(acc, __dmul_rn(th[q][k], th[l][k]));
+            s[slot++] = acc;
         }
+    const int nq = (a.mode == 1) ? 4 : 14;
+    block_sums<14, NW>(s, red, nq, lane, warp, tid, tot);
+    if (tid < nq) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
 }
 
 // one CTA: totals of the tile partials, thetaBar, V_t, cholesky(h^2 V_t)
 __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwArgs a)
 {
-    __shared__ double red[32];
+    __shared__ double red[32 * 14];
     __shared__ double tot[14];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = (a.mode == 1) ? 4 : 14;
-    for (int q = 0; q < nq; ++q) {
-        const double* p = a.part + (size_t)q * a.s.nb;
-        const int b0 = tid * a.s.Lp;
-        double s = 0.0;
-        for (int k = 0; k < a.s.Lp; ++k) {
-            const double v = (b0 + k < a.s.nb) ? p[b0 + k] : 0.0;
-            s = (k == 0) ? v : __dadd_rn(s, v);
+    const int b0 = tid * a.s.Lp;
+    double s[14];
+#pragma unroll
+    for (int q = 0; q < 14; ++q) {
+        s[q] = 0.0;
+        if (q < nq) {
+            const double* p = a.part + (size_t)q * a.s.nb;
+            for (int k = 0; k < a.s.Lp; ++k) {
+                const double v = (b0 + k < a.s.nb) ? p[b0 + k] : 0.0;
+                s[q] = (k == 0) ? v : __dadd_rn(s[q], v);
+            }
         }
-        const double t = block_sum_finish<32>(s, red, lane, warp);
-        if (tid == 0) tot[q] = t;
     }
-    __syncthreads();
+    block_sums<14, 32>(s, red, nq, lane, warp, tid, tot);
     if (tid != 0) return;
     const double dN = (double)a.s.N;
     if (a.mode == 1) {
