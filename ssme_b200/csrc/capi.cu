@@ -231,8 +231,9 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         return fail(SSME_B200_EINVAL, "unknown model id %d", cfg->model);
     if (cfg->num_particles < 1) return fail(SSME_B200_EINVAL, "num_particles must be >= 1");
     if (cfg->resample_every < 1) return fail(SSME_B200_EINVAL, "resample_every must be >= 1");
-    if (cfg->resampler != SSME_B200_RESAMP_MULTINOMIAL && cfg->resampler != SSME_B200_RESAMP_SYSTEMATIC)
-        return fail(SSME_B200_EUNSUPPORTED, "resampler %d is not built into this library yet", cfg->resampler);
+    if (cfg->resampler != SSME_B200_RESAMP_MULTINOMIAL && cfg->resampler != SSME_B200_RESAMP_SYSTEMATIC &&
+        cfg->resampler != SSME_B200_RESAMP_SORTED_MULTINOMIAL)
+        return fail(SSME_B200_EINVAL, "unknown resampler %d", cfg->resampler);
     if (cfg->dtype != SSME_B200_DTYPE_F64) return fail(SSME_B200_EUNSUPPORTED, "only the fp64 path is built");
     if (cfg->rng_mode != SSME_B200_RNG_PHILOX && cfg->rng_mode != SSME_B200_RNG_INJECTED)
         return fail(SSME_B200_EINVAL, "unknown rng_mode %d", cfg->rng_mode);
@@ -254,6 +255,8 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     const bool use_cluster = cfg->use_cluster != 0 && !spill;
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
+    if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL && (use_cluster || spill))
+        return fail(SSME_B200_EUNSUPPORTED, "the sorted-multinomial resampler is built into the resident kernel only (N <= 8192, no cluster)");
     if (use_cluster) {
         // K2: tiles of 512 particles, one CTA each, cluster of ceil(N/512) CTAs (cluster_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");

@@ -19,6 +19,10 @@ namespace ssme {
 #define SSME_INST_L(L)                                   \
     SSME_INST(L, kModelSV, kResampMultinomial, 0)         \
     SSME_INST(L, kModelSV, kResampMultinomial, 1)         \
+    SSME_INST(L, kModelSV, kResampSortedMultinomial, 0)   \
+    SSME_INST(L, kModelSV, kResampSortedMultinomial, 1)   \
+    SSME_INST(L, kModelSVLeverage, kResampSortedMultinomial, 0) \
+    SSME_INST(L, kModelSVLeverage, kResampSortedMultinomial, 1) \
     SSME_INST(L, kModelSV, kResampSystematic, 0)          \
     SSME_INST(L, kModelSV, kResampSystematic, 1)          \
     SSME_INST(L, kModelSVLeverage, kResampMultinomial, 0) \

@@ -57,7 +57,7 @@ __host__ __device__ constexpr int obs_stride(int model) { return model == kModel
 template <int L, int NT, int MODEL>
 __host__ __device__ constexpr size_t filter_smem_bytes()
 {
-    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * obs_stride(MODEL) + 64 + 64) + 16;
+    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * obs_stride(MODEL) + 64 + 64 + 32) + 16;
 }
 
 // ---- mbarrier / bulk-TMA helpers (PTX ISA: mbarrier, cp.async.bulk) ---------------------------
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     double* red_sum = red_max + 32;                    // [32]
     double* clM = red_sum + 32;                        // [32]
     double* clS = clM + 32;                            // [32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(clS + 32);  // [2]
+    double* red_e = clS + 32;                          // [32] second scan of the sorted-multinomial resampler
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red_e + 32);  // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long f = a.filter_offset + blockIdx.x;
@@ -389,6 +390,62 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
                 }
             }
+        } else if (RESAMP == kResampSortedMultinomial) {
+            // mn_resamp_states_and_params (liu_west_filter.h:104-139, = pf's mn_resamp_fast1): N+1 exponential spacings
+            // E_j = -log U_j give the uniform order statistics U_(j) = (E_0 + .. + E_j) / (E_0 + .. + E_N); the targets
+            // tau_j = U_(j) * S come out sorted.  Their prefix sums are a second scan in the canonical order.
+            double sce[L];
+            if (DEBUG && a.inject) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const double u = (i0 + k < N) ? a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k] : 1.0;
+                    sce[k] = (i0 + k < N) ? -dlog_unit(u) : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < L / 2; ++q) {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                    double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
+                    ua = (ua == 0.0) ? 0x1p-53 : ua;
+                    ub = (ub == 0.0) ? 0x1p-53 : ub;
+                    sce[2 * q + 0] = (i0 + 2 * q < N) ? -dlog_unit(ua) : 0.0;
+                    sce[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
+                }
+            }
+            double uN;
+            if (DEBUG && a.inject) {
+                uN = a.u_inj[((size_t)f * T + t) * a.stride_u + N];
+            } else {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
+                uN = (uN == 0.0) ? 0x1p-53 : uN;
+            }
+            const double EN = -dlog_unit(uN);
+#pragma unroll
+            for (int k = 1; k < L; ++k) sce[k] = __dadd_rn(sce[k - 1], sce[k]);
+            double einc = sce[L - 1];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double other = shfl_up_d(einc, d);
+                einc = (lane >= d) ? __dadd_rn(other, einc) : einc;
+            }
+            if (lane == 31) red_e[warp] = einc;
+            __syncthreads();
+            double ewv = (lane < NW) ? red_e[lane] : 0.0;
+#pragma unroll
+            for (int d = 1; d < NW; d <<= 1) {
+                const double other = shfl_up_d(ewv, d);
+                ewv = (lane >= d) ? __dadd_rn(other, ewv) : ewv;
+            }
+            const double G = __dadd_rn(shfl_d(ewv, NW - 1), EN);
+            double ewex = shfl_d(ewv, (warp > 0) ? warp - 1 : 0);
+            ewex = (warp > 0) ? ewex : 0.0;
+            double elex = shfl_up_d(einc, 1);
+            elex = (lane > 0) ? elex : 0.0;
+            const double ebase = __dadd_rn(ewex, elex);
+            const double sg = __ddiv_rn(S, G);
+#pragma unroll
+            for (int k = 0; k < L; ++k) tau[k] = __dmul_rn(__dadd_rn(ebase, sce[k]), sg);
         } else {  // systematic
             double u0;
             if (DEBUG && a.inject) {

@@ -21,16 +21,17 @@ def _theta(model):
 
 
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
-@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T,rs", [(32, 1, 1), (32, 2, 1), (500, 64, 1), (1024, 130, 1), (100, 65, 2), (500, 40, 5)])
 def test_injected_streams_trace_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, rs):
     """Identical pre-generated normal and uniform streams -> identical ancestors, states, cond-likes."""
     rng = np.random.default_rng(N * 1000 + T)
     y = sv_series(T, seed=3)
     F = 2
-    stride_u = N if resampler == sb.RESAMP_MULTINOMIAL else 1
+    stride_u = {sb.RESAMP_MULTINOMIAL: N, sb.RESAMP_SORTED_MULTINOMIAL: N + 1, sb.RESAMP_SYSTEMATIC: 1}[resampler]
     z = rng.standard_normal((F, T, N))
     u = rng.random((F, T, stride_u))
+    u[u == 0.0] = 0.5  # -log(u) of the sorted-multinomial resampler
     theta = np.stack([_theta(model), _theta(model) * np.array([1.05, 0.9, 1.2, 1.0][: len(_theta(model))])])
     be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, resample_every=rs, rng_mode=sb.RNG_INJECTED)
     be.add_observed_data(y)
@@ -51,7 +52,7 @@ def test_injected_streams_trace_bit_exact(oracle, sv_series, gpu_backend_factory
 
 
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
-@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T", [(500, 100), (1024, 257), (37, 33), (2048, 64), (8192, 40)])
 def test_philox_fast_path_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T):
     """Production path (on-device Philox, no tracing): log-likelihoods equal the oracle's bit for bit."""
@@ -115,8 +116,6 @@ def test_golden_vectors(gpu_backend_factory):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "filter_vectors.npz"))
     for name in g["cases"]:
         model, res, N, T, rs = (int(v) for v in g[name + "/cfg"])
-        if res == sb.RESAMP_SORTED_MULTINOMIAL:
-            continue  # not built into the kernel yet
         be = gpu_backend_factory(model=model, num_particles=N, resampler=res, resample_every=rs, rng_mode=sb.RNG_INJECTED,
                                  scan_items_per_lane=4)
         be.add_observed_data(g[name + "/y"])
