@@ -1,0 +1,89 @@
+// include/ssme_b200/liu_west_filter.hpp -- Liu-West joint state / parameter filter on the GPU backend.
+//
+// Mirrors the user-facing part of LWFilter2WithCovs (include/ssme/liu_west_filter.h:1949-2188): constructed from the
+// transform names, delta and the resampling schedule (:2100-2113), `getLogCondLike()` (:2180-2184), and the prior the
+// user's subclass supplies through `paramPriorSamp` (test/test_liu_west.cpp:339-349: independent uniforms).  The
+// reference is streaming -- `filter(y_t, z_t)` once per observation, with the state-space model given as seven pure
+// virtuals on Eigen vectors; here the model is the device functor of svol_lw_2_par (test/test_liu_west.cpp:213-358)
+// and the whole series is filtered by one call, after which the per-step results are read back.
+#ifndef SSME_B200_LIU_WEST_FILTER_HPP
+#define SSME_B200_LIU_WEST_FILTER_HPP
+
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../ssme_b200.h"
+#include "gpu_pool.hpp"
+
+namespace ssme_b200 {
+
+template <size_t nparts, typename float_t = double>
+class LWFilter2WithCovs_svol {
+public:
+    using psv = vec<float_t, 4>;  // phi, mu, sigma, rho
+
+    // transforms must be {"logit", "null", "log", "twice_fisher"} -- the ones svol_lw_2_par passes (test_liu_west.cpp:263)
+    LWFilter2WithCovs_svol(std::vector<std::string> transforms, float_t delta, const psv& prior_lower, const psv& prior_upper,
+                           const unsigned int& rs = 1, const gpu_options& opt = gpu_options())
+        : m_delta(delta), m_lo(prior_lower), m_hi(prior_upper)
+    {
+        const std::vector<std::string> want{"logit", "null", "log", "twice_fisher"};
+        if (transforms != want) throw std::invalid_argument("the device model uses the transforms logit, null, log, twice_fisher");
+        if (rs != 1) throw std::invalid_argument("the GPU Liu-West filter resamples at every step (rs = 1)");
+        ssme_b200_config c{};
+        c.struct_size = (int32_t)sizeof(c);
+        c.device = opt.device;
+        c.model = SSME_B200_MODEL_SV_LEVERAGE;
+        c.num_particles = (int32_t)nparts;
+        c.resampler = opt.resampler;
+        c.resample_every = 1;
+        c.dtype = SSME_B200_DTYPE_F64;
+        c.rng_mode = SSME_B200_RNG_PHILOX;
+        c.seed = opt.seed;
+        c.force_global_memory = 1;
+        throw_on_error(ssme_b200_create(&c, &m_h));
+    }
+    ~LWFilter2WithCovs_svol() { ssme_b200_destroy(m_h); }
+    LWFilter2WithCovs_svol(const LWFilter2WithCovs_svol&) = delete;
+    LWFilter2WithCovs_svol& operator=(const LWFilter2WithCovs_svol&) = delete;
+
+    // filter(obs_data, cov_data) for t = 0 .. T-1 in one call; cov[t] is the covariate z_t (the lagged observation)
+    void filter_series(const std::vector<float_t>& obs, const std::vector<float_t>& cov, std::uint64_t stream_id = 0)
+    {
+        if (obs.empty() || obs.size() != cov.size()) throw std::length_error("observations and covariates must be non-empty and of equal length");
+        std::vector<double> rows(2 * obs.size());
+        for (size_t t = 0; t < obs.size(); ++t) { rows[2 * t] = (double)obs[t]; rows[2 * t + 1] = (double)cov[t]; }
+        throw_on_error(ssme_b200_set_observations(m_h, rows.data(), obs.size(), 2));
+        m_cond_like.assign(obs.size(), 0.0);
+        m_theta_bar.assign(obs.size() * 4, 0.0);
+        double lo[4], hi[4];
+        for (int k = 0; k < 4; ++k) { lo[k] = (double)m_lo(k); hi[k] = (double)m_hi(k); }
+        throw_on_error(ssme_b200_lw_filter(m_h, lo, hi, (double)m_delta, stream_id, &m_loglik, m_cond_like.data(), m_theta_bar.data(),
+                                           m_final_mean.data(), nullptr));
+    }
+
+    // log p(y_t | y_{1:t-1}) of step t (the reference returns the latest one; :2180-2184)
+    float_t getLogCondLike(size_t t) const { return (float_t)m_cond_like.at(t); }
+    float_t getLogCondLike() const { return (float_t)m_cond_like.back(); }
+    float_t getLogLike() const { return (float_t)m_loglik; }
+    // mean of the untransformed parameter particles after the last step: E[theta | y_{1:T}]
+    psv getParamMeans() const
+    {
+        psv r;
+        for (int k = 0; k < 4; ++k) r(k) = (float_t)m_final_mean[k];
+        return r;
+    }
+
+private:
+    ssme_b200_handle m_h = nullptr;
+    float_t m_delta;
+    psv m_lo, m_hi;
+    double m_loglik = 0.0;
+    std::vector<double> m_cond_like, m_theta_bar;
+    std::array<double, 4> m_final_mean{};
+};
+
+}  // namespace ssme_b200
+#endif

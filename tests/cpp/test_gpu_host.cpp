@@ -8,6 +8,8 @@
 
 #include <ssme_b200/ada_pmmh_mvn.hpp>
 #include <ssme_b200/gpu_pool.hpp>
+#include <ssme_b200/liu_west_filter.hpp>
+#include <ssme_b200/pswarm_filter.hpp>
 #include <ssme_b200/rv_eval.hpp>
 
 #include "../../examples/estimate_univ_svol.hpp"
@@ -109,6 +111,42 @@ int main(int argc, char** argv)
         REQUIRE(mrows == iters);
         std::remove(samples_file.c_str());
         std::remove(messages_file.c_str());
+    }
+    TEST_CASE("test filter without funcs for type 2 filters with covariates [filter method]")  // test_liu_west.cpp:365-375
+    {
+        // svol_lw_2_par<NPARTS,FLOATTYPE> mod(.99, .8, .99, -.1, .1, .01, .1, -.5, -.01, 10); one filter() call; logCondLike^2 > 0
+        using lw_t = ssme_b200::LWFilter2WithCovs_svol<10, double>;
+        lw_t mod({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5}, lw_t::psv{.99, .1, .1, -.01});
+        mod.filter_series({0.3}, {0.0});
+        REQUIRE(std::pow(mod.getLogCondLike(), 2) > 0.0);
+        REQUIRE_THROWS_AS((lw_t({"null", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5}, lw_t::psv{.99, .1, .1, -.01})),
+                          std::invalid_argument);
+        // a longer run learns something: posterior means stay inside the prior box and cond-likes are finite
+        ssme_b200::LWFilter2WithCovs_svol<20000, double> big({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5},
+                                                             lw_t::psv{.99, .1, .3, -.01});
+        std::vector<double> cov(y.size(), 0.0);
+        for (size_t t = 1; t < y.size(); ++t) cov[t] = y[t - 1];
+        big.filter_series(y, cov);
+        const auto pm = big.getParamMeans();
+        REQUIRE(pm(0) > .8 && pm(0) < .99 && pm(2) > .01 && pm(2) < .3 && pm(3) > -.5 && pm(3) < -.01);
+        REQUIRE(std::isfinite(big.getLogLike()));
+    }
+    TEST_CASE("swarm: 10 x 10 particles, assertions of test_pswarm.cpp:251-252")
+    {
+        struct my_swarm : ssme_b200::Swarm<10, 10, 4, double> {
+            std::mt19937 g{3};
+            my_swarm() : ssme_b200::Swarm<10, 10, 4, double>([] { ssme_b200::gpu_options o; o.model = SSME_B200_MODEL_SV_LEVERAGE; return o; }()) {}
+            psv samp_untrans_params() override
+            {  // the uniform priors of svol_swarm_1 (test_pswarm.cpp:244): phi, mu, sigma, rho
+                std::uniform_real_distribution<double> a(.8, .99), b(-.1, .1), c(.01, .1), d(-.5, -.01);
+                return psv{a(g), b(g), c(g), d(g)};
+            }
+        } sw;
+        std::vector<double> rows(2 * 40);
+        for (size_t t = 0; t < 40; ++t) { rows[2 * t] = y[t]; rows[2 * t + 1] = t ? y[t - 1] : 0.0; }
+        sw.update_series(rows, 2);
+        REQUIRE(sw.num_obs() == 40);
+        for (size_t t = 0; t < 40; ++t) REQUIRE(std::pow(sw.getLogCondLike(t), 2) > 0.0);
     }
     return finish();
 }
