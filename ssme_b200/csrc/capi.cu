@@ -184,8 +184,11 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
         memset(&lc, 0, sizeof(lc));
         lc.gridDim = dim3((unsigned)(F * (size_t)h->cluster_size));
         lc.blockDim = dim3(kClNT);
-        lc.dynamicSmemBytes = 0;
+        lc.dynamicSmemBytes = sizeof(ClusterShared);
         lc.stream = st;
+        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(2 * kClMax * kClTile));
+        if (rc2) return rc2;
+        double* scratch = h->d_cluster_scratch;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)h->cluster_size;
@@ -193,7 +196,7 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
         attr[0].val.clusterDim.z = 1;
         lc.attrs = attr;
         lc.numAttrs = 1;
-        void* cparams[] = {&ca};
+        void* cparams[] = {&ca, &scratch};
         SSME_CUDA(cudaLaunchKernelExC(&lc, fn, cparams));
         g_launches.fetch_add(1);
         return SSME_B200_OK;
@@ -310,6 +313,7 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
                              (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampSystematic>};
         for (const void* fn : fns) {
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterShared));
             if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
         }
     } else if (!spill) {
@@ -337,6 +341,7 @@ int ssme_b200_destroy(ssme_b200_handle h)
     if (h->d_theta) cudaFree(h->d_theta);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_per_filter) cudaFree(h->d_per_filter);
+    if (h->d_cluster_scratch) cudaFree(h->d_cluster_scratch);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     delete h;
     return SSME_B200_OK;

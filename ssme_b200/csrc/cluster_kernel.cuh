@@ -1,16 +1,21 @@
 // ssme_b200/csrc/cluster_kernel.cuh -- K2: one bootstrap filter per thread-block CLUSTER.
 //
-// K1 keeps a filter inside one CTA, so its time-step latency is what one SM can issue: ~20 us per step at
+// K1 keeps a filter inside one CTA, so its time-step latency is what one SM can issue: ~17 us per step at
 // N = 8192, which is what paces PMMH when there are fewer chains than SMs (BASELINE.json config 3:
 // 64 chains x 8192 particles; 8 chains per GPU on 8 GPUs).  K2 spreads one filter over up to 16 SMs:
-// CTA r of the cluster owns the tile of particles r*512 .. r*512+511 (64 threads x 8) in registers / its
-// own shared memory; the three filter-wide quantities per step travel through distributed shared memory:
-//   max of the log-weights   each CTA publishes its tile maximum, cluster barrier, every CTA reads all of them
-//   CDF offsets              each CTA publishes its tile weight sum, cluster barrier, every CTA scans all tile sums
-//   resampling               a slot's target is located among the tile ends (local), then by a 9-level descent in
-//                            the OWNER's shared memory (ld.shared::cluster) and the ancestor's state is read from there
+// CTA r of the cluster owns the tile of particles r*512 .. r*512+511 (128 threads x 4).  Per step:
+//   max of the log-weights   each CTA publishes its tile maximum in its shared memory, cluster barrier, every CTA
+//                            reads all of them through distributed shared memory
+//   CDF and states           each CTA writes its tile-local CDF (breadth-first) and states to an L2-resident scratch
+//                            and then MULTICASTS them with one bulk TMA copy each
+//                            (cp.async.bulk ... .multicast::cluster) into the shared memory of every CTA of the cluster:
+//                            after one mbarrier wait every CTA holds the whole filter's CDF and states locally
+//   resampling               tile ends scanned redundantly by every CTA; each slot's 4+9-level descent and its gather
+//                            run in LOCAL shared memory (the first version probed the owner's shared memory with
+//                            ld.shared::cluster: 5120 remote 8-byte loads per CTA per step, slower than K1 --
+//                            profiles/r1_k2_cluster.md)
 // Same per-particle arithmetic and Philox streams as K1/K3; scan and search order = the oracle's "tiled" order with
-// tiles of 512 (oracle/pf_oracle.c: tiled_build / tiled_search with L = 8, NT = 64), bit-identical to it, and
+// tiles of 512 (oracle/pf_oracle.c: tiled_build / tiled_search with L = 4, NT = 128), bit-identical to it, and
 // therefore independent of how the clusters are spread over GPUs.
 // Reference replaced: the same BSFilter::filter step as K1 (liu_west_filter.h:1608-1761 twin).
 #pragma once
@@ -22,34 +27,51 @@ namespace ssme {
 
 namespace cg = cooperative_groups;
 
-constexpr int kClL = 8;
-constexpr int kClNT = 64;
+constexpr int kClL = 4;
+constexpr int kClNT = 128;
 constexpr int kClTile = kClL * kClNT;  // 512 particles per CTA
 constexpr int kClMax = 16;             // CTAs per cluster (non-portable size, opt-in)
+constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
 
 struct ClusterShared {
-    double X[2][kClTile];      // this tile's states, double-buffered (peers gather from the previous step's buffer)
-    double C[kClTile];         // tile-local inclusive CDF, breadth-first order
-    double E[kClMax];          // inclusive tile ends (every CTA computes all of them)
-    double red[4];
-    double pub_max, pub_tot;   // published to the cluster
+    double C[kClMax][kClTile];  // every tile's local inclusive CDF, breadth-first order (filled by multicast)
+    double X[kClMax][kClTile];  // every tile's states (filled by multicast)
+    double E[kClMax];           // inclusive tile ends
+    double red[8];
+    double pub_max, pub_tot;    // published to the cluster through DSMEM
     double clM[32], clS[32];
+    unsigned long long bar;     // mbarrier of the multicast copies
 };
 
+__device__ __forceinline__ void tma_multicast_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar, uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+
 template <int MODEL, int RESAMP>
-__global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs a)
+__global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
 {
     constexpr int OS = obs_stride(MODEL);
     constexpr int K = 9;  // log2(kClTile)
-    __shared__ ClusterShared sh;
+    constexpr int NW = kClNT / 32;
+    extern __shared__ __align__(128) unsigned char cl_smem[];
+    ClusterShared& sh = *reinterpret_cast<ClusterShared*>(cl_smem);
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long f = a.filter_offset + blockIdx.x / CS;
+    const unsigned long long floc = blockIdx.x / CS;  // filter index within this launch
+    const unsigned long long f = a.filter_offset + floc;
     const int N = a.N, T = a.T;
-    const int i0 = rank * kClTile + tid * kClL;  // first particle of this thread (global index within the filter)
+    const int i0 = rank * kClTile + tid * kClL;  // first particle of this thread (index within the filter)
     const int l0 = tid * kClL;                   // ... within the tile
+    // L2-resident scratch of this filter: [CS][512] CDF tiles, then [CS][512] state tiles
+    double* gC = scratch + floc * (size_t)(2 * kClMax * kClTile) + (size_t)rank * kClTile;
+    double* gX = gC + (size_t)kClMax * kClTile;
 
     uint32_t eoff[kClL];
 #pragma unroll
@@ -57,7 +79,7 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         const uint32_t v = (uint32_t)(l0 + k + 1);
         const int tz = __ffs((int)v) - 1;
         const uint32_t node = (v == (uint32_t)kClTile) ? (uint32_t)(kClTile - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
-        eoff[k] = node * 8u;
+        eoff[k] = node;
     }
     const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
@@ -66,10 +88,15 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
     const double logN = dlog((double)N);
     const double dN = (double)N;
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    const uint16_t cta_mask = (uint16_t)((1u << CS) - 1u);
+    const int nb = (N + kClTile - 1) / kClTile;
 
-    // peers' shared-memory blocks
     const ClusterShared* peer = cluster.map_shared_rank(&sh, (lane < CS) ? lane : 0);
 
+    if (tid == 0) {
+        mbar_init(reinterpret_cast<uint64_t*>(&sh.bar), 1);
+        mbar_fence_init();
+    }
     double x[kClL];
 #pragma unroll
     for (int k = 0; k < kClL; ++k) x[k] = 0.0;
@@ -80,13 +107,12 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         const double y = a.obs[(size_t)t * OS];
         const double cov = (OS == 2) ? a.obs[(size_t)t * OS + 1] : 0.0;
         double z[kClL];
-#pragma unroll
-        for (int q = 0; q < kClL / 4; ++q) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
+        {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), key);
             float z0, z1, z2, z3;
             box_muller(r.x, r.y, z0, z1);
             box_muller(r.z, r.w, z2, z3);
-            z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
+            z[0] = (double)z0; z[1] = (double)z1; z[2] = (double)z2; z[3] = (double)z3;
         }
         const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[kClL];
@@ -110,9 +136,9 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;
         }
-        double* Xcur = sh.X[t & 1];
+        // this tile's states go to the scratch now (multicast later together with the CDF)
 #pragma unroll
-        for (int k = 0; k < kClL; k += 2) *reinterpret_cast<double2*>(Xcur + l0 + k) = make_double2(x[k], x[k + 1]);
+        for (int k = 0; k < kClL; k += 2) *reinterpret_cast<double2*>(gX + l0 + k) = make_double2(x[k], x[k + 1]);
 
         // ---- filter-wide max: tile max -> published -> all tiles' maxima read through DSMEM --------
 #pragma unroll
@@ -122,7 +148,12 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         }
         if (lane == 0) sh.red[warp] = mloc;
         __syncthreads();
-        if (tid == 0) sh.pub_max = (sh.red[1] > sh.red[0]) ? sh.red[1] : sh.red[0];
+        if (tid == 0) {
+            double m = sh.red[0];
+#pragma unroll
+            for (int g = 1; g < NW; ++g) m = (sh.red[g] > m) ? sh.red[g] : m;
+            sh.pub_max = m;
+        }
         cluster.sync();  // C1
         double M = (lane < CS) ? peer->pub_max : ninf;
 #pragma unroll
@@ -146,7 +177,7 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             __syncwarp();
         }
 
-        // ---- weights, tile-local scan (lanes, then the tile's two warps) ---------------------------
+        // ---- weights, tile-local scan (lanes, then the tile's warps) -> scratch ------------------
         double sc[kClL];
 #pragma unroll
         for (int k = 0; k < kClL; ++k) {
@@ -159,20 +190,34 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             const double other = shfl_up_d(incl, d);
             incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
         }
-        if (lane == 31) sh.red[2 + warp] = incl;
+        if (lane == 31) sh.red[4 + warp] = incl;
         __syncthreads();
-        // Kogge-Stone over the tile's 2 warps: inclusive (w0, w0 + w1)
-        const double w0 = sh.red[2], w1 = sh.red[3];
-        const double tile_total = __dadd_rn(w0, w1);
-        const double wex = (warp > 0) ? w0 : 0.0;
+        double wv = (lane < NW) ? sh.red[4 + lane] : 0.0;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            const double other = shfl_up_d(wv, d);
+            wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+        }
+        const double tile_total = shfl_d(wv, NW - 1);
+        double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
+        wex = (warp > 0) ? wex : 0.0;
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
-        unsigned char* Cb = reinterpret_cast<unsigned char*>(sh.C);
 #pragma unroll
-        for (int k = 0; k < kClL; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
-        if (tid == 0) sh.pub_tot = tile_total;
-        cluster.sync();  // C2: tile sums, tile CDFs and states of this step are visible cluster-wide
+        for (int k = 0; k < kClL; ++k) gC[eoff[k]] = __dadd_rn(base, sc[k]);
+        if (tid == 0) {
+            sh.pub_tot = tile_total;
+            // this CTA will receive every tile's CDF and states: arm before anybody can start copying
+            mbar_expect_tx(reinterpret_cast<uint64_t*>(&sh.bar), (uint32_t)CS * 2u * kClTileBytes);
+        }
+        __threadfence();  // scratch writes visible to the other SMs' copy engines
+        cluster.sync();   // C2: every tile is in the scratch, every mbarrier is armed, every tile sum is published
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores before async-proxy (TMA) reads
+            tma_multicast_1d(&sh.C[rank][0], gC, kClTileBytes, &sh.bar, cta_mask);
+            tma_multicast_1d(&sh.X[rank][0], gX, kClTileBytes, &sh.bar, cta_mask);
+        }
 
         // ---- scan of the tile sums (every warp, redundantly): oracle's 1024-lane scan with one item per lane ----
         double tt = (lane < CS) ? peer->pub_tot : 0.0;
@@ -191,10 +236,8 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             sh.clM[t & 31] = M;
             sh.clS[t & 31] = S;
         }
-        if (t == T - 1) break;  // the last resampling does not enter the likelihood
-        __syncthreads();        // E visible to both warps
 
-        // ---- resampling targets -----------------------------------------------------------------
+        // ---- resampling targets (overlap the multicast) --------------------------------------------
         double tau[kClL];
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
@@ -210,44 +253,28 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
 #pragma unroll
             for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(__dadd_rn((double)(i0 + k), u0), sN);
         }
-        // ---- tile of each target: the padded 1024-entry descent always goes left above 16 (padding = S >= tau) ----
-        const int nb = (N + kClTile - 1) / kClTile;
-        int b[kClL];
+        __syncthreads();  // E visible to every warp
+        mbar_wait(reinterpret_cast<uint64_t*>(&sh.bar), (uint32_t)(t & 1));  // the whole filter's CDF and states have landed
+
+        // ---- tile of each target (the padded 1024-entry descent always goes left above 16: padding = S >= tau),
+        //      then the 9-level descent and the gather, all in local shared memory ------------------------
 #pragma unroll
         for (int k = 0; k < kClL; ++k) {
             int bb = 0;
 #pragma unroll
             for (int s = kClMax / 2; s >= 1; s >>= 1) bb += (sh.E[bb + s - 1] < tau[k]) ? s : 0;
-            b[k] = min(bb, nb - 1);
+            bb = min(bb, nb - 1);
+            const double O = (bb > 0) ? sh.E[bb - 1] : 0.0;
+            const double* Ct = sh.C[bb];
+            uint32_t node = 0u;
+#pragma unroll
+            for (int lvl = 0; lvl < K; ++lvl) node = 2u * node + ((__dadd_rn(O, Ct[node]) < tau[k]) ? 2u : 1u);
+            int idx = (int)node - (kClTile - 1);
+            const long long i = (long long)bb * kClTile + idx;
+            if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)bb * kClTile);
+            x[k] = (i0 + k < N) ? sh.X[bb][idx] : 0.0;
         }
-        // ---- descent in the owner's shared memory, then gather its state ---------------------------
-        const unsigned char* pC[kClL];
-        double O[kClL];
-#pragma unroll
-        for (int k = 0; k < kClL; ++k) {
-            pC[k] = reinterpret_cast<const unsigned char*>(cluster.map_shared_rank(&sh, b[k])->C);
-            O[k] = (b[k] > 0) ? sh.E[b[k] - 1] : 0.0;
-        }
-        uint32_t nbp[kClL];
-#pragma unroll
-        for (int k = 0; k < kClL; ++k) nbp[k] = 0u;
-#pragma unroll
-        for (int lvl = 0; lvl < K; ++lvl) {
-#pragma unroll
-            for (int k = 0; k < kClL; ++k) {
-                const double v = __dadd_rn(O[k], *reinterpret_cast<const double*>(pC[k] + nbp[k]));
-                nbp[k] = 2u * nbp[k] + ((v < tau[k]) ? 16u : 8u);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kClL; ++k) {
-            int idx = (int)(nbp[k] >> 3) - (kClTile - 1);
-            long long i = (long long)b[k] * kClTile + idx;
-            if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)b[k] * kClTile);
-            const ClusterShared* owner = cluster.map_shared_rank(&sh, b[k]);
-            x[k] = (i0 + k < N) ? owner->X[t & 1][idx] : 0.0;
-        }
-        cluster.sync();  // C3: every read of this step's CDFs / maxima / sums is done before they are overwritten
+        cluster.sync();  // C3: every CTA is done with this step's shared memory and scratch before they are reused
     }
 
     // ---- epilogue: the cond-likes still buffered -------------------------------------------------

@@ -1,5 +1,5 @@
 """-m gpu: K2, one filter per thread-block cluster (distributed shared memory), against the oracle's tiled order
-with tiles of 512 particles (L = 8, NT = 64) -- bit for bit."""
+with tiles of 512 particles (L = 4, NT = 128) -- bit for bit."""
 import numpy as np
 import pytest
 
@@ -22,12 +22,12 @@ def test_cluster_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     theta = np.stack([th, th * 0.98, th * 1.01])
     out, pf = be.work_batch(theta, R=2, stream_base=30, return_per_filter=True)
     for p in range(3):
-        ref = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=8, NT=64, tiled=True, seed=12,
+        ref = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=4, NT=128, tiled=True, seed=12,
                                  filter_id=30 + 2 * p + r, trace=False)["loglik"] for r in range(2)]
         assert pf[p].tolist() == ref
         assert out[p] == oracle.log_mean_exp(np.array(ref))
     tr = be.trace(theta[:1], stream_base=30, want=("loglik", "cond_like"))
-    ref = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, L=8, NT=64, tiled=True, seed=12, filter_id=30)
+    ref = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, L=4, NT=128, tiled=True, seed=12, filter_id=30)
     assert np.array_equal(tr["cond_like"][0], ref["cond_like"]) and tr["loglik"][0] == ref["loglik"]
     fai = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=12, filter_id=30)
     assert abs(tr["loglik"][0] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
@@ -41,7 +41,7 @@ def test_cluster_pmmh_matches_oracle_driven_chain(oracle, sv_series, gpu_backend
     gpu = be.pmmh_run(start, 2, 8, t0=2, t1=100, c0_diag=0.02, proposal_seed=4)
 
     def ev(th, R_, base):
-        return np.array([oracle.filter_run(th[f // R_], y, 2048, L=8, NT=64, tiled=True, seed=13, filter_id=base + f, trace=False)["loglik"]
+        return np.array([oracle.filter_run(th[f // R_], y, 2048, L=4, NT=128, tiled=True, seed=13, filter_id=base + f, trace=False)["loglik"]
                          for f in range(th.shape[0] * R_)])
     cpu = sb.pmmh_run_custom(sb.MODEL_SV, ev, start, 2, 8, t0=2, t1=100, c0_diag=0.02, proposal_seed=4)
     for k in ("final_theta", "accept_rate", "last_loglik"):
