@@ -160,6 +160,14 @@ int ensure_pinned(ssme_b200_handle h, size_t bytes)
 
 namespace {
 
+const void* cluster_kernel_fn(int model, int res, int nt)
+{
+#define SSME_CL(M, R) (nt == 128 ? (const void*)&cluster_filter_kernel<M, R, 128> : (const void*)&cluster_filter_kernel<M, R, 256>)
+    if (model == SSME_B200_MODEL_SV) return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSV, kResampMultinomial) : SSME_CL(kModelSV, kResampSystematic);
+    return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampMultinomial) : SSME_CL(kModelSVLeverage, kResampSystematic);
+#undef SSME_CL
+}
+
 int next_pow2(int v)
 {
     int p = 1;
@@ -174,19 +182,14 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
     if (F > 0x7fffffffull) return fail(SSME_B200_EINVAL, "too many filters in one launch: %zu", F);
     if (h->cluster) {
         FilterArgs ca = args;
-        const int model = h->cfg.model, res = h->cfg.resampler;
-        const void* fn = model == SSME_B200_MODEL_SV
-                             ? (res == SSME_B200_RESAMP_MULTINOMIAL ? (const void*)&cluster_filter_kernel<kModelSV, kResampMultinomial>
-                                                                    : (const void*)&cluster_filter_kernel<kModelSV, kResampSystematic>)
-                             : (res == SSME_B200_RESAMP_MULTINOMIAL ? (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampMultinomial>
-                                                                    : (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampSystematic>);
+        const void* fn = cluster_kernel_fn(h->cfg.model, h->cfg.resampler, h->NT);
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
         lc.gridDim = dim3((unsigned)(F * (size_t)h->cluster_size));
-        lc.blockDim = dim3(kClNT);
-        lc.dynamicSmemBytes = sizeof(ClusterShared);
+        lc.blockDim = dim3((unsigned)h->NT);
+        lc.dynamicSmemBytes = cluster_smem_bytes(h->NT, h->cluster_size);
         lc.stream = st;
-        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(2 * kClMax * kClTile));
+        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(kClMax * kClL * h->NT));
         if (rc2) return rc2;
         double* scratch = h->d_cluster_scratch;
         cudaLaunchAttribute attr[1];
@@ -254,19 +257,24 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         return fail(SSME_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
                     prop.minor);
 
-    const bool spill = cfg->force_global_memory != 0 || cfg->num_particles > 8192;
-    const bool use_cluster = cfg->use_cluster != 0 && !spill;
+    // K2 (one filter per thread-block cluster) takes up to 16 tiles of 4*threads particles
+    const int cl_nt = (cfg->threads_per_filter == 128 || cfg->threads_per_filter == 256) ? cfg->threads_per_filter : 256;
+    const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0 && cfg->num_particles <= kClMax * kClL * cl_nt;
+    const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
     if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL && (use_cluster || spill))
         return fail(SSME_B200_EUNSUPPORTED, "the sorted-multinomial resampler is built into the resident kernel only (N <= 8192, no cluster)");
     if (use_cluster) {
-        // K2: tiles of 512 particles, one CTA each, cluster of ceil(N/512) CTAs (cluster_kernel.cuh)
+        // K2: tiles of 4*NT particles, one CTA each, cluster of ceil(N/tile) CTAs (cluster_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");
         if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel uses the on-device Philox streams");
-        if (cfg->num_particles <= kClTile) return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", kClTile);
+        if (cfg->threads_per_filter != 0 && cfg->threads_per_filter != cl_nt)
+            return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel runs 128 or 256 threads per tile (got %d)", cfg->threads_per_filter);
+        if (cfg->num_particles <= kClL * cl_nt)
+            return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", kClL * cl_nt);
         L = kClL;
-        NT = kClNT;
+        NT = cl_nt;
     } else if (spill) {
         // K3: particles in HBM, tiles of 4096 (spill_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels resample at every step (resample_every = 1)");
@@ -305,17 +313,14 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->debug = dbg;
     h->spill = spill;
     h->cluster = use_cluster;
-    h->cluster_size = use_cluster ? (cfg->num_particles + kClTile - 1) / kClTile : 1;
+    h->cluster_size = use_cluster ? (cfg->num_particles + kClL * NT - 1) / (kClL * NT) : 1;
     int occ = 0;
     if (use_cluster) {
-        const void* fns[] = {(const void*)&cluster_filter_kernel<kModelSV, kResampMultinomial>, (const void*)&cluster_filter_kernel<kModelSV, kResampSystematic>,
-                             (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampMultinomial>,
-                             (const void*)&cluster_filter_kernel<kModelSVLeverage, kResampSystematic>};
-        for (const void* fn : fns) {
-            e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterShared));
-            if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
-        }
+        const void* fn = cluster_kernel_fn(cfg->model, cfg->resampler, NT);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(NT, kClMax));
+        if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
     } else if (!spill) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
         if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e)); }

@@ -65,7 +65,7 @@ struct ssme_b200_filter_s {
     // one filter per thread-block cluster (K2)
     bool cluster = false;
     int cluster_size = 1;
-    double* d_cluster_scratch = nullptr;  // [filters][2][16][512]: L2-resident staging of the tiles the clusters multicast
+    double* d_cluster_scratch = nullptr;  // [filters][16][512]: L2-resident staging of the CDF tiles the clusters multicast
     size_t cap_cluster_scratch = 0;
     // N beyond one CTA: particles live in HBM
     bool spill = false;

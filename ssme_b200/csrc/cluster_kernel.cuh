@@ -4,16 +4,21 @@
 // N = 8192, which is what paces PMMH when there are fewer chains than SMs (BASELINE.json config 3:
 // 64 chains x 8192 particles; 8 chains per GPU on 8 GPUs).  K2 spreads one filter over up to 16 SMs:
 // CTA r of the cluster owns the tile of particles r*512 .. r*512+511 (128 threads x 4).  Per step:
-//   max of the log-weights   each CTA publishes its tile maximum in its shared memory, cluster barrier, every CTA
-//                            reads all of them through distributed shared memory
+//   max of the log-weights   each CTA PUSHES its tile maximum into every peer's shared memory with st.async, which
+//                            completes bytes on the peer's mbarrier: one one-way DSMEM hop, no cluster barrier
 //   CDF and states           each CTA writes its tile-local CDF (breadth-first) and states to an L2-resident scratch
 //                            and then MULTICASTS them with one bulk TMA copy each
 //                            (cp.async.bulk ... .multicast::cluster) into the shared memory of every CTA of the cluster:
 //                            after one mbarrier wait every CTA holds the whole filter's CDF and states locally
-//   resampling               tile ends scanned redundantly by every CTA; each slot's 4+9-level descent and its gather
+//   tile sums                pushed the same way onto the mbarrier the multicast copies complete on
+//   resampling               tile ends scanned redundantly by every warp; each slot's 4+9-level descent and its gather
 //                            run in LOCAL shared memory (the first version probed the owner's shared memory with
 //                            ld.shared::cluster: 5120 remote 8-byte loads per CTA per step, slower than K1 --
 //                            profiles/r1_k2_cluster.md)
+// There is NO cluster barrier inside the time loop (barrier.cluster.arrive.release is a MEMBAR.ALL.GPU: three of them
+// per step cost more than the arithmetic).  Ordering comes from the data flow alone: a CTA can issue step t+1's
+// multicast only after it holds every peer's step-t+1 maximum, which a peer pushes only after its own step-t search
+// and gather have finished -- so nobody's shared memory is overwritten while it is still being read.
 // Same per-particle arithmetic and Philox streams as K1/K3; scan and search order = the oracle's "tiled" order with
 // tiles of 512 (oracle/pf_oracle.c: tiled_build / tiled_search with L = 4, NT = 128), bit-identical to it, and
 // therefore independent of how the clusters are spread over GPUs.
@@ -27,21 +32,43 @@ namespace ssme {
 
 namespace cg = cooperative_groups;
 
-constexpr int kClL = 4;
-constexpr int kClNT = 128;
-constexpr int kClTile = kClL * kClNT;  // 512 particles per CTA
-constexpr int kClMax = 16;             // CTAs per cluster (non-portable size, opt-in)
-constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
+constexpr int kClL = 4;    // particles per thread
+constexpr int kClMax = 16; // CTAs per cluster (non-portable size, opt-in)
+constexpr int kClMaxWarps = 8;
 
+// Fixed part of a CTA's shared memory; behind it: X[2][tile] (THIS tile's states, double-buffered by step parity, peers
+// gather from it through DSMEM) and C[cluster size][tile] (every tile's local inclusive CDF in breadth-first order,
+// filled by the multicast copies).
 struct ClusterShared {
-    double C[kClMax][kClTile];  // every tile's local inclusive CDF, breadth-first order (filled by multicast)
-    double X[kClMax][kClTile];  // every tile's states (filled by multicast)
-    double E[kClMax];           // inclusive tile ends
-    double red[8];
-    double pub_max, pub_tot;    // published to the cluster through DSMEM
+    double E[kClMaxWarps][kClMax];  // inclusive tile ends, one copy per warp
+    double red[2 * kClMaxWarps];
+    double maxes[kClMax];       // tile maxima, pushed by the peers (st.async)
+    double tots[kClMax];        // tile sums, pushed by the peers (st.async)
     double clM[32], clS[32];
-    unsigned long long bar;     // mbarrier of the multicast copies
+    unsigned long long bar_max;  // completes when every peer's maximum has landed
+    unsigned long long bar_cdf;  // completes when every peer's tile sum, CDF tile and state tile have landed
 };
+
+// shared::cluster address of `local` (a shared::cta address of this CTA's window) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t cluster_addr(uint32_t local, uint32_t cta)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(cta));
+    return r;
+}
+// remote 8-byte store that completes 8 bytes on the destination CTA's mbarrier
+__device__ __forceinline__ double ld_cluster_f64(uint32_t remote_addr)
+{
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
 
 __device__ __forceinline__ void tma_multicast_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar, uint16_t mask)
 {
@@ -52,14 +79,24 @@ __device__ __forceinline__ void tma_multicast_1d(void* dst_smem, const void* src
         : "memory");
 }
 
-template <int MODEL, int RESAMP>
-__global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
+constexpr size_t cluster_smem_bytes(int nt, int cluster_size)
 {
+    return sizeof(ClusterShared) + sizeof(double) * (size_t)(kClL * nt) * (size_t)(2 + cluster_size);
+}
+
+template <int MODEL, int RESAMP, int NT>
+__global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
+{
+    static_assert(NT == 128 || NT == 256, "tile of 512 or 1024 particles");
     constexpr int OS = obs_stride(MODEL);
-    constexpr int K = 9;  // log2(kClTile)
-    constexpr int NW = kClNT / 32;
+    constexpr int kClTile = kClL * NT;
+    constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
+    constexpr int K = (NT == 128) ? 9 : 10;  // log2(kClTile)
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char cl_smem[];
     ClusterShared& sh = *reinterpret_cast<ClusterShared*>(cl_smem);
+    double* const shX = reinterpret_cast<double*>(cl_smem + sizeof(ClusterShared));  // [2][tile]
+    double* const shC = shX + 2 * kClTile;                                            // [CS][tile]
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -69,9 +106,9 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
     const int N = a.N, T = a.T;
     const int i0 = rank * kClTile + tid * kClL;  // first particle of this thread (index within the filter)
     const int l0 = tid * kClL;                   // ... within the tile
-    // L2-resident scratch of this filter: [CS][512] CDF tiles, then [CS][512] state tiles
-    double* gC = scratch + floc * (size_t)(2 * kClMax * kClTile) + (size_t)rank * kClTile;
-    double* gX = gC + (size_t)kClMax * kClTile;
+    // L2-resident scratch of this filter: [CS][512] CDF tiles (the source of the multicast)
+    double* gC = scratch + floc * (size_t)(kClMax * kClTile) + (size_t)rank * kClTile;
+    const uint32_t x_base = smem_u32(shX);
 
     uint32_t eoff[kClL];
 #pragma unroll
@@ -91,10 +128,18 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
     const uint16_t cta_mask = (uint16_t)((1u << CS) - 1u);
     const int nb = (N + kClTile - 1) / kClTile;
 
-    const ClusterShared* peer = cluster.map_shared_rank(&sh, (lane < CS) ? lane : 0);
+    uint64_t* const bar_max = reinterpret_cast<uint64_t*>(&sh.bar_max);
+    uint64_t* const bar_cdf = reinterpret_cast<uint64_t*>(&sh.bar_cdf);
+    // lane p < CS of warp 0 pushes this CTA's tile maximum / sum into slot [rank] of peer p
+    const uint32_t peer_cta = (uint32_t)((lane < CS) ? lane : 0);
+    const uint32_t peer_max_slot = cluster_addr(smem_u32(&sh.maxes[rank]), peer_cta);
+    const uint32_t peer_tot_slot = cluster_addr(smem_u32(&sh.tots[rank]), peer_cta);
+    const uint32_t peer_bar_max = cluster_addr(smem_u32(bar_max), peer_cta);
+    const uint32_t peer_bar_cdf = cluster_addr(smem_u32(bar_cdf), peer_cta);
 
     if (tid == 0) {
-        mbar_init(reinterpret_cast<uint64_t*>(&sh.bar), 1);
+        mbar_init(bar_max, 1);
+        mbar_init(bar_cdf, 1);
         mbar_fence_init();
     }
     double x[kClL];
@@ -136,11 +181,11 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;
         }
-        // this tile's states go to the scratch now (multicast later together with the CDF)
+        // this tile's states: buffer t&1 (peers may still be gathering step t-1 from the other one)
 #pragma unroll
-        for (int k = 0; k < kClL; k += 2) *reinterpret_cast<double2*>(gX + l0 + k) = make_double2(x[k], x[k + 1]);
+        for (int k = 0; k < kClL; k += 2) *reinterpret_cast<double2*>(&shX[(t & 1) * kClTile + l0 + k]) = make_double2(x[k], x[k + 1]);
 
-        // ---- filter-wide max: tile max -> published -> all tiles' maxima read through DSMEM --------
+        // ---- filter-wide max: tile max -> pushed into every peer -> wait for all 16 to land --------
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             const double other = shfl_xor_d(mloc, d);
@@ -148,14 +193,15 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         }
         if (lane == 0) sh.red[warp] = mloc;
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             double m = sh.red[0];
 #pragma unroll
             for (int g = 1; g < NW; ++g) m = (sh.red[g] > m) ? sh.red[g] : m;
-            sh.pub_max = m;
+            if (lane == 0) mbar_expect_tx(bar_max, (uint32_t)CS * 8u);
+            if (lane < CS) st_async_f64(peer_max_slot, m, peer_bar_max);
         }
-        cluster.sync();  // C1
-        double M = (lane < CS) ? peer->pub_max : ninf;
+        mbar_wait(bar_max, (uint32_t)(t & 1));
+        double M = (lane < CS) ? sh.maxes[lane] : ninf;
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             const double other = shfl_xor_d(M, d);
@@ -190,9 +236,9 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
             const double other = shfl_up_d(incl, d);
             incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
         }
-        if (lane == 31) sh.red[4 + warp] = incl;
+        if (lane == 31) sh.red[kClMaxWarps + warp] = incl;
         __syncthreads();
-        double wv = (lane < NW) ? sh.red[4 + lane] : 0.0;
+        double wv = (lane < NW) ? sh.red[kClMaxWarps + lane] : 0.0;
 #pragma unroll
         for (int d = 1; d < NW; d <<= 1) {
             const double other = shfl_up_d(wv, d);
@@ -206,21 +252,36 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         const double base = __dadd_rn(wex, lex);
 #pragma unroll
         for (int k = 0; k < kClL; ++k) gC[eoff[k]] = __dadd_rn(base, sc[k]);
-        if (tid == 0) {
-            sh.pub_tot = tile_total;
-            // this CTA will receive every tile's CDF and states: arm before anybody can start copying
-            mbar_expect_tx(reinterpret_cast<uint64_t*>(&sh.bar), (uint32_t)CS * 2u * kClTileBytes);
-        }
-        __threadfence();  // scratch writes visible to the other SMs' copy engines
-        cluster.sync();   // C2: every tile is in the scratch, every mbarrier is armed, every tile sum is published
-        if (tid == 0) {
-            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores before async-proxy (TMA) reads
-            tma_multicast_1d(&sh.C[rank][0], gC, kClTileBytes, &sh.bar, cta_mask);
-            tma_multicast_1d(&sh.X[rank][0], gX, kClTileBytes, &sh.bar, cta_mask);
+        // this CTA's own scratch writes (generic proxy) are read back by its own bulk copy (async proxy); the same
+        // fence (a gpu-scope membar) orders this step's X stores before the pushes that let the peers read them
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            // peers may complete bytes before this arrives: the transaction count just goes negative for a while
+            if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)CS * (kClTileBytes + 8u));
+            if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
+            if (lane == 0) {
+                tma_multicast_1d(shC + rank * kClTile, gC, kClTileBytes, &sh.bar_cdf, cta_mask);
+            }
         }
 
+        // ---- resampling uniforms (overlap the copies) ------------------------------------------------
+        double tau[kClL];
+        if (RESAMP == kResampMultinomial) {
+#pragma unroll
+            for (int q = 0; q < kClL / 2; ++q) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                tau[2 * q + 0] = uniform53(r.x, r.y);
+                tau[2 * q + 1] = uniform53(r.z, r.w);
+            }
+        } else {
+            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
+            tau[0] = uniform53(r.x, r.y);
+        }
+        mbar_wait(bar_cdf, (uint32_t)(t & 1));  // every tile sum, the whole filter's CDF and states have landed
+
         // ---- scan of the tile sums (every warp, redundantly): oracle's 1024-lane scan with one item per lane ----
-        double tt = (lane < CS) ? peer->pub_tot : 0.0;
+        double tt = (lane < CS) ? sh.tots[lane] : 0.0;
         double tincl = tt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -231,30 +292,22 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         double tlex = shfl_up_d(tincl, 1);
         tlex = (lane > 0) ? tlex : 0.0;
         const double Eb = __dadd_rn(__dadd_rn(0.0, tlex), tt);  // inclusive end of tile `lane`
-        if (warp == 0 && lane < kClMax) sh.E[lane] = Eb;
+        double* const Ew = sh.E[warp];
+        if (lane < kClMax) Ew[lane] = Eb;
         if (rank == 0 && tid == 0) {
             sh.clM[t & 31] = M;
             sh.clS[t & 31] = S;
         }
-
-        // ---- resampling targets (overlap the multicast) --------------------------------------------
-        double tau[kClL];
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
-            for (int q = 0; q < kClL / 2; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
-                tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
-                tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
-            }
+            for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(tau[k], S);
         } else {
-            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
-            const double u0 = uniform53(r.x, r.y);
+            const double u0 = tau[0];
             const double sN = __ddiv_rn(S, dN);
 #pragma unroll
             for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(__dadd_rn((double)(i0 + k), u0), sN);
         }
-        __syncthreads();  // E visible to every warp
-        mbar_wait(reinterpret_cast<uint64_t*>(&sh.bar), (uint32_t)(t & 1));  // the whole filter's CDF and states have landed
+        __syncwarp();  // this warp's copy of E
 
         // ---- tile of each target (the padded 1024-entry descent always goes left above 16: padding = S >= tau),
         //      then the 9-level descent and the gather, all in local shared memory ------------------------
@@ -262,19 +315,20 @@ __global__ void __launch_bounds__(kClNT) cluster_filter_kernel(const FilterArgs 
         for (int k = 0; k < kClL; ++k) {
             int bb = 0;
 #pragma unroll
-            for (int s = kClMax / 2; s >= 1; s >>= 1) bb += (sh.E[bb + s - 1] < tau[k]) ? s : 0;
+            for (int s = kClMax / 2; s >= 1; s >>= 1) bb += (Ew[bb + s - 1] < tau[k]) ? s : 0;
             bb = min(bb, nb - 1);
-            const double O = (bb > 0) ? sh.E[bb - 1] : 0.0;
-            const double* Ct = sh.C[bb];
+            const double O = (bb > 0) ? Ew[bb - 1] : 0.0;
+            const double* Ct = shC + bb * kClTile;
             uint32_t node = 0u;
 #pragma unroll
             for (int lvl = 0; lvl < K; ++lvl) node = 2u * node + ((__dadd_rn(O, Ct[node]) < tau[k]) ? 2u : 1u);
             int idx = (int)node - (kClTile - 1);
             const long long i = (long long)bb * kClTile + idx;
             if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)bb * kClTile);
-            x[k] = (i0 + k < N) ? sh.X[bb][idx] : 0.0;
+            const double xa = ld_cluster_f64(cluster_addr(x_base + (uint32_t)(((t & 1) * kClTile + idx) * 8), (uint32_t)bb));
+            x[k] = (i0 + k < N) ? xa : 0.0;
         }
-        cluster.sync();  // C3: every CTA is done with this step's shared memory and scratch before they are reused
+        __syncwarp();  // E is rewritten next step
     }
 
     // ---- epilogue: the cond-likes still buffered -------------------------------------------------
