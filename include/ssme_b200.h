@@ -68,8 +68,9 @@ typedef struct {
     int32_t filters_per_sm;      /* resident CTAs per SM; 0 = library default */
     int32_t force_global_memory; /* 1 = use the global-memory ("spilled") kernels even when N fits one CTA (parity runs);
                                     they are selected automatically for N > 8192 */
-    int32_t use_cluster;         /* 1 = one filter per thread-block cluster (tiles of 512 particles, one per SM, up to 16):
-                                    lower time-step latency when there are fewer filters than SMs (512 < N <= 8192) */
+    int32_t use_cluster;         /* 1 = one filter per thread-block cluster: tiles of 4*threads_per_filter particles
+                                    (threads 256 by default, or 128), one tile per SM, up to 16 tiles (N <= 16384):
+                                    2-3x lower time-step latency when a GPU runs fewer filters than it has SMs */
     int32_t reserved;
 } ssme_b200_config;
 
