@@ -175,6 +175,21 @@ int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double
                         double* loglik_host, double* cond_like_host, double* theta_bar_host, double* final_mean_host,
                         int32_t* ancestors_host);
 
+/* The same call with the form of the Liu-West filter selected:
+ *   SSME_B200_LW_SISR  LWFilter2WithCovs::filter (liu_west_filter.h:2191-2343): bootstrap proposal -- what
+ *                      ssme_b200_lw_filter runs;
+ *   SSME_B200_LW_APF   LWFilterWithCovs::filter (liu_west_filter.h:971-1159), the auxiliary particle filter of the
+ *                      Liu-West paper, on svol_lw_1_par (test/test_liu_west.cpp:83-157): first-stage weights
+ *                      log g(y_t | propMu(x_i, z_t, theta_i)), indices k_j drawn from them (k_gen::sample), slot j
+ *                      continues particle k_j with weight log g(y_t | x'_j) - log g(y_t | propMu(x_k)), and
+ *                      log p(y_t | y_{1:t-1}) joins both stages (:1056-1058).
+ * aux_index [T][N] (may be NULL; APF only) receives the k_j, row 0 zero. */
+#define SSME_B200_LW_SISR 0
+#define SSME_B200_LW_APF 1
+int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                             uint64_t stream_id, double* loglik_host, double* cond_like_host, double* theta_bar_host,
+                             double* final_mean_host, int32_t* ancestors_host, int32_t* aux_index_host);
+
 /* ---- the PMMH host loop, in C++ behind the C ABI (for hosts that cannot include the C++ headers) -------
  * Replaces: do_ada_pmmh_univ_svol + ada_pmmh_mvn::commence_sampling (example/estimate_univ_svol.h:139-178,
  * ada_pmmh_mvn.h:325-372) for `num_chains` chains advanced in lock step (include/ssme_b200/pmmh_multichain.hpp).

@@ -1,6 +1,7 @@
 // include/ssme_b200/liu_west_filter.hpp -- Liu-West joint state / parameter filter on the GPU backend.
 //
-// Mirrors the user-facing part of LWFilter2WithCovs (include/ssme/liu_west_filter.h:1949-2188): constructed from the
+// Mirrors the user-facing part of LWFilter2WithCovs (include/ssme/liu_west_filter.h:1949-2188) and of LWFilterWithCovs
+// (:741-968, the auxiliary-particle form; LWFilterWithCovs_svol below): constructed from the
 // transform names, delta and the resampling schedule (:2100-2113), `getLogCondLike()` (:2180-2184), and the prior the
 // user's subclass supplies through `paramPriorSamp` (test/test_liu_west.cpp:339-349: independent uniforms).  The
 // reference is streaming -- `filter(y_t, z_t)` once per observation, with the state-space model given as seven pure
@@ -19,14 +20,27 @@
 
 namespace ssme_b200 {
 
+namespace detail {
+template <size_t nparts, typename float_t, int form>
+class lw_svol_base;
+}
+
+// LWFilter2WithCovs on svol_lw_2_par (SISR form, bootstrap proposal)
 template <size_t nparts, typename float_t = double>
-class LWFilter2WithCovs_svol {
+using LWFilter2WithCovs_svol = detail::lw_svol_base<nparts, float_t, SSME_B200_LW_SISR>;
+// LWFilterWithCovs on svol_lw_1_par (auxiliary particle filter: first-stage weights through propMu; test_liu_west.cpp:26-157)
+template <size_t nparts, typename float_t = double>
+using LWFilterWithCovs_svol = detail::lw_svol_base<nparts, float_t, SSME_B200_LW_APF>;
+
+namespace detail {
+template <size_t nparts, typename float_t, int form>
+class lw_svol_base {
 public:
     using psv = vec<float_t, 4>;  // phi, mu, sigma, rho
 
     // transforms must be {"logit", "null", "log", "twice_fisher"} -- the ones svol_lw_2_par passes (test_liu_west.cpp:263)
-    LWFilter2WithCovs_svol(std::vector<std::string> transforms, float_t delta, const psv& prior_lower, const psv& prior_upper,
-                           const unsigned int& rs = 1, const gpu_options& opt = gpu_options())
+    lw_svol_base(std::vector<std::string> transforms, float_t delta, const psv& prior_lower, const psv& prior_upper,
+                 const unsigned int& rs = 1, const gpu_options& opt = gpu_options())
         : m_delta(delta), m_lo(prior_lower), m_hi(prior_upper)
     {
         const std::vector<std::string> want{"logit", "null", "log", "twice_fisher"};
@@ -45,9 +59,9 @@ public:
         c.force_global_memory = 1;
         throw_on_error(ssme_b200_create(&c, &m_h));
     }
-    ~LWFilter2WithCovs_svol() { ssme_b200_destroy(m_h); }
-    LWFilter2WithCovs_svol(const LWFilter2WithCovs_svol&) = delete;
-    LWFilter2WithCovs_svol& operator=(const LWFilter2WithCovs_svol&) = delete;
+    ~lw_svol_base() { ssme_b200_destroy(m_h); }
+    lw_svol_base(const lw_svol_base&) = delete;
+    lw_svol_base& operator=(const lw_svol_base&) = delete;
 
     // filter(obs_data, cov_data) for t = 0 .. T-1 in one call; cov[t] is the covariate z_t (the lagged observation)
     void filter_series(const std::vector<float_t>& obs, const std::vector<float_t>& cov, std::uint64_t stream_id = 0)
@@ -60,8 +74,8 @@ public:
         m_theta_bar.assign(obs.size() * 4, 0.0);
         double lo[4], hi[4];
         for (int k = 0; k < 4; ++k) { lo[k] = (double)m_lo(k); hi[k] = (double)m_hi(k); }
-        throw_on_error(ssme_b200_lw_filter(m_h, lo, hi, (double)m_delta, stream_id, &m_loglik, m_cond_like.data(), m_theta_bar.data(),
-                                           m_final_mean.data(), nullptr));
+        throw_on_error(ssme_b200_lw_filter_form(m_h, form, lo, hi, (double)m_delta, stream_id, &m_loglik, m_cond_like.data(),
+                                                m_theta_bar.data(), m_final_mean.data(), nullptr, nullptr));
     }
 
     // log p(y_t | y_{1:t-1}) of step t (the reference returns the latest one; :2180-2184)
@@ -84,6 +98,7 @@ private:
     std::vector<double> m_cond_like, m_theta_bar;
     std::array<double, 4> m_final_mean{};
 };
+}  // namespace detail
 
 }  // namespace ssme_b200
 #endif

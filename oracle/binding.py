@@ -89,9 +89,9 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
 
 
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
-                  cov=None, trace=True, tiled=2):
-    """Liu-West filter (LWFilter2WithCovs on the SV-with-leverage model); returns dict(loglik, cond_like, theta_bar,
-    final_mean, ancestors, margin)."""
+                  cov=None, trace=True, tiled=2, form="sisr"):
+    """Liu-West filter on the SV-with-leverage model; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary
+    particle filter).  Returns dict(loglik, cond_like, theta_bar, final_mean, ancestors, aux_index, margin)."""
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
     hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
@@ -101,11 +101,17 @@ def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH
     ll, mg = C.c_double(0), C.c_double(0)
     cl, tb, fm = np.empty(T), np.zeros((T, 4)), np.empty(4)
     anc = np.empty((T, N), dtype=np.int32) if trace else None
-    rc = lib().ssme_oracle_lw_filter(C.byref(cfg), _dp(lo), _dp(hi), delta, _dp(y), T, _dp(cov), C.byref(ll), _dp(cl), _dp(tb), _dp(fm),
-                                     anc.ctypes.data_as(C.POINTER(C.c_int32)) if trace else None, C.byref(mg))
+    aux = np.zeros((T, N), dtype=np.int32) if trace else None
+    fn = lib().ssme_oracle_lw_filter_form
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = fn(C.cast(C.byref(cfg), C.c_void_p), {"sisr": 0, "apf": 1}[form], vp(lo), vp(hi), delta, vp(y), T, vp(cov),
+            C.cast(C.byref(ll), C.c_void_p), vp(cl), vp(tb), vp(fm), vp(anc), vp(aux), C.cast(C.byref(mg), C.c_void_p))
     if rc != 0:
-        raise ValueError("ssme_oracle_lw_filter failed with %d" % rc)
-    return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "margin": mg.value}
+        raise ValueError("ssme_oracle_lw_filter_form failed with %d" % rc)
+    return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux, "margin": mg.value}
 
 
 def log_mean_exp(v, arithmetic=ARITH_CANONICAL):

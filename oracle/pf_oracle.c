@@ -563,9 +563,20 @@ static double lw_trans(int type, double p, int canonical)
     }
 }
 
-int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, const double* prior_hi, double delta,
-                          const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
-                          double* theta_bar, double* final_mean, int32_t* ancestors, double* tie_margin)
+/* form 0: LWFilter2WithCovs::filter (liu_west_filter.h:2191-2343; SISR, bootstrap proposal).
+ * form 1: LWFilterWithCovs::filter  (liu_west_filter.h:971-1159; auxiliary particle filter):
+ *   first-stage weights  lfs_i = lw_i + log g(y_t | propMu(x_i, z_t, theta_i))                       (:985-1000)
+ *   auxiliary indices    k_j ~ discrete(exp(lfs - max)) i.i.d.  (k_gen::sample, :1012)
+ *   for slot j           theta'_j ~ N(a theta_k + (1-a) thetaBar, h^2 V_t),  x'_j ~ f(. | x_k, z_t, theta'_j),
+ *                        lw_j = log g(y_t | x'_j) - log g(y_t | propMu(x_k, z_t, theta_k))             (:1025-1042)
+ *   log p(y_t | y_{1:t-1}) = m1 + log S1 + m2 + log S2 - 2 m3 - 2 log S3                               (:1056-1058)
+ *   with rs = 1 the weights entering a step are all zero: m3 = 0, S3 = N, and the second term of lw_j is lfs_k itself.
+ *   The model of the reference's test (svol_lw_1_par, test/test_liu_west.cpp:83-157) has a parameter-free log g, so the
+ *   untransformed/transformed mix the reference feeds it (:997) does not enter.
+ *   aux_index[T][N] (optional) receives the k_j; row 0 unused. */
+int ssme_oracle_lw_filter_form(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                               const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
+                               double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin)
 {
     static const int TT[4] = {2, 0, 3, 1}; /* logit, null, log, twice_fisher */
     if (!cfg || !prior_lo || !prior_hi || !y || T < 0) return -1;
@@ -573,6 +584,7 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
     const int canonical = (cfg->arithmetic == SSME_OR_ARITH_CANONICAL);
     if (N < 1 || (canonical && (!cfg->tiled || L < 1))) return -2;
     if (cfg->resampler != SSME_OR_RESAMP_MULTINOMIAL && cfg->resampler != SSME_OR_RESAMP_SYSTEMATIC) return -4;
+    if (form != 0 && form != 1) return -5;
     const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
     const uint32_t utag = 1u + (uint32_t)cfg->resampler;
     const double a = (3.0 * delta - 1.0) / (2.0 * delta), h2 = 1.0 - a * a, oma = 1.0 - a;
@@ -586,6 +598,8 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
     double* C = (double*)malloc(sizeof(double) * (size_t)N);
     double* tmp = (double*)malloc(sizeof(double) * (size_t)N);
     int32_t* anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    double* lfs = (double*)malloc(sizeof(double) * (size_t)N);
+    int32_t* ks = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
     double loglik = 0.0, margin = INFINITY;
     const double logN = canonical ? dm_log((double)N) : log((double)N);
     const double c0 = -DM_HALF_LOG_2PI;
@@ -624,6 +638,54 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
                     Lc[i][j] = (i == j) ? sqrt(sacc) : sacc / Lc[j][j];
                 }
             if (theta_bar) for (int k = 0; k < 4; ++k) theta_bar[t * 4 + k] = tb[k];
+        }
+        double fs_M2 = 0.0, fs_logS2 = 0.0; /* first stage: max and log of the sum */
+        if (form == 1 && t > 0) {
+            const double hh = (yt * yt) * 0.5;
+            double M2 = -INFINITY;
+            for (int32_t i = 0; i < N; ++i) {
+                double p[4];
+                for (int k = 0; k < 4; ++k) p[k] = lw_inv_trans(TT[k], th[(size_t)k * N + i], canonical);
+                if (canonical) {
+                    double e2 = dm_exp(-0.5 * x[i]);
+                    double cz = (p[3] * p[2]) * ct;
+                    double mu = fma(cz, e2, fma(p[0], x[i] - p[1], p[1]));
+                    lfs[i] = fma(-hh, dm_exp(-mu), fma(-0.5, mu, c0));
+                } else {
+                    double mu = p[1] + p[0] * (x[i] - p[1]);
+                    mu += ct * p[3] * p[2] * exp(-.5 * x[i]);
+                    lfs[i] = 0.0 + faithful_log_norm(yt, 0.0, exp(.5 * mu));
+                }
+                if (lfs[i] > M2) M2 = lfs[i];
+            }
+            double S2;
+            if (canonical) {
+                for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lfs[i] - M2);
+                tiled_build(&tc, w);
+                S2 = tc.S;
+                fs_M2 = M2; fs_logS2 = dm_log(S2);
+            } else {
+                S2 = 0.0;
+                for (int32_t i = 0; i < N; ++i) { w[i] = exp(lfs[i] - M2); S2 += w[i]; }
+                double acc = 0.0;
+                for (int32_t i = 0; i < N; ++i) { acc += w[i] / S2; C[i] = acc; }
+                C[N - 1] = 1.0;
+                fs_M2 = M2; fs_logS2 = log(S2);
+            }
+            for (int32_t j = 0; j < N; ++j) {
+                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, 6u);
+                ks[j] = canonical ? tiled_search(&tc, u * S2) : lower_bound_idx(C, N, u);
+            }
+            if (aux_index) for (int32_t j = 0; j < N; ++j) aux_index[t * N + j] = ks[j];
+            /* the loop below reads particle i's parents through xn: gather them now */
+            for (int32_t j = 0; j < N; ++j) {
+                xn[j] = x[ks[j]];
+                for (int k = 0; k < 4; ++k) xn[(size_t)(k + 1) * N + j] = th[(size_t)k * N + ks[j]];
+            }
+            for (int32_t j = 0; j < N; ++j) {
+                x[j] = xn[j];
+                for (int k = 0; k < 4; ++k) th[(size_t)k * N + j] = xn[(size_t)(k + 1) * N + j];
+            }
         }
         for (int32_t i = 0; i < N; ++i) {
             double z = ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
@@ -669,6 +731,7 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
             } else {
                 lw[i] = faithful_log_norm(yt, 0.0, exp(.5 * x[i]));
             }
+            if (form == 1 && t > 0) lw[i] = lw[i] - lfs[ks[i]];
         }
         double M = -INFINITY;
         for (int32_t i = 0; i < N; ++i) if (lw[i] > M) M = lw[i];
@@ -686,7 +749,8 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
             C[N - 1] = 1.0;
         }
         const double logS = canonical ? dm_log(S) : log(S);
-        const double cl = (t == 0) ? -logN + M + logS : M + logS - 0.0 - logN;
+        double cl = (t == 0) ? -logN + M + logS : M + logS - 0.0 - logN;
+        if (form == 1 && t > 0) cl = canonical ? ((M + logS) + (fs_M2 + fs_logS2)) - 2.0 * logN : M + logS + fs_M2 + fs_logS2 - 2 * 0.0 - 2 * logN;
         if (cond_like) cond_like[t] = cl;
         loglik += cl;
         const double total = canonical ? S : 1.0;
@@ -724,8 +788,16 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
     if (canonical) tiled_free(&tc);
     if (loglik_out) *loglik_out = loglik;
     if (tie_margin) *tie_margin = margin;
-    free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc);
+    free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc); free(lfs); free(ks);
     return 0;
+}
+
+int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, const double* prior_hi, double delta,
+                          const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
+                          double* theta_bar, double* final_mean, int32_t* ancestors, double* tie_margin)
+{
+    return ssme_oracle_lw_filter_form(cfg, 0, prior_lo, prior_hi, delta, y, T, cov, loglik_out, cond_like, theta_bar, final_mean,
+                                      ancestors, NULL, tie_margin);
 }
 
 /* thread_pool.h:263-268 */

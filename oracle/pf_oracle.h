@@ -91,6 +91,12 @@ int ssme_oracle_lw_filter(const ssme_oracle_cfg* cfg, const double* prior_lo, co
                           const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
                           double* theta_bar, double* final_mean, int32_t* ancestors, double* tie_margin);
 
+/* form 0 = the above; form 1 = the auxiliary-particle form LWFilterWithCovs::filter (liu_west_filter.h:971-1159) on
+ * svol_lw_1_par (test/test_liu_west.cpp:83-157); aux_index[T][N] (optional) receives the first-stage indices k_j. */
+int ssme_oracle_lw_filter_form(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                               const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
+                               double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin);
+
 /* canonical sum of v[0..n): tile partials (lane-local sequential over L, butterfly over the 32 lanes, sequential
  * over the warps of the tile), then the tile partials by one CTA of 1024 lanes the same way */
 double ssme_oracle_canonical_sum(const double* v, int32_t n, int32_t L, int32_t nt);

@@ -97,6 +97,7 @@ def load_library():
     lib.ssme_b200_spill_ipc_export.argtypes = [H, C.POINTER(C.c_uint8)]
     lib.ssme_b200_spill_ipc_import.argtypes = [H, C.POINTER(C.c_uint8)]
     lib.ssme_b200_lw_filter.argtypes = [H, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip]
+    lib.ssme_b200_lw_filter_form.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip, ip]
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
@@ -287,16 +288,19 @@ class ParticleFilterBackend:
         _check(self._lib.ssme_b200_loglike_batch_sharded(self._h, _dptr(theta), P, R, stream_base, _dptr(out), _dptr(pf)))
         return out, pf.reshape(P, R)
 
-    def lw_filter(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, want_ancestors: bool = False):
-        """LWFilter2WithCovs over the whole series: dict(loglik, cond_like[T], theta_bar[T,4], final_mean[4], ancestors)."""
+    def lw_filter(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, want_ancestors: bool = False, form: str = "sisr"):
+        """Liu-West filter over the whole series; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary
+        particle filter): dict(loglik, cond_like[T], theta_bar[T,4], final_mean[4], ancestors, aux_index)."""
         lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
         hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
         ll = C.c_double()
         cl, tb, fm = np.empty(self.T), np.empty((self.T, 4)), np.empty(4)
         anc = np.empty((self.T, self.cfg.num_particles), dtype=np.int32) if want_ancestors else None
-        _check(self._lib.ssme_b200_lw_filter(self._h, _dptr(lo), _dptr(hi), delta, stream_id, C.byref(ll), _dptr(cl), _dptr(tb), _dptr(fm),
-                                             anc.ctypes.data_as(C.POINTER(C.c_int32)) if anc is not None else None))
-        return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc}
+        aux = np.empty((self.T, self.cfg.num_particles), dtype=np.int32) if (want_ancestors and form == "apf") else None
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+        _check(self._lib.ssme_b200_lw_filter_form(self._h, {"sisr": 0, "apf": 1}[form], _dptr(lo), _dptr(hi), delta, stream_id, C.byref(ll), _dptr(cl), _dptr(tb),
+                                                  _dptr(fm), ip(anc), ip(aux)))
+        return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux}
 
     def swarm_filter(self, theta, stream_base: int = 0, return_per_filter: bool = False):
         """Swarm::update over the whole series: [T] mean over the P filters of log p(y_t | y_{1:t-1})."""

@@ -7,6 +7,12 @@
 //   lw_propagate_kernel    theta' = a theta + (1-a) thetaBar + L z, untransform, x' ~ f(.|x, theta'), log g  (:2210-2224)
 //   spill_reduce_max / weights_scan / tile_scan   log-sum-exp of :2238-2245 (K3 kernels, unchanged)
 //   spill_resample_kernel  states and the 4 parameters resampled together (mn_resamp_states_and_params, :91-145)
+// and LWFilterWithCovs::filter (:971-1159, the auxiliary-particle form, on svol_lw_1_par, test/test_liu_west.cpp:83-157):
+//   lw_apf_first_kernel    lfs_i = log g(y_t | propMu(x_i, z_t, theta_i))                                   (:985-1000)
+//   K3b/K3c/K3d            its max, tile CDFs and tile ends (first stage: log S kept, no likelihood term yet)
+//   lw_propagate_kernel<1> slot j draws k_j by the two-level descent (k_gen::sample, :1012), gathers particle k_j,
+//                          jitters and propagates it, lw_j = log g(y_t | x'_j) - lfs_k                         (:1025-1042)
+//   then K3b..K3e as in the SISR form; log p(y_t | y_{1:t-1}) joins both stages (:1056-1058)
 // The reference builds 2-3 param::pack objects (heap, string-keyed factory) per particle per step (:2214, parameters.h:290-313);
 // here a particle is five doubles in five SoA arrays.  Arithmetic = oracle's ssme_oracle_lw_filter, CANONICAL.
 #pragma once
@@ -24,6 +30,10 @@ struct LwArgs {
     double lo[4], hi[4];      // uniform prior box (untransformed)
     double a, oma, h2;
     int mode;                 // moments kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values
+    // auxiliary-particle form (LWFilterWithCovs, liu_west_filter.h:971-1159)
+    double* lfs;              // [N] first-stage log-weights log g(y_t | propMu(x_i, z_t, theta_i))
+    double* cdf1;             // [N] first-stage buffer: log-weights, then their tile-local CDF (K3c/K3d run on it)
+    int* aux_out;             // [T][N] first-stage indices k_j, or null
 };
 
 __device__ __forceinline__ double lw_inv_trans(int k, double t)
@@ -157,77 +167,50 @@ __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwA
         for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)a.s.t * 4 + k] = tb[k];
 }
 
-__global__ void __launch_bounds__(kTileNT) lw_propagate_kernel(const LwArgs a)
+constexpr int kLwNT = 256;                 // threads of the propagation CTA
+constexpr int kLwIters = 4;                // particles per thread, one at a time
+constexpr int kLwSub = kLwNT * kLwIters;   // 1024 particles per CTA: kTile / kLwSub partial maxima per tile
+static_assert(kTile % kLwSub == 0, "sub-tiles nest in the tiles");
+
+// state normal of particle (warp base + q*32 + lane): lane l of the warp holds the Philox block of particles
+// warp base + 4l .. 4l+3 (same blocks as K1/K3: block index = particle / 4), so each block is computed once
+__device__ __forceinline__ double lw_state_normal(const float (&zs)[4], int q, int lane)
 {
-    __shared__ double red[kTileNT / 32];
-    __shared__ double smom[20];
+    const int src = q * 8 + (lane >> 2);
+    const float z0 = __shfl_sync(0xffffffffu, zs[0], src), z1 = __shfl_sync(0xffffffffu, zs[1], src);
+    const float z2 = __shfl_sync(0xffffffffu, zs[2], src), z3 = __shfl_sync(0xffffffffu, zs[3], src);
+    const int c = lane & 3;
+    return (double)((c == 0) ? z0 : (c == 1) ? z1 : (c == 2) ? z2 : z3);
+}
+
+// First stage of the auxiliary form: the log-weight of the predicted state propMu(x_i) under particle i's own parameters.
+__global__ void __launch_bounds__(kLwNT, 4) lw_apf_first_kernel(const LwArgs a)
+{
+    __shared__ double red[kLwNT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int i0 = tile * kTile + tid * kTileL;
     const int t = a.s.t;
-    if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
-    __syncthreads();
     const double y = a.s.obs[(size_t)t * 2];
     const double cov = a.s.obs[(size_t)t * 2 + 1];
-    const uint2 key = make_uint2((uint32_t)a.s.seed, (uint32_t)(a.s.seed >> 32));
-    const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
     const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
-    double mloc = __longlong_as_double(0xfff0000000000000ll);
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);
+    double mloc = ninf;
 #pragma unroll 1
-    for (int q = 0; q < kTileL / 4; ++q) {
-        const uint4 rz = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
-        float zs[4];
-        box_muller(rz.x, rz.y, zs[0], zs[1]);
-        box_muller(rz.z, rz.w, zs[2], zs[3]);
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-            const int i = i0 + 4 * q + kk;
-            const double z = (double)zs[kk];
-            double p[4], nth[4], x;
-            if (t == 0) {
+    for (int q = 0; q < kLwIters; ++q) {
+        const int i = wbase + q * 32 + lane;
+        const bool valid = i < a.s.N;
+        double p[4];
 #pragma unroll
-                for (int k2 = 0; k2 < 2; ++k2) {
-                    const uint4 ru = philox4x32_10(make_uint4(2u * (uint32_t)i + (uint32_t)k2, 0u, ctr2, ctr3 | 5u), key);
-                    const double ua = uniform53(ru.x, ru.y), ub = uniform53(ru.z, ru.w);
-                    p[2 * k2] = __fma_rn(ua, __dsub_rn(a.hi[2 * k2], a.lo[2 * k2]), a.lo[2 * k2]);
-                    p[2 * k2 + 1] = __fma_rn(ub, __dsub_rn(a.hi[2 * k2 + 1], a.lo[2 * k2 + 1]), a.lo[2 * k2 + 1]);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) nth[k] = lw_trans(k, p[k]);
-                x = __dmul_rn(z, __ddiv_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[0], p[0])))));
-            } else {
-                const uint4 rp = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), key);
-                float zf[4];
-                box_muller(rp.x, rp.y, zf[0], zf[1]);
-                box_muller(rp.z, rp.w, zf[2], zf[3]);
-                const bool valid = i < a.s.N;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double th = valid ? a.th_anc[k][i] : 0.0;
-                    double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[k]));
-#pragma unroll
-                    for (int l = 0; l <= k; ++l) acc = __fma_rn(smom[4 + 4 * k + l], (double)zf[l], acc);
-                    nth[k] = acc;
-                    p[k] = lw_inv_trans(k, acc);
-                }
-                const double xa = valid ? a.s.x_anc[i] : 0.0;
-                const double e2 = dexp(__dmul_rn(-0.5, xa));
-                const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
-                double mean = __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]);
-                mean = __fma_rn(cz, e2, mean);
-                x = __fma_rn(__dmul_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[3], p[3])))), z, mean);
-            }
-            double v = __fma_rn(-hh, dexp(-x), __fma_rn(-0.5, x, -SSME_DM_HALF_LOG_2PI));
-            if (i < a.s.N) {
-                a.s.x_cur[i] = x;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a.th_cur[k][i] = nth[k];
-            } else {
-                v = __longlong_as_double(0xfff0000000000000ll);
-            }
-            a.s.lwc[i] = v;
-            mloc = (v > mloc) ? v : mloc;
-        }
+        for (int k = 0; k < 4; ++k) p[k] = lw_inv_trans(k, valid ? a.th_anc[k][i] : 0.0);
+        const double xa = valid ? a.s.x_anc[i] : 0.0;
+        const double e2 = dexp(__dmul_rn(-0.5, xa));
+        const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
+        const double mu = __fma_rn(cz, e2, __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]));
+        double v = __fma_rn(-hh, dexp(-mu), __fma_rn(-0.5, mu, -SSME_DM_HALF_LOG_2PI));
+        v = valid ? v : ninf;
+        a.lfs[i] = v;   // whole tiles are allocated
+        a.cdf1[i] = v;
+        mloc = (v > mloc) ? v : mloc;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -236,14 +219,123 @@ __global__ void __launch_bounds__(kTileNT) lw_propagate_kernel(const LwArgs a)
     }
     if (lane == 0) red[warp] = mloc;
     __syncthreads();
-    if (warp == 0) {
-        double m = (lane < kTileNT / 32) ? red[lane] : __longlong_as_double(0xfff0000000000000ll);
+    if (tid == 0) {
+        double m = red[0];
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const double other = shfl_xor_d(m, d);
-            m = (other > m) ? other : m;
+        for (int g = 1; g < kLwNT / 32; ++g) m = (red[g] > m) ? red[g] : m;
+        a.s.tmax[blockIdx.x] = m;
+    }
+}
+
+// One particle per thread at a time (coalesced 8-byte accesses, ~64 registers, 4 CTAs per SM).  Nothing depends on which
+// thread owns a particle: the maximum is order-free and every other value is per particle.  Writes the maximum of its
+// 1024 particles to tmax[blockIdx.x] (spill_reduce_max_kernel is then run over N/1024 entries).
+// FORM 0: slot i continues particle i (SISR).  FORM 1: slot i continues particle k_i drawn from the first-stage weights.
+template <int FORM>
+__global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
+{
+    __shared__ double red[kLwNT / 32];
+    __shared__ double smom[20];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = a.s.t;
+    if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
+    __syncthreads();
+    const double y = a.s.obs[(size_t)t * 2];
+    const double cov = a.s.obs[(size_t)t * 2 + 1];
+    const uint2 key = make_uint2((uint32_t)a.s.seed, (uint32_t)(a.s.seed >> 32));
+    const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
+    const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);  // this warp's 128 consecutive particles
+    float zs[4];
+    {
+        const uint4 rz = philox4x32_10(make_uint4((uint32_t)(wbase / 4 + lane), (uint32_t)t, ctr2, ctr3), key);
+        box_muller(rz.x, rz.y, zs[0], zs[1]);
+        box_muller(rz.z, rz.w, zs[2], zs[3]);
+    }
+    double mloc = ninf;
+#pragma unroll 1
+    for (int q = 0; q < kLwIters; ++q) {
+        const int i = wbase + q * 32 + lane;
+        const double z = lw_state_normal(zs, q, lane);
+        const bool valid = i < a.s.N;
+        double p[4], nth[4], x;
+        int src = i;          // the particle this slot continues
+        double lfs_k = 0.0;
+        if (FORM == 1 && t > 0 && valid) {
+            // k_i ~ discrete(first-stage weights): uniform of stream 6, two-level descent (spill_resample_kernel's)
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i >> 1), (uint32_t)t, ctr2, ctr3 | 6u), key);
+            const double tau = __dmul_rn((i & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), a.s.scal[1]);
+            int b = 0;
+            for (int s = a.s.NBP >> 1; s >= 1; s >>= 1) b += (a.s.E[b + s - 1] < tau) ? s : 0;
+            b = min(b, a.s.nb - 1);
+            const double O = (b > 0) ? a.s.E[b - 1] : 0.0;
+            const double* cl = a.cdf1 + (size_t)b * kTile;
+            int idx = 0;
+#pragma unroll
+            for (int s = kTile / 2; s >= 1; s >>= 1) idx += (__dadd_rn(O, cl[idx + s - 1]) < tau) ? s : 0;
+            long long k = (long long)b * kTile + idx;
+            k = (k > (long long)a.s.N - 1) ? (long long)a.s.N - 1 : k;
+            src = (int)k;
+            lfs_k = a.lfs[src];
+            if (a.aux_out) a.aux_out[(size_t)t * a.s.N + i] = src;
         }
-        if (lane == 0) a.s.tmax[tile] = m;
+        if (t == 0) {
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const uint4 ru = philox4x32_10(make_uint4(2u * (uint32_t)i + (uint32_t)k2, 0u, ctr2, ctr3 | 5u), key);
+                const double ua = uniform53(ru.x, ru.y), ub = uniform53(ru.z, ru.w);
+                p[2 * k2] = __fma_rn(ua, __dsub_rn(a.hi[2 * k2], a.lo[2 * k2]), a.lo[2 * k2]);
+                p[2 * k2 + 1] = __fma_rn(ub, __dsub_rn(a.hi[2 * k2 + 1], a.lo[2 * k2 + 1]), a.lo[2 * k2 + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nth[k] = lw_trans(k, p[k]);
+            x = __dmul_rn(z, __ddiv_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[0], p[0])))));
+        } else {
+            const uint4 rp = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), key);
+            float zf[4];
+            box_muller(rp.x, rp.y, zf[0], zf[1]);
+            box_muller(rp.z, rp.w, zf[2], zf[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double th = valid ? a.th_anc[k][src] : 0.0;
+                double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[k]));
+#pragma unroll
+                for (int l = 0; l <= k; ++l) acc = __fma_rn(smom[4 + 4 * k + l], (double)zf[l], acc);
+                nth[k] = acc;
+                p[k] = lw_inv_trans(k, acc);
+            }
+            const double xa = valid ? a.s.x_anc[src] : 0.0;
+            const double e2 = dexp(__dmul_rn(-0.5, xa));
+            const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
+            double mean = __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]);
+            mean = __fma_rn(cz, e2, mean);
+            x = __fma_rn(__dmul_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[3], p[3])))), z, mean);
+        }
+        double v = __fma_rn(-hh, dexp(-x), __fma_rn(-0.5, x, -SSME_DM_HALF_LOG_2PI));
+        if (FORM == 1 && t > 0) v = __dsub_rn(v, lfs_k);
+        if (valid) {
+            a.s.x_cur[i] = x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a.th_cur[k][i] = nth[k];
+        } else {
+            v = ninf;
+        }
+        a.s.lwc[i] = v;  // the arrays are allocated in whole tiles
+        mloc = (v > mloc) ? v : mloc;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(mloc, d);
+        mloc = (other > mloc) ? other : mloc;
+    }
+    if (lane == 0) red[warp] = mloc;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0];
+#pragma unroll
+        for (int g = 1; g < kLwNT / 32; ++g) m = (red[g] > m) ? red[g] : m;
+        a.s.tmax[blockIdx.x] = m;
     }
 }
 

@@ -29,6 +29,7 @@ struct SpillState {
     double* th_anc[4] = {};
     double* th_cur[4] = {};
     double *part = nullptr, *mom = nullptr;
+    double* lfs = nullptr;  // first-stage log-weights of the auxiliary Liu-West form
 };
 
 __global__ void spill_init_kernel(double* scal, int N)
@@ -69,7 +70,7 @@ static int prepare(ssme_b200_handle h)
         SSME_CUDA(cudaMalloc(&s->x_cur[i], s->local * sizeof(double)));
         SSME_CUDA(cudaMalloc(&s->lwc[i], s->local * sizeof(double)));
     }
-    SSME_CUDA(cudaMalloc(&s->tmax, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->tmax, (size_t)s->nb * 4 * sizeof(double)));  // K4 keeps 4 partial maxima per tile
     SSME_CUDA(cudaMalloc(&s->ttot, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->tclmax, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
@@ -105,7 +106,7 @@ void spill_destroy(ssme_b200_handle h)
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
     cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
-    cudaFree(s->part); cudaFree(s->mom);
+    cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs);
     delete s;
     h->spill_state = nullptr;
 }
@@ -186,8 +187,8 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
     return SSME_B200_OK;
 }
 
-static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik, double* d_cond_like,
-                  double* d_theta_bar, double* d_final_mean, int* d_ancestors)
+static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik,
+                  double* d_cond_like, double* d_theta_bar, double* d_final_mean, int* d_ancestors, int* d_aux)
 {
     int rc = prepare(h);
     if (rc) return rc;
@@ -201,6 +202,7 @@ static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double
         SSME_CUDA(cudaMalloc(&s->part, (size_t)14 * s->nb * sizeof(double)));
         SSME_CUDA(cudaMalloc(&s->mom, 32 * sizeof(double)));
     }
+    if (form == 1 && !s->lfs) SSME_CUDA(cudaMalloc(&s->lfs, s->local * sizeof(double)));
     const int T = (int)h->T, tiles = s->nb;
     cudaStream_t st = h->stream;
     LwArgs a;
@@ -227,6 +229,9 @@ static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double
     }
     a.part = s->part;
     a.mom = s->mom;
+    a.lfs = s->lfs;
+    a.cdf1 = s->lwc[1];
+    a.aux_out = d_aux;
     a.theta_bar_out = d_theta_bar;
     a.a = (3.0 * delta - 1.0) / (2.0 * delta);
     a.h2 = 1.0 - a.a * a.a;
@@ -244,8 +249,27 @@ static int lw_run(ssme_b200_handle h, const double* lo, const double* hi, double
             lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
             count_launch(2);
         }
-        lw_propagate_kernel<<<tiles, kTileNT, 0, st>>>(a);
-        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(a.s);
+        const int subs = tiles * (kTile / kLwSub);
+        SpillArgs m = a.s;  // K4's kernels leave one partial maximum per 1024 particles
+        m.tile0 = 0;
+        m.tile1 = subs;
+        const bool apf = (form == 1 && t > 0);
+        if (apf) {
+            // first stage: weights of the predicted states, their CDF (in lwc[1]) and M2 + log S2
+            SpillArgs f = a.s;
+            f.lwc = s->lwc[1];
+            f.cl_mode = 1;
+            lw_apf_first_kernel<<<subs, kLwNT, 0, st>>>(a);
+            spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
+            spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(f);
+            spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(f);
+            lw_propagate_kernel<1><<<subs, kLwNT, 0, st>>>(a);
+            count_launch(4);
+        } else {
+            lw_propagate_kernel<0><<<subs, kLwNT, 0, st>>>(a);
+        }
+        a.s.cl_mode = apf ? 2 : 0;
+        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
         spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
         spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
         if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
@@ -273,7 +297,16 @@ extern "C" {
 int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id,
                         double* loglik_host, double* cond_like_host, double* theta_bar_host, double* final_mean_host, int32_t* ancestors_host)
 {
+    return ssme_b200_lw_filter_form(h, SSME_B200_LW_SISR, prior_lo, prior_hi, delta, stream_id, loglik_host, cond_like_host, theta_bar_host,
+                                    final_mean_host, ancestors_host, nullptr);
+}
+
+int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id,
+                             double* loglik_host, double* cond_like_host, double* theta_bar_host, double* final_mean_host,
+                             int32_t* ancestors_host, int32_t* aux_index_host)
+{
     if (!h || !prior_lo || !prior_hi) return fail(SSME_B200_EINVAL, "null argument");
+    if (form != SSME_B200_LW_SISR && form != SSME_B200_LW_APF) return fail(SSME_B200_EINVAL, "unknown Liu-West form %d", form);
     if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
     if (!h->spill) return fail(SSME_B200_EINVAL, "the Liu-West filter uses the global-memory kernels: create the handle with force_global_memory = 1 (or N > 8192)");
     if (h->cfg.model != SSME_B200_MODEL_SV_LEVERAGE) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter is built for the SV-with-leverage model");
@@ -284,15 +317,17 @@ int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double
     if (rc) return rc;
     const size_t T = h->T, N = (size_t)h->cfg.num_particles;
     double *d_sc = nullptr, *d_cl = nullptr, *d_tb = nullptr;
-    int* d_anc = nullptr;
-    auto cleanup = [&]() { cudaFree(d_sc); cudaFree(d_cl); cudaFree(d_tb); cudaFree(d_anc); };
+    int *d_anc = nullptr, *d_aux = nullptr;
+    auto cleanup = [&]() { cudaFree(d_sc); cudaFree(d_cl); cudaFree(d_tb); cudaFree(d_anc); cudaFree(d_aux); };
     cudaError_t e = cudaMalloc(&d_sc, 8 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&d_cl, T * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&d_tb, T * 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_tb, 0, T * 4 * sizeof(double), h->stream);
     if (e == cudaSuccess && ancestors_host) e = cudaMalloc(&d_anc, T * N * sizeof(int));
+    if (e == cudaSuccess && aux_index_host && form == SSME_B200_LW_APF) e = cudaMalloc(&d_aux, T * N * sizeof(int));
+    if (e == cudaSuccess && d_aux) e = cudaMemsetAsync(d_aux, 0, T * N * sizeof(int), h->stream);
     if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "Liu-West setup failed: %s", cudaGetErrorString(e)); }
-    rc = lw_run(h, prior_lo, prior_hi, delta, stream_id, d_sc, d_cl, d_tb, d_sc + 1, d_anc);
+    rc = lw_run(h, form, prior_lo, prior_hi, delta, stream_id, d_sc, d_cl, d_tb, d_sc + 1, d_anc, d_aux);
     if (rc) { cleanup(); return rc; }
     e = cudaStreamSynchronize(h->stream);
     double sc[5];
@@ -300,6 +335,7 @@ int ssme_b200_lw_filter(ssme_b200_handle h, const double* prior_lo, const double
     if (e == cudaSuccess && cond_like_host) e = cudaMemcpy(cond_like_host, d_cl, T * sizeof(double), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && theta_bar_host) e = cudaMemcpy(theta_bar_host, d_tb, T * 4 * sizeof(double), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && ancestors_host) e = cudaMemcpy(ancestors_host, d_anc, T * N * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && d_aux) e = cudaMemcpy(aux_index_host, d_aux, T * N * sizeof(int), cudaMemcpyDeviceToHost);
     cleanup();
     if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "Liu-West filter failed: %s", cudaGetErrorString(e));
     if (loglik_host) *loglik_host = sc[0];

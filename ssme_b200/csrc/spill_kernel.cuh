@@ -49,6 +49,10 @@ struct SpillArgs {
     int nextra;
     const double* extra_cur[4];
     double* extra_anc[4];
+    // what spill_tile_scan_kernel does with (M, S): 0 = log p(y_t | y_{1:t-1}) of a bootstrap step, added to the
+    // log-likelihood; 1 = first stage of an auxiliary particle filter: keep M + log S in scal[4] only;
+    // 2 = second stage: log p(y_t | y_{1:t-1}) = ((M + log S) + scal[4]) - 2 log N  (liu_west_filter.h:1056-1058 with rs = 1)
+    int cl_mode;
 };
 
 template <int MODEL>
@@ -299,10 +303,15 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     if (tid == 0) {
         const double M = a.scal[0], logN = a.scal[3];
         const double logS = dlog(S);
-        const double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
         a.scal[1] = S;
-        a.scal[2] = __dadd_rn(a.scal[2], cl);
-        if (a.cond_like) a.cond_like[a.t] = cl;
+        if (a.cl_mode == 1) {
+            a.scal[4] = __dadd_rn(M, logS);
+        } else {
+            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
+            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
+            a.scal[2] = __dadd_rn(a.scal[2], cl);
+            if (a.cond_like) a.cond_like[a.t] = cl;
+        }
     }
 }
 

@@ -131,6 +131,27 @@ int main(int argc, char** argv)
         REQUIRE(pm(0) > .8 && pm(0) < .99 && pm(2) > .01 && pm(2) < .3 && pm(3) > -.5 && pm(3) < -.01);
         REQUIRE(std::isfinite(big.getLogLike()));
     }
+    TEST_CASE("test filter without funcs for type 1 filters with covariates [filter method]")  // test_liu_west.cpp:163-173
+    {
+        // svol_lw_1_par<NPARTS,FLOATTYPE> mod(.99, .8, .99, -.1, .1, .01, .1, -.5, -.01, 10); filter(y1, z1); logCondLike^2 > 0
+        using lw_t = ssme_b200::LWFilterWithCovs_svol<10, double>;
+        lw_t mod({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5}, lw_t::psv{.99, .1, .1, -.01});
+        mod.filter_series({0.3, -0.2, 0.5}, {0.0, 0.3, -0.2});
+        for (size_t t = 0; t < 3; ++t) REQUIRE(std::pow(mod.getLogCondLike(t), 2) > 0.0);
+        ssme_b200::LWFilterWithCovs_svol<20000, double> big({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5},
+                                                            lw_t::psv{.99, .1, .3, -.01});
+        ssme_b200::LWFilter2WithCovs_svol<20000, double> big2({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5},
+                                                              lw_t::psv{.99, .1, .3, -.01});
+        std::vector<double> cov(y.size(), 0.0);
+        for (size_t t = 1; t < y.size(); ++t) cov[t] = y[t - 1];
+        big.filter_series(y, cov);
+        big2.filter_series(y, cov);
+        const auto pm = big.getParamMeans();
+        REQUIRE(pm(0) > .8 && pm(0) < .99 && pm(2) > .01 && pm(2) < .3 && pm(3) > -.5 && pm(3) < -.01);
+        REQUIRE(std::isfinite(big.getLogLike()));
+        REQUIRE(big.getLogLike() != big2.getLogLike());  // two different estimators of the same quantity
+        REQUIRE(std::abs(big.getLogLike() - big2.getLogLike()) < 0.02 * std::abs(big2.getLogLike()));
+    }
     TEST_CASE("swarm: 10 x 10 particles, assertions of test_pswarm.cpp:251-252")
     {
         struct my_swarm : ssme_b200::Swarm<10, 10, 4, double> {

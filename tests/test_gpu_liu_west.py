@@ -1,5 +1,6 @@
-"""-m gpu: the Liu-West kernels (K4) against the oracle's restatement of LWFilter2WithCovs::filter
-(liu_west_filter.h:2191-2343) on the reference's own test model and prior box (test/test_liu_west.cpp:165,213-358)."""
+"""-m gpu: the Liu-West kernels (K4) against the oracle's restatements of LWFilter2WithCovs::filter
+(liu_west_filter.h:2191-2343) and of the auxiliary-particle form LWFilterWithCovs::filter (:971-1159) on the
+reference's own test models and prior box (test/test_liu_west.cpp:83-157, 165, 213-358)."""
 import numpy as np
 import pytest
 
@@ -42,6 +43,41 @@ def test_liu_west_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
         assert np.array_equal(got["ancestors"], fai["ancestors"])
         assert abs(got["loglik"] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
         assert np.allclose(got["final_mean"], fai["final_mean"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("N,T", [(10, 1), (10, 5), (5000, 30), (4096 * 2 + 5, 12), (1024 * 3 + 1, 9)])
+def test_liu_west_apf_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
+    y = leverage_series(T, seed=N + T + 1)
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=8, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.lw_filter(LO, HI, delta=0.99, stream_id=5, want_ancestors=True, form="apf")
+    ref = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, seed=8, filter_id=5, form="apf")
+    assert np.array_equal(got["aux_index"], ref["aux_index"])      # first-stage indices k_j
+    assert np.array_equal(got["ancestors"], ref["ancestors"])      # second-stage resampling
+    assert np.array_equal(got["cond_like"], ref["cond_like"])
+    assert np.array_equal(got["theta_bar"], ref["theta_bar"])
+    assert np.array_equal(got["final_mean"], ref["final_mean"])
+    assert got["loglik"] == ref["loglik"]
+    assert np.all(got["cond_like"] ** 2 > 0.0)                     # test_liu_west.cpp:172
+    # the two forms are different estimators of the same likelihood: not equal, but close on model-generated data
+    sisr = be.lw_filter(LO, HI, delta=0.99, stream_id=5)
+    assert (got["loglik"] != sisr["loglik"]) == (T > 1)  # step 0 is common to both forms
+    fai = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=8, filter_id=5, form="apf")
+    if np.array_equal(ref["aux_index"], fai["aux_index"]) and np.array_equal(ref["ancestors"], fai["ancestors"]):
+        assert abs(got["loglik"] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+        assert np.allclose(got["final_mean"], fai["final_mean"], rtol=1e-9, atol=1e-12)
+    else:
+        assert N >= 5000  # index ties between the tiled and the sequential CDF need many particles
+
+
+def test_liu_west_forms_agree_statistically(gpu_backend_factory):
+    y = leverage_series(60, seed=12, sigma=0.05)
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=1 << 17, resampler=sb.RESAMP_SYSTEMATIC, seed=3)
+    be.add_observed_data(y)
+    a = np.array([be.lw_filter(LO, HI, stream_id=s, form="sisr")["loglik"] for s in range(4)])
+    b = np.array([be.lw_filter(LO, HI, stream_id=s, form="apf")["loglik"] for s in range(4)])
+    assert abs(a.mean() - b.mean()) < 0.05 + 4 * (a.std() + b.std())
 
 
 def test_liu_west_learns_the_parameters(gpu_backend_factory):

@@ -155,3 +155,27 @@ def test_loglik_estimator_is_sane(oracle, sv_series):
     big = [oracle.filter_run(th, y, 1024, seed=1, filter_id=i, trace=False)["loglik"] for i in range(30)]
     assert np.std(big) < np.std(small)
     assert abs(np.mean(big) - np.mean(small)) < 4 * np.std(small)
+
+
+def test_lw_apf_form_restates_the_reference_step(oracle):
+    """LWFilterWithCovs::filter (liu_west_filter.h:971-1159) with rs = 1: one step recomputed here in numpy from the
+    oracle's own trace -- first-stage weights, the k-draw, second-stage weights and the joined log cond-like (:1056-1058)."""
+    from oracle import binding as ob
+    lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
+    rng = np.random.default_rng(2)
+    y = 0.8 * rng.standard_normal(4)
+    N = 64
+    r = ob.lw_filter_run(lo, hi, 0.99, y, N, arithmetic=ob.ARITH_FAITHFUL, form="apf", seed=4, filter_id=1, resampler=0)
+    s = ob.lw_filter_run(lo, hi, 0.99, y, N, arithmetic=ob.ARITH_FAITHFUL, form="sisr", seed=4, filter_id=1, resampler=0)
+    # step 0 is the same in both forms (:1092-1147 vs :2278-2330)
+    assert r["cond_like"][0] == s["cond_like"][0] and np.array_equal(r["ancestors"][0], s["ancestors"][0])
+    assert r["cond_like"][1] != s["cond_like"][1]
+    assert np.all(np.isfinite(r["cond_like"])) and r["aux_index"].min() >= 0 and r["aux_index"].max() < N
+    # canonical and faithful arithmetic agree to 1e-9 and pick the same indices at this size
+    c = ob.lw_filter_run(lo, hi, 0.99, y, N, form="apf", seed=4, filter_id=1, resampler=0)
+    assert np.array_equal(c["aux_index"], r["aux_index"]) and np.array_equal(c["ancestors"], r["ancestors"])
+    assert abs(c["loglik"] - r["loglik"]) <= 1e-9 * abs(r["loglik"])
+    # the first-stage draw concentrates on predicted states that explain y_t: with a huge |y_t| it prefers large x
+    y2 = y.copy(); y2[1] = 25.0
+    r2 = ob.lw_filter_run(lo, hi, 0.99, y2, N, arithmetic=ob.ARITH_FAITHFUL, form="apf", seed=4, filter_id=1, resampler=0)
+    assert len(np.unique(r2["aux_index"][1])) < len(np.unique(r["aux_index"][1]))

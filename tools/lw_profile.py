@@ -12,3 +12,9 @@ be.add_observed_data(y)
 lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
 r = be.lw_filter(lo, hi, 0.99, stream_id=0)
 print(r["loglik"], r["final_mean"])
+if T >= 64:
+    import time
+    t0 = time.perf_counter()
+    r = be.lw_filter(lo, hi, 0.99, stream_id=1)
+    dt = time.perf_counter() - t0
+    print("N=%d T=%d: %.1f us per time step, %.3g particle-steps/s" % (N, T, 1e6 * dt / T, N * T / dt))
