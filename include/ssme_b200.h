@@ -162,6 +162,15 @@ int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host
 int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
                            double* log_cond_like_host, double* per_filter_host);
 
+/* Replaces: the expectation outputs of the same call -- Swarm::getExpectations after each update
+ * (pswarm_filter.h:96-160: per filter numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m) before resampling, in-tree
+ * twin liu_west_filter.h:1662-1683; then the mean over the parameter particles) for the two functions h(x) = x and
+ * h(x) = x^2 (the reference takes std::function callbacks; a device kernel cannot call host lambdas, so the filtering
+ * mean and second moment of the log-volatility are built in).  expectations_host [T][2]; per_filter [P][T][2] and
+ * log_cond_like_host [T] may be NULL.  Runs the tracing instantiation of the resident kernel. */
+int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
+                                 double* log_cond_like_host, double* expectations_host, double* per_filter_expectations_host);
+
 /* Replaces: LWFilter2WithCovs::filter called over a whole series (liu_west_filter.h:2191-2343, with
  * update_parameter_proposal_components :2346-2360 and mn_resamp_states_and_params :91-145) for the SV-with-leverage
  * model svol_lw_2_par (test/test_liu_west.cpp:213-358): joint state / parameter learning with kernel shrinkage

@@ -47,7 +47,9 @@ public:
     virtual psv samp_untrans_params() = 0;
 
     // update(y_t) for t = 0 .. T-1 in one call; obs is row-major [T][dimy], dimy = 1 or 2 (y_t, z_t)
-    void update_series(const std::vector<double>& obs, size_t dimy, std::uint64_t stream_base = 0)
+    // with_expectations: also form E[x_t | y_{1:t}] and E[x_t^2 | y_{1:t}] averaged over the parameter particles
+    // (Swarm::update(yt, fs) + getExpectations, pswarm_filter.h:223-239, 96-160, for h(x) = x and h(x) = x^2)
+    void update_series(const std::vector<double>& obs, size_t dimy, std::uint64_t stream_base = 0, bool with_expectations = false)
     {
         if (obs.empty() || obs.size() % dimy != 0) throw std::length_error("bad observation array");
         const size_t T = obs.size() / dimy;
@@ -58,17 +60,26 @@ public:
         }
         throw_on_error(ssme_b200_set_observations(m_h, obs.data(), T, dimy));
         m_log_cond_like.assign(T, 0.0);
-        throw_on_error(ssme_b200_swarm_filter(m_h, theta.data(), nparamparts, stream_base, m_log_cond_like.data(), nullptr));
+        if (with_expectations) {
+            m_expectations.assign(2 * T, 0.0);
+            throw_on_error(ssme_b200_swarm_expectations(m_h, theta.data(), nparamparts, stream_base, m_log_cond_like.data(),
+                                                        m_expectations.data(), nullptr));
+        } else {
+            m_expectations.clear();
+            throw_on_error(ssme_b200_swarm_filter(m_h, theta.data(), nparamparts, stream_base, m_log_cond_like.data(), nullptr));
+        }
         m_num_obs = (unsigned)T;
     }
 
     float_t getLogCondLike(size_t t) const { return (float_t)m_log_cond_like.at(t); }
     float_t getLogCondLike() const { return (float_t)m_log_cond_like.back(); }
     unsigned num_obs() const { return m_num_obs; }
+    // getExpectations()[which] at step t: which = 0 -> E[x_t | y_{1:t}], 1 -> E[x_t^2 | y_{1:t}]
+    float_t getExpectation(size_t t, size_t which) const { return (float_t)m_expectations.at(2 * t + which); }
 
 private:
     ssme_b200_handle m_h = nullptr;
-    std::vector<double> m_log_cond_like;
+    std::vector<double> m_log_cond_like, m_expectations;
     unsigned m_num_obs;
 };
 

@@ -81,11 +81,16 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
     cl = np.empty(T) if trace else None
     anc = np.empty((T, N), dtype=np.int32) if trace else None
     xs = np.empty((T, N)) if trace else None
-    rc = lib().ssme_oracle_filter(C.byref(cfg), _dp(theta), _dp(y), T, _dp(cov), _dp(z), _dp(u), C.byref(ll), _dp(cl),
-                                  anc.ctypes.data_as(C.POINTER(C.c_int32)) if trace else None, _dp(xs), C.byref(mg))
+    ex = np.empty((T, 2)) if (trace and not (tiled and arithmetic == ARITH_CANONICAL)) else None
+    fn = lib().ssme_oracle_filter_expect
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 9
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = fn(C.cast(C.byref(cfg), C.c_void_p), vp(theta), vp(y), T, vp(cov), vp(z), vp(u), C.cast(C.byref(ll), C.c_void_p), vp(cl),
+            vp(anc), vp(xs), C.cast(C.byref(mg), C.c_void_p), vp(ex))
     if rc != 0:
         raise ValueError("ssme_oracle_filter failed with %d" % rc)
-    return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs, "margin": mg.value}
+    return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs, "margin": mg.value, "expect": ex}
 
 
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,

@@ -305,10 +305,48 @@ static void upd_margin(double* margin, const double* C, int32_t a, double tau, d
     if (m < *margin) *margin = m;
 }
 
+/* sum_i w_i x_i^p (p = 1, 2) in the resident kernel's order: lane l owns items lL .. lL+L-1 and accumulates them with
+ * fma from zero, butterfly over the 32 lanes of each warp, warps added in order */
+static double block_sum_wx(const double* w, const double* x, int32_t n, int32_t L, int32_t lanes, int power)
+{
+    double* t = (double*)calloc((size_t)lanes, sizeof(double));
+    for (int32_t l = 0; l < lanes; ++l) {
+        double s = 0.0;
+        for (int32_t k = 0; k < L; ++k) {
+            int64_t i = (int64_t)l * L + k;
+            if (i < n) s = (power == 1) ? fma(w[i], x[i], s) : fma(w[i] * x[i], x[i], s);
+        }
+        t[l] = s;
+    }
+    double acc = 0.0;
+    for (int32_t g = 0; g < lanes / 32; ++g) {
+        double* v = t + g * 32;
+        for (int32_t d = 16; d >= 1; d >>= 1) {
+            double tmp[32];
+            for (int32_t l = 0; l < 32; ++l) tmp[l] = v[l] + v[l ^ d];
+            for (int32_t l = 0; l < 32; ++l) v[l] = tmp[l];
+        }
+        acc = (g == 0) ? v[0] : acc + v[0];
+    }
+    free(t);
+    return acc;
+}
+
 int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
                        const double* cov, const double* z_inj, const double* u_inj,
                        double* loglik_out, double* cond_like, int32_t* ancestors, double* x_trace,
                        double* tie_margin)
+{
+    return ssme_oracle_filter_expect(cfg, theta, y, T, cov, z_inj, u_inj, loglik_out, cond_like, ancestors, x_trace, tie_margin, NULL);
+}
+
+/* as ssme_oracle_filter, plus expect[T][2] = E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}]: the weighted means the reference
+ * forms before resampling, numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m) (pswarm / BSFilter expectations;
+ * in-tree twin liu_west_filter.h:1662-1683), with h(x) = x and h(x) = x^2 */
+int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
+                              const double* cov, const double* z_inj, const double* u_inj,
+                              double* loglik_out, double* cond_like, int32_t* ancestors, double* x_trace,
+                              double* tie_margin, double* expect)
 {
     if (!cfg || !theta || !y || T < 0) return -1;
     const int32_t N = cfg->num_particles;
@@ -415,6 +453,18 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
         }
         if (cond_like) cond_like[t] = cl;
         loglik += cl; /* estimate_univ_svol.h:125 */
+        if (expect) {
+            if (canonical) {
+                if (tiled) return -9; /* expectations are an output of the resident kernel */
+                expect[2 * t + 0] = block_sum_wx(w, x, N, L, NP / L, 1) / S;
+                expect[2 * t + 1] = block_sum_wx(w, x, N, L, NP / L, 2) / S;
+            } else {
+                double n1 = 0.0, n2 = 0.0, den = 0.0;
+                for (int32_t i = 0; i < N; ++i) { n1 += x[i] * w[i]; n2 += x[i] * x[i] * w[i]; den += w[i]; }
+                expect[2 * t + 0] = n1 / den;
+                expect[2 * t + 1] = n2 / den;
+            }
+        }
 
         if ((t + 1) % rs == 0) {
             const double* ut = injected ? (u_inj ? u_inj + t * stride_u : NULL) : NULL;

@@ -74,6 +74,13 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
                        double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
                        double* tie_margin);
 
+/* the same, plus expect[T][2] = E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] formed before resampling (reference:
+ * expectation callbacks of the filters, in-tree twin liu_west_filter.h:1662-1683; swarm average pswarm_filter.h:96-160) */
+int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
+                              const double* cov, const double* z_inj, const double* u_inj,
+                              double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
+                              double* tie_margin, double* expect);
+
 /*
  * Liu-West joint state/parameter filter, SISR form with the bootstrap proposal: LWFilter2WithCovs::filter
  * (reference include/ssme/liu_west_filter.h:2191-2343, update_parameter_proposal_components :2346-2360, shrinkage

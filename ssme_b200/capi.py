@@ -99,6 +99,7 @@ def load_library():
     lib.ssme_b200_lw_filter.argtypes = [H, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip]
     lib.ssme_b200_lw_filter_form.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip, ip]
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
+    lib.ssme_b200_swarm_expectations.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp, dp]
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_model.argtypes = [H]
@@ -310,6 +311,15 @@ class ParticleFilterBackend:
         pf = np.empty((P, self.T)) if return_per_filter else None
         _check(self._lib.ssme_b200_swarm_filter(self._h, _dptr(theta), P, stream_base, _dptr(out), _dptr(pf)))
         return (out, pf) if return_per_filter else out
+
+    def swarm_expectations(self, theta, stream_base: int = 0, return_per_filter: bool = False):
+        """Swarm::getExpectations over the whole series for h(x) = x, x^2: dict(log_cond_like[T], expectations[T,2], per_filter[P,T,2])."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
+        P = theta.shape[0]
+        cl, ex = np.empty(self.T), np.empty((self.T, 2))
+        pf = np.empty((P, self.T, 2)) if return_per_filter else None
+        _check(self._lib.ssme_b200_swarm_expectations(self._h, _dptr(theta), P, stream_base, _dptr(cl), _dptr(ex), _dptr(pf)))
+        return {"log_cond_like": cl, "expectations": ex, "per_filter": pf}
 
     def pmmh_run(self, start_theta, num_pfilters, iterations, t0=150, t1=1000, c0_diag=0.15, proposal_seed=1):
         """ada_pmmh_mvn::commence_sampling for C chains in lock step (C++ host loop behind the C ABI)."""

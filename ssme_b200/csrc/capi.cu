@@ -575,6 +575,46 @@ int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t 
     return SSME_B200_OK;
 }
 
+int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base, double* log_cond_like_host,
+                                 double* expectations_host, double* per_filter_expectations_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (P == 0) return fail(SSME_B200_EINVAL, "the swarm needs at least one parameter particle");
+    if (!theta_host || !expectations_host) return fail(SSME_B200_EINVAL, "null host buffer");
+    if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
+    if (h->spill || h->cluster) return fail(SSME_B200_EUNSUPPORTED, "expectations are an output of the resident one-CTA kernel (num_particles <= 8192, no cluster)");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t np = (size_t)h->num_params, T = h->T;
+    double *d_theta = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_ex = nullptr, *d_mean = nullptr;
+    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_ex); cudaFree(d_mean); };
+    cudaError_t e = cudaMalloc(&d_theta, P * np * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ll, P * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cl, P * T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ex, P * T * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mean, T * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_theta, theta_host, P * np * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "swarm setup failed: %s", cudaGetErrorString(e)); }
+    FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
+    a.cond_like = d_cl;
+    a.expect = d_ex;
+    rc = launch_filters(h, h->debug, a, P, h->stream);  // the tracing instantiation carries the extra reduction
+    if (rc) { cleanup(); return rc; }
+    swarm_mean_kernel<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(d_cl, P, (int)T, d_mean);
+    swarm_mean_kernel<<<(unsigned)((2 * T + 127) / 128), 128, 0, h->stream>>>(d_ex, P, (int)(2 * T), d_mean + T);
+    g_launches.fetch_add(2);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && log_cond_like_host) e = cudaMemcpyAsync(log_cond_like_host, d_mean, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(expectations_host, d_mean + T, 2 * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && per_filter_expectations_host)
+        e = cudaMemcpyAsync(per_filter_expectations_host, d_ex, P * T * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "swarm expectations failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_shard_range(uint64_t F, int32_t world, int32_t rank, uint64_t* first, uint64_t* count, uint64_t* chunk)
 {
     if (world < 1 || rank < 0 || rank >= world) return fail(SSME_B200_EINVAL, "bad rank %d of %d", rank, world);

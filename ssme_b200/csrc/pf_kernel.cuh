@@ -49,7 +49,8 @@ struct FilterArgs {
     const double* u_inj;  // [F][T][stride_u]
     double* cond_like;    // [F][T]
     int* ancestors;       // [F][T][N]
-    double* x_trace;      // [F][T][N]
+    double* x_trace;
+    double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
 __host__ __device__ constexpr int obs_stride(int model) { return model == kModelSVLeverage ? 2 : 1; }
@@ -340,6 +341,39 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         for (int k = 0; k < L; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
 
         const bool do_resample = DEBUG ? ((t + 1) % a.rs == 0) : true;
+
+        if (DEBUG && a.expect) {
+            // E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] before resampling: numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m)
+            // (the filters' expectation callbacks; in-tree twin liu_west_filter.h:1662-1683).  Order = oracle block_sum_wx.
+            double n1 = 0.0, n2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                if (i0 + k < N) {
+                    const double w = dexp_nonpos(__dsub_rn(lw[k], M));
+                    n1 = __fma_rn(w, x[k], n1);
+                    n2 = __fma_rn(__dmul_rn(w, x[k]), x[k], n2);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                n1 = __dadd_rn(n1, shfl_xor_d(n1, d));
+                n2 = __dadd_rn(n2, shfl_xor_d(n2, d));
+            }
+            if (lane == 0) {  // clM / clS only buffer cond-likes in the fast path
+                clM[warp] = n1;
+                clS[warp] = n2;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double a1 = clM[0], a2 = clS[0];
+                for (int g = 1; g < NW; ++g) {
+                    a1 = __dadd_rn(a1, clM[g]);
+                    a2 = __dadd_rn(a2, clS[g]);
+                }
+                a.expect[((size_t)f * T + t) * 2 + 0] = __ddiv_rn(a1, S);
+                a.expect[((size_t)f * T + t) * 2 + 1] = __ddiv_rn(a2, S);
+            }
+        }
 
         if (DEBUG) {
             if (tid == 0) {

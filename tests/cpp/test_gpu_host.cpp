@@ -168,6 +168,14 @@ int main(int argc, char** argv)
         sw.update_series(rows, 2);
         REQUIRE(sw.num_obs() == 40);
         for (size_t t = 0; t < 40; ++t) REQUIRE(std::pow(sw.getLogCondLike(t), 2) > 0.0);
+        // "test update with funcs" (test_pswarm.cpp:323-346): expectations come back finite and consistent
+        my_swarm sw2;  // same parameter draws (same generator seed), same random streams
+        sw2.update_series(rows, 2, 0, true);
+        for (size_t t = 0; t < 40; ++t) {
+            REQUIRE(sw2.getLogCondLike(t) == sw.getLogCondLike(t));
+            REQUIRE(std::isfinite(sw2.getExpectation(t, 0)));
+            REQUIRE(sw2.getExpectation(t, 1) >= 0.0);
+        }
     }
     return finish();
 }

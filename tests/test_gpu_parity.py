@@ -154,3 +154,34 @@ def test_swarm_per_step_cond_likes(oracle, sv_series, gpu_backend_factory, model
     assert np.array_equal(mean, acc / P)
     # the likelihood entry point is unchanged by the extra output
     assert be.work_batch(theta, R=1, stream_base=50).tolist() == [oracle.filter_run(theta[j], y, 100, model=model, L=L, NT=NT, seed=4, filter_id=50 + j, trace=False)["loglik"] for j in range(P)]
+
+
+@pytest.mark.parametrize("model,N,L", [(sb.MODEL_SV, 500, 4), (sb.MODEL_SV, 1024, 8), (sb.MODEL_SV_LEVERAGE, 300, 8), (sb.MODEL_SV, 37, 4)])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+def test_swarm_expectations_bit_exact(oracle, sv_series, gpu_backend_factory, model, N, L, resampler):
+    """Swarm::getExpectations (pswarm_filter.h:96-160) for h(x) = x, x^2: per filter the weighted means before resampling
+    (bit-exact against the oracle), then the mean over the parameter particles in filter order."""
+    T, P = 25, 5
+    y = sv_series(T, seed=77)
+    base = np.array([1.0, 0.95, 0.0625]) if model == sb.MODEL_SV else np.array([0.9, 0.0, 0.3, -0.1])
+    theta = np.stack([base * (1 + 0.01 * p) for p in range(P)])
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=21, scan_items_per_lane=L)
+    be.add_observed_data(y)
+    got = be.swarm_expectations(theta, stream_base=9, return_per_filter=True)
+    lay = be.layout
+    refs = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=lay["scan_items_per_lane"], NT=lay["threads_per_filter"],
+                              seed=21, filter_id=9 + p) for p in range(P)]
+    for p in range(P):
+        assert np.array_equal(got["per_filter"][p], refs[p]["expect"])
+    acc_e, acc_c = np.zeros((T, 2)), np.zeros(T)
+    for p in range(P):
+        acc_e = acc_e + refs[p]["expect"]
+        acc_c = acc_c + refs[p]["cond_like"]
+    assert np.array_equal(got["expectations"], acc_e / P)
+    assert np.array_equal(got["log_cond_like"], acc_c / P)
+    # agrees with the reference-order (libm, sequential) weighted means to 1e-9
+    fai = oracle.filter_run(theta[0], y, N, model=model, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=21, filter_id=9)
+    if np.array_equal(fai["ancestors"], refs[0]["ancestors"]):
+        assert np.allclose(got["per_filter"][0], fai["expect"], rtol=1e-9, atol=1e-12)
+    # h = const: the reference's own test expects the constant back (test_pswarm.cpp:345, 42.0); here E[x^2] >= E[x]^2
+    assert np.all(got["expectations"][:, 1] >= got["expectations"][:, 0] ** 2 - 1e-12)
