@@ -223,10 +223,11 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
     if os.path.exists(spy):
         g = np.load(spy)
         C1_N, C1_R, C1_ITERS = 500, 100, 12
-        # 100 filters do not fill 148 SMs, so the step latency of one CTA sets the pace: 4 particles per thread
-        # (128 threads per filter) measured 1.58 us/step against 2.69 us/step for the throughput layout (8 per thread)
+        # 100 filters do not fill 148 SMs, so the step latency of one CTA sets the pace: 2 particles per thread
+        # (256 threads per filter) measured 1.57 us/step against 1.98 (4 per thread), 2.75 (8, the throughput layout)
+        # and 1.91 (1 per thread, 512 threads: the barriers and cross-warp scans grow) -- tools/pmmh_latency.py
         be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=C1_N, seed=SEED_FILTER + 1, device=local_rank,
-                                                      scan_items_per_lane=4))
+                                                      scan_items_per_lane=2))
         be.add_observed_data(g["y"])
         comm(be)
         be.pmmh_run(g["theta"][None, :], C1_R, 3, proposal_seed=1)

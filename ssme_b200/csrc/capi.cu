@@ -287,7 +287,9 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     // default: 8 particles per thread once that still fills a warp (measured on B200, configs[1]:
     // L=8/NT=128 1.06e11 particle-steps/s vs L=4/NT=256 0.95e11), else 4
     if (L == 0) L = (cfg->num_particles > 8 * 24) ? 8 : 4;
-    if (L != 4 && L != 8) return fail(SSME_B200_EUNSUPPORTED, "scan_items_per_lane must be 4 or 8 (got %d)", L);
+    if (L != 1 && L != 2 && L != 4 && L != 8) return fail(SSME_B200_EUNSUPPORTED, "scan_items_per_lane must be 1, 2, 4 or 8 (got %d)", L);
+    if (L < 4 && cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL)
+        return fail(SSME_B200_EUNSUPPORTED, "the latency layouts (scan_items_per_lane 1, 2) are built for multinomial and systematic resampling");
     NT = cfg->threads_per_filter;
     const int need = (cfg->num_particles + L - 1) / L;
     if (NT == 0) NT = next_pow2(need < 32 ? 32 : need);

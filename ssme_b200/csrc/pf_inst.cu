@@ -30,7 +30,18 @@ namespace ssme {
     SSME_INST(L, kModelSVLeverage, kResampSystematic, 0)  \
     SSME_INST(L, kModelSVLeverage, kResampSystematic, 1)
 
-static const KernelEntry kTable[] = {SSME_INST_L(4) SSME_INST_L(8)};
+// latency layouts (1 or 2 particles per thread, for batches that do not fill the GPU): i.i.d. and systematic targets
+#define SSME_INST_LAT(L)                                  \
+    SSME_INST(L, kModelSV, kResampMultinomial, 0)         \
+    SSME_INST(L, kModelSV, kResampMultinomial, 1)         \
+    SSME_INST(L, kModelSV, kResampSystematic, 0)          \
+    SSME_INST(L, kModelSV, kResampSystematic, 1)          \
+    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 0) \
+    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 1) \
+    SSME_INST(L, kModelSVLeverage, kResampSystematic, 0)  \
+    SSME_INST(L, kModelSVLeverage, kResampSystematic, 1)
+
+static const KernelEntry kTable[] = {SSME_INST_LAT(1) SSME_INST_LAT(2) SSME_INST_L(4) SSME_INST_L(8)};
 
 const KernelEntry* SSME_CAT(kernel_table_nt, SSME_NT)(int* count)
 {

@@ -131,7 +131,7 @@ __device__ __forceinline__ ModelConst model_init(const double* th)
 template <int L, int NT, int MODEL, int RESAMP, bool DEBUG>
 __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a)
 {
-    static_assert(L % 4 == 0, "Philox blocks serve 4 particles");
+    static_assert(L == 1 || L == 2 || L % 4 == 0, "Philox blocks serve 4 particles; L = 1, 2 share a block between threads");
     static_assert(NT % 32 == 0 && NT >= 32 && NT <= 1024, "whole warps");
     constexpr int NP = L * NT;
     constexpr int NW = NT / 32;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
             for (int k = 0; k < L; ++k)
                 z[k] = (i0 + k < N) ? a.z_inj[((size_t)f * T + t) * N + i0 + k] : 0.0;
-        } else {
+        } else if (L >= 4) {
 #pragma unroll
             for (int q = 0; q < L / 4; ++q) {
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
@@ -224,6 +224,19 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                 z[4 * q + 1] = (double)z1;
                 z[4 * q + 2] = (double)z2;
                 z[4 * q + 3] = (double)z3;
+            }
+        } else {
+            // latency layouts (1 or 2 particles per thread): the 2 or 4 threads that share a Philox block each compute it
+            // and keep their own Box-Muller pair -- redundant integer work buys shorter dependent chains per step
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), key);
+            const bool hi = (i0 & 2) != 0;
+            float za, zb;
+            box_muller(hi ? r.z : r.x, hi ? r.w : r.y, za, zb);
+            if (L == 2) {
+                z[0] = (double)za;
+                z[L - 1] = (double)zb;
+            } else {
+                z[0] = (double)((i0 & 1) ? zb : za);
             }
         }
 
@@ -252,9 +265,13 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             mloc = (v > mloc) ? v : mloc;
         }
         double* Xcur = Xs + (t & 1) * NP;
+        if (L == 1) {
+            Xcur[i0] = x[0];
+        } else {
 #pragma unroll
-        for (int k = 0; k < L; k += 2)
-            *reinterpret_cast<double2*>(Xcur + i0 + k) = make_double2(x[k], x[k + 1]);
+            for (int k = 0; k + 1 < L; k += 2)
+                *reinterpret_cast<double2*>(Xcur + i0 + k) = make_double2(x[k], x[k + 1]);
+        }
         if (DEBUG && a.x_trace) {
 #pragma unroll
             for (int k = 0; k < L; ++k)
@@ -416,13 +433,16 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
                 for (int k = 0; k < L; ++k)
                     tau[k] = (i0 + k < N) ? __dmul_rn(a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k], S) : 0.0;
-            } else {
+            } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
                     const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
                     tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
                     tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
                 }
+            } else {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                tau[0] = __dmul_rn((i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
             }
         } else if (RESAMP == kResampSortedMultinomial) {
             // mn_resamp_states_and_params (liu_west_filter.h:104-139, = pf's mn_resamp_fast1): N+1 exponential spacings
@@ -435,7 +455,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     const double u = (i0 + k < N) ? a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k] : 1.0;
                     sce[k] = (i0 + k < N) ? -dlog_unit(u) : 0.0;
                 }
-            } else {
+            } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
                     const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), key);
@@ -445,6 +465,11 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     sce[2 * q + 0] = (i0 + 2 * q < N) ? -dlog_unit(ua) : 0.0;
                     sce[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
                 }
+            } else {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                double ua = (i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
+                ua = (ua == 0.0) ? 0x1p-53 : ua;
+                sce[0] = (i0 < N) ? -dlog_unit(ua) : 0.0;
             }
             double uN;
             if (DEBUG && a.inject) {

@@ -185,3 +185,25 @@ def test_swarm_expectations_bit_exact(oracle, sv_series, gpu_backend_factory, mo
         assert np.allclose(got["per_filter"][0], fai["expect"], rtol=1e-9, atol=1e-12)
     # h = const: the reference's own test expects the constant back (test_pswarm.cpp:345, 42.0); here E[x^2] >= E[x]^2
     assert np.all(got["expectations"][:, 1] >= got["expectations"][:, 0] ** 2 - 1e-12)
+
+
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("N,T,L,rs", [(500, 70, 1, 1), (500, 70, 2, 1), (33, 20, 1, 1), (1000, 40, 2, 3), (1024, 33, 1, 1), (63, 9, 2, 1)])
+def test_latency_layouts_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, L, rs):
+    """1 and 2 particles per thread (threads sharing a Philox block each compute it): same streams, so the fast kernel, the
+    tracing kernel and the oracle at the same (L, NT) agree bit for bit -- and the ancestors do not depend on the layout."""
+    y = sv_series(T, seed=5)
+    theta = np.stack([_theta(model), _theta(model) * 0.97])
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, resample_every=rs, seed=31, scan_items_per_lane=L)
+    be.add_observed_data(y)
+    lay = be.layout
+    assert lay["scan_items_per_lane"] == L
+    got = be.trace(theta, stream_base=4)
+    out, pf = be.work_batch(theta, R=1, stream_base=4, return_per_filter=True)
+    for f in range(2):
+        ref = oracle.filter_run(theta[f], y, N, model=model, resampler=resampler, rs=rs, L=L, NT=lay["threads_per_filter"], seed=31, filter_id=4 + f)
+        assert np.array_equal(got["ancestors"][f], ref["ancestors"])
+        assert np.array_equal(got["x"][f], ref["x"])
+        assert np.array_equal(got["cond_like"][f], ref["cond_like"])
+        assert got["loglik"][f] == ref["loglik"] == pf[f, 0]

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ssme_b200 as sb
 g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "spy_config1.npz"))
-for L, NT in ((8, 64), (4, 128), (4, 256), (8, 128), (4, 512), (4, 1024), (8, 1024)):
+for L, NT in ((8, 64), (4, 128), (2, 256), (1, 512), (2, 512), (1, 1024)):
     try:
         be = sb.ParticleFilterBackend(sb.FilterConfig(num_particles=500, seed=1, scan_items_per_lane=L, threads_per_filter=NT))
     except Exception as e:
