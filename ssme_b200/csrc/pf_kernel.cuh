@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     const unsigned long long f = a.filter_offset + blockIdx.x;
     const int N = a.N, T = a.T;
     const int i0 = tid * L;
+    const bool full = (i0 + L <= N);  // every particle of this thread is real (not padding)
     const int nchunks = (T + kYChunk - 1) / kYChunk;
 
     // Eytzinger slot (byte offset) of each of this thread's CDF entries: sorted index i is probed by
@@ -244,25 +245,38 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[L];
         double mloc = __longlong_as_double(0xfff0000000000000ll);
+        // one uniform branch per step (inside the particle loop the compiler keeps a test per particle)
+        if (t == 0) {
 #pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if (t == 0) {
-                x[k] = __dmul_rn(z[k], mc.sd0);
-            } else if (MODEL == kModelSV) {
-                x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
-            } else {
+            for (int k = 0; k < L; ++k) x[k] = __dmul_rn(z[k], mc.sd0);
+        } else if (MODEL == kModelSV) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+        } else {
+            const double cz = __dmul_rn(mc.rho_sigma, cov);
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
                 const double e2 = dexp(__dmul_rn(-0.5, x[k]));
-                const double cz = __dmul_rn(mc.rho_sigma, cov);
                 double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
                 mean = __fma_rn(cz, e2, mean);
                 x[k] = __fma_rn(mc.sdv, z[k], mean);
             }
+        }
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
             const double e = dexp(-x[k]);
             const double g = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
-            double v = DEBUG ? __dadd_rn(lwacc[k], g) : g;
-            v = (i0 + k < N) ? v : __longlong_as_double(0xfff0000000000000ll);
+            const double v = DEBUG ? __dadd_rn(lwacc[k], g) : g;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;
+        }
+        if (!full) {  // only the thread(s) holding the padding beyond particle N-1
+            mloc = __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                lw[k] = (i0 + k < N) ? lw[k] : __longlong_as_double(0xfff0000000000000ll);
+                mloc = (lw[k] > mloc) ? lw[k] : mloc;
+            }
         }
         double* Xcur = Xs + (t & 1) * NP;
         if (L == 1) {
@@ -536,8 +550,12 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
         for (int k = 0; k < L; ++k) {
             idx[k] = min((int)(nb[k] >> 3) - (NP - 1), N - 1);
-            x[k] = (i0 + k < N) ? Xcur[idx[k]] : 0.0;
+            x[k] = Xcur[idx[k]];
             lwacc[k] = 0.0;
+        }
+        if (!full) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) x[k] = (i0 + k < N) ? x[k] : 0.0;
         }
         if (DEBUG && a.ancestors) {
 #pragma unroll
