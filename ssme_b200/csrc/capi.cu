@@ -407,6 +407,7 @@ static FilterArgs base_args(ssme_b200_handle h, const double* theta_dev, unsigne
     a.R = R;
     a.rs = h->cfg.resample_every;
     a.seed = h->cfg.seed;
+    a.rk = philox_round_keys(h->cfg.seed);
     a.filter_base = stream_base;
     a.loglik = loglik_dev;
     return a;

@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
     }
     const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
     const double logN = dlog((double)N);
     const double dN = (double)N;
@@ -153,7 +152,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         const double cov = (OS == 2) ? a.obs[(size_t)t * OS + 1] : 0.0;
         double z[kClL];
         {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), key);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), a.rk);
             float z0, z1, z2, z3;
             box_muller(r.x, r.y, z0, z1);
             box_muller(r.z, r.w, z2, z3);
@@ -270,12 +269,12 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
             for (int q = 0; q < kClL / 2; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
                 tau[2 * q + 0] = uniform53(r.x, r.y);
                 tau[2 * q + 1] = uniform53(r.z, r.w);
             }
         } else {
-            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
+            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
             tau[0] = uniform53(r.x, r.y);
         }
         mbar_wait(bar_cdf, (uint32_t)(t & 1));  // every tile sum, the whole filter's CDF and states have landed

@@ -50,6 +50,7 @@ struct FilterArgs {
     double* cond_like;    // [F][T]
     int* ancestors;       // [F][T][N]
     double* x_trace;
+    PhiloxRoundKeys rk;  // key schedule of `seed` (host: philox_round_keys)
     double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
@@ -186,7 +187,6 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 
     const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
     const double logN = dlog((double)N);
     const double dN = (double)N;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else if (L >= 4) {
 #pragma unroll
             for (int q = 0; q < L / 4; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), key);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
                 float z0, z1, z2, z3;
                 box_muller(r.x, r.y, z0, z1);
                 box_muller(r.z, r.w, z2, z3);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else {
             // latency layouts (1 or 2 particles per thread): the 2 or 4 threads that share a Philox block each compute it
             // and keep their own Box-Muller pair -- redundant integer work buys shorter dependent chains per step
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), key);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), a.rk);
             const bool hi = (i0 & 2) != 0;
             float za, zb;
             box_muller(hi ? r.z : r.x, hi ? r.w : r.y, za, zb);
@@ -450,12 +450,12 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
                     tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
                     tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
                 }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 1u), key);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
                 tau[0] = __dmul_rn((i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
             }
         } else if (RESAMP == kResampSortedMultinomial) {
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
                     double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
                     ua = (ua == 0.0) ? 0x1p-53 : ua;
                     ub = (ub == 0.0) ? 0x1p-53 : ub;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     sce[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
                 }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
                 double ua = (i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 ua = (ua == 0.0) ? 0x1p-53 : ua;
                 sce[0] = (i0 < N) ? -dlog_unit(ua) : 0.0;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 uN = a.u_inj[((size_t)f * T + t) * a.stride_u + N];
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), key);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
                 uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 uN = (uN == 0.0) ? 0x1p-53 : uN;
             }
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 u0 = a.u_inj[((size_t)f * T + t) * a.stride_u];
             } else {
-                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), key);
+                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
                 u0 = uniform53(r.x, r.y);
             }
             const double sN = __ddiv_rn(S, dN);
