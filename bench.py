@@ -410,6 +410,31 @@ def run_ours(args):
         spilled = run_spilled_leg(sb, dist, rank, world, local_rank, hbm)
         liu_west = run_liu_west_leg(sb, local_rank, hbm) if rank == 0 else None
 
+    # ---- optional fp32 mode on the same workload (rank 0; device-resident, CUDA events) --------------------
+    fp32_mode = None
+    if not args.no_pmmh and rank == 0:
+        be32 = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=N_PARTICLES, seed=SEED_FILTER, device=local_rank,
+                                                        dtype=sb.DTYPE_F32))
+        be32.add_observed_data(y)
+        s32 = torch.cuda.ExternalStream(be32.stream, device=dev)
+        d_out32 = torch.empty(P_PROPOSALS, dtype=torch.float64, device=dev)
+        for i in range(2):
+            be32.work_batch_device(d_theta.data_ptr(), P_PROPOSALS, R_REPL, F_base + i * P_PROPOSALS, d_out32.data_ptr(), d_pf.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s32)
+        be32.work_batch_device(d_theta.data_ptr(), P_PROPOSALS, R_REPL, F_base + args.warmup * world * P_PROPOSALS * R_REPL, d_out32.data_ptr(),
+                               d_pf.data_ptr())
+        e1.record(s32)
+        torch.cuda.synchronize()
+        ms32 = e0.elapsed_time(e1)
+        # same stream ids as the first timed fp64 step: the two modes estimate the same likelihoods from the same draws
+        fp32_mode = {"particle_steps_per_sec": steps_per_pass / (ms32 * 1e-3), "ms_per_step": ms32, "dtype": "f32",
+                     "mean_loglik_f32": float(d_out32.mean().item()),
+                     "note": "pf_kernel_f32.cuh: float state, weights, scan and search (the precision of the reference's example, "
+                             "example/main.cpp:13); log p(y_t|y_1:t-1) accumulated in double; bit-exact vs oracle/pf_oracle_f32.c"}
+        be32.close()
+
     if rank == 0:
         # ---- roofline of the dominant kernel (bootstrap_filter_kernel): FP64 pipe ----------------
         fma_rate = sb.measure_fp64_fma_rate(local_rank, 1 << 15)  # thread-level FMA instructions / s, measured now
@@ -457,7 +482,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(P_PROPOSALS * 8)},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "pmmh": pmmh, "spilled_filter": spilled, "liu_west": liu_west,
+            "pmmh": pmmh, "spilled_filter": spilled, "liu_west": liu_west, "fp32_mode": fp32_mode,
             "layout": layout, "wall_s_timed_region": t_wall, "checksum": checksum,
             "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-10); all filter arithmetic f64",
         }

@@ -60,7 +60,8 @@ typedef struct {
     int32_t num_particles;       /* N: template parameter nparts of svol_bs / BSFilter */
     int32_t resampler;           /* SSME_B200_RESAMP_*  */
     int32_t resample_every;      /* rs: resample when (t+1) % rs == 0 (pf BSFilter ctor arg; liu_west_filter.h:1686) */
-    int32_t dtype;               /* SSME_B200_DTYPE_*   */
+    int32_t dtype;               /* SSME_B200_DTYPE_F64, or _F32: the precision of the reference's example program
+                                    (example/main.cpp:13); resident kernel, rs = 1, multinomial / systematic */
     int32_t rng_mode;            /* SSME_B200_RNG_*     */
     uint64_t seed;               /* Philox key; the reference seeds mt19937 from the clock (liu_west_filter.h:75-76) */
     int32_t scan_items_per_lane; /* L of the canonical scan order; 0 = library default */

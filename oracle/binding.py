@@ -93,6 +93,34 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
     return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs, "margin": mg.value, "expect": ex}
 
 
+def filter_run_f32(theta, y, N, model=0, resampler=0, L=8, NT=0, seed=20260101, filter_id=0, cov=None, trace=True):
+    """The float32 filter (fp32 mode); returns dict(loglik, cond_like, ancestors, x)."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    theta = np.ascontiguousarray(theta, dtype=np.float64).ravel()
+    T = y.shape[0]
+    cfg = _Cfg(model, N, resampler, 1, ARITH_CANONICAL, L, RNG_PHILOX, NT, seed, filter_id, 0, 0)
+    cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
+    ll = C.c_double(0)
+    cl = np.empty(T)
+    anc = np.empty((T, N), dtype=np.int32) if trace else None
+    xs = np.empty((T, N)) if trace else None
+    fn = lib().ssme_oracle_filter_f32
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 5
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = fn(C.cast(C.byref(cfg), C.c_void_p), vp(theta), vp(y), T, vp(cov), C.cast(C.byref(ll), C.c_void_p), vp(cl), vp(anc), vp(xs))
+    if rc != 0:
+        raise ValueError("ssme_oracle_filter_f32 failed with %d" % rc)
+    return {"loglik": ll.value, "cond_like": cl, "ancestors": anc, "x": xs}
+
+
+def fexp(x):
+    fn = lib().ssme_oracle_fexp
+    fn.restype = C.c_float
+    fn.argtypes = [C.c_float]
+    return float(fn(float(x)))
+
+
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
                   cov=None, trace=True, tiled=2, form="sisr"):
     """Liu-West filter on the SV-with-leverage model; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary

@@ -132,6 +132,31 @@ static inline void dm_box_muller(uint32_t a, uint32_t b, float* z0, float* z1)
 }
 
 /* 53-bit uniform in [0,1) from two 32-bit words */
+/* ---- float32 exp for the optional fp32 mode: Cody-Waite reduction with the 1.5*2^23 shift, degree-5 polynomial on
+ * (e^r - 1 - r)/r^2 (Cephes expf coefficients), every operation a correctly rounded float operation in this order.
+ * NaN -> NaN; x <= -87 -> +0; x > 88 -> +inf. */
+static inline float dm_fexp(float x)
+{
+    if (x != x) return x;
+    if (x <= -87.0f) return 0.0f;
+    if (x > 88.0f) return INFINITY;
+    float t = fmaf(x, 0x1.715476p+0f, 0x1.8p23f);
+    int32_t k = (int32_t)dm_f2u(t) - 0x4B400000;
+    float kd = t - 0x1.8p23f;
+    float r = fmaf(kd, -0x1.62e400p-1f, x);
+    r = fmaf(kd, -0x1.7f7d1cp-20f, r);
+    float p = 0x1.a0d2cep-13f;
+    p = fmaf(p, r, 0x1.6e879cp-10f);
+    p = fmaf(p, r, 0x1.1112fap-7f);
+    p = fmaf(p, r, 0x1.555502p-5f);
+    p = fmaf(p, r, 0x1.555550p-3f);
+    p = fmaf(p, r, 0x1.000000p-1f);
+    float v = fmaf(r * r, p, r) + 1.0f;
+    return v * dm_u2f((uint32_t)(k + 127) << 23);
+}
+/* 24-bit uniform in [0,1) */
+static inline float dm_uniform24(uint32_t w) { return (float)(w >> 8) * 0x1p-24f; }
+
 static inline double dm_uniform53(uint32_t hi, uint32_t lo)
 {
     uint64_t v = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);

@@ -81,6 +81,12 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
                               double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
                               double* tie_margin, double* expect);
 
+/* The bootstrap filter in float32 (oracle/pf_oracle_f32.c): the precision of the reference's example program
+ * (example/main.cpp:13), canonical float arithmetic, resampling at every step, Philox streams; x_trace is widened to double. */
+int ssme_oracle_filter_f32(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T, const double* cov,
+                           double* loglik, double* cond_like, int32_t* ancestors, double* x_trace);
+float ssme_oracle_fexp(float x);
+
 /*
  * Liu-West joint state/parameter filter, SISR form with the bootstrap proposal: LWFilter2WithCovs::filter
  * (reference include/ssme/liu_west_filter.h:2191-2343, update_parameter_proposal_components :2346-2360, shrinkage

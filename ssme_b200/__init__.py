@@ -23,4 +23,6 @@ from .capi import (  # noqa: F401
     RESAMP_SYSTEMATIC,
     RNG_PHILOX,
     RNG_INJECTED,
+    DTYPE_F64,
+    DTYPE_F32,
 )

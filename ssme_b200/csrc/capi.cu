@@ -240,7 +240,18 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     if (cfg->resampler != SSME_B200_RESAMP_MULTINOMIAL && cfg->resampler != SSME_B200_RESAMP_SYSTEMATIC &&
         cfg->resampler != SSME_B200_RESAMP_SORTED_MULTINOMIAL)
         return fail(SSME_B200_EINVAL, "unknown resampler %d", cfg->resampler);
-    if (cfg->dtype != SSME_B200_DTYPE_F64) return fail(SSME_B200_EUNSUPPORTED, "only the fp64 path is built");
+    if (cfg->dtype != SSME_B200_DTYPE_F64 && cfg->dtype != SSME_B200_DTYPE_F32) return fail(SSME_B200_EINVAL, "unknown dtype %d", cfg->dtype);
+    const bool f32 = (cfg->dtype == SSME_B200_DTYPE_F32);
+    if (f32) {
+        // fp32 mode (pf_kernel_f32.cuh): the resident one-CTA kernel, resampling at every step, on-device streams
+        if (cfg->num_particles > 8192 || cfg->force_global_memory || cfg->use_cluster)
+            return fail(SSME_B200_EUNSUPPORTED, "the fp32 mode runs the resident one-CTA kernel (num_particles <= 8192, no cluster, no global-memory kernels)");
+        if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the fp32 mode resamples at every step (resample_every = 1)");
+        if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the fp32 mode uses the on-device Philox streams");
+        if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) return fail(SSME_B200_EUNSUPPORTED, "the fp32 mode offers multinomial and systematic resampling");
+        if (cfg->scan_items_per_lane != 0 && cfg->scan_items_per_lane != 4 && cfg->scan_items_per_lane != 8)
+            return fail(SSME_B200_EUNSUPPORTED, "the fp32 mode is built for scan_items_per_lane 4 or 8");
+    }
     if (cfg->rng_mode != SSME_B200_RNG_PHILOX && cfg->rng_mode != SSME_B200_RNG_INJECTED)
         return fail(SSME_B200_EINVAL, "unknown rng_mode %d", cfg->rng_mode);
 
@@ -297,8 +308,8 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         return fail(SSME_B200_EUNSUPPORTED,
                     "num_particles %d needs %d threads at L=%d; the resident kernel supports power-of-two CTAs of 32..1024 threads",
                     cfg->num_particles, need, L);
-    fast = find_kernel(L, NT, cfg->model, cfg->resampler, 0);
-    dbg = find_kernel(L, NT, cfg->model, cfg->resampler, 1);
+    fast = find_kernel(L, NT, cfg->model, cfg->resampler, f32 ? 2 : 0);
+    dbg = find_kernel(L, NT, cfg->model, cfg->resampler, f32 ? 2 : 1);  // the fp32 kernel traces through run-time pointers
     if (!fast || !dbg) return fail(SSME_B200_EUNSUPPORTED, "no kernel built for L=%d NT=%d model=%d resampler=%d", L, NT, cfg->model, cfg->resampler);
     int rc;
     if ((rc = prepare_kernel(fast)) != SSME_B200_OK) return rc;
@@ -586,7 +597,8 @@ int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, s
     if (P == 0) return fail(SSME_B200_EINVAL, "the swarm needs at least one parameter particle");
     if (!theta_host || !expectations_host) return fail(SSME_B200_EINVAL, "null host buffer");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
-    if (h->spill || h->cluster) return fail(SSME_B200_EUNSUPPORTED, "expectations are an output of the resident one-CTA kernel (num_particles <= 8192, no cluster)");
+    if (h->spill || h->cluster || h->cfg.dtype != SSME_B200_DTYPE_F64)
+        return fail(SSME_B200_EUNSUPPORTED, "expectations are an output of the resident one-CTA fp64 kernel (num_particles <= 8192, no cluster)");
     int rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, T = h->T;

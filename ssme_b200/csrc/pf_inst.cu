@@ -1,6 +1,7 @@
 // ssme_b200/csrc/pf_inst.cu -- compiled once per CTA size (-DSSME_NT=32..1024): instantiates K1.
 #include "pf_dispatch.h"
 #include "pf_kernel.cuh"
+#include "pf_kernel_f32.cuh"
 
 #ifndef SSME_NT
 #error "compile with -DSSME_NT=<threads per filter>"
@@ -41,7 +42,18 @@ namespace ssme {
     SSME_INST(L, kModelSVLeverage, kResampSystematic, 0)  \
     SSME_INST(L, kModelSVLeverage, kResampSystematic, 1)
 
-static const KernelEntry kTable[] = {SSME_INST_LAT(1) SSME_INST_LAT(2) SSME_INST_L(4) SSME_INST_L(8)};
+// fp32 mode (pf_kernel_f32.cuh): table slot debug = 2
+#define SSME_INST_F32(L, MODEL, RESAMP)                                                        \
+    {L, SSME_NT, MODEL, RESAMP, 2,                                                             \
+     reinterpret_cast<const void*>(&bootstrap_filter_f32_kernel<L, SSME_NT, MODEL, RESAMP>),   \
+     filter_f32_smem_bytes<L, SSME_NT, MODEL>()},
+#define SSME_INST_F32_L(L)                                \
+    SSME_INST_F32(L, kModelSV, kResampMultinomial)        \
+    SSME_INST_F32(L, kModelSV, kResampSystematic)         \
+    SSME_INST_F32(L, kModelSVLeverage, kResampMultinomial) \
+    SSME_INST_F32(L, kModelSVLeverage, kResampSystematic)
+
+static const KernelEntry kTable[] = {SSME_INST_LAT(1) SSME_INST_LAT(2) SSME_INST_L(4) SSME_INST_L(8) SSME_INST_F32_L(4) SSME_INST_F32_L(8)};
 
 const KernelEntry* SSME_CAT(kernel_table_nt, SSME_NT)(int* count)
 {

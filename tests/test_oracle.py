@@ -179,3 +179,21 @@ def test_lw_apf_form_restates_the_reference_step(oracle):
     y2 = y.copy(); y2[1] = 25.0
     r2 = ob.lw_filter_run(lo, hi, 0.99, y2, N, arithmetic=ob.ARITH_FAITHFUL, form="apf", seed=4, filter_id=1, resampler=0)
     assert len(np.unique(r2["aux_index"][1])) < len(np.unique(r["aux_index"][1]))
+
+
+def test_fp32_exp_and_filter(oracle):
+    """det_math's float exp is within 1.5 ulp of the correctly rounded value; the float filter tracks the double one."""
+    from oracle import binding as ob
+    xs = np.concatenate([np.linspace(-86.9, 88.0, 4001), np.random.default_rng(0).normal(0, 3, 4000)]).astype(np.float32)
+    got = np.array([ob.fexp(v) for v in xs], dtype=np.float32)
+    ref = np.exp(xs.astype(np.float64))
+    ulp = np.abs(got.astype(np.float64) - ref) / np.spacing(ref.astype(np.float32)).astype(np.float64)
+    assert ulp.max() < 1.5
+    assert ob.fexp(-100.0) == 0.0 and ob.fexp(89.0) == np.inf and np.isnan(ob.fexp(float("nan"))) and ob.fexp(0.0) == 1.0
+    y = np.random.default_rng(1).standard_normal(3)
+    th = np.array([1.0, 0.95, 0.0625])
+    a = ob.filter_run_f32(th, y, 1024, seed=3, filter_id=2, L=8)
+    b = ob.filter_run(th, y, 1024, L=8, seed=3, filter_id=2)
+    assert abs(a["loglik"] - b["loglik"]) <= 2e-5 * abs(b["loglik"])
+    assert (a["ancestors"][0] == b["ancestors"][0]).mean() > 0.99   # same normals, same (truncated) uniforms
+    assert np.allclose(a["x"][0], b["x"][0], rtol=1e-6, atol=1e-7)
