@@ -448,8 +448,8 @@ def run_ours(args):
             "frac_definition": "FP64-pipe issue slots: (31 FMA + 13 add/mul/cvt + 12 compare) per particle-step x particle-steps/s "
                                "/ measured FP64 FMA instruction rate (micro-benchmark in this run)",
             "frac_flops": achieved_tflops / peak_tflops,
-            "issue_slots": {"thread_instr_per_particle_step": 223.0, "source": "ncu SASS count, profiles/r1_k1_eytzinger_L8_NT128.txt",
-                            "frac": (per_gpu * 223.0 / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
+            "issue_slots": {"thread_instr_per_particle_step": 201.7, "source": "ncu SASS count, profiles/r1_k1_v2_L8_NT128.txt",
+                            "frac": (per_gpu * 201.7 / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
                             "note": "what actually binds K1 (DESIGN.md section 5): 4 warp-instructions per SM per clock"},
             "peak_source": "measured in-run (ssme_b200_measure_fp64_fma_rate); "
             "MEASURED_PEAKS.json has no FP64 entry", "traffic": None,
