@@ -5,6 +5,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -162,7 +163,11 @@ namespace {
 
 const void* cluster_kernel_fn(int model, int res, int nt)
 {
-#define SSME_CL(M, R) (nt == 128 ? (const void*)&cluster_filter_kernel<M, R, 128> : (const void*)&cluster_filter_kernel<M, R, 256>)
+#define SSME_CL(M, R)                                                             \
+    (nt == 128   ? (const void*)&cluster_filter_kernel<M, R, 128>                 \
+     : nt == 256 ? (const void*)&cluster_filter_kernel<M, R, 256>                 \
+     : nt == 512 ? (const void*)&cluster_filter_kernel<M, R, 512>                 \
+                 : (const void*)&cluster_filter_kernel<M, R, 1024>)
     if (model == SSME_B200_MODEL_SV) return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSV, kResampMultinomial) : SSME_CL(kModelSV, kResampSystematic);
     return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampMultinomial) : SSME_CL(kModelSVLeverage, kResampSystematic);
 #undef SSME_CL
@@ -268,9 +273,13 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         return fail(SSME_B200_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
                     prop.minor);
 
-    // K2 (one filter per thread-block cluster) takes up to 16 tiles of 4*threads particles
-    const int cl_nt = (cfg->threads_per_filter == 128 || cfg->threads_per_filter == 256) ? cfg->threads_per_filter : 256;
-    const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0 && cfg->num_particles <= kClMax * kClL * cl_nt;
+    // K2 (one filter per thread-block cluster) takes up to 16 tiles of 4*threads particles, as far as every tile's CDF fits
+    // into each CTA's shared memory
+    const int tpf = cfg->threads_per_filter;
+    const int cl_nt = (tpf == 128 || tpf == 256 || tpf == 512 || tpf == 1024) ? tpf : 256;
+    const int cl_size = (cfg->num_particles + kClL * cl_nt - 1) / (kClL * cl_nt);
+    const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0 && cl_size <= kClMax &&
+                             cluster_smem_bytes(cl_nt, cl_size) <= (size_t)227 * 1024;
     const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
@@ -281,7 +290,7 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");
         if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel uses the on-device Philox streams");
         if (cfg->threads_per_filter != 0 && cfg->threads_per_filter != cl_nt)
-            return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel runs 128 or 256 threads per tile (got %d)", cfg->threads_per_filter);
+            return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel runs 128, 256, 512 or 1024 threads per tile (got %d)", cfg->threads_per_filter);
         if (cfg->num_particles <= kClL * cl_nt)
             return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", kClL * cl_nt);
         L = kClL;
@@ -332,7 +341,7 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         const void* fn = cluster_kernel_fn(cfg->model, cfg->resampler, NT);
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(NT, kClMax));
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>((size_t)227 * 1024, cluster_smem_bytes(NT, kClMax)));  // per function, not per handle
         if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
     } else if (!spill) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);

@@ -3,7 +3,8 @@
 // K1 keeps a filter inside one CTA, so its time-step latency is what one SM can issue: ~17 us per step at
 // N = 8192, which is what paces PMMH when there are fewer chains than SMs (BASELINE.json config 3:
 // 64 chains x 8192 particles; 8 chains per GPU on 8 GPUs).  K2 spreads one filter over up to 16 SMs:
-// CTA r of the cluster owns the tile of particles r*512 .. r*512+511 (128 threads x 4).  Per step:
+// CTA r of the cluster owns tile r of the particles (tiles of 512 .. 4096 = 128 .. 1024 threads x 4: pick the tile so that
+// filters x tiles-per-filter is about the number of SMs).  Per step:
 //   max of the log-weights   each CTA PUSHES its tile maximum into every peer's shared memory with st.async, which
 //                            completes bytes on the peer's mbarrier: one one-way DSMEM hop, no cluster barrier
 //   CDF and states           each CTA writes its tile-local CDF (breadth-first) and states to an L2-resident scratch
@@ -34,7 +35,7 @@ namespace cg = cooperative_groups;
 
 constexpr int kClL = 4;    // particles per thread
 constexpr int kClMax = 16; // CTAs per cluster (non-portable size, opt-in)
-constexpr int kClMaxWarps = 8;
+constexpr int kClMaxWarps = 32;
 
 // Fixed part of a CTA's shared memory; behind it: X[2][tile] (THIS tile's states, double-buffered by step parity, peers
 // gather from it through DSMEM) and C[cluster size][tile] (every tile's local inclusive CDF in breadth-first order,
@@ -87,11 +88,11 @@ constexpr size_t cluster_smem_bytes(int nt, int cluster_size)
 template <int MODEL, int RESAMP, int NT>
 __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
 {
-    static_assert(NT == 128 || NT == 256, "tile of 512 or 1024 particles");
+    static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "tiles of 512 .. 4096 particles");
     constexpr int OS = obs_stride(MODEL);
     constexpr int kClTile = kClL * NT;
     constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
-    constexpr int K = (NT == 128) ? 9 : 10;  // log2(kClTile)
+    constexpr int K = (NT == 128) ? 9 : (NT == 256) ? 10 : (NT == 512) ? 11 : 12;  // log2(kClTile)
     constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char cl_smem[];
     ClusterShared& sh = *reinterpret_cast<ClusterShared*>(cl_smem);
@@ -161,19 +162,24 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[kClL];
         double mloc = ninf;
+        if (t == 0) {
 #pragma unroll
-        for (int k = 0; k < kClL; ++k) {
-            if (t == 0) {
-                x[k] = __dmul_rn(z[k], mc.sd0);
-            } else if (MODEL == kModelSV) {
-                x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
-            } else {
+            for (int k = 0; k < kClL; ++k) x[k] = __dmul_rn(z[k], mc.sd0);
+        } else if (MODEL == kModelSV) {
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+        } else {
+            const double cz = __dmul_rn(mc.rho_sigma, cov);
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) {
                 const double e2 = dexp(__dmul_rn(-0.5, x[k]));
-                const double cz = __dmul_rn(mc.rho_sigma, cov);
                 double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
                 mean = __fma_rn(cz, e2, mean);
                 x[k] = __fma_rn(mc.sdv, z[k], mean);
             }
+        }
+#pragma unroll
+        for (int k = 0; k < kClL; ++k) {
             const double e = dexp(-x[k]);
             double v = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
             v = (i0 + k < N) ? v : ninf;

@@ -14,7 +14,8 @@ LEV_THETA = np.array([0.9, 0.0, 0.3, -0.1])
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
 @pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
 @pytest.mark.parametrize("N,T,NT", [(1024, 40, 128), (8192, 33, 128), (5000, 65, 128), (600, 7, 128), (4096, 1, 128),
-                                    (8192, 33, 256), (5000, 40, 256), (1025, 9, 256), (16384, 12, 256), (2048, 1, 0)])
+                                    (8192, 33, 256), (5000, 40, 256), (1025, 9, 256), (16384, 12, 256), (2048, 1, 0),
+                                    (8192, 20, 1024), (8192, 20, 512), (4097, 9, 1024), (16000, 6, 1024), (6000, 11, 512)])
 def test_cluster_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, NT):
     y = sv_series(T, seed=41)
     th = SV_THETA if model == sb.MODEL_SV else LEV_THETA
@@ -54,4 +55,4 @@ def test_cluster_argument_checks():
     with pytest.raises(ValueError):
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=256, use_cluster=1))
     with pytest.raises(RuntimeError):
-        sb.ParticleFilterBackend(sb.FilterConfig(num_particles=4096, use_cluster=1, threads_per_filter=512))
+        sb.ParticleFilterBackend(sb.FilterConfig(num_particles=4096, use_cluster=1, threads_per_filter=64))

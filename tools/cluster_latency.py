@@ -7,10 +7,10 @@ rng = np.random.default_rng(1)
 T = 1024
 y = np.exp(0.1 * np.cumsum(rng.standard_normal(T)) * 0.3) * rng.standard_normal(T)
 for model, th in ((sb.MODEL_SV, [1.0, 0.95, 0.0625]), (sb.MODEL_SV_LEVERAGE, [0.9, 0.0, 0.3, -0.1])):
-    for N in (1024, 2048, 8192):
-        for chains in (8, 16, 64):
+    for N in (8192,):
+        for chains in (8, 16, 32, 64):
             row = []
-            for use_cluster, nt in ((0, 0), (1, 128), (1, 256)):
+            for use_cluster, nt in ((0, 0), (1, 256), (1, 512), (1, 1024)):
                 if use_cluster and N <= 4 * nt:
                     row.append(float("nan"))
                     continue
@@ -21,5 +21,5 @@ for model, th in ((sb.MODEL_SV, [1.0, 0.95, 0.0625]), (sb.MODEL_SV_LEVERAGE, [0.
                 r = be.pmmh_run(start, 1, 10, c0_diag=1e-3, proposal_seed=2)
                 row.append(1e3 * r["seconds"] / 10)
                 be.close()
-            print("model %d N=%5d chains=%2d: K1 %.2f us/step   K2/128 %.2f us/step (x%.2f)   K2/256 %.2f us/step (x%.2f)" % (
-                model, N, chains, 1e3 * row[0] / T, 1e3 * row[1] / T, row[0] / row[1], 1e3 * row[2] / T, row[0] / row[2]))
+            print("model %d N=%5d chains=%2d: K1 %.2f us/step   K2/256 %.2f (x%.2f)   K2/512 %.2f (x%.2f)   K2/1024 %.2f (x%.2f)" % (
+                model, N, chains, 1e3 * row[0] / T, 1e3 * row[1] / T, row[0] / row[1], 1e3 * row[2] / T, row[0] / row[2], 1e3 * row[3] / T, row[0] / row[3]))
