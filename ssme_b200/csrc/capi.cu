@@ -161,16 +161,15 @@ int ensure_pinned(ssme_b200_handle h, size_t bytes)
 
 namespace {
 
-const void* cluster_kernel_fn(int model, int res, int nt)
+const void* cluster_kernel_fn(int model, int res, int nt, int L)
 {
-#define SSME_CL(M, R)                                                             \
-    (nt == 128   ? (const void*)&cluster_filter_kernel<M, R, 128>                 \
-     : nt == 256 ? (const void*)&cluster_filter_kernel<M, R, 256>                 \
-     : nt == 512 ? (const void*)&cluster_filter_kernel<M, R, 512>                 \
-                 : (const void*)&cluster_filter_kernel<M, R, 1024>)
+    // tiles of L * nt <= 4096 particles
+#define SSME_CL2(M, R, NTV) (L == 8 ? (const void*)&cluster_filter_kernel<M, R, NTV, (NTV <= 512 ? 8 : 4)> : (const void*)&cluster_filter_kernel<M, R, NTV, 4>)
+#define SSME_CL(M, R) (nt == 128 ? SSME_CL2(M, R, 128) : nt == 256 ? SSME_CL2(M, R, 256) : nt == 512 ? SSME_CL2(M, R, 512) : SSME_CL2(M, R, 1024))
     if (model == SSME_B200_MODEL_SV) return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSV, kResampMultinomial) : SSME_CL(kModelSV, kResampSystematic);
     return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampMultinomial) : SSME_CL(kModelSVLeverage, kResampSystematic);
 #undef SSME_CL
+#undef SSME_CL2
 }
 
 int next_pow2(int v)
@@ -187,14 +186,14 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
     if (F > 0x7fffffffull) return fail(SSME_B200_EINVAL, "too many filters in one launch: %zu", F);
     if (h->cluster) {
         FilterArgs ca = args;
-        const void* fn = cluster_kernel_fn(h->cfg.model, h->cfg.resampler, h->NT);
+        const void* fn = cluster_kernel_fn(h->cfg.model, h->cfg.resampler, h->NT, h->L);
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
         lc.gridDim = dim3((unsigned)(F * (size_t)h->cluster_size));
         lc.blockDim = dim3((unsigned)h->NT);
-        lc.dynamicSmemBytes = cluster_smem_bytes(h->NT, h->cluster_size);
+        lc.dynamicSmemBytes = cluster_smem_bytes(h->L * h->NT, h->cluster_size);
         lc.stream = st;
-        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(kClMax * kClL * h->NT));
+        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(kClMax * h->L * h->NT));
         if (rc2) return rc2;
         double* scratch = h->d_cluster_scratch;
         cudaLaunchAttribute attr[1];
@@ -277,9 +276,11 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     // into each CTA's shared memory
     const int tpf = cfg->threads_per_filter;
     const int cl_nt = (tpf == 128 || tpf == 256 || tpf == 512 || tpf == 1024) ? tpf : 256;
-    const int cl_size = (cfg->num_particles + kClL * cl_nt - 1) / (kClL * cl_nt);
+    const int cl_L = (cfg->scan_items_per_lane == 8) ? 8 : 4;
+    const int cl_tile = cl_L * cl_nt;
+    const int cl_size = (cfg->num_particles + cl_tile - 1) / cl_tile;
     const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0 && cl_size <= kClMax &&
-                             cluster_smem_bytes(cl_nt, cl_size) <= (size_t)227 * 1024;
+                             cluster_smem_bytes(cl_tile, cl_size) <= (size_t)227 * 1024;
     const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
@@ -291,9 +292,12 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel uses the on-device Philox streams");
         if (cfg->threads_per_filter != 0 && cfg->threads_per_filter != cl_nt)
             return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel runs 128, 256, 512 or 1024 threads per tile (got %d)", cfg->threads_per_filter);
-        if (cfg->num_particles <= kClL * cl_nt)
-            return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", kClL * cl_nt);
-        L = kClL;
+        if (cfg->scan_items_per_lane != 0 && cfg->scan_items_per_lane != 4 && cfg->scan_items_per_lane != 8)
+            return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel holds 4 or 8 particles per thread (got %d)", cfg->scan_items_per_lane);
+        if (cl_tile > 4096) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel's tiles hold at most 4096 particles (threads x particles per thread)");
+        if (cfg->num_particles <= cl_tile)
+            return fail(SSME_B200_EINVAL, "use_cluster needs more than %d particles (one tile per CTA)", cl_tile);
+        L = cl_L;
         NT = cl_nt;
     } else if (spill) {
         // K3: particles in HBM, tiles of 4096 (spill_kernel.cuh)
@@ -335,13 +339,13 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->debug = dbg;
     h->spill = spill;
     h->cluster = use_cluster;
-    h->cluster_size = use_cluster ? (cfg->num_particles + kClL * NT - 1) / (kClL * NT) : 1;
+    h->cluster_size = use_cluster ? cl_size : 1;
     int occ = 0;
     if (use_cluster) {
-        const void* fn = cluster_kernel_fn(cfg->model, cfg->resampler, NT);
+        const void* fn = cluster_kernel_fn(cfg->model, cfg->resampler, NT, L);
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>((size_t)227 * 1024, cluster_smem_bytes(NT, kClMax)));  // per function, not per handle
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>((size_t)227 * 1024, cluster_smem_bytes(L * NT, kClMax)));  // per function, not per handle
         if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
     } else if (!spill) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);

@@ -33,7 +33,6 @@ namespace ssme {
 
 namespace cg = cooperative_groups;
 
-constexpr int kClL = 4;    // particles per thread
 constexpr int kClMax = 16; // CTAs per cluster (non-portable size, opt-in)
 constexpr int kClMaxWarps = 32;
 
@@ -80,19 +79,22 @@ __device__ __forceinline__ void tma_multicast_1d(void* dst_smem, const void* src
         : "memory");
 }
 
-constexpr size_t cluster_smem_bytes(int nt, int cluster_size)
+constexpr size_t cluster_smem_bytes(int tile, int cluster_size)
 {
-    return sizeof(ClusterShared) + sizeof(double) * (size_t)(kClL * nt) * (size_t)(2 + cluster_size);
+    return sizeof(ClusterShared) + sizeof(double) * (size_t)tile * (size_t)(2 + cluster_size);
 }
 
-template <int MODEL, int RESAMP, int NT>
+template <int MODEL, int RESAMP, int NT, int L>
 __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
 {
-    static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "tiles of 512 .. 4096 particles");
+    static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "128 .. 1024 threads per tile");
+    static_assert(L == 4 || L == 8, "4 or 8 particles per thread");
+    constexpr int kClL = L;
     constexpr int OS = obs_stride(MODEL);
     constexpr int kClTile = kClL * NT;
+    static_assert(kClTile <= 4096, "tiles of 512 .. 4096 particles");
     constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
-    constexpr int K = (NT == 128) ? 9 : (NT == 256) ? 10 : (NT == 512) ? 11 : 12;  // log2(kClTile)
+    constexpr int K = 31 - __builtin_clz((unsigned)kClTile);  // log2(kClTile)
     constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char cl_smem[];
     ClusterShared& sh = *reinterpret_cast<ClusterShared*>(cl_smem);
@@ -152,12 +154,13 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         const double y = a.obs[(size_t)t * OS];
         const double cov = (OS == 2) ? a.obs[(size_t)t * OS + 1] : 0.0;
         double z[kClL];
-        {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), a.rk);
+#pragma unroll
+        for (int q = 0; q < kClL / 4; ++q) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
             float z0, z1, z2, z3;
             box_muller(r.x, r.y, z0, z1);
             box_muller(r.z, r.w, z2, z3);
-            z[0] = (double)z0; z[1] = (double)z1; z[2] = (double)z2; z[3] = (double)z3;
+            z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
         }
         const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[kClL];

@@ -36,6 +36,28 @@ def test_cluster_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     assert abs(tr["loglik"][0] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
 
 
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("N,T,NT", [(8192, 20, 512), (8192, 15, 256), (5000, 9, 128), (4097, 33, 512), (16384, 5, 512)])
+def test_cluster_filter_eight_per_thread(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, NT):
+    """tiles of 8 particles per thread (2 tiles of 4096 for 8192 particles: the layout for many chains per GPU)"""
+    y = sv_series(T, seed=43)
+    th = SV_THETA if model == sb.MODEL_SV else LEV_THETA
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=14, use_cluster=1, threads_per_filter=NT,
+                             scan_items_per_lane=8)
+    be.add_observed_data(y)
+    assert be.layout["scan_items_per_lane"] == 8 and be.layout["threads_per_filter"] == NT
+    theta = np.stack([th, th * 0.99])
+    out, pf = be.work_batch(theta, R=2, stream_base=7, return_per_filter=True)
+    tr = be.trace(theta[:1], stream_base=7, want=("loglik", "cond_like"))
+    for p in range(2):
+        ref = [oracle.filter_run(theta[p], y, N, model=model, resampler=resampler, L=8, NT=NT, tiled=True, seed=14,
+                                 filter_id=7 + 2 * p + r, trace=(p == 0 and r == 0)) for r in range(2)]
+        assert pf[p].tolist() == [v["loglik"] for v in ref]
+        if p == 0:
+            assert np.array_equal(tr["cond_like"][0], ref[0]["cond_like"])
+
+
 def test_cluster_pmmh_matches_oracle_driven_chain(oracle, sv_series, gpu_backend_factory):
     y = sv_series(50, seed=42)
     be = gpu_backend_factory(num_particles=2048, seed=13, use_cluster=1, threads_per_filter=128)
