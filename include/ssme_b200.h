@@ -200,6 +200,18 @@ int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* pri
                              uint64_t stream_id, double* loglik_host, double* cond_like_host, double* theta_bar_host,
                              double* final_mean_host, int32_t* ancestors_host, int32_t* aux_index_host);
 
+/* Streaming form of the same filter, one observation per call -- what LWFilter*::filter(obs_data, cov_data) is
+ * (liu_west_filter.h:971, :2191): the particle cloud stays in HBM between calls.
+ *   ssme_b200_lw_begin   draws nothing yet; fixes form, prior box, delta and the random stream, resets the step counter
+ *   ssme_b200_lw_step    advances by (y_t, z_t); returns getLogCondLike() of this step and thetaBar entering it
+ *   ssme_b200_lw_state   running log-likelihood, mean of the untransformed parameter particles, steps done
+ * T calls of _step give bit for bit the outputs of one ssme_b200_lw_filter_form call on the same series.
+ * No ssme_b200_set_observations needed.  One streaming run per handle at a time; a whole-series call ends it. */
+int ssme_b200_lw_begin(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                       uint64_t stream_id);
+int ssme_b200_lw_step(ssme_b200_handle h, double y_t, double z_t, double* cond_like_host, double* theta_bar_host);
+int ssme_b200_lw_state(ssme_b200_handle h, double* loglik_host, double* param_means_host, int64_t* steps_done);
+
 /* ---- the PMMH host loop, in C++ behind the C ABI (for hosts that cannot include the C++ headers) -------
  * Replaces: do_ada_pmmh_univ_svol + ada_pmmh_mvn::commence_sampling (example/estimate_univ_svol.h:139-178,
  * ada_pmmh_mvn.h:325-372) for `num_chains` chains advanced in lock step (include/ssme_b200/pmmh_multichain.hpp).

@@ -70,12 +70,33 @@ public:
         std::vector<double> rows(2 * obs.size());
         for (size_t t = 0; t < obs.size(); ++t) { rows[2 * t] = (double)obs[t]; rows[2 * t + 1] = (double)cov[t]; }
         throw_on_error(ssme_b200_set_observations(m_h, rows.data(), obs.size(), 2));
+        m_streaming = false;
         m_cond_like.assign(obs.size(), 0.0);
         m_theta_bar.assign(obs.size() * 4, 0.0);
         double lo[4], hi[4];
         for (int k = 0; k < 4; ++k) { lo[k] = (double)m_lo(k); hi[k] = (double)m_hi(k); }
         throw_on_error(ssme_b200_lw_filter_form(m_h, form, lo, hi, (double)m_delta, stream_id, &m_loglik, m_cond_like.data(),
                                                 m_theta_bar.data(), m_final_mean.data(), nullptr, nullptr));
+    }
+
+    // The reference's streaming call: filter(obs_data, cov_data) once per observation (:971, :2191).  The first call
+    // starts the run (stream id fixed by set_stream); results equal filter_series on the same data bit for bit.
+    void set_stream(std::uint64_t stream_id) { m_stream = stream_id; }
+    void filter(float_t y_t, float_t z_t)
+    {
+        if (!m_streaming) {
+            double lo[4], hi[4];
+            for (int k = 0; k < 4; ++k) { lo[k] = (double)m_lo(k); hi[k] = (double)m_hi(k); }
+            throw_on_error(ssme_b200_lw_begin(m_h, form, lo, hi, (double)m_delta, m_stream));
+            m_cond_like.clear();
+            m_theta_bar.clear();
+            m_streaming = true;
+        }
+        double cl = 0.0, tb[4];
+        throw_on_error(ssme_b200_lw_step(m_h, (double)y_t, (double)z_t, &cl, tb));
+        m_cond_like.push_back(cl);
+        m_theta_bar.insert(m_theta_bar.end(), tb, tb + 4);
+        throw_on_error(ssme_b200_lw_state(m_h, &m_loglik, m_final_mean.data(), nullptr));
     }
 
     // log p(y_t | y_{1:t-1}) of step t (the reference returns the latest one; :2180-2184)
@@ -95,6 +116,8 @@ private:
     float_t m_delta;
     psv m_lo, m_hi;
     double m_loglik = 0.0;
+    bool m_streaming = false;
+    std::uint64_t m_stream = 0;
     std::vector<double> m_cond_like, m_theta_bar;
     std::array<double, 4> m_final_mean{};
 };

@@ -99,6 +99,9 @@ def load_library():
     lib.ssme_b200_lw_filter.argtypes = [H, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip]
     lib.ssme_b200_lw_filter_form.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip, ip]
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
+    lib.ssme_b200_lw_begin.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64]
+    lib.ssme_b200_lw_step.argtypes = [H, C.c_double, C.c_double, dp, dp]
+    lib.ssme_b200_lw_state.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
     lib.ssme_b200_swarm_expectations.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp, dp]
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
@@ -302,6 +305,25 @@ class ParticleFilterBackend:
         _check(self._lib.ssme_b200_lw_filter_form(self._h, {"sisr": 0, "apf": 1}[form], _dptr(lo), _dptr(hi), delta, stream_id, C.byref(ll), _dptr(cl), _dptr(tb),
                                                   _dptr(fm), ip(anc), ip(aux)))
         return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux}
+
+    def lw_begin(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, form: str = "sisr"):
+        """Start a streaming Liu-West run (LWFilter*::filter called once per observation)."""
+        lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
+        hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+        _check(self._lib.ssme_b200_lw_begin(self._h, {"sisr": 0, "apf": 1}[form], _dptr(lo), _dptr(hi), delta, stream_id))
+
+    def lw_step(self, y_t: float, z_t: float = 0.0):
+        """filter(y_t, z_t): returns (log cond-like of this step, thetaBar[4] entering it)."""
+        cl = C.c_double()
+        tb = np.zeros(4)
+        _check(self._lib.ssme_b200_lw_step(self._h, float(y_t), float(z_t), C.byref(cl), _dptr(tb)))
+        return cl.value, tb
+
+    def lw_state(self):
+        ll, n = C.c_double(), C.c_int64()
+        pm = np.zeros(4)
+        _check(self._lib.ssme_b200_lw_state(self._h, C.byref(ll), _dptr(pm), C.byref(n)))
+        return {"loglik": ll.value, "param_means": pm, "steps": n.value}
 
     def swarm_filter(self, theta, stream_base: int = 0, return_per_filter: bool = False):
         """Swarm::update over the whole series: [T] mean over the P filters of log p(y_t | y_{1:t-1})."""

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwA
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) a.mom[4 + 4 * i + j] = Lc[i][j];
     if (a.theta_bar_out)
-        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)a.s.t * 4 + k] = tb[k];
+        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)(a.s.t - a.s.row0) * 4 + k] = tb[k];
 }
 
 constexpr int kLwNT = 256;                 // threads of the propagation CTA
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_apf_first_kernel(const LwArgs a)
     __shared__ double red[kLwNT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = a.s.t;
-    const double y = a.s.obs[(size_t)t * 2];
-    const double cov = a.s.obs[(size_t)t * 2 + 1];
+    const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
+    const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
     const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
     const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
     const int t = a.s.t;
     if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
     __syncthreads();
-    const double y = a.s.obs[(size_t)t * 2];
-    const double cov = a.s.obs[(size_t)t * 2 + 1];
+    const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
+    const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
     const uint2 key = make_uint2((uint32_t)a.s.seed, (uint32_t)(a.s.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
     const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);

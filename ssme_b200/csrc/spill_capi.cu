@@ -30,6 +30,10 @@ struct SpillState {
     double* th_cur[4] = {};
     double *part = nullptr, *mom = nullptr;
     double* lfs = nullptr;  // first-stage log-weights of the auxiliary Liu-West form
+    // streaming Liu-West run (ssme_b200_lw_begin / _step): arguments of the run in progress, next step, one-step buffers
+    LwArgs lw_args;
+    int lw_form = 0, lw_t = -1;
+    double* lw_row = nullptr;  // device: [0..1] observation row, [2] cond-like, [3..6] thetaBar of the step, [7..10] means
 };
 
 __global__ void spill_init_kernel(double* scal, int N)
@@ -106,7 +110,7 @@ void spill_destroy(ssme_b200_handle h)
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
     cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
-    cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs);
+    cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
     h->spill_state = nullptr;
 }
@@ -187,8 +191,8 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
     return SSME_B200_OK;
 }
 
-static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik,
-                  double* d_cond_like, double* d_theta_bar, double* d_final_mean, int* d_ancestors, int* d_aux)
+// Arguments of a Liu-West run (whole series or streaming): buffers of the handle, prior box, shrinkage constants.
+static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, LwArgs* out)
 {
     int rc = prepare(h);
     if (rc) return rc;
@@ -203,21 +207,21 @@ static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* 
         SSME_CUDA(cudaMalloc(&s->mom, 32 * sizeof(double)));
     }
     if (form == 1 && !s->lfs) SSME_CUDA(cudaMalloc(&s->lfs, s->local * sizeof(double)));
-    const int T = (int)h->T, tiles = s->nb;
-    cudaStream_t st = h->stream;
-    LwArgs a;
+    LwArgs& a = *out;
     memset(&a, 0, sizeof(a));
     a.s.obs = h->d_obs;
     a.s.N = s->N; a.s.nb = s->nb; a.s.Lp = s->Lp; a.s.NBP = s->NBP;
     a.s.tile0 = 0; a.s.tile1 = s->nb; a.s.tiles_per_rank = s->nb;
-    a.s.T = T;
+    a.s.T = (int)h->T;
     a.s.seed = h->cfg.seed;
     a.s.fid = stream_id;
     a.s.x_anc = s->x_anc;
     a.s.tmax = s->tmax; a.s.ttot = s->ttot; a.s.tclmax = s->tclmax; a.s.carry = s->carry; a.s.E = s->E; a.s.scal = s->scal;
     a.s.peer_x_anc[0] = s->x_anc;
-    a.s.cond_like = d_cond_like;
-    a.s.ancestors = d_ancestors;
+    a.s.x_cur = s->x_cur[0];
+    a.s.lwc = s->lwc[0];
+    a.s.peer_x[0] = s->x_cur[0];
+    a.s.peer_lwc[0] = s->lwc[0];
     a.s.nextra = 4;
     for (int k = 0; k < 4; ++k) {
         a.th_anc[k] = s->th_anc[k];
@@ -231,59 +235,86 @@ static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* 
     a.mom = s->mom;
     a.lfs = s->lfs;
     a.cdf1 = s->lwc[1];
-    a.aux_out = d_aux;
-    a.theta_bar_out = d_theta_bar;
     a.a = (3.0 * delta - 1.0) / (2.0 * delta);
     a.h2 = 1.0 - a.a * a.a;
     a.oma = 1.0 - a.a;
-    spill_init_kernel<<<1, 1, 0, st>>>(s->scal, s->N);
-    for (int t = 0; t < T; ++t) {
-        a.s.t = t;
-        a.s.x_cur = s->x_cur[0];
-        a.s.lwc = s->lwc[0];
-        a.s.peer_x[0] = s->x_cur[0];
-        a.s.peer_lwc[0] = s->lwc[0];
-        if (t > 0) {
-            a.mode = 0;
-            lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
-            lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
-            count_launch(2);
-        }
-        const int subs = tiles * (kTile / kLwSub);
-        SpillArgs m = a.s;  // K4's kernels leave one partial maximum per 1024 particles
-        m.tile0 = 0;
-        m.tile1 = subs;
-        const bool apf = (form == 1 && t > 0);
-        if (apf) {
-            // first stage: weights of the predicted states, their CDF (in lwc[1]) and M2 + log S2
-            SpillArgs f = a.s;
-            f.lwc = s->lwc[1];
-            f.cl_mode = 1;
-            lw_apf_first_kernel<<<subs, kLwNT, 0, st>>>(a);
-            spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
-            spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(f);
-            spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(f);
-            lw_propagate_kernel<1><<<subs, kLwNT, 0, st>>>(a);
-            count_launch(4);
-        } else {
-            lw_propagate_kernel<0><<<subs, kLwNT, 0, st>>>(a);
-        }
-        a.s.cl_mode = apf ? 2 : 0;
-        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
-        spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
-        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
-        if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
-        else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
-        count_launch(5);
-    }
-    if (T > 0 && d_final_mean) {
-        a.mode = 1;
+    spill_init_kernel<<<1, 1, 0, h->stream>>>(s->scal, s->N);
+    SSME_CUDA(cudaGetLastError());
+    return SSME_B200_OK;
+}
+
+// One time step of the Liu-West filter (both forms); `a` carries the output pointers and row0.
+static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
+{
+    SpillState* s = h->spill_state;
+    const int tiles = s->nb;
+    cudaStream_t st = h->stream;
+    a.s.t = t;
+    if (t > 0) {
+        a.mode = 0;
         lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
         lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
-        SSME_CUDA(cudaMemcpyAsync(d_final_mean, s->mom + 20, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
         count_launch(2);
     }
-    spill_store_kernel<<<1, 1, 0, st>>>(s->scal, d_loglik);
+    const int subs = tiles * (kTile / kLwSub);
+    SpillArgs m = a.s;  // K4's kernels leave one partial maximum per 1024 particles
+    m.tile0 = 0;
+    m.tile1 = subs;
+    const bool apf = (form == 1 && t > 0);
+    if (apf) {
+        // first stage: weights of the predicted states, their CDF (in lwc[1]) and M2 + log S2
+        SpillArgs f = a.s;
+        f.lwc = s->lwc[1];
+        f.cl_mode = 1;
+        lw_apf_first_kernel<<<subs, kLwNT, 0, st>>>(a);
+        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
+        spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(f);
+        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(f);
+        lw_propagate_kernel<1><<<subs, kLwNT, 0, st>>>(a);
+        count_launch(4);
+    } else {
+        lw_propagate_kernel<0><<<subs, kLwNT, 0, st>>>(a);
+    }
+    a.s.cl_mode = apf ? 2 : 0;
+    spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
+    spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+    spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
+    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
+    else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+    count_launch(5);
+    SSME_CUDA(cudaGetLastError());
+    return SSME_B200_OK;
+}
+
+// mean of the untransformed parameter particles -> d_mean[4]
+static int lw_means(ssme_b200_handle h, LwArgs& a, double* d_mean)
+{
+    SpillState* s = h->spill_state;
+    a.mode = 1;
+    lw_moments_kernel<<<s->nb, kTileNT, 0, h->stream>>>(a);
+    lw_moments_final_kernel<<<1, kTileScanNT, 0, h->stream>>>(a);
+    SSME_CUDA(cudaMemcpyAsync(d_mean, s->mom + 20, 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    count_launch(2);
+    return SSME_B200_OK;
+}
+
+static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik,
+                  double* d_cond_like, double* d_theta_bar, double* d_final_mean, int* d_ancestors, int* d_aux)
+{
+    LwArgs a;
+    int rc = lw_setup(h, form, lo, hi, delta, stream_id, &a);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    s->lw_t = -1;  // a whole-series run overwrites the particle buffers of a streaming run in progress
+    a.s.cond_like = d_cond_like;
+    a.s.ancestors = d_ancestors;
+    a.aux_out = d_aux;
+    a.theta_bar_out = d_theta_bar;
+    const int T = (int)h->T;
+    for (int t = 0; t < T; ++t)
+        if ((rc = lw_step(h, a, form, t))) return rc;
+    if (T > 0 && d_final_mean && (rc = lw_means(h, a, d_final_mean))) return rc;
+    spill_store_kernel<<<1, 1, 0, h->stream>>>(s->scal, d_loglik);
     SSME_CUDA(cudaGetLastError());
     return SSME_B200_OK;
 }
@@ -340,6 +371,70 @@ int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* pri
     if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "Liu-West filter failed: %s", cudaGetErrorString(e));
     if (loglik_host) *loglik_host = sc[0];
     if (final_mean_host) memcpy(final_mean_host, sc + 1, 4 * sizeof(double));
+    return SSME_B200_OK;
+}
+
+int ssme_b200_lw_begin(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id)
+{
+    if (!h || !prior_lo || !prior_hi) return fail(SSME_B200_EINVAL, "null argument");
+    if (form != SSME_B200_LW_SISR && form != SSME_B200_LW_APF) return fail(SSME_B200_EINVAL, "unknown Liu-West form %d", form);
+    if (!h->spill) return fail(SSME_B200_EINVAL, "the Liu-West filter uses the global-memory kernels: create the handle with force_global_memory = 1 (or N > 8192)");
+    if (h->cfg.model != SSME_B200_MODEL_SV_LEVERAGE) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter is built for the SV-with-leverage model");
+    if (!(delta > 1.0 / 3.0 && delta <= 1.0)) return fail(SSME_B200_EINVAL, "delta must lie in (1/3, 1]");
+    for (int k = 0; k < 4; ++k)
+        if (!(prior_hi[k] > prior_lo[k])) return fail(SSME_B200_EINVAL, "prior box %d is empty", k);
+    int rc = set_device(h);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    if ((rc = lw_setup(h, form, prior_lo, prior_hi, delta, stream_id, &s->lw_args))) return rc;
+    if (!s->lw_row) SSME_CUDA(cudaMalloc(&s->lw_row, 16 * sizeof(double)));
+    s->lw_form = form;
+    s->lw_t = 0;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_lw_step(ssme_b200_handle h, double y_t, double z_t, double* cond_like_host, double* theta_bar_host)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->spill || !h->spill_state || h->spill_state->lw_t < 0) return fail(SSME_B200_ERUNTIME, "call ssme_b200_lw_begin first");
+    int rc = set_device(h);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    const int t = s->lw_t;
+    const double row[2] = {y_t, z_t};
+    SSME_CUDA(cudaMemcpyAsync(s->lw_row, row, sizeof(row), cudaMemcpyHostToDevice, h->stream));  // pageable: staged before return
+    SSME_CUDA(cudaMemsetAsync(s->lw_row + 3, 0, 4 * sizeof(double), h->stream));
+    LwArgs& a = s->lw_args;
+    a.s.obs = s->lw_row;
+    a.s.row0 = t;  // step t reads row 0 of the one-step buffers
+    a.s.cond_like = s->lw_row + 2;
+    a.theta_bar_out = s->lw_row + 3;
+    if ((rc = lw_step(h, a, s->lw_form, t))) return rc;
+    double out[5];
+    SSME_CUDA(cudaMemcpyAsync(out, s->lw_row + 2, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    if (cond_like_host) *cond_like_host = out[0];
+    if (theta_bar_host) memcpy(theta_bar_host, out + 1, 4 * sizeof(double));
+    s->lw_t = t + 1;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_lw_state(ssme_b200_handle h, double* loglik_host, double* param_means_host, int64_t* steps_done)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!h->spill || !h->spill_state || h->spill_state->lw_t < 0) return fail(SSME_B200_ERUNTIME, "call ssme_b200_lw_begin first");
+    int rc = set_device(h);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    double out[5] = {0, 0, 0, 0, 0};
+    if (s->lw_t > 0 && param_means_host && (rc = lw_means(h, s->lw_args, s->lw_row + 7))) return rc;
+    spill_store_kernel<<<1, 1, 0, h->stream>>>(s->scal, s->lw_row + 11);
+    SSME_CUDA(cudaGetLastError());
+    SSME_CUDA(cudaMemcpyAsync(out, s->lw_row + 7, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    if (param_means_host) memcpy(param_means_host, out, 4 * sizeof(double));
+    if (loglik_host) *loglik_host = out[4];
+    if (steps_done) *steps_done = s->lw_t;
     return SSME_B200_OK;
 }
 

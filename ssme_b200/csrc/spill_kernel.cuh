@@ -53,6 +53,9 @@ struct SpillArgs {
     // log-likelihood; 1 = first stage of an auxiliary particle filter: keep M + log S in scal[4] only;
     // 2 = second stage: log p(y_t | y_{1:t-1}) = ((M + log S) + scal[4]) - 2 log N  (liu_west_filter.h:1056-1058 with rs = 1)
     int cl_mode;
+    // streaming use (one observation per call): row of `obs`, `cond_like` and `theta_bar_out` that belongs to step t is
+    // t - row0; the whole-series entry points leave row0 = 0
+    int row0;
 };
 
 template <int MODEL>
@@ -65,8 +68,8 @@ __global__ void __launch_bounds__(kTileNT) spill_propagate_kernel(const SpillArg
     const int i0 = tile * kTile + tid * kTileL;                      // global particle index
     const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;  // index into this rank's arrays
     const ModelConst mc = model_init<MODEL>(a.theta);
-    const double y = a.obs[(size_t)a.t * OS];
-    const double cov = (OS == 2) ? a.obs[(size_t)a.t * OS + 1] : 0.0;
+    const double y = a.obs[(size_t)(a.t - a.row0) * OS];
+    const double cov = (OS == 2) ? a.obs[(size_t)(a.t - a.row0) * OS + 1] : 0.0;
     const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
     double z[kTileL];
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
             double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
             if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
             a.scal[2] = __dadd_rn(a.scal[2], cl);
-            if (a.cond_like) a.cond_like[a.t] = cl;
+            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
         }
     }
 }

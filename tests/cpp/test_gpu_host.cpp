@@ -150,6 +150,13 @@ int main(int argc, char** argv)
         REQUIRE(pm(0) > .8 && pm(0) < .99 && pm(2) > .01 && pm(2) < .3 && pm(3) > -.5 && pm(3) < -.01);
         REQUIRE(std::isfinite(big.getLogLike()));
         REQUIRE(big.getLogLike() != big2.getLogLike());  // two different estimators of the same quantity
+        // the reference's streaming call, one observation at a time, gives the same numbers as the whole-series call
+        ssme_b200::LWFilterWithCovs_svol<20000, double> online({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5},
+                                                               lw_t::psv{.99, .1, .3, -.01});
+        for (size_t t = 0; t < y.size(); ++t) online.filter(y[t], cov[t]);
+        REQUIRE(online.getLogLike() == big.getLogLike());
+        REQUIRE(online.getLogCondLike() == big.getLogCondLike());
+        REQUIRE(online.getParamMeans()(0) == big.getParamMeans()(0));
         REQUIRE(std::abs(big.getLogLike() - big2.getLogLike()) < 0.02 * std::abs(big2.getLogLike()));
     }
     TEST_CASE("swarm: 10 x 10 particles, assertions of test_pswarm.cpp:251-252")

@@ -80,6 +80,42 @@ def test_liu_west_forms_agree_statistically(gpu_backend_factory):
     assert abs(a.mean() - b.mean()) < 0.05 + 4 * (a.std() + b.std())
 
 
+@pytest.mark.parametrize("form", ["sisr", "apf"])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+def test_liu_west_streaming_equals_whole_series(gpu_backend_factory, form, resampler):
+    """filter(y_t, z_t) once per observation (the reference's call, liu_west_filter.h:971 / :2191) == one call over the series."""
+    N, T = 4096 * 3 + 17, 14
+    y = leverage_series(T, seed=21)
+    z = np.concatenate([[0.0], y[:-1]])
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=9, force_global_memory=1)
+    be.add_observed_data(y)
+    whole = be.lw_filter(LO, HI, delta=0.99, stream_id=3, form=form)
+    be2 = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=9, force_global_memory=1)
+    be2.lw_begin(LO, HI, delta=0.99, stream_id=3, form=form)   # no observations registered: they arrive one at a time
+    cls, tbs = [], []
+    for t in range(T):
+        cl, tb = be2.lw_step(y[t], z[t])
+        cls.append(cl)
+        tbs.append(tb)
+        if t == 5:
+            mid = be2.lw_state()
+            assert mid["steps"] == 6 and mid["loglik"] == _seq_sum(cls[:6])
+    st = be2.lw_state()
+    assert np.array_equal(np.array(cls), whole["cond_like"])
+    assert np.array_equal(np.array(tbs), whole["theta_bar"])
+    assert st["loglik"] == whole["loglik"] and st["steps"] == T
+    assert np.array_equal(st["param_means"], whole["final_mean"])
+    with pytest.raises(RuntimeError):
+        gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=64, force_global_memory=1).lw_step(0.1, 0.0)
+
+
+def _seq_sum(v):
+    acc = 0.0
+    for c in v:
+        acc += c
+    return acc
+
+
 def test_liu_west_learns_the_parameters(gpu_backend_factory):
     """2^18 particles, wide prior: the posterior mean moves from the prior centre towards the generating values."""
     true = dict(phi=0.95, mu=0.0, sigma=0.25, rho=-0.4)
