@@ -172,6 +172,14 @@ int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t 
 int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
                                  double* log_cond_like_host, double* expectations_host, double* per_filter_expectations_host);
 
+/* Streaming form: Swarm::update(y_t) once per observation (pswarm_filter.h:223-239).  _begin fixes the P parameter
+ * particles (untransformed, [P][numparams]) and the random streams; each _step advances all P filters by one
+ * observation row ([1] = y_t, or [2] = (y_t, z_t) for the leverage model) and returns the swarm's log cond-like of that
+ * step and, if expectations_host != NULL, the two expectations.  T steps == the whole-series calls above, bit for bit.
+ * The resampled states wait in HBM between calls; no ssme_b200_set_observations needed. */
+int ssme_b200_swarm_begin(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base);
+int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_cond_like_host, double* expectations_host);
+
 /* Replaces: LWFilter2WithCovs::filter called over a whole series (liu_west_filter.h:2191-2343, with
  * update_parameter_proposal_components :2346-2360 and mn_resamp_states_and_params :91-145) for the SV-with-leverage
  * model svol_lw_2_par (test/test_liu_west.cpp:213-358): joint state / parameter learning with kernel shrinkage

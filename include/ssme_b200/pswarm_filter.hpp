@@ -71,6 +71,29 @@ public:
         m_num_obs = (unsigned)T;
     }
 
+    // The reference's streaming call: update(y_t) once per observation (pswarm_filter.h:223-239); row = (y_t) or (y_t, z_t).
+    // The first call draws every model's parameters (finish_construction) and fixes the random streams.
+    void update(const std::vector<double>& row, bool with_expectations = false, std::uint64_t stream_base = 0)
+    {
+        if (!m_streaming) {
+            std::vector<double> theta(nparamparts * dimparam);
+            for (size_t j = 0; j < nparamparts; ++j) {
+                const psv p = samp_untrans_params();
+                for (size_t k = 0; k < dimparam; ++k) theta[j * dimparam + k] = (double)p(k);
+            }
+            throw_on_error(ssme_b200_swarm_begin(m_h, theta.data(), nparamparts, stream_base));
+            m_log_cond_like.clear();
+            m_expectations.clear();
+            m_num_obs = 0;
+            m_streaming = true;
+        }
+        double cl = 0.0, ex[2] = {0.0, 0.0};
+        throw_on_error(ssme_b200_swarm_step(m_h, row.data(), &cl, with_expectations ? ex : nullptr));
+        m_log_cond_like.push_back(cl);
+        if (with_expectations) m_expectations.insert(m_expectations.end(), ex, ex + 2);
+        m_num_obs += 1;
+    }
+
     float_t getLogCondLike(size_t t) const { return (float_t)m_log_cond_like.at(t); }
     float_t getLogCondLike() const { return (float_t)m_log_cond_like.back(); }
     unsigned num_obs() const { return m_num_obs; }
@@ -80,7 +103,8 @@ public:
 private:
     ssme_b200_handle m_h = nullptr;
     std::vector<double> m_log_cond_like, m_expectations;
-    unsigned m_num_obs;
+    unsigned m_num_obs = 0;
+    bool m_streaming = false;
 };
 
 }  // namespace ssme_b200

@@ -99,6 +99,8 @@ def load_library():
     lib.ssme_b200_lw_filter.argtypes = [H, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip]
     lib.ssme_b200_lw_filter_form.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp, dp, ip, ip]
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
+    lib.ssme_b200_swarm_begin.argtypes = [H, dp, C.c_size_t, C.c_uint64]
+    lib.ssme_b200_swarm_step.argtypes = [H, dp, dp, dp]
     lib.ssme_b200_lw_begin.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64]
     lib.ssme_b200_lw_step.argtypes = [H, C.c_double, C.c_double, dp, dp]
     lib.ssme_b200_lw_state.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
@@ -305,6 +307,18 @@ class ParticleFilterBackend:
         _check(self._lib.ssme_b200_lw_filter_form(self._h, {"sisr": 0, "apf": 1}[form], _dptr(lo), _dptr(hi), delta, stream_id, C.byref(ll), _dptr(cl), _dptr(tb),
                                                   _dptr(fm), ip(anc), ip(aux)))
         return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux}
+
+    def swarm_begin(self, theta, stream_base: int = 0):
+        """Start a streaming swarm (Swarm::update once per observation)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
+        _check(self._lib.ssme_b200_swarm_begin(self._h, _dptr(theta), theta.shape[0], stream_base))
+
+    def swarm_step(self, obs_row, want_expectations: bool = False):
+        row = np.ascontiguousarray(np.atleast_1d(obs_row), dtype=np.float64)
+        cl = C.c_double()
+        ex = np.zeros(2) if want_expectations else None
+        _check(self._lib.ssme_b200_swarm_step(self._h, _dptr(row), C.byref(cl), _dptr(ex)))
+        return (cl.value, ex) if want_expectations else cl.value
 
     def lw_begin(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, form: str = "sisr"):
         """Start a streaming Liu-West run (LWFilter*::filter called once per observation)."""

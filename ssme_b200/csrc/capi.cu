@@ -373,6 +373,7 @@ int ssme_b200_destroy(ssme_b200_handle h)
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_per_filter) cudaFree(h->d_per_filter);
     if (h->d_cluster_scratch) cudaFree(h->d_cluster_scratch);
+    cudaFree(h->d_sw_theta); cudaFree(h->d_sw_x); cudaFree(h->d_sw_buf);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     delete h;
     return SSME_B200_OK;
@@ -640,6 +641,71 @@ int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, s
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cleanup();
     if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "swarm expectations failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
+// Streaming swarm: Swarm::update(y_t) once per observation (pswarm_filter.h:223-239).  The tracing instantiation of the
+// resident kernel runs one step per call; the resampled states of the P filters wait in HBM between calls.
+int ssme_b200_swarm_begin(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base)
+{
+    if (!h || !theta_host) return fail(SSME_B200_EINVAL, "null argument");
+    if (P == 0) return fail(SSME_B200_EINVAL, "the swarm needs at least one parameter particle");
+    if (h->spill || h->cluster || h->cfg.dtype != SSME_B200_DTYPE_F64)
+        return fail(SSME_B200_EUNSUPPORTED, "the streaming swarm runs the resident one-CTA fp64 kernel (num_particles <= 8192, no cluster)");
+    if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX || h->cfg.resample_every != 1)
+        return fail(SSME_B200_EUNSUPPORTED, "the streaming swarm needs rng_mode PHILOX and resampling at every step");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t np = (size_t)h->num_params, N = (size_t)h->cfg.num_particles;
+    if (P != h->sw_P) {
+        cudaFree(h->d_sw_theta); cudaFree(h->d_sw_x); cudaFree(h->d_sw_buf);
+        h->d_sw_theta = h->d_sw_x = h->d_sw_buf = nullptr;
+        h->sw_P = 0;
+        SSME_CUDA(cudaMalloc(&h->d_sw_theta, P * np * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&h->d_sw_x, P * N * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&h->d_sw_buf, (128 + 4 * P + 4) * sizeof(double)));
+        h->sw_P = P;
+    }
+    SSME_CUDA(cudaMemcpyAsync(h->d_sw_theta, theta_host, P * np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SSME_CUDA(cudaMemsetAsync(h->d_sw_buf, 0, 128 * sizeof(double), h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    h->sw_base = stream_base;
+    h->sw_t = 0;
+    return SSME_B200_OK;
+}
+
+int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_cond_like_host, double* expectations_host)
+{
+    if (!h || !obs_row) return fail(SSME_B200_EINVAL, "null argument");
+    if (h->sw_t < 0) return fail(SSME_B200_ERUNTIME, "call ssme_b200_swarm_begin first");
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t P = h->sw_P;
+    const int OS = (h->cfg.model == SSME_B200_MODEL_SV) ? 1 : 2;
+    double* d_row = h->d_sw_buf;                 // a whole 64-step chunk is what the kernel's bulk copy reads
+    double* d_ll = h->d_sw_buf + 128;            // [P]
+    double* d_cl = d_ll + P;                     // [P][1]
+    double* d_ex = d_cl + P;                     // [P][1][2]
+    double* d_mean = d_ex + 2 * P;               // [0] mean cond-like, [1..2] mean expectations
+    SSME_CUDA(cudaMemcpyAsync(d_row, obs_row, (size_t)OS * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FilterArgs a = base_args(h, h->d_sw_theta, 1u, h->sw_base, d_ll);
+    a.obs = d_row;
+    a.T = 1;
+    a.t_begin = (int)h->sw_t;
+    a.x_state = h->d_sw_x;
+    a.cond_like = d_cl;
+    a.expect = expectations_host ? d_ex : nullptr;
+    if ((rc = launch_filters(h, h->debug, a, P, h->stream))) return rc;
+    swarm_mean_kernel<<<1, 128, 0, h->stream>>>(d_cl, P, 1, d_mean);
+    if (expectations_host) swarm_mean_kernel<<<1, 128, 0, h->stream>>>(d_ex, P, 2, d_mean + 1);
+    g_launches.fetch_add(expectations_host ? 2 : 1);
+    SSME_CUDA(cudaGetLastError());
+    double out[3] = {0, 0, 0};
+    SSME_CUDA(cudaMemcpyAsync(out, d_mean, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    SSME_CUDA(cudaStreamSynchronize(h->stream));
+    if (log_cond_like_host) *log_cond_like_host = out[0];
+    if (expectations_host) { expectations_host[0] = out[1]; expectations_host[1] = out[2]; }
+    h->sw_t += 1;
     return SSME_B200_OK;
 }
 

@@ -67,6 +67,13 @@ struct ssme_b200_filter_s {
     int cluster_size = 1;
     double* d_cluster_scratch = nullptr;  // [filters][16][512]: L2-resident staging of the CDF tiles the clusters multicast
     size_t cap_cluster_scratch = 0;
+    // streaming swarm (ssme_b200_swarm_begin / _step): parameter particles, states between calls, one-step buffers
+    double* d_sw_theta = nullptr;
+    double* d_sw_x = nullptr;    // [P][N]
+    double* d_sw_buf = nullptr;  // [0..127] observation chunk (row 0 used), then per-filter outputs and the means
+    size_t sw_P = 0;
+    long long sw_t = -1;
+    uint64_t sw_base = 0;
     // N beyond one CTA: particles live in HBM
     bool spill = false;
     ssme::SpillState* spill_state = nullptr;

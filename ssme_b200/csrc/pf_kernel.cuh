@@ -51,6 +51,10 @@ struct FilterArgs {
     int* ancestors;       // [F][T][N]
     double* x_trace;
     PhiloxRoundKeys rk;  // key schedule of `seed` (host: philox_round_keys)
+    // streaming (tracing kernels, rs = 1): this launch covers steps t_begin .. t_begin + T - 1 of the series; x_state [F][N]
+    // holds the resampled states between launches
+    int t_begin;
+    double* x_state;
     double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
@@ -201,7 +205,13 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 
     __syncthreads();  // mbarrier init visible to every waiter
 
+    if (DEBUG && a.x_state && a.t_begin > 0) {  // streaming: continue from the states the previous call left (rs = 1)
+#pragma unroll
+        for (int k = 0; k < L; ++k) x[k] = (i0 + k < N) ? a.x_state[(size_t)f * N + i0 + k] : 0.0;
+    }
+
     for (int t = 0; t < T; ++t) {
+        const int tg = DEBUG ? t + a.t_begin : t;  // step number of the series (random streams, time-1 formulas)
         const int c = t / kYChunk, o = t % kYChunk;
         if (o == 0) mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
         const double* yrow = ybuf + (c & 1) * (kYChunk * OS) + o * OS;
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else if (L >= 4) {
 #pragma unroll
             for (int q = 0; q < L / 4; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3), a.rk);
                 float z0, z1, z2, z3;
                 box_muller(r.x, r.y, z0, z1);
                 box_muller(r.z, r.w, z2, z3);
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else {
             // latency layouts (1 or 2 particles per thread): the 2 or 4 threads that share a Philox block each compute it
             // and keep their own Box-Muller pair -- redundant integer work buys shorter dependent chains per step
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)t, ctr2, ctr3), a.rk);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3), a.rk);
             const bool hi = (i0 & 2) != 0;
             float za, zb;
             box_muller(hi ? r.z : r.x, hi ? r.w : r.y, za, zb);
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         double lw[L];
         double mloc = __longlong_as_double(0xfff0000000000000ll);
         // one uniform branch per step (inside the particle loop the compiler keeps a test per particle)
-        if (t == 0) {
+        if (tg == 0) {
 #pragma unroll
             for (int k = 0; k < L; ++k) x[k] = __dmul_rn(z[k], mc.sd0);
         } else if (MODEL == kModelSV) {
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (tid == 0) {
                 const double logS = dlog(S);
                 double cl;
-                if (t == 0) {
+                if (tg == 0) {
                     cl = __dadd_rn(__dadd_rn(-logN, M), logS);
                 } else {
                     const double Mo = prev_resampled ? 0.0 : M_prev;
@@ -450,12 +460,12 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
                     tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
                     tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
                 }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
                 tau[0] = __dmul_rn((i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
             }
         } else if (RESAMP == kResampSortedMultinomial) {
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                     double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
                     ua = (ua == 0.0) ? 0x1p-53 : ua;
                     ub = (ub == 0.0) ? 0x1p-53 : ub;
@@ -480,7 +490,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     sce[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
                 }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                 double ua = (i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 ua = (ua == 0.0) ? 0x1p-53 : ua;
                 sce[0] = (i0 < N) ? -dlog_unit(ua) : 0.0;
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 uN = a.u_inj[((size_t)f * T + t) * a.stride_u + N];
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                 uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 uN = (uN == 0.0) ? 0x1p-53 : uN;
             }
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 u0 = a.u_inj[((size_t)f * T + t) * a.stride_u];
             } else {
-                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
+                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)tg, ctr2, ctr3 | 3u), a.rk);
                 u0 = uniform53(r.x, r.y);
             }
             const double sN = __ddiv_rn(S, dN);
@@ -562,6 +572,12 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             for (int k = 0; k < L; ++k)
                 if (i0 + k < N) a.ancestors[((size_t)f * T + t) * N + i0 + k] = idx[k];
         }
+    }
+
+    if (DEBUG && a.x_state) {
+#pragma unroll
+        for (int k = 0; k < L; ++k)
+            if (i0 + k < N) a.x_state[(size_t)f * N + i0 + k] = x[k];
     }
 
     // ---- epilogue: the cond-likes still buffered (fast path) -----------------------------------

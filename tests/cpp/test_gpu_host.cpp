@@ -176,6 +176,10 @@ int main(int argc, char** argv)
         REQUIRE(sw.num_obs() == 40);
         for (size_t t = 0; t < 40; ++t) REQUIRE(std::pow(sw.getLogCondLike(t), 2) > 0.0);
         // "test update with funcs" (test_pswarm.cpp:323-346): expectations come back finite and consistent
+        my_swarm sw3;  // the reference's streaming call, one observation at a time
+        for (size_t t = 0; t < 40; ++t) sw3.update({rows[2 * t], rows[2 * t + 1]});
+        REQUIRE(sw3.num_obs() == 40);
+        for (size_t t = 0; t < 40; ++t) REQUIRE(sw3.getLogCondLike(t) == sw.getLogCondLike(t));
         my_swarm sw2;  // same parameter draws (same generator seed), same random streams
         sw2.update_series(rows, 2, 0, true);
         for (size_t t = 0; t < 40; ++t) {

@@ -207,3 +207,27 @@ def test_latency_layouts_bit_exact(oracle, sv_series, gpu_backend_factory, model
         assert np.array_equal(got["x"][f], ref["x"])
         assert np.array_equal(got["cond_like"][f], ref["cond_like"])
         assert got["loglik"][f] == ref["loglik"] == pf[f, 0]
+
+
+@pytest.mark.parametrize("model,N", [(sb.MODEL_SV, 500), (sb.MODEL_SV_LEVERAGE, 1024), (sb.MODEL_SV, 37)])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+def test_streaming_swarm_equals_whole_series(sv_series, gpu_backend_factory, model, N, resampler):
+    """Swarm::update(y_t) once per observation (pswarm_filter.h:223-239) == the whole-series call, bit for bit
+    (70 steps: crosses the 64-step observation chunk of the whole-series kernel)."""
+    T, P = 70, 4
+    y = sv_series(T, seed=78)
+    base = np.array([1.0, 0.95, 0.0625]) if model == sb.MODEL_SV else np.array([0.9, 0.0, 0.3, -0.1])
+    theta = np.stack([base * (1 + 0.01 * p) for p in range(P)])
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=23)
+    be.add_observed_data(y)
+    whole = be.swarm_expectations(theta, stream_base=5)
+    fast = be.swarm_filter(theta, stream_base=5)
+    be2 = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=23)
+    be2.swarm_begin(theta, stream_base=5)
+    for t in range(T):
+        row = [y[t]] if model == sb.MODEL_SV else [y[t], y[t - 1] if t else 0.0]
+        cl, ex = be2.swarm_step(row, want_expectations=True)
+        assert cl == whole["log_cond_like"][t] == fast[t]
+        assert np.array_equal(ex, whole["expectations"][t])
+    with pytest.raises(RuntimeError):
+        gpu_backend_factory(model=model, num_particles=N).swarm_step([0.1, 0.0])
