@@ -20,6 +20,7 @@ struct SpillState {
     double* x_cur[2] = {nullptr, nullptr};
     double* lwc[2] = {nullptr, nullptr};
     double *tmax = nullptr, *ttot = nullptr, *tclmax = nullptr, *carry = nullptr, *E = nullptr, *scal = nullptr, *sync_word = nullptr;
+    double* scan2 = nullptr;  // two-launch tile scan: lanepref[1024], lanetot[1024], wtot[32], cmax[32]
     const double* peer_x[2][kMaxPeers] = {};
     const double* peer_lwc[2][kMaxPeers] = {};
     double* peer_x_anc[kMaxPeers] = {};
@@ -78,6 +79,7 @@ static int prepare(ssme_b200_handle h)
     SSME_CUDA(cudaMalloc(&s->ttot, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->tclmax, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->sync_word, sizeof(double)));
     SSME_CUDA(cudaMemset(s->sync_word, 0, sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->E, (size_t)s->NBP * sizeof(double)));
@@ -108,11 +110,34 @@ void spill_destroy(ssme_b200_handle h)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
+    cudaFree(s->scan2); cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
     h->spill_state = nullptr;
+}
+
+// Scan of the tile totals: one CTA for a few tiles, two launches of 32 CTAs beyond 4096 tiles (same result, bit for bit).
+static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
+{
+    if (s->Lp >= 4 && s->Lp <= 256) {
+        a.lanepref = s->scan2;
+        a.lanetot = s->scan2 + 1024;
+        a.wtot = s->scan2 + 2048;
+        a.cmax = s->scan2 + 2048 + 32;
+        static bool attr_set = false;
+        const size_t smem_b = (size_t)2 * s->Lp * 33 * sizeof(double);
+        if (!attr_set) {
+            cudaFuncSetAttribute(spill_tile_scan_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 33 * (int)sizeof(double));
+            attr_set = true;
+        }
+        spill_tile_scan_a_kernel<<<32, kScan2NT, (size_t)s->Lp * 33 * sizeof(double), st>>>(a);
+        spill_tile_scan_b_kernel<<<32, kScan2NT, smem_b, st>>>(a);
+        count_launch(1);
+    } else {
+        a.cmax = nullptr;
+        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
+    }
 }
 
 template <int MODEL>
@@ -169,7 +194,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
                 if (nrc == 0) nrc = nccl->AllGather(s->tclmax + s->tile0, s->tclmax, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
                 if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", nccl->GetErrorString(nrc));
             }
-            spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
+            launch_tile_scan(s, a, st);
             count_launch(4);
             if (t + 1 < T || a.ancestors) {
                 if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
@@ -269,7 +294,7 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         lw_apf_first_kernel<<<subs, kLwNT, 0, st>>>(a);
         spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
         spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(f);
-        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(f);
+        launch_tile_scan(s, f, st);
         lw_propagate_kernel<1><<<subs, kLwNT, 0, st>>>(a);
         count_launch(4);
     } else {
@@ -278,7 +303,7 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
     a.s.cl_mode = apf ? 2 : 0;
     spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
     spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
-    spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a.s);
+    launch_tile_scan(s, a.s, st);
     if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
     else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
     count_launch(5);

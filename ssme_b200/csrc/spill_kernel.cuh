@@ -53,6 +53,13 @@ struct SpillArgs {
     // log-likelihood; 1 = first stage of an auxiliary particle filter: keep M + log S in scal[4] only;
     // 2 = second stage: log p(y_t | y_{1:t-1}) = ((M + log S) + scal[4]) - 2 log N  (liu_west_filter.h:1056-1058 with rs = 1)
     int cl_mode;
+    // two-launch scan of the tile totals (many tiles): per virtual lane of the canonical 1024-lane scan its inclusive
+    // Kogge-Stone value and its own total; per virtual warp its total and the maximum of O_b + tclmax_b over its tiles.
+    // With cmax != null, carry[b] holds the running maximum over the earlier tiles of b's OWN virtual warp only.
+    double* lanepref;  // [1024]
+    double* lanetot;   // [1024]
+    double* wtot;      // [32]
+    double* cmax;      // [32] or null
     // streaming use (one observation per call): row of `obs`, `cond_like` and `theta_bar_out` that belongs to step t is
     // t - row0; the whole-series entry points leave row0 = 0
     int row0;
@@ -318,6 +325,131 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     }
 }
 
+// ---- the same scan of the tile totals in two launches of 32 CTAs (one per virtual warp of the canonical 1024-lane scan) ----
+// Used when there are thousands of tiles (Lp >= 4): the single CTA above walks its Lp items per lane with strided,
+// uncoalesced loads through one SM (329 us at 65536 tiles); here every virtual warp stages its 32*Lp totals through
+// shared memory (transposed, conflict-free) and the 32 CTAs run on 32 SMs.  Same additions in the same order.
+constexpr int kScan2NT = 256;
+
+__global__ void __launch_bounds__(kScan2NT) spill_tile_scan_a_kernel(const SpillArgs a)
+{
+    extern __shared__ double sh2[];  // [Lp][33]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x, Lp = a.Lp, per = 32 * Lp, first = w * per;
+    for (int i = tid; i < per; i += kScan2NT) {
+        const int b = first + i;
+        sh2[(i % Lp) * 33 + i / Lp] = (b < a.nb) ? a.ttot[b] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            const double v = sh2[k * 33 + lane];
+            tot = (k == 0) ? v : __dadd_rn(tot, v);
+        }
+        double incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(incl, d);
+            incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+        }
+        a.lanetot[w * 32 + lane] = tot;
+        a.lanepref[w * 32 + lane] = incl;
+        if (lane == 31) a.wtot[w] = incl;
+    }
+}
+
+__global__ void __launch_bounds__(kScan2NT) spill_tile_scan_b_kernel(const SpillArgs a)
+{
+    extern __shared__ double sh2[];  // totals [Lp][33], then results [Lp][33]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x, Lp = a.Lp, per = 32 * Lp, first = w * per;
+    double* shT = sh2;
+    double* shE = sh2 + Lp * 33;
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    for (int i = tid; i < per; i += kScan2NT) {
+        const int b = first + i;
+        shT[(i % Lp) * 33 + i / Lp] = (b < a.nb) ? a.ttot[b] : 0.0;
+    }
+    __syncthreads();
+    double S = 0.0, Eprev = 0.0;  // total; inclusive end of the tile before this virtual warp's first
+    if (warp == 0) {
+        double wv = a.wtot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(wv, d);
+            wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+        }
+        S = shfl_d(wv, 31);
+        double wex = shfl_d(wv, (w > 0) ? w - 1 : 0);
+        wex = (w > 0) ? wex : 0.0;
+        const double lex = (lane > 0) ? a.lanepref[w * 32 + lane - 1] : 0.0;
+        const double base = __dadd_rn(wex, lex);
+        double run = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            const double v = shT[k * 33 + lane];
+            run = (k == 0) ? v : __dadd_rn(run, v);
+            shE[k * 33 + lane] = __dadd_rn(base, run);
+        }
+        if (w > 0) {  // E of the last tile of virtual warp w-1, formed exactly as that warp's lane 31 forms it
+            double wex1 = shfl_d(wv, (w > 1) ? w - 2 : 0);
+            wex1 = (w > 1) ? wex1 : 0.0;
+            Eprev = __dadd_rn(__dadd_rn(wex1, a.lanepref[(w - 1) * 32 + 30]), a.lanetot[(w - 1) * 32 + 31]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < per; i += kScan2NT) a.E[first + i] = shE[(i % Lp) * 33 + i / Lp];
+    __syncthreads();
+    // exclusive running maximum of v_b = O_b + tclmax_b (O_b = E_{b-1}) over the tiles of this virtual warp; exact, order-free
+    if (warp == 0) {
+        double loc = ninf;
+        for (int k = 0; k < Lp; ++k) {
+            const int b = first + lane * Lp + k;
+            if (b < a.nb) {
+                const double O = (k > 0) ? shE[(k - 1) * 33 + lane] : (lane > 0 ? shE[(Lp - 1) * 33 + lane - 1] : Eprev);
+                const double v = __dadd_rn((b > 0) ? O : 0.0, a.tclmax[b]);
+                loc = (v > loc) ? v : loc;
+            }
+        }
+        double inc = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(inc, d);
+            inc = (lane >= d && other > inc) ? other : inc;
+        }
+        double run = shfl_up_d(inc, 1);
+        run = (lane > 0) ? run : ninf;
+        for (int k = 0; k < Lp; ++k) {
+            const int b = first + lane * Lp + k;
+            shT[k * 33 + lane] = run;  // carry of tile b within this virtual warp
+            if (b < a.nb) {
+                const double O = (k > 0) ? shE[(k - 1) * 33 + lane] : (lane > 0 ? shE[(Lp - 1) * 33 + lane - 1] : Eprev);
+                const double v = __dadd_rn((b > 0) ? O : 0.0, a.tclmax[b]);
+                run = (v > run) ? v : run;
+            }
+        }
+        if (lane == 31) a.cmax[w] = inc;
+    }
+    __syncthreads();
+    for (int i = tid; i < per; i += kScan2NT) {
+        const int b = first + i;
+        if (b < a.nb) a.carry[b] = shT[(i % Lp) * 33 + i / Lp];
+    }
+    if (w == 0 && tid == 0) {
+        const double M = a.scal[0], logN = a.scal[3];
+        const double logS = dlog(S);
+        a.scal[1] = S;
+        if (a.cl_mode == 1) {
+            a.scal[4] = __dadd_rn(M, logS);
+        } else {
+            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
+            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
+            a.scal[2] = __dadd_rn(a.scal[2], cl);
+            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
+        }
+    }
+}
+
 // A = #{ j in [0,N) : tau_j <= c },  tau_j = fl(fl(j + u0) * sN)  (oracle: count_targets).  The estimate q only has to
 // land near the answer: tau_j is non-decreasing in j, so the two fix-up loops end at the largest j with tau_j <= c
 // whatever the starting point -- the oracle starts from c / sN - u0, the kernel from the cheaper c * (1/sN) - u0.
@@ -384,6 +516,13 @@ __global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a
     if (tid == 0) { sh_range[0] = 0; sh_range[1] = 0; }
     __syncthreads();
     double prevmax = a.carry[tile];
+    if (a.cmax) {  // two-launch tile scan: add the maxima of the earlier virtual warps
+        const int vw = tile / (32 * a.Lp);
+        for (int g = 0; g < vw; ++g) {
+            const double cg = a.cmax[g];
+            prevmax = (cg > prevmax) ? cg : prevmax;
+        }
+    }
     for (int g = 0; g < warp; ++g) prevmax = (red[g] > prevmax) ? red[g] : prevmax;
     double excl = shfl_up_d(inc, 1);
     excl = (lane > 0) ? excl : ninf;

@@ -54,3 +54,18 @@ def test_spilled_mode_argument_checks():
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, resample_every=2))
     with pytest.raises(sb.SsmeB200Error):
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, rng_mode=sb.RNG_INJECTED))
+
+
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+def test_spilled_filter_many_tiles_two_launch_scan(oracle, sv_series, gpu_backend_factory, resampler):
+    """4097 tiles (16.8 M particles): the tile totals are scanned by the two-launch kernels (Lp = 8 items per virtual
+    lane); bit for bit the oracle's single-CTA order."""
+    N, T = 4096 * 4096 + 5, 3
+    y = sv_series(T, seed=33)
+    be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=10)
+    be.add_observed_data(y)
+    got = be.trace(SV_THETA[None, :], stream_base=1, want=("loglik", "cond_like", "ancestors"))
+    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=10, filter_id=1)
+    assert np.array_equal(got["cond_like"][0], ref["cond_like"])
+    assert got["loglik"][0] == ref["loglik"]
+    assert np.array_equal(got["ancestors"][0], ref["ancestors"])
