@@ -168,6 +168,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
         a.tile0 = s->tile0; a.tile1 = s->tile1; a.tiles_per_rank = s->tiles_per_rank;
         a.T = T;
         a.seed = h->cfg.seed;
+        a.rk = philox_round_keys(h->cfg.seed);
         a.fid = stream_base + f;
         a.x_anc = s->x_anc;
         a.tmax = s->tmax; a.ttot = s->ttot; a.tclmax = s->tclmax; a.carry = s->carry; a.E = s->E; a.scal = s->scal;
@@ -239,6 +240,7 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     a.s.tile0 = 0; a.s.tile1 = s->nb; a.s.tiles_per_rank = s->nb;
     a.s.T = (int)h->T;
     a.s.seed = h->cfg.seed;
+    a.s.rk = philox_round_keys(h->cfg.seed);
     a.s.fid = stream_id;
     a.s.x_anc = s->x_anc;
     a.s.tmax = s->tmax; a.s.ttot = s->ttot; a.s.tclmax = s->tclmax; a.s.carry = s->carry; a.s.E = s->E; a.s.scal = s->scal;

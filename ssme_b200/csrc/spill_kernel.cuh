@@ -31,6 +31,7 @@ struct SpillArgs {
     int tiles_per_rank;   // nb / world
     int t, T;
     unsigned long long seed, fid;
+    PhiloxRoundKeys rk;  // key schedule of `seed`
     double* x_anc;   // [local] state of the ancestors (input of the propagation), local tile range
     double* x_cur;   // [local] propagated states x'
     double* lwc;     // [local] log-weights, overwritten by the tile-local CDF
@@ -77,12 +78,11 @@ __global__ void __launch_bounds__(kTileNT) spill_propagate_kernel(const SpillArg
     const ModelConst mc = model_init<MODEL>(a.theta);
     const double y = a.obs[(size_t)(a.t - a.row0) * OS];
     const double cov = (OS == 2) ? a.obs[(size_t)(a.t - a.row0) * OS + 1] : 0.0;
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
     double z[kTileL];
 #pragma unroll
     for (int q = 0; q < kTileL / 4; ++q) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), key);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
         float z0, z1, z2, z3;
         box_muller(r.x, r.y, z0, z1);
         box_muller(r.z, r.w, z2, z3);
@@ -466,6 +466,37 @@ __device__ __forceinline__ int count_targets(double c, double u0, double sN, dou
     return k + 1;
 }
 
+// The same count with the usual case decided without a loop or an integer round trip: floor(q) is formed in double, the
+// two neighbouring targets are evaluated exactly as the oracle evaluates them, and only a mismatch (the estimate q off by
+// one after rounding) falls back to the loops above.  tau0 = fl(fl(0 + u0) * sN), Nm1 = (double)(N - 1).
+__device__ __forceinline__ int count_targets_fast(double c, double tau0, double u0, double sN, double inv_sN, int N, double Nm1)
+{
+    const double q = __fma_rn(c, inv_sN, -u0);
+    double kd = floor(q);
+    kd = (kd > Nm1) ? Nm1 : kd;
+    kd = (kd > 0.0) ? kd : 0.0;
+    const double kd1 = __dadd_rn(kd, 1.0);
+    const double t0 = __dmul_rn(__dadd_rn(kd, u0), sN);
+    const double t1 = __dmul_rn(__dadd_rn(kd1, u0), sN);
+    const bool below = !(c >= tau0);
+    const bool ok = below || ((t0 <= c) && (kd1 > Nm1 || t1 > c));
+    int res = (int)kd + 1;
+    if (!ok) res = count_targets(c, u0, sN, inv_sN, N);
+    return below ? 0 : res;
+}
+
+// maximum over the lanes of a warp of non-negative doubles (-inf allowed, returned as +0: every caller maxes the result
+// with a non-negative value or discards it): two REDUX on the bit patterns instead of five shuffle-compare-select steps
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    const long long b = __double_as_longlong(v);
+    const unsigned hi = (b < 0) ? 0u : (unsigned)(b >> 32);
+    const unsigned lo = (b < 0) ? 0u : (unsigned)b;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wider slot ranges (degenerate weights) are written directly
 
 // Systematic resampling WITHOUT a search (oracle: systematic_by_counts).  Each CTA takes a tile of PARTICLES: it forms
@@ -478,20 +509,35 @@ __global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a
 {
     extern __shared__ __align__(16) double ebuf[];  // [kExpandBuf]
     __shared__ double red[kTileNT / 32];
+    __shared__ double sh_par[5];
     __shared__ int sh_range[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = a.tile0 + blockIdx.x;
     const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
     const int i0 = tile * kTile + tid * kTileL;
     const int N = a.N;
-    const double S = a.scal[1];
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-    const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), key);
-    const double u0 = uniform53(r.x, r.y);
-    const double sN = __ddiv_rn(S, (double)a.N);
-    const double inv_sN = __ddiv_rn(1.0, sN);
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    if (tid == 0) {  // one thread draws the offset and forms the grid constants for the CTA
+        const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
+        const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), a.rk);
+        const double u0_ = uniform53(r.x, r.y);
+        const double sN_ = __ddiv_rn(a.scal[1], (double)a.N);
+        double carry = a.carry[tile];
+        if (a.cmax) {  // two-launch tile scan: add the maxima of the earlier virtual warps
+            const int vw = tile / (32 * a.Lp);
+            for (int g = 0; g < vw; ++g) {
+                const double cg = a.cmax[g];
+                carry = (cg > carry) ? cg : carry;
+            }
+        }
+        sh_par[0] = u0_;
+        sh_par[1] = sN_;
+        sh_par[2] = __ddiv_rn(1.0, sN_);
+        sh_par[3] = __dmul_rn(__dadd_rn(0.0, u0_), sN_);
+        sh_par[4] = carry;
+        sh_range[0] = 0;
+        sh_range[1] = 0;
+    }
     const double O = (tile > 0) ? a.E[tile - 1] : 0.0;
     double c[kTileL];
 #pragma unroll
@@ -513,33 +559,38 @@ __global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a
         inc = (lane >= d && other > inc) ? other : inc;
     }
     if (lane == 31) red[warp] = inc;
-    if (tid == 0) { sh_range[0] = 0; sh_range[1] = 0; }
     __syncthreads();
-    double prevmax = a.carry[tile];
-    if (a.cmax) {  // two-launch tile scan: add the maxima of the earlier virtual warps
-        const int vw = tile / (32 * a.Lp);
-        for (int g = 0; g < vw; ++g) {
-            const double cg = a.cmax[g];
-            prevmax = (cg > prevmax) ? cg : prevmax;
-        }
-    }
-    for (int g = 0; g < warp; ++g) prevmax = (red[g] > prevmax) ? red[g] : prevmax;
+    const double u0 = sh_par[0], sN = sh_par[1], inv_sN = sh_par[2], tau0 = sh_par[3], Nm1 = (double)(N - 1);
+    // running maximum of the CDF over every particle before this thread's first: earlier tiles, earlier warps, earlier lanes
+    // (all non-negative; -inf only where nothing precedes, i.e. particle 0, which is handled explicitly below)
+    double prevmax = sh_par[4];
+    const double wprev = warp_max_nonneg((lane < warp) ? red[lane] : ninf);
+    prevmax = (wprev > prevmax) ? wprev : prevmax;
     double excl = shfl_up_d(inc, 1);
     excl = (lane > 0) ? excl : ninf;
-    prevmax = (excl > prevmax) ? excl : prevmax;  // running maximum of the CDF over every particle before this thread's first
+    prevmax = (excl > prevmax) ? excl : prevmax;
     // cumulative offspring counts of this thread's particles
     int A[kTileL + 1];
-    A[0] = (i0 == 0 || i0 >= N) ? 0 : count_targets(prevmax, u0, sN, inv_sN, N);
+    A[0] = (i0 == 0 || i0 >= N) ? 0 : count_targets_fast(prevmax, tau0, u0, sN, inv_sN, N, Nm1);
+    if (i0 + kTileL < N) {  // every particle of this thread is real and none is the last one
 #pragma unroll
-    for (int k = 0; k < kTileL; ++k) {
-        const int i = i0 + k;
-        int Ak = A[k];
-        if (i < N) {
+        for (int k = 0; k < kTileL; ++k) {
             const double ct = (c[k] > prevmax) ? c[k] : prevmax;
-            Ak = (i == N - 1) ? N : count_targets(ct, u0, sN, inv_sN, N);
-            Ak = (Ak < A[k]) ? A[k] : Ak;
+            const int Ak = count_targets_fast(ct, tau0, u0, sN, inv_sN, N, Nm1);
+            A[k + 1] = (Ak < A[k]) ? A[k] : Ak;
         }
-        A[k + 1] = Ak;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kTileL; ++k) {
+            const int i = i0 + k;
+            int Ak = A[k];
+            if (i < N) {
+                const double ct = (c[k] > prevmax) ? c[k] : prevmax;
+                Ak = (i == N - 1) ? N : count_targets(ct, u0, sN, inv_sN, N);
+                Ak = (Ak < A[k]) ? A[k] : Ak;
+            }
+            A[k + 1] = Ak;
+        }
     }
     const int tile_first = tile * kTile;
     const int tile_last = min(tile_first + kTile, N) - 1;  // last real particle of this tile
@@ -562,8 +613,13 @@ __global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a
         double* dst_local = (fld == 0) ? a.x_anc : a.extra_anc[fld - 1];
         if (staged) {
 #pragma unroll
-            for (int k = 0; k < kTileL; ++k)
-                for (int sl = A[k]; sl < A[k + 1]; ++sl) ebuf[sl - s_lo] = v[k];
+            for (int k = 0; k < kTileL; ++k) {  // offspring counts are mostly 0..3: predicated stores, a loop for the rest
+                const int a0 = A[k] - s_lo, cnt = A[k + 1] - A[k];
+                if (cnt > 0) ebuf[a0] = v[k];
+                if (cnt > 1) ebuf[a0 + 1] = v[k];
+                if (cnt > 2) ebuf[a0 + 2] = v[k];
+                for (int j = 3; j < cnt; ++j) ebuf[a0 + j] = v[k];
+            }
             __syncthreads();
             for (int q = tid; q < s_hi - s_lo; q += kTileNT) {
                 const long long sl = (long long)s_lo + q;
@@ -603,13 +659,12 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
     const int tid = threadIdx.x;
     const int tile = a.tile0 + blockIdx.x;
     const double S = a.scal[1];
-    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
 #pragma unroll 2
     for (int k = 0; k < kTileL; ++k) {
         const int j = tile * kTile + k * kTileNT + tid;  // coalesced over the CTA
         if (j >= a.N) continue;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), key);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), a.rk);
         const double tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
         int b = 0;
         for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;
