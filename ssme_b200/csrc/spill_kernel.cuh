@@ -505,7 +505,7 @@ constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wide
 // A_i = #{targets <= Ct_i} in O(1) per particle; particle i fathers the slots A_{i-1} .. A_i - 1, which are contiguous
 // over the CTA: they are staged in shared memory and written out coalesced (to the slot owner's HBM when the filter is
 // sharded over ranks).  HBM traffic: read CDF 8 + read x' 8 + write 8 B per particle.
-__global__ void __launch_bounds__(kTileNT) spill_expand_kernel(const SpillArgs a)
+__global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArgs a)
 {
     extern __shared__ __align__(16) double ebuf[];  // [kExpandBuf]
     __shared__ double red[kTileNT / 32];
