@@ -231,3 +231,17 @@ def test_streaming_swarm_equals_whole_series(sv_series, gpu_backend_factory, mod
         assert np.array_equal(ex, whole["expectations"][t])
     with pytest.raises(RuntimeError):
         gpu_backend_factory(model=model, num_particles=N).swarm_step([0.1, 0.0])
+
+
+def test_long_series_ten_thousand_steps(oracle, sv_series, gpu_backend_factory):
+    """T = 10000 (BASELINE.json config 4's length): 157 observation chunks through the bulk-copy ring, bit for bit."""
+    T, N = 10000, 256
+    y = sv_series(T, seed=91)
+    be = gpu_backend_factory(num_particles=N, seed=41)
+    be.add_observed_data(y)
+    out, pf = be.work_batch(np.stack([SV_THETA, SV_THETA * 0.98]), R=1, stream_base=2, return_per_filter=True)
+    lay = be.layout
+    for f in range(2):
+        th = SV_THETA if f == 0 else SV_THETA * 0.98
+        ref = oracle.filter_run(th, y, N, L=lay["scan_items_per_lane"], NT=lay["threads_per_filter"], seed=41, filter_id=2 + f, trace=False)
+        assert pf[f, 0] == ref["loglik"]
