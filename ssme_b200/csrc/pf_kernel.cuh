@@ -545,21 +545,24 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 
         // ---- branch-free descent over the breadth-first CDF, then gather -------------------------
         // Probe sequence identical to "for (s = NP/2; s >= 1; s >>= 1) if (C[idx+s-1] < tau) idx += s".
+        // nb = 8 * (node + 1): children 2*node+1 / 2*node+2 become 2*nb / 2*nb + 8, the probe address is Cb - 8 + nb
         uint32_t nb[L];
 #pragma unroll
-        for (int k = 0; k < L; ++k) nb[k] = 0u;
+        for (int k = 0; k < L; ++k) nb[k] = 8u;
+        const unsigned char* Cm = Cb - 8;
 #pragma unroll
         for (int lvl = 0; lvl < K; ++lvl) {
 #pragma unroll
             for (int k = 0; k < L; ++k) {
-                const double v = *reinterpret_cast<const double*>(Cb + nb[k]);
-                nb[k] = 2u * nb[k] + ((v < tau[k]) ? 16u : 8u);
+                const double v = *reinterpret_cast<const double*>(Cm + nb[k]);
+                nb[k] += nb[k];
+                if (v < tau[k]) nb[k] += 8u;
             }
         }
         int idx[L];
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            idx[k] = min((int)(nb[k] >> 3) - (NP - 1), N - 1);
+            idx[k] = min((int)(nb[k] >> 3) - NP, N - 1);
             x[k] = Xcur[idx[k]];
             lwacc[k] = 0.0;
         }

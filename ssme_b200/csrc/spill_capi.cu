@@ -80,6 +80,9 @@ static int prepare(ssme_b200_handle h)
     SSME_CUDA(cudaMalloc(&s->tclmax, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
+    // per device: the two-launch tile scan stages up to 2 x 256 x 33 doubles
+    SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 33 * (int)sizeof(double)));
+    SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * (int)sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->sync_word, sizeof(double)));
     SSME_CUDA(cudaMemset(s->sync_word, 0, sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->E, (size_t)s->NBP * sizeof(double)));
@@ -125,12 +128,7 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         a.lanetot = s->scan2 + 1024;
         a.wtot = s->scan2 + 2048;
         a.cmax = s->scan2 + 2048 + 32;
-        static bool attr_set = false;
         const size_t smem_b = (size_t)2 * s->Lp * 33 * sizeof(double);
-        if (!attr_set) {
-            cudaFuncSetAttribute(spill_tile_scan_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 33 * (int)sizeof(double));
-            attr_set = true;
-        }
         spill_tile_scan_a_kernel<<<32, kScan2NT, (size_t)s->Lp * 33 * sizeof(double), st>>>(a);
         spill_tile_scan_b_kernel<<<32, kScan2NT, smem_b, st>>>(a);
         count_launch(1);
