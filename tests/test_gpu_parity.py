@@ -245,3 +245,28 @@ def test_long_series_ten_thousand_steps(oracle, sv_series, gpu_backend_factory):
         th = SV_THETA if f == 0 else SV_THETA * 0.98
         ref = oracle.filter_run(th, y, N, L=lay["scan_items_per_lane"], NT=lay["threads_per_filter"], seed=41, filter_id=2 + f, trace=False)
         assert pf[f, 0] == ref["loglik"]
+
+
+@pytest.mark.parametrize("N", [1, 2, 5, 31, 33])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC, sb.RESAMP_SORTED_MULTINOMIAL])
+@pytest.mark.parametrize("force_global", [0, 1])
+def test_tiny_particle_counts(oracle, sv_series, gpu_backend_factory, N, resampler, force_global):
+    """One particle, two particles, ragged warps; an observation that is exactly zero (example/spy_returns.csv has one)."""
+    if force_global and resampler == sb.RESAMP_SORTED_MULTINOMIAL:
+        pytest.skip("sorted-multinomial is built into the resident kernel")
+    T = 12
+    y = sv_series(T, seed=92).copy()
+    y[3] = 0.0
+    be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=43, force_global_memory=force_global)
+    be.add_observed_data(y)
+    got = be.trace(SV_THETA[None, :], stream_base=6, want=("loglik", "cond_like", "ancestors"))
+    lay = be.layout
+    if force_global:
+        ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=43, filter_id=6)
+    else:
+        ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=lay["scan_items_per_lane"], NT=lay["threads_per_filter"], seed=43, filter_id=6)
+    assert np.array_equal(got["ancestors"][0], ref["ancestors"])
+    assert np.array_equal(got["cond_like"][0], ref["cond_like"])
+    assert got["loglik"][0] == ref["loglik"] and np.isfinite(ref["loglik"])
+    if N == 1:  # a single particle always fathers itself
+        assert np.all(got["ancestors"][0] == 0)
