@@ -208,6 +208,13 @@ int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* pri
                              uint64_t stream_id, double* loglik_host, double* cond_like_host, double* theta_bar_host,
                              double* final_mean_host, int32_t* ancestors_host, int32_t* aux_index_host);
 
+/* The same filter with the expectations the reference forms before resampling when filter() is given functions
+ * (liu_west_filter.h:1087-1101, :2263-2276; tests "test filter with funcs", test_liu_west.cpp:177-199, 379-401):
+ * expectations_host [T][5] = E[h | y_{1:t}] for h = x_t, phi, mu, sigma, rho (untransformed parameters) -- the reference
+ * takes std::function callbacks; a device kernel cannot call host lambdas, so these five are built in. */
+int ssme_b200_lw_expectations(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                              uint64_t stream_id, double* loglik_host, double* cond_like_host, double* expectations_host);
+
 /* Streaming form of the same filter, one observation per call -- what LWFilter*::filter(obs_data, cov_data) is
  * (liu_west_filter.h:971, :2191): the particle cloud stays in HBM between calls.
  *   ssme_b200_lw_begin   draws nothing yet; fixes form, prior box, delta and the random stream, resets the step counter

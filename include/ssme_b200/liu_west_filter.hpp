@@ -79,6 +79,23 @@ public:
                                                 m_theta_bar.data(), m_final_mean.data(), nullptr, nullptr));
     }
 
+    // filter(obs, cov, fs) over the series: also E[h | y_{1:t}] before resampling for h = x_t, phi, mu, sigma, rho
+    // (getExpectations, liu_west_filter.h:1087-1101 / :2263-2276); read back with getExpectation(t, which)
+    void filter_series_with_expectations(const std::vector<float_t>& obs, const std::vector<float_t>& cov, std::uint64_t stream_id = 0)
+    {
+        if (obs.empty() || obs.size() != cov.size()) throw std::length_error("observations and covariates must be non-empty and of equal length");
+        std::vector<double> rows(2 * obs.size());
+        for (size_t t = 0; t < obs.size(); ++t) { rows[2 * t] = (double)obs[t]; rows[2 * t + 1] = (double)cov[t]; }
+        throw_on_error(ssme_b200_set_observations(m_h, rows.data(), obs.size(), 2));
+        m_streaming = false;
+        m_cond_like.assign(obs.size(), 0.0);
+        m_expect.assign(obs.size() * 5, 0.0);
+        double lo[4], hi[4];
+        for (int k = 0; k < 4; ++k) { lo[k] = (double)m_lo(k); hi[k] = (double)m_hi(k); }
+        throw_on_error(ssme_b200_lw_expectations(m_h, form, lo, hi, (double)m_delta, stream_id, &m_loglik, m_cond_like.data(), m_expect.data()));
+    }
+    float_t getExpectation(size_t t, size_t which) const { return (float_t)m_expect.at(5 * t + which); }
+
     // The reference's streaming call: filter(obs_data, cov_data) once per observation (:971, :2191).  The first call
     // starts the run (stream id fixed by set_stream); results equal filter_series on the same data bit for bit.
     void set_stream(std::uint64_t stream_id) { m_stream = stream_id; }
@@ -118,7 +135,7 @@ private:
     double m_loglik = 0.0;
     bool m_streaming = false;
     std::uint64_t m_stream = 0;
-    std::vector<double> m_cond_like, m_theta_bar;
+    std::vector<double> m_cond_like, m_theta_bar, m_expect;
     std::array<double, 4> m_final_mean{};
 };
 }  // namespace detail

@@ -135,16 +135,18 @@ def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH
     cl, tb, fm = np.empty(T), np.zeros((T, 4)), np.empty(4)
     anc = np.empty((T, N), dtype=np.int32) if trace else None
     aux = np.zeros((T, N), dtype=np.int32) if trace else None
-    fn = lib().ssme_oracle_lw_filter_form
+    ex = np.zeros((T, 5))
+    fn = lib().ssme_oracle_lw_filter_expect
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     rc = fn(C.cast(C.byref(cfg), C.c_void_p), {"sisr": 0, "apf": 1}[form], vp(lo), vp(hi), delta, vp(y), T, vp(cov),
-            C.cast(C.byref(ll), C.c_void_p), vp(cl), vp(tb), vp(fm), vp(anc), vp(aux), C.cast(C.byref(mg), C.c_void_p))
+            C.cast(C.byref(ll), C.c_void_p), vp(cl), vp(tb), vp(fm), vp(anc), vp(aux), C.cast(C.byref(mg), C.c_void_p), vp(ex))
     if rc != 0:
-        raise ValueError("ssme_oracle_lw_filter_form failed with %d" % rc)
-    return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux, "margin": mg.value}
+        raise ValueError("ssme_oracle_lw_filter_expect failed with %d" % rc)
+    return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux, "margin": mg.value,
+            "expect": ex}
 
 
 def log_mean_exp(v, arithmetic=ARITH_CANONICAL):

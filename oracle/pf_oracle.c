@@ -628,6 +628,17 @@ int ssme_oracle_lw_filter_form(const ssme_oracle_cfg* cfg, int32_t form, const d
                                const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
                                double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin)
 {
+    return ssme_oracle_lw_filter_expect(cfg, form, prior_lo, prior_hi, delta, y, T, cov, loglik_out, cond_like, theta_bar, final_mean,
+                                        ancestors, aux_index, tie_margin, NULL);
+}
+
+/* the same, plus expect[T][5] = E[h | y_{1:t}] for h = x_t, phi, mu, sigma, rho, formed before resampling as the reference
+ * does when filter() is given functions (liu_west_filter.h:1087-1101, :2263-2276): numer += h exp(lw - m), denom += exp(lw - m) */
+int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                                 const double* y, int64_t T, const double* cov, double* loglik_out, double* cond_like,
+                                 double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin,
+                                 double* expect)
+{
     static const int TT[4] = {2, 0, 3, 1}; /* logit, null, log, twice_fisher */
     if (!cfg || !prior_lo || !prior_hi || !y || T < 0) return -1;
     const int32_t N = cfg->num_particles, L = cfg->scan_items_per_lane;
@@ -797,6 +808,25 @@ int ssme_oracle_lw_filter_form(const ssme_oracle_cfg* cfg, int32_t form, const d
             double acc = 0.0;
             for (int32_t i = 0; i < N; ++i) { acc += w[i] / S; C[i] = acc; }
             C[N - 1] = 1.0;
+        }
+        if (expect) {
+            for (int q = 0; q < 5; ++q) {
+                if (canonical) {
+                    for (int32_t i = 0; i < N; ++i) {
+                        double hv = (q == 0) ? x[i] : lw_inv_trans(TT[q - 1], th[(size_t)(q - 1) * N + i], 1);
+                        tmp[i] = w[i] * hv;
+                    }
+                    expect[t * 5 + q] = ssme_oracle_canonical_sum(tmp, N, L, nt) / S;
+                } else {
+                    double num = 0.0, den = 0.0;
+                    for (int32_t i = 0; i < N; ++i) {
+                        double hv = (q == 0) ? x[i] : lw_inv_trans(TT[q - 1], th[(size_t)(q - 1) * N + i], 0);
+                        num += hv * w[i];
+                        den += w[i];
+                    }
+                    expect[t * 5 + q] = num / den;
+                }
+            }
         }
         const double logS = canonical ? dm_log(S) : log(S);
         double cl = (t == 0) ? -logN + M + logS : M + logS - 0.0 - logN;

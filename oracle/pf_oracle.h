@@ -110,6 +110,12 @@ int ssme_oracle_lw_filter_form(const ssme_oracle_cfg* cfg, int32_t form, const d
                                const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
                                double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin);
 
+/* ... plus expect[T][5] = E[h | y_{1:t}], h = x_t, phi, mu, sigma, rho, before resampling (liu_west_filter.h:1087-1101, :2263-2276) */
+int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                                 const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
+                                 double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin,
+                                 double* expect);
+
 /* canonical sum of v[0..n): tile partials (lane-local sequential over L, butterfly over the 32 lanes, sequential
  * over the warps of the tile), then the tile partials by one CTA of 1024 lanes the same way */
 double ssme_oracle_canonical_sum(const double* v, int32_t n, int32_t L, int32_t nt);

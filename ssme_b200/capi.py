@@ -101,6 +101,7 @@ def load_library():
     lib.ssme_b200_swarm_filter.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp]
     lib.ssme_b200_swarm_begin.argtypes = [H, dp, C.c_size_t, C.c_uint64]
     lib.ssme_b200_swarm_step.argtypes = [H, dp, dp, dp]
+    lib.ssme_b200_lw_expectations.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp]
     lib.ssme_b200_lw_begin.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64]
     lib.ssme_b200_lw_step.argtypes = [H, C.c_double, C.c_double, dp, dp]
     lib.ssme_b200_lw_state.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
@@ -319,6 +320,16 @@ class ParticleFilterBackend:
         ex = np.zeros(2) if want_expectations else None
         _check(self._lib.ssme_b200_swarm_step(self._h, _dptr(row), C.byref(cl), _dptr(ex)))
         return (cl.value, ex) if want_expectations else cl.value
+
+    def lw_expectations(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, form: str = "sisr"):
+        """Liu-West filter with the expectations E[h | y_1:t], h = x_t, phi, mu, sigma, rho: dict(loglik, cond_like[T], expect[T,5])."""
+        lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
+        hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+        ll = C.c_double()
+        cl, ex = np.empty(self.T), np.empty((self.T, 5))
+        _check(self._lib.ssme_b200_lw_expectations(self._h, {"sisr": 0, "apf": 1}[form], _dptr(lo), _dptr(hi), delta, stream_id,
+                                                   C.byref(ll), _dptr(cl), _dptr(ex)))
+        return {"loglik": ll.value, "cond_like": cl, "expect": ex}
 
     def lw_begin(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, form: str = "sisr"):
         """Start a streaming Liu-West run (LWFilter*::filter called once per observation)."""

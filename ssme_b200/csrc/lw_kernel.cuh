@@ -29,7 +29,9 @@ struct LwArgs {
     double* theta_bar_out;    // [T][4] or null
     double lo[4], hi[4];      // uniform prior box (untransformed)
     double a, oma, h2;
-    int mode;                 // moments kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values
+    int mode;                 // moments kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values,
+                              // 2 = 5 weighted sums  sum_i exp(lw_i - M) h(x_i, theta_i)  for the expectations (h = x, phi, mu, sigma, rho)
+    double* expect_out;       // [T][5] E[h | y_{1:t}] formed before resampling, or null
     // auxiliary-particle form (LWFilterWithCovs, liu_west_filter.h:971-1159)
     double* lfs;              // [N] first-stage log-weights log g(y_t | propMu(x_i, z_t, theta_i))
     double* cdf1;             // [N] first-stage buffer: log-weights, then their tile-local CDF (K3c/K3d run on it)
@@ -86,6 +88,33 @@ __global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
+    double s[14];
+    if (a.mode == 2) {
+        // expectations before resampling (liu_west_filter.h:1087-1101 / :2263-2276): numer += h(x_i, theta_i) exp(lw_i - m);
+        // the denominator is the weight total S of the scan that follows.  Runs between the max and the weights/scan kernels.
+        const double M = a.s.scal[0];
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < kTileL; ++k) {
+            const size_t i = (size_t)i0 + k;
+            const bool valid = i0 + k < a.s.N;
+            const double w = valid ? dexp_nonpos(__dsub_rn(a.s.lwc[i], M)) : 0.0;
+            double hv[5];
+            hv[0] = valid ? a.s.x_cur[i] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hv[1 + q] = valid ? lw_inv_trans(q, a.th_cur[q][i]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const double p = __dmul_rn(w, hv[q]);
+                acc[q] = (k == 0) ? p : __dadd_rn(acc[q], p);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 14; ++q) s[q] = (q < 5) ? acc[q] : 0.0;
+        block_sums<14, NW>(s, red, 5, lane, warp, tid, tot);
+        if (tid < 5) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
+        return;
+    }
     double th[4][kTileL];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -95,7 +124,6 @@ __global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
             if (a.mode == 1 && i0 + k < a.s.N) v = lw_inv_trans(q, v);
             th[q][k] = v;
         }
-    double s[14];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         s[q] = th[q][0];
@@ -123,7 +151,7 @@ __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwA
     __shared__ double red[32 * 14];
     __shared__ double tot[14];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nq = (a.mode == 1) ? 4 : 14;
+    const int nq = (a.mode == 1) ? 4 : (a.mode == 2) ? 5 : 14;
     const int b0 = tid * a.s.Lp;
     double s[14];
 #pragma unroll
@@ -142,6 +170,11 @@ __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwA
     const double dN = (double)a.s.N;
     if (a.mode == 1) {
         for (int k = 0; k < 4; ++k) a.mom[20 + k] = __ddiv_rn(tot[k], dN);
+        return;
+    }
+    if (a.mode == 2) {  // runs after the scan of the tile totals: scal[1] = S
+        const double S = a.s.scal[1];
+        for (int k = 0; k < 5; ++k) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + k] = __ddiv_rn(tot[k], S);
         return;
     }
     double tb[4], V[4][4], Lc[4][4];

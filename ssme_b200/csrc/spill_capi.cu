@@ -302,8 +302,18 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
     }
     a.s.cl_mode = apf ? 2 : 0;
     spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
+    if (a.expect_out) {  // weighted sums of h(x, theta) while the log-weights are still in lwc
+        a.mode = 2;
+        lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
+        count_launch(1);
+    }
     spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
     launch_tile_scan(s, a.s, st);
+    if (a.expect_out) {
+        a.mode = 2;
+        lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        count_launch(1);
+    }
     if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
     else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
     count_launch(5);
@@ -324,7 +334,7 @@ static int lw_means(ssme_b200_handle h, LwArgs& a, double* d_mean)
 }
 
 static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, double* d_loglik,
-                  double* d_cond_like, double* d_theta_bar, double* d_final_mean, int* d_ancestors, int* d_aux)
+                  double* d_cond_like, double* d_theta_bar, double* d_final_mean, int* d_ancestors, int* d_aux, double* d_expect = nullptr)
 {
     LwArgs a;
     int rc = lw_setup(h, form, lo, hi, delta, stream_id, &a);
@@ -335,6 +345,7 @@ static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* 
     a.s.ancestors = d_ancestors;
     a.aux_out = d_aux;
     a.theta_bar_out = d_theta_bar;
+    a.expect_out = d_expect;
     const int T = (int)h->T;
     for (int t = 0; t < T; ++t)
         if ((rc = lw_step(h, a, form, t))) return rc;
@@ -396,6 +407,37 @@ int ssme_b200_lw_filter_form(ssme_b200_handle h, int32_t form, const double* pri
     if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "Liu-West filter failed: %s", cudaGetErrorString(e));
     if (loglik_host) *loglik_host = sc[0];
     if (final_mean_host) memcpy(final_mean_host, sc + 1, 4 * sizeof(double));
+    return SSME_B200_OK;
+}
+
+int ssme_b200_lw_expectations(ssme_b200_handle h, int32_t form, const double* prior_lo, const double* prior_hi, double delta, uint64_t stream_id,
+                              double* loglik_host, double* cond_like_host, double* expectations_host)
+{
+    if (!h || !prior_lo || !prior_hi || !expectations_host) return fail(SSME_B200_EINVAL, "null argument");
+    if (form != SSME_B200_LW_SISR && form != SSME_B200_LW_APF) return fail(SSME_B200_EINVAL, "unknown Liu-West form %d", form);
+    if (!h->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    if (!h->spill) return fail(SSME_B200_EINVAL, "the Liu-West filter uses the global-memory kernels: create the handle with force_global_memory = 1 (or N > 8192)");
+    if (h->cfg.model != SSME_B200_MODEL_SV_LEVERAGE) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter is built for the SV-with-leverage model");
+    if (!(delta > 1.0 / 3.0 && delta <= 1.0)) return fail(SSME_B200_EINVAL, "delta must lie in (1/3, 1]");
+    for (int k = 0; k < 4; ++k)
+        if (!(prior_hi[k] > prior_lo[k])) return fail(SSME_B200_EINVAL, "prior box %d is empty", k);
+    int rc = set_device(h);
+    if (rc) return rc;
+    const size_t T = h->T;
+    double *d_sc = nullptr, *d_cl = nullptr, *d_ex = nullptr;
+    auto cleanup = [&]() { cudaFree(d_sc); cudaFree(d_cl); cudaFree(d_ex); };
+    cudaError_t e = cudaMalloc(&d_sc, 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cl, T * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ex, T * 5 * sizeof(double));
+    if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "Liu-West setup failed: %s", cudaGetErrorString(e)); }
+    rc = lw_run(h, form, prior_lo, prior_hi, delta, stream_id, d_sc, d_cl, nullptr, nullptr, nullptr, nullptr, d_ex);
+    if (rc) { cleanup(); return rc; }
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && loglik_host) e = cudaMemcpy(loglik_host, d_sc, sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cond_like_host) e = cudaMemcpy(cond_like_host, d_cl, T * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(expectations_host, d_ex, T * 5 * sizeof(double), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "Liu-West filter failed: %s", cudaGetErrorString(e));
     return SSME_B200_OK;
 }
 

@@ -109,6 +109,24 @@ def test_liu_west_streaming_equals_whole_series(gpu_backend_factory, form, resam
         gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=64, force_global_memory=1).lw_step(0.1, 0.0)
 
 
+@pytest.mark.parametrize("form", ["sisr", "apf"])
+@pytest.mark.parametrize("N,T", [(10, 4), (5000, 12), (4096 * 2 + 5, 7)])
+def test_liu_west_expectations_bit_exact(oracle, gpu_backend_factory, form, N, T):
+    """filter(y, z, fs): E[h | y_{1:t}] before resampling (liu_west_filter.h:1087-1101, :2263-2276) for h = x, phi, mu, sigma, rho."""
+    y = leverage_series(T, seed=N + T + 3)
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=sb.RESAMP_SYSTEMATIC, seed=11, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.lw_expectations(LO, HI, delta=0.99, stream_id=4, form=form)
+    ref = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=sb.RESAMP_SYSTEMATIC, seed=11, filter_id=4, form=form)
+    assert np.array_equal(got["expect"], ref["expect"])
+    assert np.array_equal(got["cond_like"], ref["cond_like"]) and got["loglik"] == ref["loglik"]
+    # weighted means of the parameters stay inside the prior box; h = const comes back as the constant (test_liu_west.cpp:199)
+    assert np.all((got["expect"][:, 1:] > LO) & (got["expect"][:, 1:] < HI))
+    fai = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=sb.RESAMP_SYSTEMATIC, arithmetic=oracle.ARITH_FAITHFUL, seed=11, filter_id=4, form=form)
+    if np.array_equal(fai["ancestors"], ref["ancestors"]) and np.array_equal(fai["aux_index"], ref["aux_index"]):
+        assert np.allclose(got["expect"], fai["expect"], rtol=1e-9, atol=1e-12)
+
+
 def _seq_sum(v):
     acc = 0.0
     for c in v:
