@@ -149,6 +149,7 @@ static void tiled_alloc(tiled_cdf_t* c, int32_t N, int32_t TS, int32_t L)
     c->E = (double*)malloc(sizeof(double) * (size_t)c->NBP);
 }
 static void tiled_free(tiled_cdf_t* c) { free(c->cl); free(c->E); }
+static int injected_mode(const ssme_oracle_cfg* cfg) { return cfg->rng_mode == SSME_OR_RNG_INJECTED; }
 
 static void tiled_build(tiled_cdf_t* c, const double* w)
 {
@@ -363,12 +364,14 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         NP = nt * L;
     }
     const int tiled = canonical && cfg->tiled;
-    tiled_cdf_t tc;
+    tiled_cdf_t tc, te; /* weights; exponential spacings of the sorted-multinomial resampler */
+    te.cl = NULL; te.E = NULL;
     if (tiled) {
-        if (cfg->resampler != SSME_OR_RESAMP_SYSTEMATIC && cfg->resampler != SSME_OR_RESAMP_MULTINOMIAL) return -8;
+        if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL && injected_mode(cfg)) return -8;
         int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
         if ((nt & (nt - 1)) != 0) return -7;
         tiled_alloc(&tc, N, nt * L, L);
+        if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL) tiled_alloc(&te, N, nt * L, L);
         NP = N; /* C below holds the global values O_b + cl_i, for the margin report only */
     }
     if (cfg->model != SSME_OR_MODEL_SV && cfg->model != SSME_OR_MODEL_SV_LEVERAGE) return -3;
@@ -495,7 +498,17 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
                     if (!injected && u == 0.0) u = 0x1p-53;
                     E[j] = canonical ? -dm_log(u) : -log(u);
                 }
-                if (canonical) {
+                if (tiled) {
+                    /* the spacings are scanned in the same tiled order as the weights; slot j searches for P_j * (S / G) */
+                    tiled_build(&te, E);
+                    const double G = te.S + E[N];
+                    const double sg = S / G;
+                    for (int32_t j = 0; j < N; ++j) {
+                        double tau = tiled_value(&te, j) * sg;
+                        anc[j] = tiled_search(&tc, tau);
+                        upd_margin(&margin, C, anc[j], tau, total);
+                    }
+                } else if (canonical) {
                     double G;
                     ssme_oracle_canonical_scan(E, N, L, NP, PE, &G);
                     G = G + E[N];
@@ -539,7 +552,7 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         }
         if (ancestors) for (int32_t j = 0; j < N; ++j) ancestors[t * N + j] = anc[j];
     }
-    if (tiled) tiled_free(&tc);
+    if (tiled) { tiled_free(&tc); tiled_free(&te); }
     if (loglik_out) *loglik_out = loglik;
     if (tie_margin) *tie_margin = margin;
     free(x); free(xn); free(lw); free(w); free(C); free(E); free(PE); free(anc);
@@ -644,13 +657,17 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
     const int32_t N = cfg->num_particles, L = cfg->scan_items_per_lane;
     const int canonical = (cfg->arithmetic == SSME_OR_ARITH_CANONICAL);
     if (N < 1 || (canonical && (!cfg->tiled || L < 1))) return -2;
-    if (cfg->resampler != SSME_OR_RESAMP_MULTINOMIAL && cfg->resampler != SSME_OR_RESAMP_SYSTEMATIC) return -4;
+    if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
     if (form != 0 && form != 1) return -5;
     const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
     const uint32_t utag = 1u + (uint32_t)cfg->resampler;
     const double a = (3.0 * delta - 1.0) / (2.0 * delta), h2 = 1.0 - a * a, oma = 1.0 - a;
-    tiled_cdf_t tc;
+    tiled_cdf_t tc, te; /* weights; exponential spacings of the sorted-multinomial resampler (mn_resamp_states_and_params) */
+    te.cl = NULL; te.E = NULL;
     if (canonical) tiled_alloc(&tc, N, nt * L, L);
+    const int sorted = (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL);
+    if (canonical && sorted) tiled_alloc(&te, N, nt * L, L);
+    double* Ex = sorted ? (double*)malloc(sizeof(double) * (size_t)(N + 1)) : NULL;
     double* x = (double*)malloc(sizeof(double) * (size_t)N);
     double* th = (double*)malloc(sizeof(double) * (size_t)N * 4); /* SoA: th[k*N + i], transformed */
     double* xn = (double*)malloc(sizeof(double) * (size_t)N * 5);
@@ -837,7 +854,36 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
         double u0 = 0.0, sN = S / (double)N;
         if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) u0 = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
         if (canonical && cfg->tiled == 2 && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) systematic_by_counts(&tc, N, u0, sN, anc);
-        else
+        else if (sorted) {
+            /* liu_west_filter.h:104-139: N+1 exponential spacings -> uniform order statistics */
+            for (int32_t j = 0; j <= N; ++j) {
+                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                if (u == 0.0) u = 0x1p-53;
+                Ex[j] = canonical ? -dm_log(u) : -log(u);
+            }
+            if (canonical) {
+                tiled_build(&te, Ex);
+                const double G = te.S + Ex[N];
+                const double sg = S / G;
+                for (int32_t j = 0; j < N; ++j) {
+                    double tau = tiled_value(&te, j) * sg;
+                    anc[j] = tiled_search(&tc, tau);
+                    upd_margin(&margin, C, anc[j], tau, total);
+                }
+            } else {
+                double G = 0.0;
+                for (int32_t j = 0; j < N; ++j) G += Ex[j];
+                G += Ex[N];
+                double ustat = 0.0;
+                int32_t idx = 0;
+                for (int32_t j = 0; j < N; ++j) {
+                    ustat += Ex[j] / G;
+                    while (idx < N - 1 && C[idx] < ustat) idx++;
+                    anc[j] = idx;
+                    upd_margin(&margin, C, idx, ustat, total);
+                }
+            }
+        } else
         for (int32_t j = 0; j < N; ++j) {
             double tau;
             if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
@@ -865,7 +911,8 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
             else { double sacc = 0.0; for (int32_t i = 0; i < N; ++i) sacc += tmp[i]; final_mean[k] = sacc / (double)N; }
         }
     }
-    if (canonical) tiled_free(&tc);
+    if (canonical) { tiled_free(&tc); tiled_free(&te); }
+    free(Ex);
     if (loglik_out) *loglik_out = loglik;
     if (tie_margin) *tie_margin = margin;
     free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc); free(lfs); free(ks);

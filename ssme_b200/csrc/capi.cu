@@ -284,8 +284,8 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
-    if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL && (use_cluster || spill))
-        return fail(SSME_B200_EUNSUPPORTED, "the sorted-multinomial resampler is built into the resident kernel only (N <= 8192, no cluster)");
+    if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL && use_cluster)
+        return fail(SSME_B200_EUNSUPPORTED, "the sorted-multinomial resampler is built into the resident and the global-memory kernels, not the cluster kernel");
     if (use_cluster) {
         // K2: tiles of 4*NT particles, one CTA each, cluster of ceil(N/tile) CTAs (cluster_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");

@@ -21,6 +21,8 @@ struct SpillState {
     double* lwc[2] = {nullptr, nullptr};
     double *tmax = nullptr, *ttot = nullptr, *tclmax = nullptr, *carry = nullptr, *E = nullptr, *scal = nullptr, *sync_word = nullptr;
     double* scan2 = nullptr;  // two-launch tile scan: lanepref[1024], lanetot[1024], wtot[32], cmax[32]
+    // sorted-multinomial resampling: scan of the exponential spacings (allocated on first use)
+    double *ecdf = nullptr, *ettot = nullptr, *eE = nullptr, *ecarry = nullptr;
     const double* peer_x[2][kMaxPeers] = {};
     const double* peer_lwc[2][kMaxPeers] = {};
     double* peer_x_anc[kMaxPeers] = {};
@@ -113,7 +115,7 @@ void spill_destroy(ssme_b200_handle h)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->scan2); cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
+    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
@@ -136,6 +138,35 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         a.cmax = nullptr;
         spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
     }
+}
+
+// Sorted-multinomial resampling of the step in `a` (weights already scanned): spacings, their tiled scan, one search per slot.
+static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& a, int tiles, cudaStream_t st)
+{
+    if (s->world != 1) return fail(SSME_B200_EUNSUPPORTED, "sorted-multinomial resampling of a particle-sharded filter is not built");
+    if (!s->ecdf) {
+        SSME_CUDA(cudaMalloc(&s->ecdf, s->local * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&s->ettot, (size_t)s->nb * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&s->eE, (size_t)s->NBP * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&s->ecarry, (size_t)s->nb * sizeof(double)));
+    }
+    a.ecdf = s->ecdf;
+    a.ettot = s->ettot;
+    a.eE = s->eE;
+    spill_expo_scan_kernel<<<tiles, kTileNT, 0, st>>>(a);
+    SpillArgs e = a;  // the tile-total scan kernels, pointed at the spacings; their running-maximum outputs go to scratch
+    e.ttot = s->ettot;
+    e.E = s->eE;
+    e.tclmax = s->ettot;
+    e.carry = s->ecarry;
+    e.cl_mode = 3;
+    launch_tile_scan(s, e, st);
+    a.resamp_sorted = 1;
+    spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a);
+    a.resamp_sorted = 0;
+    count_launch(3);
+    SSME_CUDA(cudaGetLastError());
+    return SSME_B200_OK;
 }
 
 template <int MODEL>
@@ -203,6 +234,8 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
                         int nrc = nccl->AllReduce(s->sync_word, s->sync_word, 1, kNcclFloat64, kNcclMax, h->nccl_comm, st);
                         if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllReduce failed: %s", nccl->GetErrorString(nrc));
                     }
+                } else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
+                    if ((rc = launch_sorted_resample(h, s, a, tiles, st))) return rc;
                 } else {
                     spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a);
                 }
@@ -315,7 +348,10 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         count_launch(1);
     }
     if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
-    else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+    else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
+        int rc = launch_sorted_resample(h, s, a.s, tiles, st);
+        if (rc) return rc;
+    } else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
     count_launch(5);
     SSME_CUDA(cudaGetLastError());
     return SSME_B200_OK;

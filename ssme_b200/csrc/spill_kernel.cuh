@@ -54,6 +54,12 @@ struct SpillArgs {
     // log-likelihood; 1 = first stage of an auxiliary particle filter: keep M + log S in scal[4] only;
     // 2 = second stage: log p(y_t | y_{1:t-1}) = ((M + log S) + scal[4]) - 2 log N  (liu_west_filter.h:1056-1058 with rs = 1)
     int cl_mode;
+    // sorted-multinomial resampling (the reference's in-tree mn_resamp_states_and_params, liu_west_filter.h:91-145): the N+1
+    // exponential spacings are scanned in the same tiled order as the weights; slot j searches for P_j * S / G
+    int resamp_sorted;  // spill_resample_kernel: 0 = i.i.d. uniforms, 1 = sorted targets from ecdf / eE
+    double* ecdf;       // [local] tile-local inclusive scan of the spacings E_j = -log U_j
+    double* ettot;      // [nb] tile totals of the spacings
+    double* eE;         // [NBP] inclusive tile ends of the spacings; their grand total goes to scal[5]
     // two-launch scan of the tile totals (many tiles): per virtual lane of the canonical 1024-lane scan its inclusive
     // Kogge-Stone value and its own total; per virtual warp its total and the maximum of O_b + tclmax_b over its tiles.
     // With cmax != null, carry[b] holds the running maximum over the earlier tiles of b's OWN virtual warp only.
@@ -232,6 +238,55 @@ __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const Spill
     }
 }
 
+// Exponential spacings E_j = -log U_j (stream 2) and their tile-local scan, for the sorted-multinomial resampler.
+// Same scan order as the weights above; padding beyond particle N-1 counts as 0.
+__global__ void __launch_bounds__(kTileNT) spill_expo_scan_kernel(const SpillArgs a)
+{
+    constexpr int NW = kTileNT / 32;
+    __shared__ double red_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = a.tile0 + blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
+    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
+    const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
+    double sc[kTileL];
+#pragma unroll
+    for (int q = 0; q < kTileL / 2; ++q) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
+        double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
+        ua = (ua == 0.0) ? 0x1p-53 : ua;
+        ub = (ub == 0.0) ? 0x1p-53 : ub;
+        sc[2 * q + 0] = (i0 + 2 * q < a.N) ? -dlog_unit(ua) : 0.0;
+        sc[2 * q + 1] = (i0 + 2 * q + 1 < a.N) ? -dlog_unit(ub) : 0.0;
+    }
+#pragma unroll
+    for (int k = 1; k < kTileL; ++k) sc[k] = __dadd_rn(sc[k - 1], sc[k]);
+    double incl = sc[kTileL - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(incl, d);
+        incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+    }
+    if (lane == 31) red_sum[warp] = incl;
+    __syncthreads();
+    double wv = (lane < NW) ? red_sum[lane] : 0.0;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+        const double other = shfl_up_d(wv, d);
+        wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+    }
+    const double tot = shfl_d(wv, NW - 1);
+    double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
+    wex = (warp > 0) ? wex : 0.0;
+    double lex = shfl_up_d(incl, 1);
+    lex = (lane > 0) ? lex : 0.0;
+    const double base = __dadd_rn(wex, lex);
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2)
+        *reinterpret_cast<double2*>(a.ecdf + l0 + k) = make_double2(__dadd_rn(base, sc[k]), __dadd_rn(base, sc[k + 1]));
+    if (tid == 0) a.ettot[tile] = tot;
+}
+
 // one CTA: canonical scan of the nb tile totals with Lp items per lane; E[b] for all NBP padded entries
 __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const SpillArgs a)
 {
@@ -312,6 +367,10 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     }
     if (tid == 0) {
         const double M = a.scal[0], logN = a.scal[3];
+        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
+            a.scal[5] = S;
+            return;
+        }
         const double logS = dlog(S);
         a.scal[1] = S;
         if (a.cl_mode == 1) {
@@ -437,6 +496,10 @@ __global__ void __launch_bounds__(kScan2NT) spill_tile_scan_b_kernel(const Spill
     }
     if (w == 0 && tid == 0) {
         const double M = a.scal[0], logN = a.scal[3];
+        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
+            a.scal[5] = S;
+            return;
+        }
         const double logS = dlog(S);
         a.scal[1] = S;
         if (a.cl_mode == 1) {
@@ -660,12 +723,25 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
     const int tile = a.tile0 + blockIdx.x;
     const double S = a.scal[1];
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
+    double sg = 0.0, Oe = 0.0;
+    if (a.resamp_sorted) {  // targets P_j * (S / G), G = total of the N+1 spacings (the last one is not in the scan)
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(a.N >> 1), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
+        double uN = (a.N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
+        uN = (uN == 0.0) ? 0x1p-53 : uN;
+        sg = __ddiv_rn(S, __dadd_rn(a.scal[5], -dlog_unit(uN)));
+        Oe = (tile > 0) ? a.eE[tile - 1] : 0.0;
+    }
 #pragma unroll 2
     for (int k = 0; k < kTileL; ++k) {
         const int j = tile * kTile + k * kTileNT + tid;  // coalesced over the CTA
         if (j >= a.N) continue;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), a.rk);
-        const double tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
+        double tau;
+        if (a.resamp_sorted) {
+            tau = __dmul_rn(__dadd_rn(Oe, a.ecdf[(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid]), sg);
+        } else {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), a.rk);
+            tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
+        }
         int b = 0;
         for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;
         b = min(b, a.nb - 1);

@@ -23,7 +23,7 @@ def leverage_series(T, seed, phi=0.9, mu=0.0, sigma=0.3, rho=-0.3):
     return y
 
 
-@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T", [(10, 1), (10, 5), (5000, 30), (4096 * 2 + 5, 12)])
 def test_liu_west_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
     y = leverage_series(T, seed=N + T)
@@ -45,7 +45,7 @@ def test_liu_west_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
         assert np.allclose(got["final_mean"], fai["final_mean"], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T", [(10, 1), (10, 5), (5000, 30), (4096 * 2 + 5, 12), (1024 * 3 + 1, 9)])
 def test_liu_west_apf_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
     y = leverage_series(T, seed=N + T + 1)

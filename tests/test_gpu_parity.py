@@ -252,8 +252,6 @@ def test_long_series_ten_thousand_steps(oracle, sv_series, gpu_backend_factory):
 @pytest.mark.parametrize("force_global", [0, 1])
 def test_tiny_particle_counts(oracle, sv_series, gpu_backend_factory, N, resampler, force_global):
     """One particle, two particles, ragged warps; an observation that is exactly zero (example/spy_returns.csv has one)."""
-    if force_global and resampler == sb.RESAMP_SORTED_MULTINOMIAL:
-        pytest.skip("sorted-multinomial is built into the resident kernel")
     T = 12
     y = sv_series(T, seed=92).copy()
     y[3] = 0.0

@@ -12,7 +12,7 @@ LEV_THETA = np.array([0.9, 0.0, 0.3, -0.1])
 
 
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
-@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T", [(5000, 20), (4096, 3), (4096 * 3 + 17, 12), (100, 9), (16384, 6)])
 def test_spilled_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model, resampler, N, T):
     y = sv_series(T, seed=31)
@@ -28,6 +28,8 @@ def test_spilled_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     if ref["margin"] > 1e-12:
         assert np.array_equal(got["ancestors"][0], fai["ancestors"])
     assert abs(got["loglik"][0] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+    if resampler == sb.RESAMP_SORTED_MULTINOMIAL:  # the reference's in-tree resampler: ancestors come out sorted
+        assert np.all(np.diff(got["ancestors"][0], axis=1) >= 0)
     # the batch entry point runs the same kernels
     out, pf = be.work_batch(np.stack([th, th]), R=1, stream_base=3, return_per_filter=True)
     assert pf[0, 0] == ref["loglik"] and out[0] == ref["loglik"]
@@ -56,7 +58,7 @@ def test_spilled_mode_argument_checks():
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, rng_mode=sb.RNG_INJECTED))
 
 
-@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
 def test_spilled_filter_many_tiles_two_launch_scan(oracle, sv_series, gpu_backend_factory, resampler):
     """4097 tiles (16.8 M particles): the tile totals are scanned by the two-launch kernels (Lp = 8 items per virtual
     lane); bit for bit the oracle's single-CTA order."""
