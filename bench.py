@@ -461,7 +461,9 @@ def run_ours(args):
                             "frac": (per_gpu * 201.7 / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
                             "note": "what actually binds K1 (DESIGN.md section 5): 4 warp-instructions per SM per clock"},
             "peak_source": "measured in-run (ssme_b200_measure_fp64_fma_rate); "
-            "MEASURED_PEAKS.json has no FP64 entry", "traffic": None,
+            "MEASURED_PEAKS.json has no FP64 entry",
+            "traffic": 258048 if (P_PROPOSALS == 4096 and T_STEPS == 4096) else None,
+            "traffic_note": "HBM bytes per launch, ncu --set full: dram__bytes_read.sum 258048 + dram__bytes_write.sum 0 (profiles/r1_k1_v2_L8_NT128.txt)",
             "hbm_note": "resident kernel: HBM traffic per launch is the observation stream + theta + outputs (~0.2 MB); not HBM-bound",
         }
         # ---- CPU baseline: the reference's thread_pool path on this box's host cores -------------
