@@ -80,7 +80,43 @@ __device__ __forceinline__ void block_sums(double (&v)[NQ], double* red /*[NW][N
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
+// thetaBar, V_t, cholesky(h^2 V_t) (or the plain means / the expectations) from the 14 totals; one thread
+__device__ __forceinline__ void lw_finalize(const LwArgs& a, const double* tot)
+{
+    const double dN = (double)a.s.N;
+    if (a.mode == 1) {
+        for (int k = 0; k < 4; ++k) a.mom[20 + k] = __ddiv_rn(tot[k], dN);
+        return;
+    }
+    if (a.mode == 2) {  // runs after the scan of the tile totals: scal[1] = S
+        const double S = a.s.scal[1];
+        for (int k = 0; k < 5; ++k) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + k] = __ddiv_rn(tot[k], S);
+        return;
+    }
+    double tb[4], V[4][4], Lc[4][4];
+    for (int k = 0; k < 4; ++k) tb[k] = __ddiv_rn(tot[k], dN);
+    int slot = 4;
+    for (int k = 0; k < 4; ++k)
+        for (int l = 0; l <= k; ++l) {
+            const double s2 = __ddiv_rn(tot[slot++], dN);
+            V[k][l] = __dmul_rn(a.h2, __dsub_rn(s2, __dmul_rn(tb[k], tb[l])));
+        }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) Lc[i][j] = 0.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double sacc = V[i][j];
+            for (int k = 0; k < j; ++k) sacc = __dsub_rn(sacc, __dmul_rn(Lc[i][k], Lc[j][k]));
+            Lc[i][j] = (i == j) ? __dsqrt_rn(sacc) : __ddiv_rn(sacc, Lc[j][j]);
+        }
+    for (int k = 0; k < 4; ++k) a.mom[k] = tb[k];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) a.mom[4 + 4 * i + j] = Lc[i][j];
+    if (a.theta_bar_out)
+        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)(a.s.t - a.s.row0) * 4 + k] = tb[k];
+}
+
+__global__ void __launch_bounds__(kTileNT, 2) lw_moments_kernel(const LwArgs a)
 {
     constexpr int NW = kTileNT / 32;
     __shared__ double red[NW * 14];
@@ -115,31 +151,51 @@ __global__ void __launch_bounds__(kTileNT) lw_moments_kernel(const LwArgs a)
         if (tid < 5) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
         return;
     }
-    double th[4][kTileL];
+    // two particles at a time (16-byte loads), the 14 running sums updated in particle order: the same additions in the same
+    // order as summing each quantity over the thread's 8 particles, with 8 + 14 live doubles instead of 32 + 14 (2 CTAs per SM)
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 14; ++q) s[q] = 0.0;
 #pragma unroll
-        for (int k = 0; k < kTileL; ++k) {
-            double v = (i0 + k < a.s.N) ? a.th_anc[q][(size_t)i0 + k] : 0.0;
-            if (a.mode == 1 && i0 + k < a.s.N) v = lw_inv_trans(q, v);
-            th[q][k] = v;
+    for (int k = 0; k < kTileL; k += 2) {
+        double th[4][2];
+        if (i0 + k + 1 < a.s.N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 v = *reinterpret_cast<const double2*>(a.th_anc[q] + (size_t)i0 + k);
+                th[q][0] = v.x; th[q][1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                th[q][0] = (i0 + k < a.s.N) ? a.th_anc[q][(size_t)i0 + k] : 0.0;
+                th[q][1] = 0.0;
+            }
+        }
+        if (a.mode == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                th[q][0] = (i0 + k < a.s.N) ? lw_inv_trans(q, th[q][0]) : 0.0;
+                th[q][1] = (i0 + k + 1 < a.s.N) ? lw_inv_trans(q, th[q][1]) : 0.0;
+            }
         }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        s[q] = th[q][0];
+        for (int j = 0; j < 2; ++j) {
+            const bool first = (k + j == 0);
 #pragma unroll
-        for (int k = 1; k < kTileL; ++k) s[q] = __dadd_rn(s[q], th[q][k]);
+            for (int q = 0; q < 4; ++q) s[q] = first ? th[q][j] : __dadd_rn(s[q], th[q][j]);
+            if (a.mode == 0) {
+                int slot = 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int l = 0; l <= q; ++l) {
+                        const double p = __dmul_rn(th[q][j], th[l][j]);
+                        s[slot] = first ? p : __dadd_rn(s[slot], p);
+                        ++slot;
+                    }
+            }
+        }
     }
-    int slot = 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int l = 0; l <= q; ++l) {
-            double acc = __dmul_rn(th[q][0], th[l][0]);
-#pragma unroll
-            for (int k = 1; k < kTileL; ++k) acc = __dadd_rn(acc, __dmul_rn(th[q][k], th[l][k]));
-            s[slot++] = acc;
-        }
     const int nq = (a.mode == 1) ? 4 : 14;
     block_sums<14, NW>(s, red, nq, lane, warp, tid, tot);
     if (tid < nq) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
@@ -166,38 +222,7 @@ __global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwA
         }
     }
     block_sums<14, 32>(s, red, nq, lane, warp, tid, tot);
-    if (tid != 0) return;
-    const double dN = (double)a.s.N;
-    if (a.mode == 1) {
-        for (int k = 0; k < 4; ++k) a.mom[20 + k] = __ddiv_rn(tot[k], dN);
-        return;
-    }
-    if (a.mode == 2) {  // runs after the scan of the tile totals: scal[1] = S
-        const double S = a.s.scal[1];
-        for (int k = 0; k < 5; ++k) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + k] = __ddiv_rn(tot[k], S);
-        return;
-    }
-    double tb[4], V[4][4], Lc[4][4];
-    for (int k = 0; k < 4; ++k) tb[k] = __ddiv_rn(tot[k], dN);
-    int slot = 4;
-    for (int k = 0; k < 4; ++k)
-        for (int l = 0; l <= k; ++l) {
-            const double s2 = __ddiv_rn(tot[slot++], dN);
-            V[k][l] = __dmul_rn(a.h2, __dsub_rn(s2, __dmul_rn(tb[k], tb[l])));
-        }
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) Lc[i][j] = 0.0;
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double sacc = V[i][j];
-            for (int k = 0; k < j; ++k) sacc = __dsub_rn(sacc, __dmul_rn(Lc[i][k], Lc[j][k]));
-            Lc[i][j] = (i == j) ? __dsqrt_rn(sacc) : __ddiv_rn(sacc, Lc[j][j]);
-        }
-    for (int k = 0; k < 4; ++k) a.mom[k] = tb[k];
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) a.mom[4 + 4 * i + j] = Lc[i][j];
-    if (a.theta_bar_out)
-        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)(a.s.t - a.s.row0) * 4 + k] = tb[k];
+    if (tid == 0) lw_finalize(a, tot);
 }
 
 constexpr int kLwNT = 256;                 // threads of the propagation CTA
