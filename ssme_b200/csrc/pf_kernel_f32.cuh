@@ -283,21 +283,24 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
         }
         __syncthreads();  // CDF and gather table complete
 
+        // nb = 4 * (node + 1): children 2*node+1 / 2*node+2 become 2*nb / 2*nb + 4, the probe address is Cb - 4 + nb
         uint32_t nb[L];
 #pragma unroll
-        for (int k = 0; k < L; ++k) nb[k] = 0u;
+        for (int k = 0; k < L; ++k) nb[k] = 4u;
+        const unsigned char* Cm = Cb - 4;
 #pragma unroll
         for (int lvl = 0; lvl < K; ++lvl) {
 #pragma unroll
             for (int k = 0; k < L; ++k) {
-                const float v = *reinterpret_cast<const float*>(Cb + nb[k]);
-                nb[k] = 2u * nb[k] + ((v < tau[k]) ? 8u : 4u);
+                const float v = *reinterpret_cast<const float*>(Cm + nb[k]);
+                nb[k] += nb[k];
+                if (v < tau[k]) nb[k] += 4u;
             }
         }
         int idx[L];
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            idx[k] = min((int)(nb[k] >> 2) - (NP - 1), N - 1);
+            idx[k] = min((int)(nb[k] >> 2) - NP, N - 1);
             x[k] = Xcur[idx[k]];
         }
         if (!full) {
