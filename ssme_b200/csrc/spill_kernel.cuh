@@ -73,7 +73,7 @@ struct SpillArgs {
 };
 
 template <int MODEL>
-__global__ void __launch_bounds__(kTileNT) spill_propagate_kernel(const SpillArgs a)
+__global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const SpillArgs a)
 {
     __shared__ double red[kTileNT / 32];
     constexpr int OS = obs_stride(MODEL);
