@@ -175,6 +175,36 @@ __global__ void __launch_bounds__(1024) spill_reduce_max_kernel(const SpillArgs 
     }
 }
 
+// The tile scan of the canonical order: sc holds a thread's lane-local inclusive prefix sums on entry and the tile-local
+// inclusive prefix sums on exit (Kogge-Stone over the 32 lanes, then over the warps; one block barrier).  Returns the tile total.
+__device__ __forceinline__ double tile_scan_finish(double (&sc)[kTileL], double* red_sum /*[32] smem*/, int lane, int warp)
+{
+    constexpr int NW = kTileNT / 32;
+    double incl = sc[kTileL - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(incl, d);
+        incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+    }
+    if (lane == 31) red_sum[warp] = incl;
+    __syncthreads();
+    double wv = (lane < NW) ? red_sum[lane] : 0.0;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+        const double other = shfl_up_d(wv, d);
+        wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+    }
+    const double total = shfl_d(wv, NW - 1);
+    double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
+    wex = (warp > 0) ? wex : 0.0;
+    double lex = shfl_up_d(incl, 1);
+    lex = (lane > 0) ? lex : 0.0;
+    const double base = __dadd_rn(wex, lex);
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) sc[k] = __dadd_rn(base, sc[k]);
+    return total;
+}
+
 // w = exp(lw - M) and the CTA scan of K1 (lane-local sequential, Kogge-Stone over lanes, Kogge-Stone over warps)
 __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const SpillArgs a)
 {
@@ -196,28 +226,7 @@ __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const Spill
         const double w = dexp_nonpos(__dsub_rn(sc[k], M));
         sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
     }
-    double incl = sc[kTileL - 1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double other = shfl_up_d(incl, d);
-        incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
-    }
-    if (lane == 31) red_sum[warp] = incl;
-    __syncthreads();
-    double wv = (lane < NW) ? red_sum[lane] : 0.0;
-#pragma unroll
-    for (int d = 1; d < NW; d <<= 1) {
-        const double other = shfl_up_d(wv, d);
-        wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
-    }
-    const double S = shfl_d(wv, NW - 1);
-    double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
-    wex = (warp > 0) ? wex : 0.0;
-    double lex = shfl_up_d(incl, 1);
-    lex = (lane > 0) ? lex : 0.0;
-    const double base = __dadd_rn(wex, lex);
-#pragma unroll
-    for (int k = 0; k < kTileL; ++k) sc[k] = __dadd_rn(base, sc[k]);
+    const double S = tile_scan_finish(sc, red_sum, lane, warp);
 #pragma unroll
     for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(sc[k], sc[k + 1]);
     // largest tile-local CDF entry (feeds the running maximum used by the systematic expansion).  Inside a thread the
@@ -242,7 +251,6 @@ __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const Spill
 // Same scan order as the weights above; padding beyond particle N-1 counts as 0.
 __global__ void __launch_bounds__(kTileNT) spill_expo_scan_kernel(const SpillArgs a)
 {
-    constexpr int NW = kTileNT / 32;
     __shared__ double red_sum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = a.tile0 + blockIdx.x;
@@ -261,29 +269,10 @@ __global__ void __launch_bounds__(kTileNT) spill_expo_scan_kernel(const SpillArg
     }
 #pragma unroll
     for (int k = 1; k < kTileL; ++k) sc[k] = __dadd_rn(sc[k - 1], sc[k]);
-    double incl = sc[kTileL - 1];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double other = shfl_up_d(incl, d);
-        incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
-    }
-    if (lane == 31) red_sum[warp] = incl;
-    __syncthreads();
-    double wv = (lane < NW) ? red_sum[lane] : 0.0;
-#pragma unroll
-    for (int d = 1; d < NW; d <<= 1) {
-        const double other = shfl_up_d(wv, d);
-        wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
-    }
-    const double tot = shfl_d(wv, NW - 1);
-    double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
-    wex = (warp > 0) ? wex : 0.0;
-    double lex = shfl_up_d(incl, 1);
-    lex = (lane > 0) ? lex : 0.0;
-    const double base = __dadd_rn(wex, lex);
+    const double tot = tile_scan_finish(sc, red_sum, lane, warp);
 #pragma unroll
     for (int k = 0; k < kTileL; k += 2)
-        *reinterpret_cast<double2*>(a.ecdf + l0 + k) = make_double2(__dadd_rn(base, sc[k]), __dadd_rn(base, sc[k + 1]));
+        *reinterpret_cast<double2*>(a.ecdf + l0 + k) = make_double2(sc[k], sc[k + 1]);
     if (tid == 0) a.ettot[tile] = tot;
 }
 
