@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
             const long long i = (long long)bb * kClTile + idx;
             if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)bb * kClTile);
             const double xa = ld_cluster_f64(cluster_addr(x_base + (uint32_t)(((t & 1) * kClTile + idx) * 8), (uint32_t)bb));
-            x[k] = (i0 + k < N) ? xa : 0.0;
+            x[k] = xa;  // consumed after the next step's normals are drawn: the gather latency overlaps them (padding is masked at the log-weight)
         }
         __syncwarp();  // E is rewritten next step
     }
