@@ -197,3 +197,35 @@ def test_fp32_exp_and_filter(oracle):
     assert abs(a["loglik"] - b["loglik"]) <= 2e-5 * abs(b["loglik"])
     assert (a["ancestors"][0] == b["ancestors"][0]).mean() > 0.99   # same normals, same (truncated) uniforms
     assert np.allclose(a["x"][0], b["x"][0], rtol=1e-6, atol=1e-7)
+
+
+def test_tiled_sorted_multinomial_follows_the_in_tree_resampler(oracle, sv_series):
+    """mn_resamp_states_and_params (liu_west_filter.h:91-145) restated twice: the reference's sequential walk (FAITHFUL) and
+    the tiled scan of the spacings + one search per slot (CANONICAL, what the global-memory kernels run): same ancestors."""
+    from oracle import binding as ob
+    y = sv_series(15, seed=61)
+    th = np.array([1.0, 0.95, 0.0625])
+    for N in (100, 4096 + 3, 9000):
+        a = ob.filter_run(th, y, N, resampler=1, L=8, NT=512, tiled=2, seed=5, filter_id=2)
+        b = ob.filter_run(th, y, N, resampler=1, arithmetic=ob.ARITH_FAITHFUL, seed=5, filter_id=2)
+        assert np.array_equal(a["ancestors"], b["ancestors"])
+        assert np.all(np.diff(a["ancestors"], axis=1) >= 0)          # sorted targets -> monotone ancestors
+        assert abs(a["loglik"] - b["loglik"]) <= 1e-9 * abs(b["loglik"])
+    lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
+    c = ob.lw_filter_run(lo, hi, 0.99, 0.3 * y, 5000, resampler=1)
+    d = ob.lw_filter_run(lo, hi, 0.99, 0.3 * y, 5000, resampler=1, arithmetic=ob.ARITH_FAITHFUL)
+    assert np.array_equal(c["ancestors"], d["ancestors"]) and abs(c["loglik"] - d["loglik"]) <= 1e-9 * abs(d["loglik"])
+
+
+def test_liu_west_expectations_oracle(oracle, sv_series):
+    """E[h | y_{1:t}] before resampling: canonical (tiled sums) vs the reference's sequential numer / denom; constants come back."""
+    from oracle import binding as ob
+    lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
+    y = 0.3 * sv_series(10, seed=62)
+    for form in ("sisr", "apf"):
+        c = ob.lw_filter_run(lo, hi, 0.99, y, 3000, form=form, seed=6)
+        f = ob.lw_filter_run(lo, hi, 0.99, y, 3000, form=form, seed=6, arithmetic=ob.ARITH_FAITHFUL)
+        if np.array_equal(c["ancestors"], f["ancestors"]) and np.array_equal(c["aux_index"], f["aux_index"]):
+            assert np.allclose(c["expect"], f["expect"], rtol=1e-9, atol=1e-12)
+        assert np.all((c["expect"][:, 1:] > lo) & (c["expect"][:, 1:] < hi))   # weighted means stay inside the prior box
+        assert np.all(np.isfinite(c["expect"]))
