@@ -199,11 +199,13 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
         x[t] = mu + phi * (x[t - 1] - mu) + rho * sigma * yv[t - 1] * np.exp(-0.5 * x[t - 1]) + sigma * np.sqrt(1 - rho * rho) * rng.standard_normal()
         yv[t] = np.exp(0.5 * x[t]) * rng.standard_normal()
     # one filter per thread-block cluster (K2), tile size chosen so that chains-per-GPU x tiles-per-chain stays within the
-    # 148 SMs: 2 tiles of 4096 particles with 64 chains on a GPU (14.4 us per time step against 17.9 for the single-CTA
-    # kernel), 8 tiles of 1024 with <= 32 chains (8.5 / 7.8 / 6.1 us at 32 / 16 / 8 chains) -- profiles/r1_k2_cluster.md
-    c3_threads = 1024 if (C3_CHAINS + world - 1) // world > 37 else 256
+    # 148 SMs: 2 tiles of 4096 particles (512 threads x 8, CDF exchanged by one DSMEM bulk copy) with 64 chains on a GPU
+    # (13.1 us per time step against 17.8 for the single-CTA kernel), 8 tiles of 1024 (256 threads x 4, multicast) with
+    # <= 32 chains (8.5 / 7.8 / 6.1 us at 32 / 16 / 8 chains) -- profiles/r1_k2_cluster.md
+    many = (C3_CHAINS + world - 1) // world > 37
+    c3_threads, c3_L = (512, 8) if many else (256, 4)
     be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV_LEVERAGE, num_particles=C3_N, seed=SEED_FILTER + 3, device=local_rank,
-                                                  use_cluster=1, threads_per_filter=c3_threads))
+                                                  use_cluster=1, threads_per_filter=c3_threads, scan_items_per_lane=c3_L))
     be.add_observed_data(yv)
     comm(be)
     start = np.tile(np.array([phi, mu, sigma, rho]), (C3_CHAINS, 1)) * (1 + 0.01 * np.random.default_rng(5).standard_normal((C3_CHAINS, 4)))
@@ -216,7 +218,7 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
                       "filters_per_proposal": C3_R, "model": "sv_leverage", "iterations_timed": C3_ITERS, "seconds": r["seconds"],
                       "mean_accept_rate": float(r["accept_rate"].mean()),
                       "particle_steps_per_sec": C3_CHAINS * C3_R * C3_N * C3_T * C3_ITERS / r["seconds"],
-                      "kernel": "K2 cluster (%d CTAs x %d threads per filter)" % (C3_N // (4 * c3_threads), c3_threads),
+                      "kernel": "K2 cluster (%d CTAs x %d threads x %d particles per filter)" % (C3_N // (c3_L * c3_threads), c3_threads, c3_L),
                       "sharding": "chains x replicates over %d rank(s), NCCL all-gather of %d log-likelihoods per iteration" % (world, C3_CHAINS * C3_R)}
     be.close()
     # config 1 (one chain: the replicates are what is sharded)

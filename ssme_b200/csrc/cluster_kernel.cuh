@@ -57,6 +57,14 @@ __device__ __forceinline__ uint32_t cluster_addr(uint32_t local, uint32_t cta)
     return r;
 }
 // remote 8-byte store that completes 8 bytes on the destination CTA's mbarrier
+// bulk copy from this CTA's shared memory into a peer's, completing bytes on the peer's mbarrier (both remote addresses
+// are shared::cluster addresses)
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst),
+                 "r"(local_src), "r"(bytes), "r"(remote_bar)
+                 : "memory");
+}
 __device__ __forceinline__ double ld_cluster_f64(uint32_t remote_addr)
 {
     double v;
@@ -258,18 +266,35 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
+        if (CS <= 2) {
+            // two tiles: the CDF goes straight from this CTA's shared memory into the peer's with one DSMEM bulk copy (32 KB at
+            // ~20 B/clk) -- no global scratch, no gpu-scope membar, no L2 round trip.  Own tile: written in place.
+            double* const Cown = shC + rank * kClTile;
 #pragma unroll
-        for (int k = 0; k < kClL; ++k) gC[eoff[k]] = __dadd_rn(base, sc[k]);
-        // this CTA's own scratch writes (generic proxy) are read back by its own bulk copy (async proxy); the same
-        // fence (a gpu-scope membar) orders this step's X stores before the pushes that let the peers read them
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-        if (warp == 0) {
-            // peers may complete bytes before this arrives: the transaction count just goes negative for a while
-            if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)CS * (kClTileBytes + 8u));
-            if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
-            if (lane == 0) {
-                tma_multicast_1d(shC + rank * kClTile, gC, kClTileBytes, &sh.bar_cdf, cta_mask);
+            for (int k = 0; k < kClL; ++k) Cown[eoff[k]] = __dadd_rn(base, sc[k]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores before the async-proxy read of the copy
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");          // this step's X stores before the pushes that let the peer gather
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)(CS - 1) * kClTileBytes + (uint32_t)CS * 8u);
+                if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
+                if (lane < CS && lane != rank)
+                    dsmem_bulk_copy(cluster_addr(smem_u32(Cown), (uint32_t)lane), smem_u32(Cown), kClTileBytes, peer_bar_cdf);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) gC[eoff[k]] = __dadd_rn(base, sc[k]);
+            // this CTA's own scratch writes (generic proxy) are read back by its own bulk copy (async proxy); the same
+            // fence (a gpu-scope membar) orders this step's X stores before the pushes that let the peers read them
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                // peers may complete bytes before this arrives: the transaction count just goes negative for a while
+                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)CS * (kClTileBytes + 8u));
+                if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
+                if (lane == 0) {
+                    tma_multicast_1d(shC + rank * kClTile, gC, kClTileBytes, &sh.bar_cdf, cta_mask);
+                }
             }
         }
 
