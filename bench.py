@@ -189,7 +189,7 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
             be.comm_init(uid[0], rank, world)
 
     # config 3
-    C3_CHAINS, C3_N, C3_T, C3_R, C3_ITERS = 64, 8192, 1024, 1, 12
+    C3_CHAINS, C3_N, C3_T, C3_R, C3_ITERS = 64, 8192, 1024, 1, 32
     rng = np.random.default_rng(SEED_SERIES + 3)
     phi, mu, sigma, rho = 0.9, 0.0, 0.3, -0.1
     x = np.empty(C3_T); yv = np.empty(C3_T)
@@ -225,7 +225,7 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
     spy = os.path.join(ROOT, "tests", "golden", "spy_config1.npz")
     if os.path.exists(spy):
         g = np.load(spy)
-        C1_N, C1_R, C1_ITERS = 500, 100, 12
+        C1_N, C1_R, C1_ITERS = 500, 100, 32
         # 100 filters do not fill 148 SMs, so the step latency of one CTA sets the pace: 2 particles per thread
         # (256 threads per filter) measured 1.57 us/step against 1.98 (4 per thread), 2.75 (8, the throughput layout)
         # and 1.91 (1 per thread, 512 threads: the barriers and cross-warp scans grow) -- tools/pmmh_latency.py
