@@ -433,6 +433,7 @@ static FilterArgs base_args(ssme_b200_handle h, const double* theta_dev, unsigne
     a.rs = h->cfg.resample_every;
     a.seed = h->cfg.seed;
     a.rk = philox_round_keys(h->cfg.seed);
+    a.k2_dsmem_max = 2;  // measured: DSMEM bulk copies win for two-tile clusters, the multicast from 4 tiles up (profiles/r1_k2_cluster.md)
     a.filter_base = stream_base;
     a.loglik = loglik_dev;
     return a;

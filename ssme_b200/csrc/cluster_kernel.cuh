@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
-        if (CS <= 2) {
+        if (CS <= a.k2_dsmem_max) {
             // two tiles: the CDF goes straight from this CTA's shared memory into the peer's with one DSMEM bulk copy (32 KB at
             // ~20 B/clk) -- no global scratch, no gpu-scope membar, no L2 round trip.  Own tile: written in place.
             double* const Cown = shC + rank * kClTile;

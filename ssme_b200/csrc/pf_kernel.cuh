@@ -55,6 +55,7 @@ struct FilterArgs {
     // holds the resampled states between launches
     int t_begin;
     double* x_state;
+    int k2_dsmem_max;    // cluster kernel: largest cluster size that exchanges the CDF tiles by DSMEM bulk copies
     double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
