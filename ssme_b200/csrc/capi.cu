@@ -345,7 +345,7 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         const void* fn = cluster_kernel_fn(cfg->model, cfg->resampler, NT, L);
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>((size_t)227 * 1024, cluster_smem_bytes(L * NT, kClMax)));  // per function, not per handle
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>((size_t)227 * 1024, std::max(cluster_smem_bytes(L * NT, kClMax), cluster_smem_bytes(L * NT, kClDsmemMax))));  // per function, not per handle
         if (e != cudaSuccess) { delete h; return fail(SSME_B200_ECUDA, "cluster attribute failed: %s", cudaGetErrorString(e)); }
     } else if (!spill) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast->fn, NT, fast->smem_bytes);
@@ -433,7 +433,7 @@ static FilterArgs base_args(ssme_b200_handle h, const double* theta_dev, unsigne
     a.rs = h->cfg.resample_every;
     a.seed = h->cfg.seed;
     a.rk = philox_round_keys(h->cfg.seed);
-    a.k2_dsmem_max = 2;  // measured: DSMEM bulk copies win for two-tile clusters, the multicast from 4 tiles up (profiles/r1_k2_cluster.md)
+    a.k2_dsmem_max = kClDsmemMax;  // measured: DSMEM bulk copies win for two-tile clusters, the multicast from 4 tiles up (profiles/r1_k2_cluster.md)
     a.filter_base = stream_base;
     a.loglik = loglik_dev;
     return a;

@@ -87,9 +87,12 @@ __device__ __forceinline__ void tma_multicast_1d(void* dst_smem, const void* src
         : "memory");
 }
 
+constexpr int kClDsmemMax = 2;  // clusters up to this size exchange tiles by DSMEM bulk copies (measured: profiles/r1_k2_cluster.md)
 constexpr size_t cluster_smem_bytes(int tile, int cluster_size)
 {
-    return sizeof(ClusterShared) + sizeof(double) * (size_t)tile * (size_t)(2 + cluster_size);
+    // X[2][tile], C[cluster][tile]; two-tile clusters also hold every tile's states (Xall[cluster][tile])
+    const int tiles = 2 + cluster_size + (cluster_size <= kClDsmemMax ? cluster_size : 0);
+    return sizeof(ClusterShared) + sizeof(double) * (size_t)tile * (size_t)tiles;
 }
 
 template <int MODEL, int RESAMP, int NT, int L>
@@ -110,6 +113,8 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
     double* const shC = shX + 2 * kClTile;                                            // [CS][tile]
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks();
+    double* const shXall = shC + CS * kClTile;  // [CS][tile] every tile's states (two-tile clusters only)
+    const bool dsmem = CS <= a.k2_dsmem_max;
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long floc = blockIdx.x / CS;  // filter index within this launch
@@ -266,20 +271,22 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
-        if (CS <= a.k2_dsmem_max) {
+        if (dsmem) {
             // two tiles: the CDF goes straight from this CTA's shared memory into the peer's with one DSMEM bulk copy (32 KB at
             // ~20 B/clk) -- no global scratch, no gpu-scope membar, no L2 round trip.  Own tile: written in place.
             double* const Cown = shC + rank * kClTile;
 #pragma unroll
             for (int k = 0; k < kClL; ++k) Cown[eoff[k]] = __dadd_rn(base, sc[k]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores before the async-proxy read of the copy
-            asm volatile("fence.acq_rel.cluster;" ::: "memory");          // this step's X stores before the pushes that let the peer gather
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores (CDF, states) before the async-proxy reads of the copies
             __syncthreads();
             if (warp == 0) {
-                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)(CS - 1) * kClTileBytes + (uint32_t)CS * 8u);
+                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)(CS - 1) * 2u * kClTileBytes + (uint32_t)CS * 8u);
                 if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
-                if (lane < CS && lane != rank)
+                if (lane < CS && lane != rank) {  // this tile's CDF and states into the peer's shared memory
                     dsmem_bulk_copy(cluster_addr(smem_u32(Cown), (uint32_t)lane), smem_u32(Cown), kClTileBytes, peer_bar_cdf);
+                    dsmem_bulk_copy(cluster_addr(smem_u32(shXall + rank * kClTile), (uint32_t)lane), smem_u32(shX + (t & 1) * kClTile),
+                                    kClTileBytes, peer_bar_cdf);
+                }
             }
         } else {
 #pragma unroll
@@ -358,7 +365,9 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
             int idx = (int)node - (kClTile - 1);
             const long long i = (long long)bb * kClTile + idx;
             if (i > (long long)N - 1) idx = (int)((long long)N - 1 - (long long)bb * kClTile);
-            const double xa = ld_cluster_f64(cluster_addr(x_base + (uint32_t)(((t & 1) * kClTile + idx) * 8), (uint32_t)bb));
+            double xa;
+            if (dsmem) xa = (bb == rank) ? shX[(t & 1) * kClTile + idx] : shXall[bb * kClTile + idx];
+            else xa = ld_cluster_f64(cluster_addr(x_base + (uint32_t)(((t & 1) * kClTile + idx) * 8), (uint32_t)bb));
             x[k] = xa;  // consumed after the next step's normals are drawn: the gather latency overlaps them (padding is masked at the log-weight)
         }
         __syncwarp();  // E is rewritten next step
