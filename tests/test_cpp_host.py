@@ -29,8 +29,30 @@ def test_host_layer_known_answers(tmp_path):
 def test_example_program_compiles(tmp_path):
     r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-B"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    usage = subprocess.run([os.path.join(ROOT, "examples", "ssme_example")], capture_output=True, text=True)
-    assert "number of pfilters" in usage.stderr  # same usage text as example/main.cpp:22-27
+    exe = os.path.join(ROOT, "examples", "ssme_example")
+    usage = subprocess.run([exe], capture_output=True, text=True)
+    assert usage.returncode == 2 and "FILTERS_PER_PROPOSAL" in usage.stderr  # the five positional arguments of example/main.cpp:17-37
+    bad = subprocess.run([exe, "data.csv", "s", "m", "ten", "5"], capture_output=True, text=True)
+    assert bad.returncode == 2
+
+
+@pytest.mark.gpu
+def test_example_program_runs_the_reference_example(tmp_path):
+    """The reference's README example: SPY returns, 500 particles, start (1, .5, 2e-4) -- here 6 iterations x 20 filters."""
+    import numpy as np
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-B"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    y = np.load(os.path.join(ROOT, "tests", "golden", "spy_config1.npz"))["y"]
+    data = tmp_path / "returns.csv"
+    np.savetxt(data, y, fmt="%.17g")
+    run = subprocess.run([os.path.join(ROOT, "examples", "ssme_example"), str(data), str(tmp_path / "samples"), str(tmp_path / "messages"), "6", "20"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    files = sorted(p for p in os.listdir(tmp_path) if p.startswith("samples"))
+    assert len(files) == 1
+    draws = np.loadtxt(tmp_path / files[0], delimiter=",", ndmin=2)
+    assert draws.shape == (6, 3) and np.all(np.isfinite(draws))
+    assert np.all(draws[:, 2] > 0) and np.all(np.abs(draws[:, 1]) < 1)   # sigma^2 > 0, |phi| < 1 on the untransformed scale
 
 
 @pytest.mark.gpu
