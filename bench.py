@@ -484,6 +484,9 @@ def run_ours(args):
             cpu = {"value": nfil * N_PARTICLES * T_STEPS / sec.value, "unit": "particle-steps/s", "cores": int(used.value), "kind": "port",
                    "sample": "%d filters of the bench workload (one thread_pool::work call, R=%d), %.1f s" % (nfil, nfil, sec.value),
                    "dispatcher": "reference include/ssme/thread_pool.h" if L.ssme_refcpu_pool_kind() else "local API-identical pool"}
+            # the PMMH half of the metric on the CPU path, derived from the same rate: one iteration of the reference's example
+            # (config 1) is 100 filters x 500 particles x 3084 steps, of config 3 64 chains x 8192 particles x 1024 steps
+            cpu["pmmh_iters_per_sec_derived"] = {"config1": cpu["value"] / (100 * 500 * 3084), "config3": 64 * cpu["value"] / (64 * 8192 * 1024)}
         except Exception as ex:  # the baseline is a reported extra; never let it sink the GPU line
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {
