@@ -468,6 +468,23 @@ def run_ours(args):
             "traffic_note": "HBM bytes per launch, ncu --set full: dram__bytes_read.sum 258048 + dram__bytes_write.sum 0 (profiles/r1_k1_v2_L8_NT128.txt)",
             "hbm_note": "resident kernel: HBM traffic per launch is the observation stream + theta + outputs (~0.2 MB); not HBM-bound",
         }
+        # ---- SURVEY.md 8(d)'s op-mix roofline: t_roof = sum_k W_k / R_k, every R_k measured now, each class alone -----
+        try:
+            om = sb.measure_opmix_rates(local_rank, 2000)
+            W = {"exp": 2, "normal": 1, "uniform": 1, "search_step": 10, "fp64_other": 18}
+            t_roof = (W["exp"] / om["exp"] + W["normal"] / om["normal"] + W["uniform"] / om["uniform"]
+                      + W["search_step"] / om["search_step"] + W["fp64_other"] / fma_rate)
+            terms = {"exp": W["exp"] / om["exp"], "normal": W["normal"] / om["normal"], "uniform": W["uniform"] / om["uniform"],
+                     "search_step": W["search_step"] / om["search_step"], "fp64_other": W["fp64_other"] / fma_rate}
+            roofline["opmix"] = {"frac": per_gpu * t_roof, "roof_particle_steps_per_sec": 1.0 / t_roof, "ops_per_particle_step": W,
+                                 "frac_if_classes_overlapped_perfectly": per_gpu * max(terms.values()),
+                                 "seconds_per_particle_step_by_class": terms,
+                                 "rates_per_sec": dict(om, fp64_other=fma_rate),
+                                 "note": "op classes of the canonical step (N = 1024: 10 search levels; 18 = 3 FMA outside the two exps "
+                                         "+ 13 add/mul/convert + 2 compares), each class timed alone on the whole GPU in this run and "
+                                         "their times ADDED (no overlap between classes assumed)"}
+        except Exception as ex:  # noqa: BLE001
+            roofline["opmix"] = {"error": repr(ex)[:200]}
         # ---- CPU baseline: the reference's thread_pool path on this box's host cores -------------
         try:
             if args.no_cpu:

@@ -298,6 +298,11 @@ const char* ssme_b200_build_info(void);
  * device, in FMA instructions (thread-level) per second.  iters = inner-loop length. */
 int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_per_second);
 
+/* Op-mix roofline of the resident filter step: rates [4] = operations per second the device sustains when
+ * it does nothing but (0) the canonical fp64 exp, (1) N(0,1) draws (Philox4x32-10 + float Box-Muller), (2) 53-bit U[0,1) draws,
+ * (3) descent steps over a 1024-entry breadth-first CDF in shared memory -- each written as the filter kernel writes it. */
+int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ from .capi import (  # noqa: F401
     library_path,
     launch_count,
     measure_fp64_fma_rate,
+    measure_opmix_rates,
     log_mean_exp,
     shard_range,
     comm_unique_id,

@@ -131,6 +131,15 @@ def launch_count() -> int:
     return int(load_library().ssme_b200_launch_count())
 
 
+def measure_opmix_rates(device: int = 0, iters: int = 2000):
+    """dict(exp, normal, uniform, search_step) operations per second, each class alone on the whole device."""
+    lib = load_library()
+    lib.ssme_b200_measure_opmix_rates.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    out = (C.c_double * 4)()
+    _check(lib.ssme_b200_measure_opmix_rates(device, iters, out))
+    return {"exp": out[0], "normal": out[1], "uniform": out[2], "search_step": out[3]}
+
+
 def measure_fp64_fma_rate(device: int = 0, iters: int = 1 << 16) -> float:
     out = C.c_double(0.0)
     _check(load_library().ssme_b200_measure_fp64_fma_rate(device, iters, C.byref(out)))

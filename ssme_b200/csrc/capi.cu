@@ -71,6 +71,77 @@ __global__ void swarm_mean_kernel(const double* __restrict__ cond_like, size_t P
     out[t] = __ddiv_rn(s, (double)P);
 }
 
+// Micro-benchmarks for the op-mix roofline of SURVEY.md section 8(d): each kernel keeps the whole GPU busy with ONE class of the
+// filter step's work, written exactly as K1 writes it, and reports how many operations of that class it completed.
+//   0 = dexp (the canonical double exp)     1 = N(0,1) draws (Philox4x32-10 + float Box-Muller, 4 per block)
+//   2 = U[0,1) draws (Philox + uniform53, 2 per block)     3 = descent steps over a 1024-entry breadth-first CDF in shared memory
+template <int WHICH>
+__global__ void __launch_bounds__(128) opmix_rate_kernel(double* out, int iters, PhiloxRoundKeys rk)
+{
+    __shared__ double tree[1024];
+    const int tid = threadIdx.x;
+    const unsigned gid = blockIdx.x * blockDim.x + tid;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = -1e-3 * (double)(k + 1) - 1e-7 * (double)(gid & 1023);
+    if (WHICH == 3) {
+        // sorted values 1..1024 in breadth-first order: node n of level l holds the ((2 * (n - (2^l - 1)) + 1) * 2^(9 - l))-th value
+        for (int n = tid; n < 1023; n += blockDim.x) {
+            const int l = 31 - __clz(n + 1);
+            tree[n] = (double)((2 * (n + 1 - (1 << l)) + 1) << (9 - l));
+        }
+        if (tid == 0) tree[1023] = 1024.0;
+        __syncthreads();
+    }
+    for (int it = 0; it < iters; ++it) {
+        if (WHICH == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = __dmul_rn(-0.75, dexp(acc[k]));  // stays in (-0.75, 0)
+        } else if (WHICH == 1) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint4 r = philox4x32_10(make_uint4(gid, (uint32_t)it, (uint32_t)q, 0u), rk);
+                float z0, z1, z2, z3;
+                box_muller(r.x, r.y, z0, z1);
+                box_muller(r.z, r.w, z2, z3);
+                acc[4 * q + 0] += (double)z0; acc[4 * q + 1] += (double)z1; acc[4 * q + 2] += (double)z2; acc[4 * q + 3] += (double)z3;
+            }
+        } else if (WHICH == 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 r = philox4x32_10(make_uint4(gid, (uint32_t)it, (uint32_t)q, 1u), rk);
+                acc[2 * q + 0] += uniform53(r.x, r.y);
+                acc[2 * q + 1] += uniform53(r.z, r.w);
+            }
+        } else {
+            // 8 descents of 10 levels, targets derived from the previous results (no generator in the loop)
+            uint32_t nb[8];
+            double tau[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                nb[k] = 8u;
+                tau[k] = (double)(((gid * 2654435761u + (uint32_t)it * 40503u + (uint32_t)k * 977u) >> 7) & 1023u) + 0.5;
+            }
+            const unsigned char* Cm = reinterpret_cast<const unsigned char*>(tree) - 8;
+#pragma unroll
+            for (int lvl = 0; lvl < 10; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double v = *reinterpret_cast<const double*>(Cm + nb[k]);
+                    nb[k] += nb[k];
+                    if (v < tau[k]) nb[k] += 8u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += (double)nb[k];
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    out[gid] = s;
+}
+
 // Roofline denominator: 8 independent FMA chains per thread keep the FP64 pipe saturated.
 __global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
 {
@@ -860,6 +931,43 @@ int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_p
     float ms = 0.f;
     SSME_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *fma_per_second = (double)blocks * threads * 8.0 * (double)iters / ((double)ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return SSME_B200_OK;
+}
+
+int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4])
+{
+    if (!rates || iters < 1) return fail(SSME_B200_EINVAL, "bad argument");
+    SSME_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SSME_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 16, threads = 128;
+    double* d_out = nullptr;
+    SSME_CUDA(cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    SSME_CUDA(cudaEventCreate(&e0));
+    SSME_CUDA(cudaEventCreate(&e1));
+    const PhiloxRoundKeys rk = philox_round_keys(20260101ull);
+    const double per_thread_iter[4] = {8.0, 8.0, 8.0, 80.0};  // exps, normals, uniforms, descent steps
+    for (int which = 0; which < 4; ++which) {
+        for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
+            if (rep == 1) SSME_CUDA(cudaEventRecord(e0));
+            switch (which) {
+            case 0: opmix_rate_kernel<0><<<blocks, threads>>>(d_out, iters, rk); break;
+            case 1: opmix_rate_kernel<1><<<blocks, threads>>>(d_out, iters, rk); break;
+            case 2: opmix_rate_kernel<2><<<blocks, threads>>>(d_out, iters, rk); break;
+            default: opmix_rate_kernel<3><<<blocks, threads>>>(d_out, iters, rk); break;
+            }
+        }
+        SSME_CUDA(cudaEventRecord(e1));
+        SSME_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SSME_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        rates[which] = (double)blocks * threads * per_thread_iter[which] * (double)iters / ((double)ms * 1e-3);
+        g_launches.fetch_add(2);
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d_out);

@@ -268,3 +268,11 @@ def test_tiny_particle_counts(oracle, sv_series, gpu_backend_factory, N, resampl
     assert got["loglik"][0] == ref["loglik"] and np.isfinite(ref["loglik"])
     if N == 1:  # a single particle always fathers itself
         assert np.all(got["ancestors"][0] == 0)
+
+
+def test_opmix_micro_benchmarks_run():
+    """The roofline denominators of SURVEY.md 8(d): each op class alone on the whole GPU."""
+    r = sb.measure_opmix_rates(0, 200)
+    assert set(r) == {"exp", "normal", "uniform", "search_step"}
+    assert all(v > 1e10 for v in r.values())
+    assert sb.measure_fp64_fma_rate(0, 1 << 12) > 1e12
