@@ -32,6 +32,13 @@ using LWFilter2WithCovs_svol = detail::lw_svol_base<nparts, float_t, SSME_B200_L
 template <size_t nparts, typename float_t = double>
 using LWFilterWithCovs_svol = detail::lw_svol_base<nparts, float_t, SSME_B200_LW_APF>;
 
+// The covariate-free twins LWFilter2 (liu_west_filter.h:1470-1761) and LWFilter (:236-552): the same filters on the same
+// model with the covariate held at zero (no leverage term in the transition) -- filter(y_t) instead of filter(y_t, z_t).
+template <size_t nparts, typename float_t = double>
+class LWFilter2_svol;
+template <size_t nparts, typename float_t = double>
+class LWFilter_svol;
+
 namespace detail {
 template <size_t nparts, typename float_t, int form>
 class lw_svol_base {
@@ -139,6 +146,30 @@ private:
     std::array<double, 4> m_final_mean{};
 };
 }  // namespace detail
+
+template <size_t nparts, typename float_t>
+class LWFilter2_svol : public detail::lw_svol_base<nparts, float_t, SSME_B200_LW_SISR> {
+public:
+    using base = detail::lw_svol_base<nparts, float_t, SSME_B200_LW_SISR>;
+    using base::base;
+    void filter(float_t y_t) { base::filter(y_t, float_t(0)); }
+    void filter_series(const std::vector<float_t>& obs, std::uint64_t stream_id = 0)
+    {
+        base::filter_series(obs, std::vector<float_t>(obs.size(), float_t(0)), stream_id);
+    }
+};
+
+template <size_t nparts, typename float_t>
+class LWFilter_svol : public detail::lw_svol_base<nparts, float_t, SSME_B200_LW_APF> {
+public:
+    using base = detail::lw_svol_base<nparts, float_t, SSME_B200_LW_APF>;
+    using base::base;
+    void filter(float_t y_t) { base::filter(y_t, float_t(0)); }
+    void filter_series(const std::vector<float_t>& obs, std::uint64_t stream_id = 0)
+    {
+        base::filter_series(obs, std::vector<float_t>(obs.size(), float_t(0)), stream_id);
+    }
+};
 
 }  // namespace ssme_b200
 #endif

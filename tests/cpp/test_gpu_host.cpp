@@ -159,6 +159,20 @@ int main(int argc, char** argv)
         REQUIRE(online.getParamMeans()(0) == big.getParamMeans()(0));
         REQUIRE(std::abs(big.getLogLike() - big2.getLogLike()) < 0.02 * std::abs(big2.getLogLike()));
     }
+    TEST_CASE("covariate-free Liu-West twins: filter(y_t)")
+    {
+        using lw_t = ssme_b200::LWFilter2_svol<5000, double>;
+        lw_t a({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5}, lw_t::psv{.99, .1, .3, -.01});
+        ssme_b200::LWFilter_svol<5000, double> b({"logit", "null", "log", "twice_fisher"}, .99, lw_t::psv{.8, -.1, .01, -.5},
+                                                 lw_t::psv{.99, .1, .3, -.01});
+        std::vector<double> head(y.begin(), y.begin() + 30);
+        a.filter_series(head);
+        for (double v : head) b.filter(v);
+        REQUIRE(std::isfinite(a.getLogLike()));
+        REQUIRE(std::isfinite(b.getLogLike()));
+        REQUIRE(std::pow(a.getLogCondLike(), 2) > 0.0);
+        REQUIRE(std::abs(a.getLogLike() - b.getLogLike()) < 0.05 * std::abs(a.getLogLike()));
+    }
     TEST_CASE("swarm: 10 x 10 particles, assertions of test_pswarm.cpp:251-252")
     {
         struct my_swarm : ssme_b200::Swarm<10, 10, 4, double> {
