@@ -237,8 +237,13 @@ const void* cluster_kernel_fn(int model, int res, int nt, int L)
     // tiles of L * nt <= 4096 particles
 #define SSME_CL2(M, R, NTV) (L == 8 ? (const void*)&cluster_filter_kernel<M, R, NTV, (NTV <= 512 ? 8 : 4)> : (const void*)&cluster_filter_kernel<M, R, NTV, 4>)
 #define SSME_CL(M, R) (nt == 128 ? SSME_CL2(M, R, 128) : nt == 256 ? SSME_CL2(M, R, 256) : nt == 512 ? SSME_CL2(M, R, 512) : SSME_CL2(M, R, 1024))
-    if (model == SSME_B200_MODEL_SV) return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSV, kResampMultinomial) : SSME_CL(kModelSV, kResampSystematic);
-    return res == SSME_B200_RESAMP_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampMultinomial) : SSME_CL(kModelSVLeverage, kResampSystematic);
+    if (model == SSME_B200_MODEL_SV)
+        return res == SSME_B200_RESAMP_MULTINOMIAL          ? SSME_CL(kModelSV, kResampMultinomial)
+               : res == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? SSME_CL(kModelSV, kResampSortedMultinomial)
+                                                            : SSME_CL(kModelSV, kResampSystematic);
+    return res == SSME_B200_RESAMP_MULTINOMIAL          ? SSME_CL(kModelSVLeverage, kResampMultinomial)
+           : res == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampSortedMultinomial)
+                                                        : SSME_CL(kModelSVLeverage, kResampSystematic);
 #undef SSME_CL
 #undef SSME_CL2
 }
@@ -355,8 +360,6 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
-    if (cfg->resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL && use_cluster)
-        return fail(SSME_B200_EUNSUPPORTED, "the sorted-multinomial resampler is built into the resident and the global-memory kernels, not the cluster kernel");
     if (use_cluster) {
         // K2: tiles of 4*NT particles, one CTA each, cluster of ceil(N/tile) CTAs (cluster_kernel.cuh)
         if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the cluster kernel resamples at every step (resample_every = 1)");

@@ -44,6 +44,8 @@ struct ClusterShared {
     double red[2 * kClMaxWarps];
     double maxes[kClMax];       // tile maxima, pushed by the peers (st.async)
     double tots[kClMax];        // tile sums, pushed by the peers (st.async)
+    double etots[kClMax];       // tile sums of the exponential spacings (sorted-multinomial resampling), pushed the same way
+    double red_e[kClMaxWarps];  // warp totals of the spacings' tile scan
     double clM[32], clS[32];
     unsigned long long bar_max;  // completes when every peer's maximum has landed
     unsigned long long bar_cdf;  // completes when every peer's tile sum, CDF tile and state tile have landed
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
     const uint32_t peer_cta = (uint32_t)((lane < CS) ? lane : 0);
     const uint32_t peer_max_slot = cluster_addr(smem_u32(&sh.maxes[rank]), peer_cta);
     const uint32_t peer_tot_slot = cluster_addr(smem_u32(&sh.tots[rank]), peer_cta);
+    const uint32_t peer_etot_slot = cluster_addr(smem_u32(&sh.etots[rank]), peer_cta);
+    constexpr bool kSorted = (RESAMP == kResampSortedMultinomial);
     const uint32_t peer_bar_max = cluster_addr(smem_u32(bar_max), peer_cta);
     const uint32_t peer_bar_cdf = cluster_addr(smem_u32(bar_cdf), peer_cta);
 
@@ -271,6 +275,48 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double lex = shfl_up_d(incl, 1);
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
+        // sorted-multinomial resampling (mn_resamp_states_and_params): this tile's exponential spacings and their lane-level scan
+        // now, the warp level after the barrier below, the tile total pushed to the peers together with the weight total
+        double pe[kClL];
+        double eincl = 0.0;
+        if (kSorted) {
+#pragma unroll
+            for (int q = 0; q < kClL / 2; ++q) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+                double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
+                ua = (ua == 0.0) ? 0x1p-53 : ua;
+                ub = (ub == 0.0) ? 0x1p-53 : ub;
+                pe[2 * q + 0] = (i0 + 2 * q < N) ? -dlog_unit(ua) : 0.0;
+                pe[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
+            }
+#pragma unroll
+            for (int k = 1; k < kClL; ++k) pe[k] = __dadd_rn(pe[k - 1], pe[k]);
+            eincl = pe[kClL - 1];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double other = shfl_up_d(eincl, d);
+                eincl = (lane >= d) ? __dadd_rn(other, eincl) : eincl;
+            }
+            if (lane == 31) sh.red_e[warp] = eincl;
+        }
+        double etot = 0.0;
+        auto finish_e_scan = [&]() {  // after a block barrier: warp-level scan, tile-local prefix sums in pe, tile total in etot
+            double ewv = (lane < NW) ? sh.red_e[lane] : 0.0;
+#pragma unroll
+            for (int d = 1; d < NW; d <<= 1) {
+                const double other = shfl_up_d(ewv, d);
+                ewv = (lane >= d) ? __dadd_rn(other, ewv) : ewv;
+            }
+            etot = shfl_d(ewv, NW - 1);
+            double ewex = shfl_d(ewv, (warp > 0) ? warp - 1 : 0);
+            ewex = (warp > 0) ? ewex : 0.0;
+            double elex = shfl_up_d(eincl, 1);
+            elex = (lane > 0) ? elex : 0.0;
+            const double ebase = __dadd_rn(ewex, elex);
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) pe[k] = __dadd_rn(ebase, pe[k]);
+        };
+        const uint32_t extra_tx = kSorted ? (uint32_t)CS * 8u : 0u;
         if (dsmem) {
             // two tiles: the CDF goes straight from this CTA's shared memory into the peer's with one DSMEM bulk copy (32 KB at
             // ~20 B/clk) -- no global scratch, no gpu-scope membar, no L2 round trip.  Own tile: written in place.
@@ -279,9 +325,11 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
             for (int k = 0; k < kClL; ++k) Cown[eoff[k]] = __dadd_rn(base, sc[k]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores (CDF, states) before the async-proxy reads of the copies
             __syncthreads();
+            if (kSorted) finish_e_scan();
             if (warp == 0) {
-                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)(CS - 1) * 2u * kClTileBytes + (uint32_t)CS * 8u);
+                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)(CS - 1) * 2u * kClTileBytes + (uint32_t)CS * 8u + extra_tx);
                 if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
+                if (kSorted && lane < CS) st_async_f64(peer_etot_slot, etot, peer_bar_cdf);
                 if (lane < CS && lane != rank) {  // this tile's CDF and states into the peer's shared memory
                     dsmem_bulk_copy(cluster_addr(smem_u32(Cown), (uint32_t)lane), smem_u32(Cown), kClTileBytes, peer_bar_cdf);
                     dsmem_bulk_copy(cluster_addr(smem_u32(shXall + rank * kClTile), (uint32_t)lane), smem_u32(shX + (t & 1) * kClTile),
@@ -295,10 +343,12 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
             // fence (a gpu-scope membar) orders this step's X stores before the pushes that let the peers read them
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncthreads();
+            if (kSorted) finish_e_scan();
             if (warp == 0) {
                 // peers may complete bytes before this arrives: the transaction count just goes negative for a while
-                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)CS * (kClTileBytes + 8u));
+                if (lane == 0) mbar_expect_tx(bar_cdf, (uint32_t)CS * (kClTileBytes + 8u) + extra_tx);
                 if (lane < CS) st_async_f64(peer_tot_slot, tile_total, peer_bar_cdf);
+                if (kSorted && lane < CS) st_async_f64(peer_etot_slot, etot, peer_bar_cdf);
                 if (lane == 0) {
                     tma_multicast_1d(shC + rank * kClTile, gC, kClTileBytes, &sh.bar_cdf, cta_mask);
                 }
@@ -314,6 +364,12 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
                 tau[2 * q + 0] = uniform53(r.x, r.y);
                 tau[2 * q + 1] = uniform53(r.z, r.w);
             }
+        } else if (kSorted) {
+            // the last spacing E_N (not in the scan), the same draw on every thread
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+            double uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
+            uN = (uN == 0.0) ? 0x1p-53 : uN;
+            tau[0] = -dlog_unit(uN);
         } else {
             const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
             tau[0] = uniform53(r.x, r.y);
@@ -341,6 +397,24 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
             for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(tau[k], S);
+        } else if (kSorted) {
+            // tile ends of the spacings (same scan as the weight totals); tau_j = (O_b + P_j) * S / G
+            const double et = (lane < CS) ? sh.etots[lane] : 0.0;
+            double eti = et;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double other = shfl_up_d(eti, d);
+                eti = (lane >= d) ? __dadd_rn(other, eti) : eti;
+            }
+            const double Ge = shfl_d(eti, 31);
+            double etlex = shfl_up_d(eti, 1);
+            etlex = (lane > 0) ? etlex : 0.0;
+            const double Eend = __dadd_rn(__dadd_rn(0.0, etlex), et);   // inclusive end of tile `lane`
+            double Oe = shfl_d(Eend, (rank > 0) ? rank - 1 : 0);
+            Oe = (rank > 0) ? Oe : 0.0;
+            const double sg = __ddiv_rn(S, __dadd_rn(Ge, tau[0]));
+#pragma unroll
+            for (int k = 0; k < kClL; ++k) tau[k] = __dmul_rn(__dadd_rn(Oe, pe[k]), sg);
         } else {
             const double u0 = tau[0];
             const double sN = __ddiv_rn(S, dN);

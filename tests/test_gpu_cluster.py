@@ -12,7 +12,7 @@ LEV_THETA = np.array([0.9, 0.0, 0.3, -0.1])
 
 
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
-@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T,NT", [(1024, 40, 128), (8192, 33, 128), (5000, 65, 128), (600, 7, 128), (4096, 1, 128),
                                     (8192, 33, 256), (5000, 40, 256), (1025, 9, 256), (16384, 12, 256), (2048, 1, 0),
                                     (8192, 20, 1024), (8192, 20, 512), (4097, 9, 1024), (16000, 6, 1024), (6000, 11, 512)])
@@ -37,7 +37,7 @@ def test_cluster_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
 
 
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
-@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC, sb.RESAMP_SORTED_MULTINOMIAL])
 @pytest.mark.parametrize("N,T,NT", [(8192, 20, 512), (8192, 15, 256), (5000, 9, 128), (4097, 33, 512), (16384, 5, 512)])
 def test_cluster_filter_eight_per_thread(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, NT):
     """tiles of 8 particles per thread (2 tiles of 4096 for 8192 particles: the layout for many chains per GPU)"""
