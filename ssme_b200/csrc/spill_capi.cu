@@ -143,7 +143,6 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
 // Sorted-multinomial resampling of the step in `a` (weights already scanned): spacings, their tiled scan, one search per slot.
 static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& a, int tiles, cudaStream_t st)
 {
-    if (s->world != 1) return fail(SSME_B200_EUNSUPPORTED, "sorted-multinomial resampling of a particle-sharded filter is not built");
     if (!s->ecdf) {
         SSME_CUDA(cudaMalloc(&s->ecdf, s->local * sizeof(double)));
         SSME_CUDA(cudaMalloc(&s->ettot, (size_t)s->nb * sizeof(double)));
@@ -154,6 +153,11 @@ static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& 
     a.ettot = s->ettot;
     a.eE = s->eE;
     spill_expo_scan_kernel<<<tiles, kTileNT, 0, st>>>(a);
+    if (s->world > 1) {  // every rank scans all tile totals of the spacings, as it does for the weights
+        NcclApi* nccl = nccl_api();
+        int nrc = nccl->AllGather(s->ettot + s->tile0, s->ettot, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
+        if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", nccl->GetErrorString(nrc));
+    }
     SpillArgs e = a;  // the tile-total scan kernels, pointed at the spacings; their running-maximum outputs go to scratch
     e.ttot = s->ettot;
     e.E = s->eE;

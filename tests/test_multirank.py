@@ -183,7 +183,7 @@ def _spill_worker(rank, world, port, q, N, T, resampler):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("resampler", [2, 0])
+@pytest.mark.parametrize("resampler", [2, 0, 1])
 def test_particle_sharded_filter_matches_single_gpu(resampler):
     """Config-5 shape at test size: ONE filter whose particles are sharded over 2 GPUs (per step: NCCL all-reduce of
     the weight maximum, all-gather of the tile sums, peer reads of ancestors) == the single-GPU run, bit for bit."""
@@ -214,8 +214,8 @@ def test_particle_sharded_filter_matches_single_gpu(resampler):
     assert np.array_equal(got[0][2], one["cond_like"]) and np.array_equal(got[1][2], one["cond_like"])
     half = N // 2
     ref = one["ancestors"][0]
-    if resampler == 0:
-        # multinomial (slot-side gather): each rank traces the ancestors of its own slots
+    if resampler in (0, 1):
+        # multinomial and sorted multinomial (slot-side gather): each rank traces the ancestors of its own slots
         assert np.array_equal(got[0][3][0][:, :half], ref[:, :half])
         assert np.array_equal(got[1][3][0][:, half:], ref[:, half:])
     else:
