@@ -684,16 +684,49 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
             }
             __syncthreads();
         } else {
+            // degenerate weights: this tile fathers more slots than the staging buffer holds.  Short runs are written by their
+            // own thread; a long run (one particle fathering thousands of slots, up to all N) is queued in shared memory and
+            // written by the whole CTA, so the time stays proportional to slots / threads instead of slots.
+            constexpr int kLongRun = 64;
+            int* qn = &sh_range[0];                              // number of queued runs (the slot range is in registers by now)
+            int* qrun = reinterpret_cast<int*>(ebuf);            // [kTile][2] first slot, end slot
+            double* qval = ebuf + kTile;                         // [kTile] value          (together: the whole staging buffer)
+            __syncthreads();  // every thread has read the slot range; the previous field's queue has been drained
+            if (tid == 0) qn[0] = 0;
+            __syncthreads();
 #pragma unroll
-            for (int k = 0; k < kTileL; ++k)
-                for (long long sl = A[k]; sl < A[k + 1]; ++sl) {
-                    if (single || fld > 0) {
-                        dst_local[sl] = v[k];
-                    } else {
-                        const int owner = (int)(sl / per_rank);
-                        a.peer_x_anc[owner][sl - (long long)owner * per_rank] = v[k];
+            for (int k = 0; k < kTileL; ++k) {
+                const int cnt = A[k + 1] - A[k];
+                if (cnt > kLongRun) {
+                    const int e = atomicAdd(qn, 1);
+                    qrun[2 * e] = A[k];
+                    qrun[2 * e + 1] = A[k + 1];
+                    qval[e] = v[k];
+                } else {
+                    for (long long sl = A[k]; sl < A[k + 1]; ++sl) {
+                        if (single || fld > 0) {
+                            dst_local[sl] = v[k];
+                        } else {
+                            const int owner = (int)(sl / per_rank);
+                            a.peer_x_anc[owner][sl - (long long)owner * per_rank] = v[k];
+                        }
                     }
                 }
+            }
+            __syncthreads();
+            const int nrun = qn[0];
+            for (int e = 0; e < nrun; ++e) {
+                const double val = qval[e];
+                for (long long sl = (long long)qrun[2 * e] + tid; sl < (long long)qrun[2 * e + 1]; sl += kTileNT) {
+                    if (single || fld > 0) {
+                        dst_local[sl] = val;
+                    } else {
+                        const int owner = (int)(sl / per_rank);
+                        a.peer_x_anc[owner][sl - (long long)owner * per_rank] = val;
+                    }
+                }
+            }
+            __syncthreads();
         }
     }
     if (a.ancestors) {

@@ -71,3 +71,22 @@ def test_spilled_filter_many_tiles_two_launch_scan(oracle, sv_series, gpu_backen
     assert np.array_equal(got["cond_like"][0], ref["cond_like"])
     assert got["loglik"][0] == ref["loglik"]
     assert np.array_equal(got["ancestors"][0], ref["ancestors"])
+
+
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
+def test_spilled_filter_degenerate_weights_and_invalid_parameters(oracle, sv_series, gpu_backend_factory, resampler):
+    """An outlying observation puts all the weight on a handful of particles: one particle fathers more slots than the
+    expansion's staging buffer holds (the direct path).  And |phi| >= 1 gives NaN, quickly, as in the resident kernel."""
+    N, T = 4096 * 5 + 11, 6
+    y = sv_series(T, seed=34).copy()
+    y[2] = 60.0   # ~ 40 standard deviations
+    be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=12, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.trace(SV_THETA[None, :], stream_base=2, want=("loglik", "cond_like", "ancestors"))
+    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=12, filter_id=2)
+    counts = np.bincount(ref["ancestors"][2], minlength=N)
+    assert counts.max() > 8192      # the degenerate step really exceeds the staging buffer
+    assert np.array_equal(got["ancestors"][0], ref["ancestors"])
+    assert np.array_equal(got["cond_like"][0], ref["cond_like"]) and got["loglik"][0] == ref["loglik"]
+    bad = be.work_batch(np.array([[1.0, 1.5, 0.0625]]), R=1)
+    assert np.isnan(bad[0])
