@@ -504,6 +504,17 @@ def run_ours(args):
             # the PMMH half of the metric on the CPU path, derived from the same rate: one iteration of the reference's example
             # (config 1) is 100 filters x 500 particles x 3084 steps, of config 3 64 chains x 8192 particles x 1024 steps
             cpu["pmmh_iters_per_sec_derived"] = {"config1": cpu["value"] / (100 * 500 * 3084), "config3": 64 * cpu["value"] / (64 * 8192 * 1024)}
+            spy = os.path.join(ROOT, "tests", "golden", "spy_config1.npz")
+            if os.path.exists(spy):  # one likelihood evaluation of the reference's example: 100 filters x 500 particles on the SPY series
+                g = np.load(spy)
+                ys = np.ascontiguousarray(g["y"], dtype=np.float64)
+                ths = np.ascontiguousarray(g["theta"], dtype=np.float64).reshape(1, -1)
+                o1 = np.zeros(1)
+                s1, u1 = C.c_double(), C.c_uint()
+                L.ssme_refcpu_loglike_batch(0, 500, ys.ctypes.data_as(dp), ys.size, ths.ctypes.data_as(dp), 3, 1, 100,
+                                            0 if cores > 1 else 1, 7, o1.ctypes.data_as(dp), C.byref(s1), C.byref(u1))
+                cpu["pmmh_config1_iters_per_sec_measured"] = 1.0 / s1.value
+                cpu["pmmh_config1_loglik_cpu"] = float(o1[0])
         except Exception as ex:  # the baseline is a reported extra; never let it sink the GPU line
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {
