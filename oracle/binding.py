@@ -121,10 +121,16 @@ def fexp(x):
     return float(fn(float(x)))
 
 
+class _LwStreams(C.Structure):
+    _fields_ = [("u_prior", C.c_void_p), ("z_state", C.c_void_p), ("z_jitter", C.c_void_p), ("u_resamp", C.c_void_p), ("u_aux", C.c_void_p)]
+
+
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
-                  cov=None, trace=True, tiled=2, form="sisr"):
+                  cov=None, trace=True, tiled=2, form="sisr", streams=None):
     """Liu-West filter on the SV-with-leverage model; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary
-    particle filter).  Returns dict(loglik, cond_like, theta_bar, final_mean, ancestors, aux_index, margin)."""
+    particle filter).  streams: optional dict(u_prior [N][4], z_state [T][N], z_jitter [T][N][4], u_resamp [T][s], u_aux [T][N])
+    of pre-generated draws replacing the Philox streams.
+    Returns dict(loglik, cond_like, theta_bar, final_mean, ancestors, aux_index, margin, expect)."""
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
     hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
@@ -136,15 +142,25 @@ def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH
     anc = np.empty((T, N), dtype=np.int32) if trace else None
     aux = np.zeros((T, N), dtype=np.int32) if trace else None
     ex = np.zeros((T, 5))
-    fn = lib().ssme_oracle_lw_filter_expect
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    st, keep = None, []
+    if streams is not None:
+        st = _LwStreams()
+        for k in ("u_prior", "z_state", "z_jitter", "u_resamp", "u_aux"):
+            a = streams.get(k)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                keep.append(a)
+                setattr(st, k, a.ctypes.data)
+    fn = lib().ssme_oracle_lw_filter_streams
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     rc = fn(C.cast(C.byref(cfg), C.c_void_p), {"sisr": 0, "apf": 1}[form], vp(lo), vp(hi), delta, vp(y), T, vp(cov),
+            C.cast(C.byref(st), C.c_void_p) if st is not None else None,
             C.cast(C.byref(ll), C.c_void_p), vp(cl), vp(tb), vp(fm), vp(anc), vp(aux), C.cast(C.byref(mg), C.c_void_p), vp(ex))
     if rc != 0:
-        raise ValueError("ssme_oracle_lw_filter_expect failed with %d" % rc)
+        raise ValueError("ssme_oracle_lw_filter_streams failed with %d" % rc)
     return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux, "margin": mg.value,
             "expect": ex}
 

@@ -652,6 +652,17 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
                                  double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin,
                                  double* expect)
 {
+    return ssme_oracle_lw_filter_streams(cfg, form, prior_lo, prior_hi, delta, y, T, cov, NULL, loglik_out, cond_like, theta_bar,
+                                         final_mean, ancestors, aux_index, tie_margin, expect);
+}
+
+/* the same with every random draw optionally taken from pre-generated streams (st != NULL): the form in which the filter
+ * is compared with the reference's own LWFilter2WithCovs / LWFilterWithCovs compiled from /root/reference (tests/test_refhdr.py) */
+int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                                  const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
+                                  double* loglik_out, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
+                                  int32_t* aux_index, double* tie_margin, double* expect)
+{
     static const int TT[4] = {2, 0, 3, 1}; /* logit, null, log, twice_fisher */
     if (!cfg || !prior_lo || !prior_hi || !y || T < 0) return -1;
     const int32_t N = cfg->num_particles, L = cfg->scan_items_per_lane;
@@ -661,6 +672,8 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
     if (form != 0 && form != 1) return -5;
     const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
     const uint32_t utag = 1u + (uint32_t)cfg->resampler;
+    const int64_t stride_u = cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL ? N : cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL ? N + 1 : 1;
+    if (st && (!st->u_prior || !st->z_state || !st->z_jitter || !st->u_resamp || (form == 1 && !st->u_aux))) return -6;
     const double a = (3.0 * delta - 1.0) / (2.0 * delta), h2 = 1.0 - a * a, oma = 1.0 - a;
     tiled_cdf_t tc, te; /* weights; exponential spacings of the sorted-multinomial resampler (mn_resamp_states_and_params) */
     te.cl = NULL; te.E = NULL;
@@ -713,7 +726,9 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
                 for (int j = 0; j <= i; ++j) {
                     double sacc = V[i][j];
                     for (int k = 0; k < j; ++k) sacc = sacc - Lc[i][k] * Lc[j][k];
-                    Lc[i][j] = (i == j) ? sqrt(sacc) : sacc / Lc[j][j];
+                    /* a non-positive pivot zeroes its column, so a zero covariance (delta = 1) draws the mean exactly */
+                    if (i == j) Lc[i][j] = (sacc > 0.0) ? sqrt(sacc) : 0.0;
+                    else Lc[i][j] = (Lc[j][j] > 0.0) ? sacc / Lc[j][j] : 0.0;
                 }
             if (theta_bar) for (int k = 0; k < 4; ++k) theta_bar[t * 4 + k] = tb[k];
         }
@@ -751,7 +766,7 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
                 fs_M2 = M2; fs_logS2 = log(S2);
             }
             for (int32_t j = 0; j < N; ++j) {
-                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, 6u);
+                double u = st ? st->u_aux[t * N + j] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, 6u);
                 ks[j] = canonical ? tiled_search(&tc, u * S2) : lower_bound_idx(C, N, u);
             }
             if (aux_index) for (int32_t j = 0; j < N; ++j) aux_index[t * N + j] = ks[j];
@@ -766,13 +781,14 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
             }
         }
         for (int32_t i = 0; i < N; ++i) {
-            double z = ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
+            double z = st ? st->z_state[t * N + i] : ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
             double p[4]; /* untransformed phi, mu, sigma, rho used by this step */
             if (t == 0) {
                 for (int k = 0; k < 4; ++k) {
                     uint32_t wd[4];
                     philox_block(cfg->seed, cfg->filter_id, 0u, 2u * (uint32_t)i + (uint32_t)(k >> 1), 5u, wd);
                     double u = (k & 1) ? dm_uniform53(wd[2], wd[3]) : dm_uniform53(wd[0], wd[1]);
+                    if (st) u = st->u_prior[(size_t)i * 4 + k];
                     p[k] = canonical ? fma(u, prior_hi[k] - prior_lo[k], prior_lo[k]) : prior_lo[k] + u * (prior_hi[k] - prior_lo[k]);
                     th[(size_t)k * N + i] = lw_trans(TT[k], p[k], canonical);
                 }
@@ -783,13 +799,21 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
                 philox_block(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i, 4u, wd);
                 dm_box_muller(wd[0], wd[1], &zf[0], &zf[1]);
                 dm_box_muller(wd[2], wd[3], &zf[2], &zf[3]);
+                double zj[4];
+                for (int k = 0; k < 4; ++k) zj[k] = st ? st->z_jitter[((size_t)t * N + i) * 4 + k] : (double)zf[k];
                 double m[4], nth[4];
                 for (int k = 0; k < 4; ++k)
                     m[k] = canonical ? fma(a, th[(size_t)k * N + i], oma * tb[k]) : a * th[(size_t)k * N + i] + oma * tb[k];
                 for (int k = 0; k < 4; ++k) {
-                    double acc = m[k];
-                    for (int l = 0; l <= k; ++l) acc = canonical ? fma(Lc[k][l], (double)zf[l], acc) : acc + Lc[k][l] * (double)zf[l];
-                    nth[k] = acc;
+                    if (canonical) {
+                        double acc = m[k];
+                        for (int l = 0; l <= k; ++l) acc = fma(Lc[k][l], zj[l], acc);
+                        nth[k] = acc;
+                    } else { /* MVNSampler::sample: mean + scale * Z, the matrix-vector product first */
+                        double acc = 0.0;
+                        for (int l = 0; l < 4; ++l) acc += Lc[k][l] * zj[l];
+                        nth[k] = m[k] + acc;
+                    }
                 }
                 for (int k = 0; k < 4; ++k) { th[(size_t)k * N + i] = nth[k]; p[k] = lw_inv_trans(TT[k], nth[k], canonical); }
                 if (canonical) {
@@ -852,12 +876,13 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
         loglik += cl;
         const double total = canonical ? S : 1.0;
         double u0 = 0.0, sN = S / (double)N;
-        if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) u0 = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
+        if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC)
+            u0 = st ? st->u_resamp[t * stride_u] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
         if (canonical && cfg->tiled == 2 && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) systematic_by_counts(&tc, N, u0, sN, anc);
         else if (sorted) {
             /* liu_west_filter.h:104-139: N+1 exponential spacings -> uniform order statistics */
             for (int32_t j = 0; j <= N; ++j) {
-                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                double u = st ? st->u_resamp[t * stride_u + j] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
                 if (u == 0.0) u = 0x1p-53;
                 Ex[j] = canonical ? -dm_log(u) : -log(u);
             }
@@ -888,7 +913,7 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
             double tau;
             if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
             else {
-                double u = ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
+                double u = st ? st->u_resamp[t * stride_u + j] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);
                 tau = canonical ? u * S : u;
             }
             anc[j] = canonical ? tiled_search(&tc, tau) : lower_bound_idx(C, N, tau);

@@ -3,14 +3,22 @@
  * log-likelihood hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may call this; the product (ssme_b200/) never does.
  *
- * Parity status: **parity unpinned at the pf boundary** -- the arithmetic of the path lives
- * in the external, unpinned library tbrown122387/pf (find_package(pf), reference
- * CMakeLists.txt:12), absent from /root/reference and from this image, and the reference's
- * own tests assert nothing about filter outputs (test/test_liu_west.cpp:172,199;
- * test/test_ada_pmmh_mvn.cpp:6-9 is empty).  What IS pinned against the reference's own
- * known answers: param::pack transforms / log-Jacobian (test/test_parameters.cpp:114,145),
- * thread_pool log-mean-exp (test/test_thread_pool.cpp:40), split pool (:184), CSV reader
- * (test/test_utils.cpp:15-18) -- see tests/test_reference_known_answers.py.
+ * Parity status: **pinned to reference code compiled here, except for the external pf library itself.**
+ * tbrown122387/pf (find_package(pf), reference CMakeLists.txt:12; unpinned) is absent from /root/reference and from this
+ * image, as are Eigen3 and Catch2.  With stand-ins for those three (oracle/refshim/), the reference's OWN headers compile
+ * unmodified (make -C oracle refhdr -> oracle/_ref/libssme_refhdr.so, oracle/ref_harness.cpp) and this oracle is checked
+ * against them on identical pre-generated streams (tests/test_refhdr.py, tests/cpp/test_ref_pmmh.cpp):
+ *   - LWFilter2::filter (liu_west_filter.h:1608-1761), the first-party twin of pf's BSFilter step, + the in-tree resampler
+ *     mn_resamp_states_and_params (:91-145): resampled states identical, cond-likes <= 1e-12 (FAITHFUL), <= 1e-9 with
+ *     identical ancestors (CANONICAL);
+ *   - LWFilter2WithCovs / LWFilterWithCovs (:2191-2343, :971-1159) on the reference's test models: theta-bar identical,
+ *     cond-likes and expectations <= 1e-12;
+ *   - param::pack / transforms (parameters.h): identical bits; ada_pmmh_mvn::commence_sampling: same chain;
+ *   - the example's svol_bs on std::discrete_distribution: bit-identical to FAITHFUL multinomial;
+ *   - the reference's test suite (19 Catch2 cases) and example program run against the stand-ins.
+ * What stays a restatement: pf's BSFilter / mn_resampler / samplers (oracle/refshim/pf/*.h), written from the reference's
+ * in-tree twin and call sites.  The reference's known answers (test/test_parameters.cpp:114,145; test_thread_pool.cpp:40,184;
+ * test_utils.cpp:15-18) are checked both through the reference's own test binary and in tests/test_reference_known_answers.py.
  *
  * Two arithmetics are restated here:
  *   FAITHFUL   the reference's formulas with libm, sequential sums, normalised CDF
@@ -115,6 +123,19 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
                                  const double* y, int64_t T, const double* cov, double* loglik, double* cond_like,
                                  double* theta_bar, double* final_mean, int32_t* ancestors, int32_t* aux_index, double* tie_margin,
                                  double* expect);
+
+/* ... with every random draw optionally taken from pre-generated streams (st may be NULL = Philox as above) */
+typedef struct {
+    const double* u_prior;  /* [N][4]     unit uniforms of paramPriorSamp, order phi, mu, sigma, rho (test_liu_west.cpp:339-347) */
+    const double* z_state;  /* [T][N]     N(0,1) of q1Samp / qSamp, one per particle per step */
+    const double* z_jitter; /* [T][N][4]  N(0,1) of the parameter jitter (MVNSampler::sample), row 0 unused */
+    const double* u_resamp; /* [T][s]     unit uniforms of the resampler, s = N (multinomial), N+1 (sorted), 1 (systematic) */
+    const double* u_aux;    /* [T][N]     unit uniforms of k_gen (form 1), row 0 unused */
+} ssme_oracle_lw_streams;
+int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                                  const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
+                                  double* loglik, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
+                                  int32_t* aux_index, double* tie_margin, double* expect);
 
 /* canonical sum of v[0..n): tile partials (lane-local sequential over L, butterfly over the 32 lanes, sequential
  * over the warps of the tile), then the tile partials by one CTA of 1024 lanes the same way */

@@ -7,12 +7,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(src, exe, tmp_path):
+def _build(src, exe, tmp_path, extra=()):
     import ssme_b200 as sb
     sb.load_library()
     libdir = os.path.dirname(sb.library_path())
     cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), "-o", str(tmp_path / exe),
-           os.path.join(ROOT, "tests", "cpp", src), "-L" + libdir, "-lssme_b200", "-Wl,-rpath," + libdir]
+           os.path.join(ROOT, "tests", "cpp", src), "-L" + libdir, "-lssme_b200", "-Wl,-rpath," + libdir, *extra]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "warning" not in r.stderr, r.stderr
@@ -21,6 +21,19 @@ def _build(src, exe, tmp_path):
 
 def test_host_layer_known_answers(tmp_path):
     exe = _build("test_host.cpp", "test_host", tmp_path)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 failed" in r.stdout
+
+
+def test_reference_pmmh_loop_and_pack_equal_the_mirror(tmp_path):
+    """The reference's own ada_pmmh_mvn::commence_sampling / update_moments_and_Ct / q_samp and param::pack, compiled
+    unmodified (oracle/_ref/libssme_refhdr.so), against pmmh_multichain.hpp / parameters.hpp on identical streams."""
+    from oracle import refhdr_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref/libssme_refhdr.so not built and /root/reference absent")
+    rb.build()
+    exe = _build("test_ref_pmmh.cpp", "test_ref_pmmh", tmp_path, extra=["-L" + rb.REF_DIR, "-lssme_refhdr", "-Wl,-rpath," + rb.REF_DIR])
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 failed" in r.stdout
