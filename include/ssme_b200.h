@@ -36,9 +36,13 @@ extern "C" {
 #define SSME_B200_ECUDA 4       /* CUDA runtime failure (std::runtime_error) */
 #define SSME_B200_EUNSUPPORTED 5 /* configuration not built into this library */
 
-/* state-space models (device functors; the reference's models are C++ virtuals on Eigen vectors) */
+/* state-space models.  The reference's models are C++ virtuals on Eigen vectors (q1Samp, fSamp, logGEv, ...:
+ * example/univ_svol_bootstrap_filter.h:37-41); here a model is a device TYPE with the same hooks
+ * (ssme_b200/csrc/models/model_api.cuh) and every filter kernel is a template over it.  Adding a model = one header in
+ * ssme_b200/csrc/models/ + one line in models/models.cuh + an id here; no kernel changes. */
 #define SSME_B200_MODEL_SV 0          /* example/univ_svol_bootstrap_filter.h:17-103; theta = (beta, phi, sigma^2) */
 #define SSME_B200_MODEL_SV_LEVERAGE 1 /* test/test_liu_west.cpp:83-157; theta = (phi, mu, sigma, rho); z_t = y_{t-1} */
+#define SSME_B200_MODEL_LINEAR_GAUSSIAN 2 /* AR(1) + Gaussian noise, theta = (phi, sigma, tau): exact likelihood known (Kalman) */
 
 /* resamplers */
 #define SSME_B200_RESAMP_MULTINOMIAL 0        /* pf::resamplers::mn_resampler (estimate_univ_svol.h:119) */
@@ -105,7 +109,8 @@ int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out);
  * log-mean-exp (thread_pool.h:263-268).  HOST buffers; the call copies theta in, runs, copies out
  * and synchronises.
  *   theta_host      [P][numparams] row-major, untransformed
- *   stream_base     first Philox filter id; filter (p, r) uses stream_base + p*R + r
+ *   stream_base     first Philox filter id; filter (p, r) uses stream_base + p*R + r.  Filter ids must stay below 2^60
+ *                   (60 bits enter the Philox counter); a range that leaves [0, 2^60) returns SSME_B200_EINVAL
  *   out_host        [P] log-mean-exp over the R replicates
  *   per_filter_host [P*R] individual filter log-likelihoods, or NULL */
 int ssme_b200_loglike_batch(ssme_b200_handle h, const double* theta_host, size_t P, uint32_t R,

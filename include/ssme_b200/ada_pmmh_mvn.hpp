@@ -230,7 +230,7 @@ private:
     ssme_b200::gpu_pool<numparams, dimobs, float_t, debug> m_pool;
     static_data_t m_data;
     std::mt19937 m_gen;
-    std::uint64_t m_single_stream = (std::uint64_t)1 << 62;  // stream ids of direct log_like_eval calls
+    std::uint64_t m_single_stream = (std::uint64_t)1 << 59;  // stream ids of direct log_like_eval calls: the upper half of the 60-bit id space
     float_t m_old_log_like, m_new_log_like, m_old_log_prior, m_new_log_prior, m_log_accept_prob;
     bool m_accepted;
 };

@@ -231,6 +231,7 @@ typedef struct {
     double c0;      /* -log(beta) - 0.5 log(2 pi) */
     double inv2b2;  /* 0.5 / beta^2 */
     double rho_sigma, sdv; /* leverage: rho*sigma, sigma*sqrt(1-rho^2) */
+    double tau, lg_h;      /* linear-Gaussian: observation sd, 0.5 / tau^2 */
 } model_t;
 
 static void model_init(model_t* m, int model, const double* theta)
@@ -240,12 +241,17 @@ static void model_init(model_t* m, int model, const double* theta)
         /* svol_bs(const pack&): beta = theta0, phi = theta1, sigma = sqrt(theta2) (:54-61) */
         m->beta = theta[0]; m->phi = theta[1]; m->sigma = sqrt(theta[2]);
         m->mu = 0.0; m->rho = 0.0;
+    } else if (model == SSME_OR_MODEL_LINEAR_GAUSSIAN) {
+        /* phi, sigma, tau (ssme_b200/csrc/models/linear_gaussian.cuh) */
+        m->beta = 1.0; m->phi = theta[0]; m->sigma = theta[1]; m->mu = 0.0; m->rho = 0.0;
     } else {
         /* phi, mu, sigma, rho (test_liu_west.cpp:70 transform order logit,null,log,twice_fisher) */
         m->beta = 1.0; m->phi = theta[0]; m->mu = theta[1]; m->sigma = theta[2]; m->rho = theta[3];
     }
+    m->tau = (model == SSME_OR_MODEL_LINEAR_GAUSSIAN) ? theta[2] : 1.0;
+    m->lg_h = 0.5 / (m->tau * m->tau);
     m->sd0 = m->sigma / sqrt(1.0 - m->phi * m->phi);
-    m->c0 = -dm_log(m->beta) - DM_HALF_LOG_2PI;
+    m->c0 = -dm_log(model == SSME_OR_MODEL_LINEAR_GAUSSIAN ? m->tau : m->beta) - DM_HALF_LOG_2PI;
     m->inv2b2 = 0.5 / (m->beta * m->beta);
     m->rho_sigma = m->rho * m->sigma;
     m->sdv = m->sigma * sqrt(1.0 - m->rho * m->rho);
@@ -255,7 +261,7 @@ static void model_init(model_t* m, int model, const double* theta)
 static double can_q1(const model_t* m, double z) { return z * m->sd0; }
 static double can_f(const model_t* m, double xa, double z, double cov)
 {
-    if (m->model == SSME_OR_MODEL_SV) return fma(m->phi, xa, m->sigma * z);
+    if (m->model != SSME_OR_MODEL_SV_LEVERAGE) return fma(m->phi, xa, m->sigma * z);
     double e2 = dm_exp(-0.5 * xa);
     double cz = m->rho_sigma * cov;
     double mean = fma(m->phi, xa - m->mu, m->mu);
@@ -264,6 +270,7 @@ static double can_f(const model_t* m, double xa, double z, double cov)
 }
 static double can_logg(const model_t* m, double y, double x)
 {
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN) { double d = y - x; return fma(-m->lg_h, d * d, m->c0); }
     double h = (y * y) * m->inv2b2;
     double e = dm_exp(-x);
     return fma(-h, e, fma(-0.5, x, m->c0));
@@ -273,13 +280,14 @@ static double can_logg(const model_t* m, double y, double x)
 static double fai_q1(const model_t* m, double z) { return z * m->sigma / sqrt(1. - m->phi * m->phi); }
 static double fai_f(const model_t* m, double xa, double z, double cov)
 {
-    if (m->model == SSME_OR_MODEL_SV) return m->phi * xa + z * m->sigma; /* univ_svol_bootstrap_filter.h:77 */
+    if (m->model != SSME_OR_MODEL_SV_LEVERAGE) return m->phi * xa + z * m->sigma; /* univ_svol_bootstrap_filter.h:77 */
     double xt = m->mu + m->phi * (xa - m->mu) + cov * m->rho * m->sigma * exp(-.5 * xa); /* test_liu_west.cpp:116 */
     xt += z * m->sigma * sqrt(1.0 - m->rho * m->rho);                                  /* :118 */
     return xt;
 }
 static double fai_logg(const model_t* m, double y, double x)
 {
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN) return faithful_log_norm(y, x, m->tau);
     return faithful_log_norm(y, 0.0, m->beta * exp(.5 * x)); /* :85 ; leverage: beta = 1 */
 }
 static double fai_logmu(const model_t* m, double x)
@@ -374,7 +382,7 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL) tiled_alloc(&te, N, nt * L, L);
         NP = N; /* C below holds the global values O_b + cl_i, for the margin report only */
     }
-    if (cfg->model != SSME_OR_MODEL_SV && cfg->model != SSME_OR_MODEL_SV_LEVERAGE) return -3;
+    if (cfg->model < SSME_OR_MODEL_SV || cfg->model > SSME_OR_MODEL_LINEAR_GAUSSIAN) return -3;
     if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
     const int injected = (cfg->rng_mode == SSME_OR_RNG_INJECTED);
     if (injected && !z_inj) return -5;

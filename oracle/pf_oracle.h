@@ -16,7 +16,7 @@
  *   - param::pack / transforms (parameters.h): identical bits; ada_pmmh_mvn::commence_sampling: same chain;
  *   - the example's svol_bs on std::discrete_distribution: bit-identical to FAITHFUL multinomial;
  *   - the reference's test suite (19 Catch2 cases) and example program run against the stand-ins.
- * What stays a restatement: pf's BSFilter / mn_resampler / samplers (oracle/refshim/pf/*.h), written from the reference's
+ * What stays a restatement: pf's BSFilter / mn_resampler / samplers (the headers under oracle/refshim/pf), written from the reference's
  * in-tree twin and call sites.  The reference's known answers (test/test_parameters.cpp:114,145; test_thread_pool.cpp:40,184;
  * test_utils.cpp:15-18) are checked both through the reference's own test binary and in tests/test_reference_known_answers.py.
  *
@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1 };
+enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1, SSME_OR_MODEL_LINEAR_GAUSSIAN = 2 };
 enum { SSME_OR_RESAMP_MULTINOMIAL = 0, SSME_OR_RESAMP_SORTED_MULTINOMIAL = 1, SSME_OR_RESAMP_SYSTEMATIC = 2 };
 enum { SSME_OR_ARITH_CANONICAL = 0, SSME_OR_ARITH_FAITHFUL = 1 };
 enum { SSME_OR_RNG_PHILOX = 0, SSME_OR_RNG_INJECTED = 1 };
@@ -67,6 +67,8 @@ typedef struct {
  * Run one bootstrap filter over y[0..T).
  *   theta      untransformed parameters: SV (beta, phi, sigma^2)  [svol_bs ctor, :54-61];
  *              SV_LEVERAGE (phi, mu, sigma, rho)                  [test/test_liu_west.cpp:83-157]
+ *              LINEAR_GAUSSIAN (phi, sigma, tau): x_t = phi x_{t-1} + sigma z, y_t ~ N(x_t, tau^2)  [not a reference model:
+ *              its exact likelihood is known (Kalman), ssme_b200/csrc/models/linear_gaussian.cuh]
  *   cov        covariate series z_t (leverage only); NULL means z_t = y_{t-1}, z_0 unused
  *   z_inj      injected N(0,1) stream [T][N]              (rng_mode INJECTED)
  *   u_inj      injected U[0,1) stream [T][stride_u]       (rng_mode INJECTED); stride_u = N

@@ -19,6 +19,7 @@ from .capi import (  # noqa: F401
     pmmh_run_custom,
     MODEL_SV,
     MODEL_SV_LEVERAGE,
+    MODEL_LINEAR_GAUSSIAN,
     RESAMP_MULTINOMIAL,
     RESAMP_SORTED_MULTINOMIAL,
     RESAMP_SYSTEMATIC,

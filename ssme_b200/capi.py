@@ -12,7 +12,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-MODEL_SV, MODEL_SV_LEVERAGE = 0, 1
+MODEL_SV, MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN = 0, 1, 2
+_NUM_PARAMS = {MODEL_SV: 3, MODEL_SV_LEVERAGE: 4, MODEL_LINEAR_GAUSSIAN: 3}
 RESAMP_MULTINOMIAL, RESAMP_SORTED_MULTINOMIAL, RESAMP_SYSTEMATIC = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
 RNG_PHILOX, RNG_INJECTED = 0, 1
@@ -229,7 +230,7 @@ class ParticleFilterBackend:
                     cfg.filters_per_sm, cfg.force_global_memory, cfg.use_cluster, 0)
         self._h = C.c_void_p()
         _check(self._lib.ssme_b200_create(C.byref(c), C.byref(self._h)))
-        self.num_params = 3 if cfg.model == MODEL_SV else 4
+        self.num_params = _NUM_PARAMS[cfg.model]
         self.T = 0
 
     def close(self):

@@ -27,6 +27,14 @@ namespace ssme {
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 
+int check_stream_ids(unsigned long long first, unsigned long long count)
+{
+    const unsigned long long lim = 1ull << 60;
+    if (first >= lim || count > lim - first)
+        return fail(SSME_B200_EINVAL, "filter stream ids %llu .. +%llu leave [0, 2^60): only 60 bits enter the Philox counter", first, count);
+    return SSME_B200_OK;
+}
+
 int fail(int code, const char* fmt, ...)
 {
     char buf[512];
@@ -187,7 +195,7 @@ static const KernelEntry* find_kernel(int L, int NT, int model, int resamp, int 
         int n = 0;
         const KernelEntry* t = tf(&n);
         for (int i = 0; i < n; ++i)
-            if (t[i].L == L && t[i].NT == NT && t[i].model == model && t[i].resamp == resamp && t[i].debug == debug)
+            if (t[i].fn && t[i].L == L && t[i].NT == NT && t[i].model == model && t[i].resamp == resamp && t[i].debug == debug)
                 return &t[i];
     }
     return nullptr;
@@ -237,13 +245,14 @@ const void* cluster_kernel_fn(int model, int res, int nt, int L)
     // tiles of L * nt <= 4096 particles
 #define SSME_CL2(M, R, NTV) (L == 8 ? (const void*)&cluster_filter_kernel<M, R, NTV, (NTV <= 512 ? 8 : 4)> : (const void*)&cluster_filter_kernel<M, R, NTV, 4>)
 #define SSME_CL(M, R) (nt == 128 ? SSME_CL2(M, R, 128) : nt == 256 ? SSME_CL2(M, R, 256) : nt == 512 ? SSME_CL2(M, R, 512) : SSME_CL2(M, R, 1024))
-    if (model == SSME_B200_MODEL_SV)
-        return res == SSME_B200_RESAMP_MULTINOMIAL          ? SSME_CL(kModelSV, kResampMultinomial)
-               : res == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? SSME_CL(kModelSV, kResampSortedMultinomial)
-                                                            : SSME_CL(kModelSV, kResampSystematic);
-    return res == SSME_B200_RESAMP_MULTINOMIAL          ? SSME_CL(kModelSVLeverage, kResampMultinomial)
-           : res == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? SSME_CL(kModelSVLeverage, kResampSortedMultinomial)
-                                                        : SSME_CL(kModelSVLeverage, kResampSystematic);
+#define SSME_CL_MODEL(M)                                                                               \
+    if (model == M::kId)                                                                                \
+        return res == SSME_B200_RESAMP_MULTINOMIAL          ? SSME_CL(M, kResampMultinomial)            \
+               : res == SSME_B200_RESAMP_SORTED_MULTINOMIAL ? SSME_CL(M, kResampSortedMultinomial)      \
+                                                            : SSME_CL(M, kResampSystematic);
+    SSME_FOR_EACH_MODEL(SSME_CL_MODEL)
+#undef SSME_CL_MODEL
+    return nullptr;
 #undef SSME_CL
 #undef SSME_CL2
 }
@@ -313,8 +322,8 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     if (cfg->struct_size != (int32_t)sizeof(ssme_b200_config))
         return fail(SSME_B200_EINVAL, "ssme_b200_config size mismatch: got %d, library expects %zu", cfg->struct_size,
                     sizeof(ssme_b200_config));
-    if (cfg->model != SSME_B200_MODEL_SV && cfg->model != SSME_B200_MODEL_SV_LEVERAGE)
-        return fail(SSME_B200_EINVAL, "unknown model id %d", cfg->model);
+    ModelInfo mi;
+    if (!model_info(cfg->model, &mi)) return fail(SSME_B200_EINVAL, "unknown model id %d", cfg->model);
     if (cfg->num_particles < 1) return fail(SSME_B200_EINVAL, "num_particles must be >= 1");
     if (cfg->resample_every < 1) return fail(SSME_B200_EINVAL, "resample_every must be >= 1");
     if (cfg->resampler != SSME_B200_RESAMP_MULTINOMIAL && cfg->resampler != SSME_B200_RESAMP_SYSTEMATIC &&
@@ -407,7 +416,8 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->cfg = *cfg;
     h->L = L;
     h->NT = NT;
-    h->num_params = (cfg->model == SSME_B200_MODEL_SV) ? 3 : 4;
+    h->num_params = mi.num_params;
+    h->obs_stride = mi.obs_stride;
     h->num_sms = prop.multiProcessorCount;
     h->fast = fast;
     h->debug = dbg;
@@ -480,7 +490,7 @@ int ssme_b200_set_observations(ssme_b200_handle h, const double* y_host, size_t 
     if (T > 0x7fffffffull) return fail(SSME_B200_EINVAL, "series too long");
     int rc = set_device(h);
     if (rc) return rc;
-    const int OS = obs_stride(h->cfg.model);
+    const int OS = h->obs_stride;
     const size_t Tpad = ((T + kYChunk - 1) / kYChunk) * kYChunk;
     std::vector<double> rows(Tpad * OS, 0.0);
     for (size_t t = 0; t < T; ++t) {
@@ -523,8 +533,9 @@ int ssme_b200_loglike_batch_device(ssme_b200_handle h, const double* theta_dev, 
     if (!theta_dev || !per_filter_dev) return fail(SSME_B200_EINVAL, "null device buffer");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX)
         return fail(SSME_B200_EINVAL, "batch evaluation needs rng_mode PHILOX; injected streams go through ssme_b200_filter_trace");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, (unsigned long long)P * R);
     if (rc) return rc;
+    if ((rc = set_device(h))) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     if (h->spill) {
         if (cuda_stream && (cudaStream_t)cuda_stream != h->stream)
@@ -583,7 +594,9 @@ int ssme_b200_filter_trace(ssme_b200_handle h, const double* theta_host, size_t 
     if (!theta_host) return fail(SSME_B200_EINVAL, "null theta");
     const bool inject = (h->cfg.rng_mode == SSME_B200_RNG_INJECTED);
     if (inject && (!z_inj_host || !u_inj_host)) return fail(SSME_B200_EINVAL, "rng_mode INJECTED needs z_inj_host and u_inj_host");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, F);
+    if (rc) return rc;
+    rc = set_device(h);
     if (rc) return rc;
     const size_t N = (size_t)h->cfg.num_particles, T = h->T, np = (size_t)h->num_params;
     const size_t stride_u = h->cfg.resampler == SSME_B200_RESAMP_MULTINOMIAL          ? N
@@ -652,7 +665,9 @@ int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t 
     if (!theta_host || !log_cond_like_host) return fail(SSME_B200_EINVAL, "null host buffer");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
     if (h->spill) return fail(SSME_B200_EUNSUPPORTED, "the swarm entry point runs resident filters (num_particles <= 8192)");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, P);
+    if (rc) return rc;
+    rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, T = h->T;
     double *d_theta = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_mean = nullptr;
@@ -688,7 +703,9 @@ int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, s
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "the swarm needs rng_mode PHILOX");
     if (h->spill || h->cluster || h->cfg.dtype != SSME_B200_DTYPE_F64)
         return fail(SSME_B200_EUNSUPPORTED, "expectations are an output of the resident one-CTA fp64 kernel (num_particles <= 8192, no cluster)");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, P);
+    if (rc) return rc;
+    rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, T = h->T;
     double *d_theta = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_ex = nullptr, *d_mean = nullptr;
@@ -729,7 +746,9 @@ int ssme_b200_swarm_begin(ssme_b200_handle h, const double* theta_host, size_t P
         return fail(SSME_B200_EUNSUPPORTED, "the streaming swarm runs the resident one-CTA fp64 kernel (num_particles <= 8192, no cluster)");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX || h->cfg.resample_every != 1)
         return fail(SSME_B200_EUNSUPPORTED, "the streaming swarm needs rng_mode PHILOX and resampling at every step");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, P);
+    if (rc) return rc;
+    rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, N = (size_t)h->cfg.num_particles;
     if (P != h->sw_P) {
@@ -756,7 +775,7 @@ int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_
     int rc = set_device(h);
     if (rc) return rc;
     const size_t P = h->sw_P;
-    const int OS = (h->cfg.model == SSME_B200_MODEL_SV) ? 1 : 2;
+    const int OS = h->obs_stride;
     double* d_row = h->d_sw_buf;                 // a whole 64-step chunk is what the kernel's bulk copy reads
     double* d_ll = h->d_sw_buf + 128;            // [P]
     double* d_cl = d_ll + P;                     // [P][1]
@@ -835,7 +854,9 @@ int ssme_b200_loglike_batch_sharded(ssme_b200_handle h, const double* theta_host
     if (P == 0) return SSME_B200_OK;
     if (!theta_host || !per_filter_host) return fail(SSME_B200_EINVAL, "null host buffer");
     if (h->cfg.rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EINVAL, "batch evaluation needs rng_mode PHILOX");
-    int rc = set_device(h);
+    int rc = check_stream_ids(stream_base, (unsigned long long)P * R);
+    if (rc) return rc;
+    rc = set_device(h);
     if (rc) return rc;
     const size_t np = (size_t)h->num_params, F = P * (size_t)R;
     if (h->spill) {

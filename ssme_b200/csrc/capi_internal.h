@@ -12,6 +12,9 @@
 namespace ssme {
 
 int fail(int code, const char* fmt, ...);
+// Filter ids enter the Philox counter as 60 bits (word 2 = low 32 bits, word 3 = next 28 bits, 4 low bits of word 3 tag the
+// draw kind): ids at or above 2^60 would alias lower ones.  Returns SSME_B200_EINVAL for a range that leaves [0, 2^60).
+int check_stream_ids(unsigned long long first, unsigned long long count);
 void count_launch(unsigned n = 1);
 
 #define SSME_CUDA(expr)                                                                              \
@@ -44,6 +47,7 @@ struct ssme_b200_filter_s {
     ssme_b200_config cfg;
     int L = 0, NT = 0;
     int num_params = 0;
+    int obs_stride = 1;  // doubles per observation row of the model (models/model_api.cuh: kObsStride)
     int num_sms = 0;
     int filters_per_sm = 0;
     const ssme::KernelEntry* fast = nullptr;

@@ -97,13 +97,13 @@ constexpr size_t cluster_smem_bytes(int tile, int cluster_size)
     return sizeof(ClusterShared) + sizeof(double) * (size_t)tile * (size_t)tiles;
 }
 
-template <int MODEL, int RESAMP, int NT, int L>
+template <typename MODEL, int RESAMP, int NT, int L>
 __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, double* __restrict__ scratch)
 {
     static_assert(NT == 128 || NT == 256 || NT == 512 || NT == 1024, "128 .. 1024 threads per tile");
     static_assert(L == 4 || L == 8, "4 or 8 particles per thread");
     constexpr int kClL = L;
-    constexpr int OS = obs_stride(MODEL);
+    constexpr int OS = MODEL::kObsStride;
     constexpr int kClTile = kClL * NT;
     static_assert(kClTile <= 4096, "tiles of 512 .. 4096 particles");
     constexpr uint32_t kClTileBytes = kClTile * sizeof(double);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         const uint32_t node = (v == (uint32_t)kClTile) ? (uint32_t)(kClTile - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
         eoff[k] = node;
     }
-    const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
+    const typename MODEL::Params mc = MODEL::init(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
     const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
     const double logN = dlog((double)N);
@@ -168,8 +168,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
     cluster.sync();
 
     for (int t = 0; t < T; ++t) {
-        const double y = a.obs[(size_t)t * OS];
-        const double cov = (OS == 2) ? a.obs[(size_t)t * OS + 1] : 0.0;
+        const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)t * OS);
         double z[kClL];
 #pragma unroll
         for (int q = 0; q < kClL / 4; ++q) {
@@ -179,29 +178,18 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
             box_muller(r.z, r.w, z2, z3);
             z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
         }
-        const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[kClL];
         double mloc = ninf;
         if (t == 0) {
 #pragma unroll
-            for (int k = 0; k < kClL; ++k) x[k] = __dmul_rn(z[k], mc.sd0);
-        } else if (MODEL == kModelSV) {
-#pragma unroll
-            for (int k = 0; k < kClL; ++k) x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+            for (int k = 0; k < kClL; ++k) x[k] = MODEL::q1(mc, ms, z[k]);
         } else {
-            const double cz = __dmul_rn(mc.rho_sigma, cov);
 #pragma unroll
-            for (int k = 0; k < kClL; ++k) {
-                const double e2 = dexp(__dmul_rn(-0.5, x[k]));
-                double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
-                mean = __fma_rn(cz, e2, mean);
-                x[k] = __fma_rn(mc.sdv, z[k], mean);
-            }
+            for (int k = 0; k < kClL; ++k) x[k] = MODEL::f(mc, ms, x[k], z[k]);
         }
 #pragma unroll
         for (int k = 0; k < kClL; ++k) {
-            const double e = dexp(-x[k]);
-            double v = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
+            double v = MODEL::logg(mc, ms, x[k]);
             v = (i0 + k < N) ? v : ninf;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;

@@ -13,47 +13,48 @@
 namespace ssme {
 
 #define SSME_INST(L, MODEL, RESAMP, DEBUG)                                                              \
-    {L, SSME_NT, MODEL, RESAMP, DEBUG,                                                                  \
+    {L, SSME_NT, MODEL::kId, RESAMP, DEBUG,                                                             \
      reinterpret_cast<const void*>(&bootstrap_filter_kernel<L, SSME_NT, MODEL, RESAMP, (DEBUG) != 0>),  \
      filter_smem_bytes<L, SSME_NT, MODEL>()},
 
-#define SSME_INST_L(L)                                   \
-    SSME_INST(L, kModelSV, kResampMultinomial, 0)         \
-    SSME_INST(L, kModelSV, kResampMultinomial, 1)         \
-    SSME_INST(L, kModelSV, kResampSortedMultinomial, 0)   \
-    SSME_INST(L, kModelSV, kResampSortedMultinomial, 1)   \
-    SSME_INST(L, kModelSVLeverage, kResampSortedMultinomial, 0) \
-    SSME_INST(L, kModelSVLeverage, kResampSortedMultinomial, 1) \
-    SSME_INST(L, kModelSV, kResampSystematic, 0)          \
-    SSME_INST(L, kModelSV, kResampSystematic, 1)          \
-    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 0) \
-    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 1) \
-    SSME_INST(L, kModelSVLeverage, kResampSystematic, 0)  \
-    SSME_INST(L, kModelSVLeverage, kResampSystematic, 1)
+// throughput layouts (4 or 8 particles per thread): all three resamplers, fast + tracing instantiation
+#define SSME_INST_L_MODEL(L, MODEL)                  \
+    SSME_INST(L, MODEL, kResampMultinomial, 0)        \
+    SSME_INST(L, MODEL, kResampMultinomial, 1)        \
+    SSME_INST(L, MODEL, kResampSortedMultinomial, 0)  \
+    SSME_INST(L, MODEL, kResampSortedMultinomial, 1)  \
+    SSME_INST(L, MODEL, kResampSystematic, 0)         \
+    SSME_INST(L, MODEL, kResampSystematic, 1)
+#define SSME_INST_L4(MODEL) SSME_INST_L_MODEL(4, MODEL)
+#define SSME_INST_L8(MODEL) SSME_INST_L_MODEL(8, MODEL)
 
 // latency layouts (1 or 2 particles per thread, for batches that do not fill the GPU): i.i.d. and systematic targets
-#define SSME_INST_LAT(L)                                  \
-    SSME_INST(L, kModelSV, kResampMultinomial, 0)         \
-    SSME_INST(L, kModelSV, kResampMultinomial, 1)         \
-    SSME_INST(L, kModelSV, kResampSystematic, 0)          \
-    SSME_INST(L, kModelSV, kResampSystematic, 1)          \
-    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 0) \
-    SSME_INST(L, kModelSVLeverage, kResampMultinomial, 1) \
-    SSME_INST(L, kModelSVLeverage, kResampSystematic, 0)  \
-    SSME_INST(L, kModelSVLeverage, kResampSystematic, 1)
+#define SSME_INST_LAT_MODEL(L, MODEL)           \
+    SSME_INST(L, MODEL, kResampMultinomial, 0)   \
+    SSME_INST(L, MODEL, kResampMultinomial, 1)   \
+    SSME_INST(L, MODEL, kResampSystematic, 0)    \
+    SSME_INST(L, MODEL, kResampSystematic, 1)
+#define SSME_INST_LAT1(MODEL) SSME_INST_LAT_MODEL(1, MODEL)
+#define SSME_INST_LAT2(MODEL) SSME_INST_LAT_MODEL(2, MODEL)
 
-// fp32 mode (pf_kernel_f32.cuh): table slot debug = 2
-#define SSME_INST_F32(L, MODEL, RESAMP)                                                        \
-    {L, SSME_NT, MODEL, RESAMP, 2,                                                             \
-     reinterpret_cast<const void*>(&bootstrap_filter_f32_kernel<L, SSME_NT, MODEL, RESAMP>),   \
-     filter_f32_smem_bytes<L, SSME_NT, MODEL>()},
-#define SSME_INST_F32_L(L)                                \
-    SSME_INST_F32(L, kModelSV, kResampMultinomial)        \
-    SSME_INST_F32(L, kModelSV, kResampSystematic)         \
-    SSME_INST_F32(L, kModelSVLeverage, kResampMultinomial) \
-    SSME_INST_F32(L, kModelSVLeverage, kResampSystematic)
+// fp32 mode (pf_kernel_f32.cuh): table slot debug = 2; a model without float hooks gets a null entry, which find_kernel skips
+template <int L, typename MODEL, int RESAMP>
+static const void* f32_kernel_ptr()
+{
+    if constexpr (MODEL::kHasF32) return reinterpret_cast<const void*>(&bootstrap_filter_f32_kernel<L, SSME_NT, MODEL, RESAMP>);
+    else return nullptr;
+}
+#define SSME_INST_F32(L, MODEL, RESAMP) \
+    {L, SSME_NT, MODEL::kId, RESAMP, 2, f32_kernel_ptr<L, MODEL, RESAMP>(), filter_f32_smem_bytes<L, SSME_NT, MODEL>()},
+#define SSME_INST_F32_MODEL(L, MODEL)              \
+    SSME_INST_F32(L, MODEL, kResampMultinomial)     \
+    SSME_INST_F32(L, MODEL, kResampSystematic)
+#define SSME_INST_F32_L4(MODEL) SSME_INST_F32_MODEL(4, MODEL)
+#define SSME_INST_F32_L8(MODEL) SSME_INST_F32_MODEL(8, MODEL)
 
-static const KernelEntry kTable[] = {SSME_INST_LAT(1) SSME_INST_LAT(2) SSME_INST_L(4) SSME_INST_L(8) SSME_INST_F32_L(4) SSME_INST_F32_L(8)};
+// every model of models/models.cuh in every layout
+static const KernelEntry kTable[] = {SSME_FOR_EACH_MODEL(SSME_INST_LAT1) SSME_FOR_EACH_MODEL(SSME_INST_LAT2) SSME_FOR_EACH_MODEL(SSME_INST_L4)
+                                     SSME_FOR_EACH_MODEL(SSME_INST_L8) SSME_FOR_EACH_MODEL(SSME_INST_F32_L4) SSME_FOR_EACH_MODEL(SSME_INST_F32_L8)};
 
 const KernelEntry* SSME_CAT(kernel_table_nt, SSME_NT)(int* count)
 {

@@ -18,13 +18,14 @@
 // nodes of one tree level contiguous, so the 32 probes of a warp spread over the banks; in sorted
 // order all probes of a level share one bank (ncu round 1: 13.5 wavefronts per LDS.64).  All arithmetic follows the canonical spec shared
 // with oracle/pf_oracle.c, so outputs are bit-identical to the oracle's CANONICAL mode.
+// The state-space model is the template parameter MODEL, a type that satisfies models/model_api.cuh; the kernel holds no
+// model-specific code.
 #pragma once
 #include "det_math.cuh"
+#include "models/models.cuh"
 
 namespace ssme {
 
-constexpr int kModelSV = 0;
-constexpr int kModelSVLeverage = 1;
 constexpr int kResampMultinomial = 0;
 constexpr int kResampSortedMultinomial = 1;
 constexpr int kResampSystematic = 2;
@@ -59,12 +60,10 @@ struct FilterArgs {
     double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
-__host__ __device__ constexpr int obs_stride(int model) { return model == kModelSVLeverage ? 2 : 1; }
-
-template <int L, int NT, int MODEL>
+template <int L, int NT, typename MODEL>
 __host__ __device__ constexpr size_t filter_smem_bytes()
 {
-    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * obs_stride(MODEL) + 64 + 64 + 32) + 16;
+    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * MODEL::kObsStride + 64 + 64 + 32) + 16;
 }
 
 // ---- mbarrier / bulk-TMA helpers (PTX ISA: mbarrier, cp.async.bulk) ---------------------------
@@ -102,46 +101,14 @@ __device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xo
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// per-filter constants of the canonical arithmetic (oracle: model_init)
-struct ModelConst {
-    double phi, sigma, mu;
-    double sd0, c0, inv2b2, rho_sigma, sdv;
-};
-
-template <int MODEL>
-__device__ __forceinline__ ModelConst model_init(const double* th)
-{
-    ModelConst m;
-    double beta;
-    double rho = 0.0;
-    if (MODEL == kModelSV) {
-        beta = th[0];
-        m.phi = th[1];
-        m.sigma = __dsqrt_rn(th[2]);
-        m.mu = 0.0;
-    } else {
-        beta = 1.0;
-        m.phi = th[0];
-        m.mu = th[1];
-        m.sigma = th[2];
-        rho = th[3];
-    }
-    m.sd0 = __ddiv_rn(m.sigma, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(m.phi, m.phi))));
-    m.c0 = __dsub_rn(-dlog(beta), SSME_DM_HALF_LOG_2PI);
-    m.inv2b2 = __ddiv_rn(0.5, __dmul_rn(beta, beta));
-    m.rho_sigma = __dmul_rn(rho, m.sigma);
-    m.sdv = __dmul_rn(m.sigma, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(rho, rho))));
-    return m;
-}
-
-template <int L, int NT, int MODEL, int RESAMP, bool DEBUG>
+template <int L, int NT, typename MODEL, int RESAMP, bool DEBUG>
 __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a)
 {
     static_assert(L == 1 || L == 2 || L % 4 == 0, "Philox blocks serve 4 particles; L = 1, 2 share a block between threads");
     static_assert(NT % 32 == 0 && NT >= 32 && NT <= 1024, "whole warps");
     constexpr int NP = L * NT;
     constexpr int NW = NT / 32;
-    constexpr int OS = obs_stride(MODEL);
+    constexpr int OS = MODEL::kObsStride;
     constexpr uint32_t kChunkBytes = kYChunk * OS * sizeof(double);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -190,7 +157,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         }
     }
 
-    const ModelConst mc = model_init<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
+    const typename MODEL::Params mc = MODEL::init(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
     const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
     const double logN = dlog((double)N);
@@ -216,8 +183,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         const int c = t / kYChunk, o = t % kYChunk;
         if (o == 0) mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
         const double* yrow = ybuf + (c & 1) * (kYChunk * OS) + o * OS;
-        const double y = yrow[0];
-        const double cov = (OS == 2) ? yrow[1] : 0.0;
+        const typename MODEL::Step ms = MODEL::step(mc, yrow);  // the step's quantities shared by all particles
 
         // ---- N(0,1) draws: one Philox block per 4 particles --------------------------------
         double z[L];
@@ -253,30 +219,19 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         }
 
         // ---- propagate (q1Samp at t = 0, fSamp afterwards) and log-weight (logGEv) ----------
-        const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
         double lw[L];
         double mloc = __longlong_as_double(0xfff0000000000000ll);
         // one uniform branch per step (inside the particle loop the compiler keeps a test per particle)
         if (tg == 0) {
 #pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = __dmul_rn(z[k], mc.sd0);
-        } else if (MODEL == kModelSV) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
+            for (int k = 0; k < L; ++k) x[k] = MODEL::q1(mc, ms, z[k]);
         } else {
-            const double cz = __dmul_rn(mc.rho_sigma, cov);
 #pragma unroll
-            for (int k = 0; k < L; ++k) {
-                const double e2 = dexp(__dmul_rn(-0.5, x[k]));
-                double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
-                mean = __fma_rn(cz, e2, mean);
-                x[k] = __fma_rn(mc.sdv, z[k], mean);
-            }
+            for (int k = 0; k < L; ++k) x[k] = MODEL::f(mc, ms, x[k], z[k]);
         }
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            const double e = dexp(-x[k]);
-            const double g = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
+            const double g = MODEL::logg(mc, ms, x[k]);
             const double v = DEBUG ? __dadd_rn(lwacc[k], g) : g;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;
@@ -458,6 +413,18 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
                 for (int k = 0; k < L; ++k)
                     tau[k] = (i0 + k < N) ? __dmul_rn(a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k], S) : 0.0;
+#ifdef SSME_U32_TAU
+            } else if (L >= 4) {
+                const double S32 = __dmul_rn(S, 0x1p-32);
+#pragma unroll
+                for (int q = 0; q < L / 4; ++q) {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
+                    tau[4 * q + 0] = __dmul_rn((double)r.x, S32);
+                    tau[4 * q + 1] = __dmul_rn((double)r.y, S32);
+                    tau[4 * q + 2] = __dmul_rn((double)r.z, S32);
+                    tau[4 * q + 3] = __dmul_rn((double)r.w, S32);
+                }
+#endif
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {

@@ -15,76 +15,23 @@
 
 namespace ssme {
 
-// exp(x) in float, all operations correctly rounded and in a fixed order (oracle/det_math.h: dm_fexp).
-// Cody-Waite reduction with the 1.5*2^23 shift, degree-5 polynomial on (e^r - 1 - r)/r^2 (Cephes expf coefficients).
-__device__ __forceinline__ float fexp_core(float x)
-{
-    const float t = __fmaf_rn(x, 0x1.715476p+0f, 0x1.8p23f);
-    const int k = __float_as_int(t) - 0x4B400000;
-    const float kd = __fsub_rn(t, 0x1.8p23f);
-    float r = __fmaf_rn(kd, -0x1.62e400p-1f, x);
-    r = __fmaf_rn(kd, -0x1.7f7d1cp-20f, r);
-    float p = 0x1.a0d2cep-13f;
-    p = __fmaf_rn(p, r, 0x1.6e879cp-10f);
-    p = __fmaf_rn(p, r, 0x1.1112fap-7f);
-    p = __fmaf_rn(p, r, 0x1.555502p-5f);
-    p = __fmaf_rn(p, r, 0x1.555550p-3f);
-    p = __fmaf_rn(p, r, 0x1.000000p-1f);
-    const float v = __fadd_rn(__fmaf_rn(__fmul_rn(r, r), p, r), 1.0f);
-    return __fmul_rn(v, __int_as_float((k + 127) << 23));
-}
-// NaN -> NaN, x <= -87 -> +0, x > 88 -> +inf
-__device__ __forceinline__ float fexp(float x)
-{
-    float v = fexp_core(x);
-    v = (x <= -87.0f) ? 0.0f : v;
-    v = (x > 88.0f) ? __int_as_float(0x7f800000) : v;
-    return v;
-}
-__device__ __forceinline__ float fexp_nonpos(float x)
-{
-    const float v = fexp_core(x);
-    return (x <= -87.0f) ? 0.0f : v;
-}
 // 24-bit uniform in [0,1)
 __device__ __forceinline__ float uniform24(uint32_t w) { return __fmul_rn((float)(w >> 8), 0x1p-24f); }
 
-struct ModelConstF {
-    float phi, sigma, mu, sd0, c0, rho_sigma, sdv;
-    double inv2b2, rho_sigma_d;
-};
-
-template <int MODEL>
-__device__ __forceinline__ ModelConstF model_init_f32(const double* th)
-{
-    const ModelConst m = model_init<MODEL>(th);  // per-filter constants in double, rounded once
-    ModelConstF f;
-    f.phi = (float)m.phi;
-    f.sigma = (float)m.sigma;
-    f.mu = (float)m.mu;
-    f.sd0 = (float)m.sd0;
-    f.c0 = (float)m.c0;
-    f.rho_sigma = (float)m.rho_sigma;
-    f.sdv = (float)m.sdv;
-    f.inv2b2 = m.inv2b2;
-    f.rho_sigma_d = m.rho_sigma;
-    return f;
-}
-
-template <int L, int NT, int MODEL>
+template <int L, int NT, typename MODEL>
 constexpr size_t filter_f32_smem_bytes()
 {
-    return sizeof(float) * (size_t)(3 * L * NT + 4 * 32) + sizeof(double) * (size_t)(2 * kYChunk * obs_stride(MODEL)) + 16;
+    return sizeof(float) * (size_t)(3 * L * NT + 4 * 32) + sizeof(double) * (size_t)(2 * kYChunk * MODEL::kObsStride) + 16;
 }
 
-template <int L, int NT, int MODEL, int RESAMP>
+template <int L, int NT, typename MODEL, int RESAMP>
 __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterArgs a)
 {
     static_assert(L % 4 == 0, "one Philox block serves 4 particles");
     static_assert(RESAMP == kResampMultinomial || RESAMP == kResampSystematic, "fp32 mode: multinomial or systematic");
     constexpr int NP = L * NT;
     constexpr int NW = NT / 32;
-    constexpr int OS = obs_stride(MODEL);
+    constexpr int OS = MODEL::kObsStride;
     constexpr uint32_t kChunkBytes = kYChunk * OS * sizeof(double);
     constexpr int K = 31 - __builtin_clz((unsigned)NP);
     static_assert((1 << K) == NP, "padded particle count must be a power of two");
@@ -128,7 +75,8 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
             tma_load_1d(ybuf + kYChunk * OS, a.obs + (size_t)kYChunk * OS, kChunkBytes, &bars[1]);
         }
     }
-    const ModelConstF mc = model_init_f32<MODEL>(a.theta + (size_t)(f / a.R) * a.theta_stride);
+    static_assert(MODEL::kHasF32, "this model has no float hooks");
+    const typename MODEL::ParamsF mc = MODEL::init_f32(a.theta + (size_t)(f / a.R) * a.theta_stride);
     const unsigned long long fid = a.filter_base + f;
     const uint32_t ctr2 = (uint32_t)fid, ctr3 = ((uint32_t)(fid >> 32)) << 4;
     const double logN = dlog((double)N);
@@ -144,8 +92,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
         const int c = t / kYChunk, o = t % kYChunk;
         if (o == 0) mbar_wait(&bars[c & 1], (uint32_t)((c >> 1) & 1));
         const double* yrow = ybuf + (c & 1) * (kYChunk * OS) + o * OS;
-        const double y = yrow[0];
-        const float h = (float)__dmul_rn(__dmul_rn(y, y), mc.inv2b2);
+        const typename MODEL::StepF ms = MODEL::step_f32(mc, yrow);
 
         float z[L];
 #pragma unroll
@@ -156,26 +103,16 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
         }
         if (t == 0) {
 #pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = __fmul_rn(z[k], mc.sd0);
-        } else if (MODEL == kModelSV) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = __fmaf_rn(mc.phi, x[k], __fmul_rn(mc.sigma, z[k]));
+            for (int k = 0; k < L; ++k) x[k] = MODEL::q1_f32(mc, ms, z[k]);
         } else {
-            const float cz = (float)__dmul_rn(mc.rho_sigma_d, yrow[OS - 1]);
 #pragma unroll
-            for (int k = 0; k < L; ++k) {
-                const float e2 = fexp(__fmul_rn(-0.5f, x[k]));
-                float mean = __fmaf_rn(mc.phi, __fsub_rn(x[k], mc.mu), mc.mu);
-                mean = __fmaf_rn(cz, e2, mean);
-                x[k] = __fmaf_rn(mc.sdv, z[k], mean);
-            }
+            for (int k = 0; k < L; ++k) x[k] = MODEL::f_f32(mc, ms, x[k], z[k]);
         }
         float lw[L];
         float mloc = ninf;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            const float e = fexp(-x[k]);
-            lw[k] = __fmaf_rn(-h, e, __fmaf_rn(-0.5f, x[k], mc.c0));
+            lw[k] = MODEL::logg_f32(mc, ms, x[k]);
             mloc = (lw[k] > mloc) ? lw[k] : mloc;
         }
         if (!full) {

@@ -173,10 +173,16 @@ static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& 
     return SSME_B200_OK;
 }
 
-template <int MODEL>
-static void launch_propagate(const SpillArgs& a, int tiles, cudaStream_t st)
+static bool launch_propagate(int model, const SpillArgs& a, int tiles, cudaStream_t st)
 {
-    spill_propagate_kernel<MODEL><<<tiles, kTileNT, 0, st>>>(a);
+#define SSME_SPILL_MODEL(M)                                        \
+    if (model == M::kId) {                                          \
+        spill_propagate_kernel<M><<<tiles, kTileNT, 0, st>>>(a);    \
+        return true;                                                \
+    }
+    SSME_FOR_EACH_MODEL(SSME_SPILL_MODEL)
+#undef SSME_SPILL_MODEL
+    return false;
 }
 
 int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, unsigned R, uint64_t stream_base, double* per_filter_dev,
@@ -215,8 +221,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
             a.x_cur = s->x_cur[cur];
             a.lwc = s->lwc[cur];
             for (int r = 0; r < s->world; ++r) { a.peer_x[r] = s->peer_x[cur][r]; a.peer_lwc[r] = s->peer_lwc[cur][r]; }
-            if (h->cfg.model == SSME_B200_MODEL_SV) launch_propagate<kModelSV>(a, tiles, st);
-            else launch_propagate<kModelSVLeverage>(a, tiles, st);
+            launch_propagate(h->cfg.model, a, tiles, st);
             spill_reduce_max_kernel<<<1, 1024, 0, st>>>(a);
             if (s->world > 1) {
                 int nrc = nccl->AllReduce(s->scal, s->scal, 1, kNcclFloat64, kNcclMax, h->nccl_comm, st);
@@ -255,6 +260,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
 // Arguments of a Liu-West run (whole series or streaming): buffers of the handle, prior box, shrinkage constants.
 static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double* hi, double delta, uint64_t stream_id, LwArgs* out)
 {
+    if (int src = check_stream_ids(stream_id, 1)) return src;
     int rc = prepare(h);
     if (rc) return rc;
     SpillState* s = h->spill_state;

@@ -72,18 +72,17 @@ struct SpillArgs {
     int row0;
 };
 
-template <int MODEL>
+template <typename MODEL>
 __global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const SpillArgs a)
 {
     __shared__ double red[kTileNT / 32];
-    constexpr int OS = obs_stride(MODEL);
+    constexpr int OS = MODEL::kObsStride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = a.tile0 + blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;                      // global particle index
     const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;  // index into this rank's arrays
-    const ModelConst mc = model_init<MODEL>(a.theta);
-    const double y = a.obs[(size_t)(a.t - a.row0) * OS];
-    const double cov = (OS == 2) ? a.obs[(size_t)(a.t - a.row0) * OS + 1] : 0.0;
+    const typename MODEL::Params mc = MODEL::init(a.theta);
+    const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)(a.t - a.row0) * OS);
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
     double z[kTileL];
 #pragma unroll
@@ -102,24 +101,12 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const Spill
             x[k] = v.x; x[k + 1] = v.y;
         }
     }
-    const double h = __dmul_rn(__dmul_rn(y, y), mc.inv2b2);
     double lw[kTileL];
     double mloc = __longlong_as_double(0xfff0000000000000ll);
 #pragma unroll
     for (int k = 0; k < kTileL; ++k) {
-        if (a.t == 0) {
-            x[k] = __dmul_rn(z[k], mc.sd0);
-        } else if (MODEL == kModelSV) {
-            x[k] = __fma_rn(mc.phi, x[k], __dmul_rn(mc.sigma, z[k]));
-        } else {
-            const double e2 = dexp(__dmul_rn(-0.5, x[k]));
-            const double cz = __dmul_rn(mc.rho_sigma, cov);
-            double mean = __fma_rn(mc.phi, __dsub_rn(x[k], mc.mu), mc.mu);
-            mean = __fma_rn(cz, e2, mean);
-            x[k] = __fma_rn(mc.sdv, z[k], mean);
-        }
-        const double e = dexp(-x[k]);
-        double v = __fma_rn(-h, e, __fma_rn(-0.5, x[k], mc.c0));
+        x[k] = (a.t == 0) ? MODEL::q1(mc, ms, z[k]) : MODEL::f(mc, ms, x[k], z[k]);
+        double v = MODEL::logg(mc, ms, x[k]);
         v = (i0 + k < a.N) ? v : __longlong_as_double(0xfff0000000000000ll);
         lw[k] = v;
         mloc = (v > mloc) ? v : mloc;

@@ -94,6 +94,12 @@ def test_error_conventions(gpu_backend_factory):
         be.add_observed_data(np.ones(10))
     with pytest.raises(ValueError):
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=0))
+    # filter ids are 60-bit: a range that reaches 2^60 would alias lower ids inside the Philox counter, so it is refused
+    with pytest.raises(ValueError):  # SSME_B200_EINVAL -> std::invalid_argument / ValueError
+        be.work_batch(SV_THETA[None, :], R=1, stream_base=1 << 60)
+    with pytest.raises(ValueError):
+        be.work_batch(np.tile(SV_THETA, (3, 1)), R=2, stream_base=(1 << 60) - 5)
+    assert np.isfinite(be.work_batch(SV_THETA[None, :], R=2, stream_base=(1 << 60) - 2)[0])
     # invalid parameters give NaN, not a trap (ada_pmmh_mvn.h:349 treats NaN as reject)
     assert np.isnan(be.work(np.array([1.0, 1.5, 0.1])))
 

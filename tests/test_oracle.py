@@ -229,3 +229,16 @@ def test_liu_west_expectations_oracle(oracle, sv_series):
             assert np.allclose(c["expect"], f["expect"], rtol=1e-9, atol=1e-12)
         assert np.all((c["expect"][:, 1:] > lo) & (c["expect"][:, 1:] < hi))   # weighted means stay inside the prior box
         assert np.all(np.isfinite(c["expect"]))
+
+
+def test_filter_ids_below_2_60_give_distinct_streams(oracle):
+    """All 60 id bits enter the Philox counter (word 2 = bits 0..31, word 3 = bits 32..59 above the 4 tag bits): ids that
+    differ in any of them draw different numbers; the C ABI refuses ids >= 2^60 (tests/test_gpu_parity.py)."""
+    L = oracle.lib()
+    base = L.ssme_oracle_draw_normal(7, 0, 3, 5)
+    seen = {base}
+    for bit in (0, 1, 31, 32, 33, 45, 58, 59):
+        v = L.ssme_oracle_draw_normal(7, 1 << bit, 3, 5)
+        assert v not in seen
+        seen.add(v)
+    assert L.ssme_oracle_draw_uniform(7, 1 << 59, 3, 5, 1) != L.ssme_oracle_draw_uniform(7, 0, 3, 5, 1)
