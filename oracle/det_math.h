@@ -163,12 +163,18 @@ static inline double dm_uniform53(uint32_t hi, uint32_t lo)
     return (double)v * 0x1p-53;
 }
 
-/* ---- Philox4x32-10 (Salmon et al., SC'11 "Parallel random numbers: as easy as 1, 2, 3") ------ */
-static inline void dm_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+/* 32-bit uniform in [0,1): word * 2^-32, exact ("detmath v2": the i.i.d. multinomial resampling targets, 4 per block) */
+static inline double dm_uniform32(uint32_t w) { return (double)w * 0x1p-32; }
+
+/* ---- Philox4x32-R (Salmon et al., SC'11 "Parallel random numbers: as easy as 1, 2, 3") ------
+ * The filters use R = DM_PHILOX_ROUNDS = 7 ("detmath v2"), the smallest round count of Philox4x32 that passes BigCrush in
+ * that paper; the round function is pinned to Random123's known answers at R = 10 (tests/test_oracle.py). */
+#define DM_PHILOX_ROUNDS 7
+static inline void dm_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < rounds; ++round) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -181,5 +187,7 @@ static inline void dm_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2]
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+static inline void dm_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { dm_philox4x32_r(ctr, key, 10, out); }
+static inline void dm_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { dm_philox4x32_r(ctr, key, DM_PHILOX_ROUNDS, out); }
 
 #endif

@@ -28,19 +28,26 @@ void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uin
 {
     dm_philox4x32_10(ctr, key, out);
 }
+void ssme_oracle_philox4x32_rounds(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4])
+{
+    dm_philox4x32_r(ctr, key, rounds, out);
+}
+int32_t ssme_oracle_philox_rounds(void) { return DM_PHILOX_ROUNDS; }
 
 /* Philox counter layout (the RNG spec shared with the kernel):
  *   key = (seed_lo, seed_hi);  ctr = (block, t, filter_lo, filter_hi << 4 | tag)
  *   tag 0: state normals   -- block q = i >> 2 serves particles 4q..4q+3:
  *                             BoxMuller(w0,w1) -> z[4q], z[4q+1];  BoxMuller(w2,w3) -> z[4q+2], z[4q+3]
- *   tag 1: multinomial uniforms, tag 2: sorted-multinomial uniforms, tag 3: systematic offset
+ *   tag 1: multinomial uniforms -- block h = j >> 2 serves slots 4h..4h+3: u_j = w[j & 3] * 2^-32 (32-bit uniforms)
+ *   tag 2: sorted-multinomial uniforms, tag 3: systematic offset (tags 4-6: Liu-West jitter, prior, first-stage index)
  *                          -- block h = j >> 1 serves slots 2h, 2h+1: u53(w0,w1), u53(w2,w3)
+ *   Philox4x32 with DM_PHILOX_ROUNDS = 7 rounds ("detmath v2").
  */
 static void philox_block(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t block, uint32_t tag, uint32_t out[4])
 {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {block, t, (uint32_t)filter_id, ((uint32_t)(filter_id >> 32) << 4) | tag};
-    dm_philox4x32_10(ctr, key, out);
+    dm_philox4x32(ctr, key, out);
 }
 
 double ssme_oracle_draw_normal(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t i)
@@ -56,6 +63,10 @@ double ssme_oracle_draw_normal(uint64_t seed, uint64_t filter_id, uint32_t t, ui
 double ssme_oracle_draw_uniform(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t j, uint32_t tag)
 {
     uint32_t w[4];
+    if (tag == 1u) { /* i.i.d. multinomial targets: four 32-bit uniforms per block */
+        philox_block(seed, filter_id, t, j >> 2, tag, w);
+        return dm_uniform32(w[j & 3u]);
+    }
     philox_block(seed, filter_id, t, j >> 1, tag, w);
     return (j & 1u) ? dm_uniform53(w[2], w[3]) : dm_uniform53(w[0], w[1]);
 }

@@ -153,6 +153,8 @@ double ssme_oracle_dlog(double x);
 void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1);
 double ssme_oracle_uniform53(uint32_t hi, uint32_t lo);
 void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void ssme_oracle_philox4x32_rounds(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4]);
+int32_t ssme_oracle_philox_rounds(void); /* rounds the filters' streams use (7) */
 /* the N(0,1) draw of particle i at time t, and the U[0,1) draw of slot j (Philox mode) */
 double ssme_oracle_draw_normal(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t i);
 double ssme_oracle_draw_uniform(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t j, uint32_t tag);

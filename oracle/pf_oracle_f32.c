@@ -28,7 +28,7 @@ static void f32_philox(uint64_t seed, uint64_t filter_id, uint32_t t, uint32_t b
 {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {block, t, (uint32_t)filter_id, ((uint32_t)(filter_id >> 32) << 4) | tag};
-    dm_philox4x32_10(ctr, key, out);
+    dm_philox4x32(ctr, key, out);
 }
 
 /* the kernel's scan order (pf_oracle.c: ssme_oracle_canonical_scan), in float */
@@ -150,8 +150,8 @@ int ssme_oracle_filter_f32(const ssme_oracle_cfg* cfg, const double* theta, cons
                 tau = ((float)j + u0) * sN;
             } else {
                 uint32_t wd[4];
-                f32_philox(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j >> 1, 1u, wd);
-                tau = dm_uniform24(wd[(j & 1) * 2]) * S;
+                f32_philox(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j >> 2, 1u, wd);
+                tau = dm_uniform24(wd[j & 3]) * S;
             }
             int32_t idx = 0;
             for (int32_t s = NP / 2; s >= 1; s >>= 1)

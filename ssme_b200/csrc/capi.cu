@@ -81,8 +81,8 @@ __global__ void swarm_mean_kernel(const double* __restrict__ cond_like, size_t P
 
 // Micro-benchmarks for the op-mix roofline of SURVEY.md section 8(d): each kernel keeps the whole GPU busy with ONE class of the
 // filter step's work, written exactly as K1 writes it, and reports how many operations of that class it completed.
-//   0 = dexp (the canonical double exp)     1 = N(0,1) draws (Philox4x32-10 + float Box-Muller, 4 per block)
-//   2 = U[0,1) draws (Philox + uniform53, 2 per block)     3 = descent steps over a 1024-entry breadth-first CDF in shared memory
+//   0 = dexp (the canonical double exp)     1 = N(0,1) draws (Philox4x32-7 + float Box-Muller, 4 per block)
+//   2 = U[0,1) draws (Philox + uniform32, 4 per block)     3 = descent steps over a 1024-entry breadth-first CDF in shared memory
 template <int WHICH>
 __global__ void __launch_bounds__(128) opmix_rate_kernel(double* out, int iters, PhiloxRoundKeys rk)
 {
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) opmix_rate_kernel(double* out, int iters,
         } else if (WHICH == 1) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const uint4 r = philox4x32_10(make_uint4(gid, (uint32_t)it, (uint32_t)q, 0u), rk);
+                const uint4 r = philox4x32(make_uint4(gid, (uint32_t)it, (uint32_t)q, 0u), rk);
                 float z0, z1, z2, z3;
                 box_muller(r.x, r.y, z0, z1);
                 box_muller(r.z, r.w, z2, z3);
@@ -116,10 +116,12 @@ __global__ void __launch_bounds__(128) opmix_rate_kernel(double* out, int iters,
             }
         } else if (WHICH == 2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint4 r = philox4x32_10(make_uint4(gid, (uint32_t)it, (uint32_t)q, 1u), rk);
-                acc[2 * q + 0] += uniform53(r.x, r.y);
-                acc[2 * q + 1] += uniform53(r.z, r.w);
+            for (int q = 0; q < 2; ++q) {
+                const uint4 r = philox4x32(make_uint4(gid, (uint32_t)it, (uint32_t)q, 1u), rk);
+                acc[4 * q + 0] += uniform32(r.x);
+                acc[4 * q + 1] += uniform32(r.y);
+                acc[4 * q + 2] += uniform32(r.z);
+                acc[4 * q + 3] += uniform32(r.w);
             }
         } else {
             // 8 descents of 10 levels, targets derived from the previous results (no generator in the loop)

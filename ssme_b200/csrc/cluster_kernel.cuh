@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double z[kClL];
 #pragma unroll
         for (int q = 0; q < kClL / 4; ++q) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
             float z0, z1, z2, z3;
             box_muller(r.x, r.y, z0, z1);
             box_muller(r.z, r.w, z2, z3);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         if (kSorted) {
 #pragma unroll
             for (int q = 0; q < kClL / 2; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
                 double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
                 ua = (ua == 0.0) ? 0x1p-53 : ua;
                 ub = (ub == 0.0) ? 0x1p-53 : ub;
@@ -347,19 +347,21 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         double tau[kClL];
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
-            for (int q = 0; q < kClL / 2; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
-                tau[2 * q + 0] = uniform53(r.x, r.y);
-                tau[2 * q + 1] = uniform53(r.z, r.w);
+            for (int q = 0; q < kClL / 4; ++q) {
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
+                tau[4 * q + 0] = uniform32(r.x);
+                tau[4 * q + 1] = uniform32(r.y);
+                tau[4 * q + 2] = uniform32(r.z);
+                tau[4 * q + 3] = uniform32(r.w);
             }
         } else if (kSorted) {
             // the last spacing E_N (not in the scan), the same draw on every thread
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(N >> 1), (uint32_t)t, ctr2, ctr3 | 2u), a.rk);
             double uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
             uN = (uN == 0.0) ? 0x1p-53 : uN;
             tau[0] = -dlog_unit(uN);
         } else {
-            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
+            const uint4 r = philox4x32(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
             tau[0] = uniform53(r.x, r.y);
         }
         mbar_wait(bar_cdf, (uint32_t)(t & 1));  // every tile sum, the whole filter's CDF and states have landed

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
     const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);  // this warp's 128 consecutive particles
     float zs[4];
     {
-        const uint4 rz = philox4x32_10(make_uint4((uint32_t)(wbase / 4 + lane), (uint32_t)t, ctr2, ctr3), a.s.rk);
+        const uint4 rz = philox4x32(make_uint4((uint32_t)(wbase / 4 + lane), (uint32_t)t, ctr2, ctr3), a.s.rk);
         box_muller(rz.x, rz.y, zs[0], zs[1]);
         box_muller(rz.z, rz.w, zs[2], zs[3]);
     }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
         double lfs_k = 0.0;
         if (FORM == 1 && t > 0 && valid) {
             // k_i ~ discrete(first-stage weights): uniform of stream 6, two-level descent (spill_resample_kernel's)
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i >> 1), (uint32_t)t, ctr2, ctr3 | 6u), a.s.rk);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(i >> 1), (uint32_t)t, ctr2, ctr3 | 6u), a.s.rk);
             const double tau = __dmul_rn((i & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), a.s.scal[1]);
             int b = 0;
             for (int s = a.s.NBP >> 1; s >= 1; s >>= 1) b += (a.s.E[b + s - 1] < tau) ? s : 0;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
         if (t == 0) {
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) {
-                const uint4 ru = philox4x32_10(make_uint4(2u * (uint32_t)i + (uint32_t)k2, 0u, ctr2, ctr3 | 5u), a.s.rk);
+                const uint4 ru = philox4x32(make_uint4(2u * (uint32_t)i + (uint32_t)k2, 0u, ctr2, ctr3 | 5u), a.s.rk);
                 const double ua = uniform53(ru.x, ru.y), ub = uniform53(ru.z, ru.w);
                 p[2 * k2] = __fma_rn(ua, __dsub_rn(a.hi[2 * k2], a.lo[2 * k2]), a.lo[2 * k2]);
                 p[2 * k2 + 1] = __fma_rn(ub, __dsub_rn(a.hi[2 * k2 + 1], a.lo[2 * k2 + 1]), a.lo[2 * k2 + 1]);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
             for (int k = 0; k < 4; ++k) nth[k] = lw_trans(k, p[k]);
             x = __dmul_rn(z, __ddiv_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[0], p[0])))));
         } else {
-            const uint4 rp = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), a.s.rk);
+            const uint4 rp = philox4x32(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), a.s.rk);
             float zf[4];
             box_muller(rp.x, rp.y, zf[0], zf[1]);
             box_muller(rp.z, rp.w, zf[2], zf[3]);

@@ -60,10 +60,21 @@ struct FilterArgs {
     double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
 };
 
+// The gather table X keeps two doubles of padding after every eight (xslot): thread tid stores its L = 8 states as four
+// 16-byte pieces at a stride of 80 bytes, which spreads each quarter-warp over all 32 banks; without the padding the stride is
+// 64 bytes and every 128-bit store runs at a four-way bank conflict (ncu round 2: 0.25 of the 0.44 store wavefronts per
+// particle-step).  The gather pays one shift-and-add for it.
+// Used by the throughput layout it was measured on (8 particles per thread, up to 4096 per filter); other layouts keep X dense.
+template <int L, int NT>
+__host__ __device__ constexpr int xslot(int i)
+{
+    return (L == 8 && NT <= 512) ? i + ((i >> 3) << 1) : i;
+}
+
 template <int L, int NT, typename MODEL>
 __host__ __device__ constexpr size_t filter_smem_bytes()
 {
-    return sizeof(double) * (size_t)(3 * L * NT + 2 * kYChunk * MODEL::kObsStride + 64 + 64 + 32) + 16;
+    return sizeof(double) * (size_t)(2 * xslot<L, NT>(L * NT) + L * NT + 2 * kYChunk * MODEL::kObsStride + 64 + 64 + 32) + 16;
 }
 
 // ---- mbarrier / bulk-TMA helpers (PTX ISA: mbarrier, cp.async.bulk) ---------------------------
@@ -112,8 +123,9 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     constexpr uint32_t kChunkBytes = kYChunk * OS * sizeof(double);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* Xs = reinterpret_cast<double*>(smem_raw);  // [2][NP]
-    double* Cs = Xs + 2 * NP;                          // [NP]
+    constexpr int NPX = xslot<L, NT>(NP);                    // padded length of one gather table
+    double* Xs = reinterpret_cast<double*>(smem_raw);  // [2][NPX]
+    double* Cs = Xs + 2 * NPX;                         // [NP]
     double* ybuf = Cs + NP;                            // [2][kYChunk*OS]
     double* red_max = ybuf + 2 * kYChunk * OS;         // [32]
     double* red_sum = red_max + 32;                    // [32]
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else if (L >= 4) {
 #pragma unroll
             for (int q = 0; q < L / 4; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3), a.rk);
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3), a.rk);
                 float z0, z1, z2, z3;
                 box_muller(r.x, r.y, z0, z1);
                 box_muller(r.z, r.w, z2, z3);
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         } else {
             // latency layouts (1 or 2 particles per thread): the 2 or 4 threads that share a Philox block each compute it
             // and keep their own Box-Muller pair -- redundant integer work buys shorter dependent chains per step
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3), a.rk);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3), a.rk);
             const bool hi = (i0 & 2) != 0;
             float za, zb;
             box_muller(hi ? r.z : r.x, hi ? r.w : r.y, za, zb);
@@ -244,13 +256,13 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                 mloc = (lw[k] > mloc) ? lw[k] : mloc;
             }
         }
-        double* Xcur = Xs + (t & 1) * NP;
+        double* Xcur = Xs + (t & 1) * NPX;
         if (L == 1) {
-            Xcur[i0] = x[0];
+            Xcur[xslot<L, NT>(i0)] = x[0];
         } else {
 #pragma unroll
-            for (int k = 0; k + 1 < L; k += 2)
-                *reinterpret_cast<double2*>(Xcur + i0 + k) = make_double2(x[k], x[k + 1]);
+            for (int k = 0; k + 1 < L; k += 2)  // i0 + k is even, so the pair never straddles a padding gap
+                *reinterpret_cast<double2*>(Xcur + xslot<L, NT>(i0 + k)) = make_double2(x[k], x[k + 1]);
         }
         if (DEBUG && a.x_trace) {
 #pragma unroll
@@ -413,28 +425,30 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
                 for (int k = 0; k < L; ++k)
                     tau[k] = (i0 + k < N) ? __dmul_rn(a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k], S) : 0.0;
-#ifdef SSME_U32_TAU
             } else if (L >= 4) {
+                // four 32-bit uniforms per Philox block: slot j uses word j & 3 of block j >> 2; tau = u * S with u = word * 2^-32
+                // (the power of two folds into S exactly)
                 const double S32 = __dmul_rn(S, 0x1p-32);
 #pragma unroll
                 for (int q = 0; q < L / 4; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
+                    const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
                     tau[4 * q + 0] = __dmul_rn((double)r.x, S32);
                     tau[4 * q + 1] = __dmul_rn((double)r.y, S32);
                     tau[4 * q + 2] = __dmul_rn((double)r.z, S32);
                     tau[4 * q + 3] = __dmul_rn((double)r.w, S32);
                 }
-#endif
-            } else if (L >= 2) {
-#pragma unroll
-                for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
-                    tau[2 * q + 0] = __dmul_rn(uniform53(r.x, r.y), S);
-                    tau[2 * q + 1] = __dmul_rn(uniform53(r.z, r.w), S);
-                }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
-                tau[0] = __dmul_rn((i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
+                // latency layouts: the 2 or 4 threads that share a block each compute it
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
+                const double S32 = __dmul_rn(S, 0x1p-32);
+                if (L == 2) {
+                    const bool hi = (i0 & 2) != 0;
+                    tau[0] = __dmul_rn((double)(hi ? r.z : r.x), S32);
+                    tau[L - 1] = __dmul_rn((double)(hi ? r.w : r.y), S32);
+                } else {
+                    const uint32_t w01 = (i0 & 1) ? r.y : r.x, w23 = (i0 & 1) ? r.w : r.z;
+                    tau[0] = __dmul_rn((double)((i0 & 2) ? w23 : w01), S32);
+                }
             }
         } else if (RESAMP == kResampSortedMultinomial) {
             // mn_resamp_states_and_params (liu_west_filter.h:104-139, = pf's mn_resamp_fast1): N+1 exponential spacings
@@ -450,7 +464,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             } else if (L >= 2) {
 #pragma unroll
                 for (int q = 0; q < L / 2; ++q) {
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
+                    const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                     double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
                     ua = (ua == 0.0) ? 0x1p-53 : ua;
                     ub = (ub == 0.0) ? 0x1p-53 : ub;
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                     sce[2 * q + 1] = (i0 + 2 * q + 1 < N) ? -dlog_unit(ub) : 0.0;
                 }
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 2), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                 double ua = (i0 & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 ua = (ua == 0.0) ? 0x1p-53 : ua;
                 sce[0] = (i0 < N) ? -dlog_unit(ua) : 0.0;
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 uN = a.u_inj[((size_t)f * T + t) * a.stride_u + N];
             } else {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(N >> 1), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
+                const uint4 r = philox4x32(make_uint4((uint32_t)(N >> 1), (uint32_t)tg, ctr2, ctr3 | 2u), a.rk);
                 uN = (N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
                 uN = (uN == 0.0) ? 0x1p-53 : uN;
             }
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
             if (DEBUG && a.inject) {
                 u0 = a.u_inj[((size_t)f * T + t) * a.stride_u];
             } else {
-                const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)tg, ctr2, ctr3 | 3u), a.rk);
+                const uint4 r = philox4x32(make_uint4(0u, (uint32_t)tg, ctr2, ctr3 | 3u), a.rk);
                 u0 = uniform53(r.x, r.y);
             }
             const double sN = __ddiv_rn(S, dN);
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
         for (int k = 0; k < L; ++k) {
             idx[k] = min((int)(nb[k] >> 3) - NP, N - 1);
-            x[k] = Xcur[idx[k]];
+            x[k] = Xcur[xslot<L, NT>(idx[k])];
             lwacc[k] = 0.0;
         }
         if (!full) {

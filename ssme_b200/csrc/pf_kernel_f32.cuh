@@ -5,7 +5,7 @@
 // with fp64 within 1e-4 relative.  Same structure as K1 (pf_kernel.cuh): one filter per CTA, particles in registers,
 // gather table and breadth-first CDF in shared memory (half the bytes), observations through the bulk-TMA ring.
 // Same Philox streams as the fp64 mode: the state normals are float32 Box-Muller variates in both, the resampling
-// uniforms are the fp64 mode's 53-bit uniforms truncated to their top 24 bits -- so the two modes follow the same
+// uniforms are the fp64 mode's 32-bit uniforms truncated to their top 24 bits -- so the two modes follow the same
 // particle genealogy except where a target falls within float rounding of a CDF boundary.  Per-particle arithmetic is float with explicit rounding (fmaf / fmul / fadd, the
 // polynomial fexp of det_math) and therefore bit-identical to the oracle's ssme_oracle_filter_f32; the per-step
 // log p(y_t | y_{1:t-1}) = M + log S - log N and the running log-likelihood are formed in double from the float M, S.
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
         float z[L];
 #pragma unroll
         for (int q = 0; q < L / 4; ++q) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3), a.rk);
             box_muller(r.x, r.y, z[4 * q + 0], z[4 * q + 1]);
             box_muller(r.z, r.w, z[4 * q + 2], z[4 * q + 3]);
         }
@@ -206,13 +206,15 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_f32_kernel(const FilterAr
         float tau[L];
         if (RESAMP == kResampMultinomial) {
 #pragma unroll
-            for (int q = 0; q < L / 2; ++q) {  // the fp64 mode's 53-bit uniforms, truncated to their top 24 bits
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
-                tau[2 * q + 0] = __fmul_rn(uniform24(r.x), S);
-                tau[2 * q + 1] = __fmul_rn(uniform24(r.z), S);
+            for (int q = 0; q < L / 4; ++q) {  // the fp64 mode's 32-bit uniforms, truncated to their top 24 bits
+                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)t, ctr2, ctr3 | 1u), a.rk);
+                tau[4 * q + 0] = __fmul_rn(uniform24(r.x), S);
+                tau[4 * q + 1] = __fmul_rn(uniform24(r.y), S);
+                tau[4 * q + 2] = __fmul_rn(uniform24(r.z), S);
+                tau[4 * q + 3] = __fmul_rn(uniform24(r.w), S);
             }
         } else {
-            const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
+            const uint4 r = philox4x32(make_uint4(0u, (uint32_t)t, ctr2, ctr3 | 3u), a.rk);
             const float u0 = uniform24(r.x);
             const float sN = __fdiv_rn(S, fN);
 #pragma unroll

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const Spill
     double z[kTileL];
 #pragma unroll
     for (int q = 0; q < kTileL / 4; ++q) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
+        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
         float z0, z1, z2, z3;
         box_muller(r.x, r.y, z0, z1);
         box_muller(r.z, r.w, z2, z3);
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kTileNT) spill_expo_scan_kernel(const SpillArg
     double sc[kTileL];
 #pragma unroll
     for (int q = 0; q < kTileL / 2; ++q) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
+        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 2 + q), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
         double ua = uniform53(r.x, r.y), ub = uniform53(r.z, r.w);
         ua = (ua == 0.0) ? 0x1p-53 : ua;
         ub = (ub == 0.0) ? 0x1p-53 : ub;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
     if (tid == 0) {  // one thread draws the offset and forms the grid constants for the CTA
         const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-        const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), a.rk);
+        const uint4 r = philox4x32(make_uint4(0u, (uint32_t)a.t, ctr2, ctr3 | 3u), a.rk);
         const double u0_ = uniform53(r.x, r.y);
         const double sN_ = __ddiv_rn(a.scal[1], (double)a.N);
         double carry = a.carry[tile];
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
     double sg = 0.0, Oe = 0.0;
     if (a.resamp_sorted) {  // targets P_j * (S / G), G = total of the N+1 spacings (the last one is not in the scan)
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)(a.N >> 1), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
+        const uint4 r = philox4x32(make_uint4((uint32_t)(a.N >> 1), (uint32_t)a.t, ctr2, ctr3 | 2u), a.rk);
         double uN = (a.N & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y);
         uN = (uN == 0.0) ? 0x1p-53 : uN;
         sg = __ddiv_rn(S, __dadd_rn(a.scal[5], -dlog_unit(uN)));
@@ -748,8 +748,9 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
         if (a.resamp_sorted) {
             tau = __dmul_rn(__dadd_rn(Oe, a.ecdf[(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid]), sg);
         } else {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)(j >> 1), (uint32_t)a.t, ctr2, ctr3 | 1u), a.rk);
-            tau = __dmul_rn((j & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), S);
+            const uint4 r = philox4x32(make_uint4((uint32_t)(j >> 2), (uint32_t)a.t, ctr2, ctr3 | 1u), a.rk);
+            const uint32_t w01 = (j & 1) ? r.y : r.x, w23 = (j & 1) ? r.w : r.z;
+            tau = __dmul_rn(uniform32((j & 2) ? w23 : w01), S);
         }
         int b = 0;
         for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;

@@ -242,3 +242,39 @@ def test_filter_ids_below_2_60_give_distinct_streams(oracle):
         assert v not in seen
         seen.add(v)
     assert L.ssme_oracle_draw_uniform(7, 1 << 59, 3, 5, 1) != L.ssme_oracle_draw_uniform(7, 0, 3, 5, 1)
+
+
+def test_detmath_v2_streams(oracle):
+    """The filters' streams: Philox4x32 with 7 rounds (the same round function the Random123 vectors pin at 10 rounds,
+    applied seven times), 32-bit resampling uniforms, four per block."""
+    L = oracle.lib()
+    assert L.ssme_oracle_philox_rounds() == 7
+    fn = L.ssme_oracle_philox4x32_rounds
+    fn.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_uint32)]
+    out10, outr = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    ctr, key = (C.c_uint32 * 4)(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (C.c_uint32 * 2)(0xa4093822, 0x299f31d0)
+    L.ssme_oracle_philox4x32_10(ctr, key, out10)
+    fn(ctr, key, 10, outr)
+    assert tuple(out10) == tuple(outr) == (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    # three more rounds on the 7-round output with the key schedule continued reproduce the 10-round answer
+    fn(ctr, key, 7, outr)
+    k7 = (C.c_uint32 * 2)((0xa4093822 + 7 * 0x9E3779B9) & 0xffffffff, (0x299f31d0 + 7 * 0xBB67AE85) & 0xffffffff)
+    out3 = (C.c_uint32 * 4)()
+    fn(outr, k7, 3, out3)
+    assert tuple(out3) == tuple(out10)
+    # slot j of the multinomial stream = word j & 3 of block j >> 2, scaled by 2^-32
+    seed, fid, t = 20260101, 77, 5
+    for j in (0, 1, 2, 3, 4, 9, 1023):
+        blk = (C.c_uint32 * 4)(j >> 2, t, fid, 1)
+        fn(blk, (C.c_uint32 * 2)(seed & 0xffffffff, seed >> 32), 7, outr)
+        assert L.ssme_oracle_draw_uniform(seed, fid, t, j, 1) == outr[j & 3] * 2.0 ** -32
+    # moments of the two streams a filter consumes
+    z = np.array([L.ssme_oracle_draw_normal(seed, 3, tt, i) for tt in range(40) for i in range(1024)])
+    u = np.array([L.ssme_oracle_draw_uniform(seed, 3, tt, i, 1) for tt in range(40) for i in range(1024)])
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs(u.mean() - 0.5) < 4 * np.sqrt(1 / 12 / n) and abs(u.var() - 1 / 12) < 0.002
+    assert abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 4 / np.sqrt(n) and abs(np.corrcoef(u, z)[0, 1]) < 4 / np.sqrt(n)
+    # equidistribution of the uniforms over 64 cells (chi-square, 63 degrees of freedom: mean 63, sd 11.2)
+    cnt = np.bincount((u * 64).astype(int), minlength=64)
+    assert ((cnt - n / 64) ** 2 / (n / 64)).sum() < 63 + 5 * 11.3
