@@ -18,6 +18,7 @@
 #include "det_math.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 /* ---------------------------------------------------------------- exported raw pieces ------- */
 double ssme_oracle_dexp(double x) { return dm_exp(x); }
@@ -134,6 +135,39 @@ static int32_t descent_search(const double* C, int32_t np, int32_t n, double tau
     for (int32_t s = np / 2; s >= 1; s >>= 1)
         if (C[idx + s - 1] < tau) idx += s;
     return idx < n - 1 ? idx : n - 1;
+}
+
+/* ---- quantised multinomial targets ("detmath v3": Philox mode of the resident kernel, pf_kernel.cuh) -------------------
+ * With S in [2^E, 2^(E+1)): K = 2^(31-E) (an exact scaling), Q_i = trunc(C_i * K) as uint32 (saturating; NaN -> 0),
+ * q = trunc(S * K) in [2^31, 2^32).  Slot j with Philox word r_j draws the integer target g_j = floor(r_j * q / 2^32) in
+ * [0, q) and takes ancestor #{i : Q_i <= g_j} by a descent on integers (descent_search_u32).  Particle i is hit by Q_i - Q_{i-1} of the
+ * q equally likely targets, so selection probabilities equal the weights to 2^-31 absolute.  Injected uniforms keep the
+ * double rule (tau = u * S, C_i < tau), which is what FAITHFUL is compared with. */
+static uint32_t u32_trunc_sat(double v) /* PTX cvt.rzi.u32.f64 */
+{
+    if (!(v > 0.0)) return 0u; /* NaN, zero, negatives */
+    if (v >= 4294967296.0) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+static double quant_scale(double S)
+{
+    uint64_t b;
+    memcpy(&b, &S, sizeof(b));
+    const uint32_t hi = (uint32_t)(b >> 32);
+    const uint64_t kb = (uint64_t)((2077u - (hi >> 20)) << 20) << 32; /* 2^(1023 + 31 - biased exponent of S) */
+    double K;
+    memcpy(&K, &kb, sizeof(K));
+    return K;
+}
+/* the kernel's integer descent: the keys Q_0 .. Q_{np-2} are probed from the top (the kernel lays them out in descending
+ * order and counts the keys above the target); equals #{i : Q_i <= g} when Q is sorted, clamped to n-1 */
+static int32_t descent_search_u32(const uint32_t* Q, int32_t np, int32_t n, uint32_t g)
+{
+    int32_t p = 0; /* number of keys found above the target */
+    for (int32_t s = np / 2; s >= 1; s >>= 1)
+        if (Q[np - 1 - p - s] > g) p += s;
+    const int32_t a = np - 1 - p;
+    return a < n - 1 ? a : n - 1;
 }
 
 /* ---- tiled order (global-memory kernels, N beyond one CTA) ---------------------------------------
@@ -501,7 +535,22 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
                 C[N - 1] = 1.0;
             }
             const double total = canonical ? S : 1.0;
-            if (cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL) {
+            if (cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL && canonical && !tiled && !injected) {
+                /* the resident kernel's quantised targets */
+                const double K = quant_scale(S);
+                const uint32_t q = u32_trunc_sat(S * K);
+                uint32_t* Q = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)NP);
+                for (int32_t i = 0; i < NP; ++i) Q[i] = u32_trunc_sat(C[i] * K);
+                for (int32_t j = 0; j < N; ++j) {
+                    uint32_t wd[4];
+                    philox_block(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j >> 2, utag, wd);
+                    const uint32_t g = (uint32_t)(((uint64_t)wd[j & 3] * (uint64_t)q) >> 32);
+                    anc[j] = descent_search_u32(Q, NP, N, g);
+                    /* margin in units of the total: the integer target sits at (g + 1/2) / q between the keys it separates */
+                    upd_margin(&margin, C, anc[j], ((double)g + 0.5) / K, total);
+                }
+                free(Q);
+            } else if (cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL) {
                 for (int32_t j = 0; j < N; ++j) {
                     double u = injected ? ut[j]
                                         : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)j, utag);

@@ -71,10 +71,25 @@ __host__ __device__ constexpr int xslot(int i)
     return (L == 8 && NT <= 512) ? i + ((i >> 3) << 1) : i;
 }
 
+// The production multinomial kernel keeps the CDF as 32-bit integers (see "quantised targets" below); every other
+// instantiation keeps doubles.  The shared-memory size is that of the double layout for all of them.
 template <int L, int NT, typename MODEL>
 __host__ __device__ constexpr size_t filter_smem_bytes()
 {
     return sizeof(double) * (size_t)(2 * xslot<L, NT>(L * NT) + L * NT + 2 * kYChunk * MODEL::kObsStride + 64 + 64 + 32) + 16;
+}
+
+// ---- quantised multinomial targets ("detmath v3", Philox mode of the resident kernel) ------------------------------
+// With S in [2^E, 2^(E+1)) let K = 2^(31-E) (exact scaling), Q_i = trunc(C_i * K) as uint32 (saturating), q = trunc(S * K)
+// in [2^31, 2^32).  Slot j with Philox word r_j draws the integer target g_j = floor(r_j * q / 2^32) in [0, q) and takes
+// ancestor #{i : Q_i <= g_j} (the same descent, on integers).  Particle i is hit by Q_i - Q_{i-1} of the q equally likely
+// targets: selection probabilities are the weights to 2^-31 absolute.  The search then runs on 4-byte keys with integer
+// compares: half the shared-memory wavefronts of the 8-byte probes, no FP64-pipe compare, and "index = 2*index + (key <=
+// target)" is one add-with-carry.  Injected uniforms (parity runs) keep the double rule tau = u * S, C_i < tau.
+__device__ __forceinline__ double quant_scale(double S)
+{
+    const uint32_t hi = (uint32_t)__double2hiint(S);
+    return __hiloint2double((int)((2077u - (hi >> 20)) << 20), 0);  // 2^(1023 + 31 - biased exponent of S)
 }
 
 // ---- mbarrier / bulk-TMA helpers (PTX ISA: mbarrier, cp.async.bulk) ---------------------------
@@ -121,11 +136,13 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     constexpr int NW = NT / 32;
     constexpr int OS = MODEL::kObsStride;
     constexpr uint32_t kChunkBytes = kYChunk * OS * sizeof(double);
+    constexpr bool QUANT = (RESAMP == kResampMultinomial) && !DEBUG;  // 32-bit integer CDF and targets
+    constexpr uint32_t CB = QUANT ? 4u : 8u;                          // bytes per CDF entry
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NPX = xslot<L, NT>(NP);                    // padded length of one gather table
     double* Xs = reinterpret_cast<double*>(smem_raw);  // [2][NPX]
-    double* Cs = Xs + 2 * NPX;                         // [NP]
+    double* Cs = Xs + 2 * NPX;                         // [NP] doubles, or [NP] uint32 in the quantised production kernel
     double* ybuf = Cs + NP;                            // [2][kYChunk*OS]
     double* red_max = ybuf + 2 * kYChunk * OS;         // [32]
     double* red_sum = red_max + 32;                    // [32]
@@ -149,10 +166,21 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
     uint32_t eoff[L];
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-        const uint32_t v = (uint32_t)(i0 + k + 1);
+        // quantised tree: the keys are laid out in DESCENDING order (tree position of sorted index i is that of
+        // j = NP - 2 - i), see the descent below; entry NP-1 parks in the spare slot either way
+        const uint32_t v = QUANT ? (uint32_t)(NP - 1 - (i0 + k)) : (uint32_t)(i0 + k + 1);
         const int tz = __ffs((int)v) - 1;
-        const uint32_t node = (v == (uint32_t)NP) ? (uint32_t)(NP - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
-        eoff[k] = node * 8u;
+        const uint32_t node = (v == (uint32_t)NP || v == 0u) ? (uint32_t)(NP - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)));
+        eoff[k] = node * CB;
+    }
+    uint32_t eoffr[DEBUG ? L : 1];  // tracing kernel: positions of the descending layout, as doubles
+    if (DEBUG) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            const uint32_t v = (uint32_t)(NP - 1 - (i0 + k));
+            const int tz = __ffs((int)v) - 1;
+            eoffr[k] = ((v == 0u) ? (uint32_t)(NP - 1) : ((1u << (K - 1 - tz)) - 1u + (v >> (tz + 1)))) * 8u;
+        }
     }
 
     if (tid == 0) {
@@ -346,8 +374,22 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         lex = (lane > 0) ? lex : 0.0;
         const double base = __dadd_rn(wex, lex);
         unsigned char* Cb = reinterpret_cast<unsigned char*>(Cs);
+        // quantised targets (Philox-mode multinomial): the tracing kernel keeps the integers Q_i as doubles so that its
+        // one descent serves both rules
+        const bool quant = QUANT || (DEBUG && RESAMP == kResampMultinomial && !a.inject);
+        const double qK = quant_scale(S);
+        if (QUANT) {
 #pragma unroll
-        for (int k = 0; k < L; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
+            for (int k = 0; k < L; ++k)
+                *reinterpret_cast<uint32_t*>(Cb + eoff[k]) = __double2uint_rz(__dmul_rn(__dadd_rn(base, sc[k]), qK));
+        } else if (quant) {
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+                *reinterpret_cast<double*>(Cb + eoffr[k]) = (double)__double2uint_rz(__dmul_rn(__dadd_rn(base, sc[k]), qK));
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) *reinterpret_cast<double*>(Cb + eoff[k]) = __dadd_rn(base, sc[k]);
+        }
 
         const bool do_resample = DEBUG ? ((t + 1) % a.rs == 0) : true;
 
@@ -420,34 +462,39 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 
         // ---- resampling targets -------------------------------------------------------------
         double tau[L];
+        uint32_t tq[L];
         if (RESAMP == kResampMultinomial) {
             if (DEBUG && a.inject) {
 #pragma unroll
                 for (int k = 0; k < L; ++k)
                     tau[k] = (i0 + k < N) ? __dmul_rn(a.u_inj[((size_t)f * T + t) * a.stride_u + i0 + k], S) : 0.0;
-            } else if (L >= 4) {
-                // four 32-bit uniforms per Philox block: slot j uses word j & 3 of block j >> 2; tau = u * S with u = word * 2^-32
-                // (the power of two folds into S exactly)
-                const double S32 = __dmul_rn(S, 0x1p-32);
-#pragma unroll
-                for (int q = 0; q < L / 4; ++q) {
-                    const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
-                    tau[4 * q + 0] = __dmul_rn((double)r.x, S32);
-                    tau[4 * q + 1] = __dmul_rn((double)r.y, S32);
-                    tau[4 * q + 2] = __dmul_rn((double)r.z, S32);
-                    tau[4 * q + 3] = __dmul_rn((double)r.w, S32);
-                }
             } else {
-                // latency layouts: the 2 or 4 threads that share a block each compute it
-                const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
-                const double S32 = __dmul_rn(S, 0x1p-32);
-                if (L == 2) {
-                    const bool hi = (i0 & 2) != 0;
-                    tau[0] = __dmul_rn((double)(hi ? r.z : r.x), S32);
-                    tau[L - 1] = __dmul_rn((double)(hi ? r.w : r.y), S32);
+                // four 32-bit words per Philox block: slot j uses word j & 3 of block j >> 2; integer target g = floor(word * q / 2^32)
+                const uint32_t q = __double2uint_rz(__dmul_rn(S, qK));
+                if (L >= 4) {
+#pragma unroll
+                    for (int b = 0; b < L / 4; ++b) {
+                        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + b), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
+                        tq[4 * b + 0] = __umulhi(r.x, q);
+                        tq[4 * b + 1] = __umulhi(r.y, q);
+                        tq[4 * b + 2] = __umulhi(r.z, q);
+                        tq[4 * b + 3] = __umulhi(r.w, q);
+                    }
                 } else {
-                    const uint32_t w01 = (i0 & 1) ? r.y : r.x, w23 = (i0 & 1) ? r.w : r.z;
-                    tau[0] = __dmul_rn((double)((i0 & 2) ? w23 : w01), S32);
+                    // latency layouts: the 2 or 4 threads that share a block each compute it
+                    const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4), (uint32_t)tg, ctr2, ctr3 | 1u), a.rk);
+                    if (L == 2) {
+                        const bool hi = (i0 & 2) != 0;
+                        tq[0] = __umulhi(hi ? r.z : r.x, q);
+                        tq[L - 1] = __umulhi(hi ? r.w : r.y, q);
+                    } else {
+                        const uint32_t w01 = (i0 & 1) ? r.y : r.x, w23 = (i0 & 1) ? r.w : r.z;
+                        tq[0] = __umulhi((i0 & 2) ? w23 : w01, q);
+                    }
+                }
+                if (!QUANT) {  // tracing kernel: the integers travel as doubles
+#pragma unroll
+                    for (int k = 0; k < L; ++k) tau[k] = (double)tq[k];
                 }
             }
         } else if (RESAMP == kResampSortedMultinomial) {
@@ -528,23 +575,62 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         // ---- branch-free descent over the breadth-first CDF, then gather -------------------------
         // Probe sequence identical to "for (s = NP/2; s >= 1; s >>= 1) if (C[idx+s-1] < tau) idx += s".
         // nb = 8 * (node + 1): children 2*node+1 / 2*node+2 become 2*nb / 2*nb + 8, the probe address is Cb - 8 + nb
-        uint32_t nb[L];
-#pragma unroll
-        for (int k = 0; k < L; ++k) nb[k] = 8u;
-        const unsigned char* Cm = Cb - 8;
-#pragma unroll
-        for (int lvl = 0; lvl < K; ++lvl) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) {
-                const double v = *reinterpret_cast<const double*>(Cm + nb[k]);
-                nb[k] += nb[k];
-                if (v < tau[k]) nb[k] += 8u;
-            }
-        }
+        // Quantised targets: the keys Q_0 .. Q_{NP-2} sit in the tree in descending order, R_j = Q_{NP-2-j}, and the descent
+        // counts p = #{j : R_j > g} ("for (s = NP/2; s >= 1; s >>= 1) if (R[p+s-1] > g) p += s"); the ancestor is NP - 1 - p.
+        // With the 1-based heap index h (children 2h, 2h + 1) a level is "h = 2h + (key > g)": the carry-out of key + ~g is
+        // set exactly when key > g, so a level is one add that only produces the carry and one add-with-carry
+        // (SASS: IADD3 + IMAD.X), plus the address and the 4-byte load.
         int idx[L];
+        if (QUANT) {
+            uint32_t h[L], ng[L];
+#pragma unroll
+            for (int k = 0; k < L; ++k) { h[k] = 1u; ng[k] = ~tq[k]; }
+            const uint32_t* Qm = reinterpret_cast<const uint32_t*>(Cb) - 1;
+#pragma unroll
+            for (int lvl = 0; lvl < K; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const uint32_t v = Qm[h[k]];
+                    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(h[k]) : "r"(v), "r"(ng[k]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < L; ++k) idx[k] = min(2 * NP - 1 - (int)h[k], N - 1);
+        } else if (DEBUG && quant) {
+            uint32_t nb[L];
+#pragma unroll
+            for (int k = 0; k < L; ++k) nb[k] = 8u;
+            const unsigned char* Cm = Cb - 8;
+#pragma unroll
+            for (int lvl = 0; lvl < K; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const double v = *reinterpret_cast<const double*>(Cm + nb[k]);
+                    nb[k] += nb[k];
+                    if (v > tau[k]) nb[k] += 8u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < L; ++k) idx[k] = min(2 * NP - 1 - (int)(nb[k] >> 3), N - 1);
+        } else {
+            uint32_t nb[L];
+#pragma unroll
+            for (int k = 0; k < L; ++k) nb[k] = 8u;
+            const unsigned char* Cm = Cb - 8;
+#pragma unroll
+            for (int lvl = 0; lvl < K; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const double v = *reinterpret_cast<const double*>(Cm + nb[k]);
+                    nb[k] += nb[k];
+                    if (v < tau[k]) nb[k] += 8u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < L; ++k) idx[k] = min((int)(nb[k] >> 3) - NP, N - 1);
+        }
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            idx[k] = min((int)(nb[k] >> 3) - NP, N - 1);
             x[k] = Xcur[xslot<L, NT>(idx[k])];
             lwacc[k] = 0.0;
         }
