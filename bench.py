@@ -167,6 +167,32 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+K1_PROFILE = os.path.join("profiles", "r2_k1_final_L8_NT128.txt")
+
+
+def read_k1_profile():
+    """Instruction count per particle-step and HBM traffic per launch of K1, read from the committed ncu summary
+    (tools/ncu_summary.py output) so that the bench line cannot drift from the profile it quotes."""
+    out = {"file": K1_PROFILE, "instr_per_pstep": None, "traffic": None, "T": None}
+    try:
+        rd = wr = None
+        for ln in open(os.path.join(ROOT, K1_PROFILE)):
+            f = ln.split()
+            if ln.startswith("dram__bytes_read.sum"):
+                rd = float(f[-1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}[f[1]]
+            elif ln.startswith("dram__bytes_write.sum"):
+                wr = float(f[-1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}[f[1]]
+            elif ln.startswith("== SASS mix"):
+                out["instr_per_pstep"] = float(ln.split("total")[1].split(")")[0])
+            elif ln.startswith("profiled T"):
+                out["T"] = int(f[-1])
+        if rd is not None and wr is not None:
+            out["traffic"] = int(rd + wr)
+    except Exception:
+        pass
+    return out
+
+
 def workload_config(n_gpus):
     return {"workload": "batched SV bootstrap-filter log-likelihood: %d proposals x %d particles x T=%d per GPU, "
                         "multinomial resampling every step, R=%d (BASELINE.json configs[1])" % (P_PROPOSALS, N_PARTICLES, T_STEPS, R_REPL),
@@ -220,6 +246,12 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
                       "particle_steps_per_sec": C3_CHAINS * C3_R * C3_N * C3_T * C3_ITERS / r["seconds"],
                       "kernel": "K2 cluster (%d CTAs x %d threads x %d particles per filter)" % (C3_N // (c3_L * c3_threads), c3_threads, c3_L),
                       "sharding": "chains x replicates over %d rank(s), NCCL all-gather of %d log-likelihoods per iteration" % (world, C3_CHAINS * C3_R)}
+    if world > 1:
+        # the sharded evaluation (each rank its range + one NCCL all-gather) against the same batch evaluated locally
+        lme_s, pf_s = be.work_batch_sharded(start, R=C3_R, stream_base=10_000)
+        lme_l, pf_l = be.work_batch(start, R=C3_R, stream_base=10_000, return_per_filter=True)
+        out["config3"]["sharded_equals_local"] = bool(np.array_equal(pf_s, pf_l) and np.array_equal(lme_s, lme_l))
+        dist.barrier()
     be.close()
     # config 1 (one chain: the replicates are what is sharded)
     spy = os.path.join(ROOT, "tests", "golden", "spy_config1.npz")
@@ -248,36 +280,67 @@ def run_pmmh_legs(sb, dist, rank, world, local_rank):
 
 def run_spilled_leg(sb, dist, rank, world, local_rank, hbm_gbs):
     """BASELINE.json config 5: ONE SV filter with 2^28 particles (global-memory kernels K3), sharded by particles over
-    the ranks (K5: per step one NCCL all-reduce of the weight maximum, one all-gather of the tile weight sums, peer
-    reads of ancestors over NVLink).  Strong scaling: the filter is the same at every N.  Systematic resampling."""
-    N, T = 1 << 28, 8
+    the ranks (K5: tile maxima / sums pushed into every peer's HBM once per step, offspring written to the slot owner's HBM
+    over NVLink).  Strong scaling: the filter is the same at every N.  Systematic resampling.  Timed over T = 64 steps with
+    CUDA events on the handle's stream; with N > 1 the same filter at 2^24 particles is also run by rank 0 alone and compared
+    bit for bit (the canonical order is defined on tiles, not ranks)."""
+    import torch
+    N, T = 1 << 28, 64
     rng = np.random.default_rng(SEED_SERIES + 5)
     y = np.exp(0.1 * np.cumsum(rng.standard_normal(T))) * rng.standard_normal(T)
-    be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=N, resampler=sb.RESAMP_SYSTEMATIC,
-                                                  seed=SEED_FILTER + 5, device=local_rank))
-    be.add_observed_data(y)
-    if world > 1:
-        uid = [sb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        be.comm_init(uid[0], rank, world)
-        handles = [None] * world
-        dist.all_gather_object(handles, be.spill_ipc_export())
-        be.spill_ipc_import(b"".join(handles))
-        dist.barrier()
     theta = np.array([[1.0, 0.95, 0.0625]])
-    be.work_batch(theta, R=1, stream_base=0)  # warm-up (allocations, NCCL channels)
+
+    def make(n, w, r, shard):
+        be = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV, num_particles=n, resampler=sb.RESAMP_SYSTEMATIC,
+                                                      seed=SEED_FILTER + 5, device=local_rank))
+        be.add_observed_data(y)
+        if shard and w > 1:
+            uid = [sb.comm_unique_id() if r == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            be.comm_init(uid[0], r, w)
+            handles = [None] * w
+            dist.all_gather_object(handles, be.spill_ipc_export())
+            be.spill_ipc_import(b"".join(handles))
+            dist.barrier()
+        return be
+
+    be = make(N, world, rank, True)
+    be.work_batch(theta, R=1, stream_base=0)  # warm-up (allocations, peer mappings)
     if dist is not None:
         dist.barrier()
-    t0 = time.perf_counter()
+    stream = torch.cuda.ExternalStream(be.stream, device=torch.device("cuda", local_rank))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     ll = be.work_batch(theta, R=1, stream_base=1)[0]
-    dt = time.perf_counter() - t0
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
     be.close()
-    rate = N * T / dt
-    return {"particle_steps_per_sec": rate, "particles": N, "T": T, "seconds": dt, "ms_per_time_step": 1e3 * dt / T, "loglik": float(ll),
-            "resampler": "systematic", "sharding": "particles over %d rank(s)" % world,
-            "roofline": {"bound": "hbm", "achieved": rate * 48 / 1e9 / world, "peak": hbm_gbs, "unit": "GB/s", "frac": rate * 48 / 1e9 / world / hbm_gbs,
-                         "algorithmic_bytes_per_particle_step": 48, "note": "per GPU; SURVEY.md 8d: write x' 8 + write lw 8 + read lw 8 + write cdf 8 "
-                         "+ read cdf 8 + gather x 8; peak = MEASURED_PEAKS.json hbm_gbs (measured) or 6650 (fallback)"}}
+    out = {"particle_steps_per_sec": N * T / dt, "particles": N, "T": T, "seconds": dt, "ms_per_time_step": 1e3 * dt / T, "loglik": float(ll),
+           "resampler": "systematic", "sharding": "particles over %d rank(s)" % world, "timing": "CUDA events on the handle's stream, max over ranks"}
+    if world > 1:
+        n_small = 1 << 24
+        bs = make(n_small, world, rank, True)
+        ll_sharded = float(bs.work_batch(theta, R=1, stream_base=2)[0])
+        bs.close()
+        ll_single = None
+        if rank == 0:
+            b1 = make(n_small, 1, 0, False)
+            ll_single = float(b1.work_batch(theta, R=1, stream_base=2)[0])
+            b1.close()
+        dist.barrier()
+        out["cross_check"] = {"particles": n_small, "loglik_sharded": ll_sharded, "loglik_1gpu": ll_single,
+                              "bit_identical_to_1gpu": (ll_single is not None and ll_sharded == ll_single)}
+    rate = out["particle_steps_per_sec"]
+    out["roofline"] = {"bound": "hbm", "achieved": rate * 48 / 1e9 / world, "peak": hbm_gbs, "unit": "GB/s", "frac": rate * 48 / 1e9 / world / hbm_gbs,
+                       "algorithmic_bytes_per_particle_step": 48,
+                       "note": "per GPU; SURVEY.md 8d: write x' 8 + write lw 8 + read lw 8 + write cdf 8 + read cdf 8 + gather x 8; "
+                               "peak = MEASURED_PEAKS.json hbm_gbs (measured) or 6650 (fallback)"}
+    return out
 
 
 def run_liu_west_leg(sb, local_rank, hbm_gbs):
@@ -397,6 +460,22 @@ def run_ours(args):
     e2e_value = world * steps_per_pass * args.steps / e2e_s
     assert np.all(np.isfinite(out_host))
 
+    # ---- parity sample: four of this rank's headline filters, full T, against the CPU oracle (the checker, untimed) ----
+    parity_sample = None
+    if rank == 0:
+        try:
+            from oracle import binding as ob
+            pick = sorted({0, P_PROPOSALS // 3, 2 * P_PROPOSALS // 3, P_PROPOSALS - 1})
+            _, pf_host = be.work_batch(h_theta, R=R_REPL, stream_base=F_base, return_per_filter=True)
+            same = 0
+            for p_ in pick:
+                ref = ob.filter_run(theta[p_], y, N_PARTICLES, L=layout["scan_items_per_lane"], NT=layout["threads_per_filter"], seed=SEED_FILTER,
+                                    filter_id=F_base + p_ * R_REPL, trace=False)["loglik"]
+                same += int(ref == pf_host[p_, 0])
+            parity_sample = {"checked": len(pick), "bit_identical": same, "T": int(T_STEPS), "against": "oracle/pf_oracle.c CANONICAL"}
+        except Exception as ex:  # noqa: BLE001
+            parity_sample = {"error": repr(ex)[:200]}
+
     # ---- PMMH iterations/s (second half of BASELINE.json's metric): the C++ host loop behind the C ABI -----
     def guarded(fn):
         # the extra legs never sink the headline line: a failure is reported in place of the leg's numbers
@@ -447,6 +526,7 @@ def run_ours(args):
     fp32_mode = guarded(run_fp32_leg) if (not args.no_pmmh and rank == 0) else None
 
     if rank == 0:
+        prof = read_k1_profile()
         # ---- roofline of the dominant kernel (bootstrap_filter_kernel): FP64 pipe ----------------
         fma_rate = sb.measure_fp64_fma_rate(local_rank, 1 << 15)  # thread-level FMA instructions / s, measured now
         per_gpu = value / world
@@ -459,13 +539,15 @@ def run_ours(args):
             "frac_definition": "FP64-pipe issue slots: (31 FMA + 13 add/mul/cvt + 12 compare) per particle-step x particle-steps/s "
                                "/ measured FP64 FMA instruction rate (micro-benchmark in this run)",
             "frac_flops": achieved_tflops / peak_tflops,
-            "issue_slots": {"thread_instr_per_particle_step": 201.7, "source": "ncu SASS count, profiles/r1_k1_v2_L8_NT128.txt",
-                            "frac": (per_gpu * 201.7 / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
+            "issue_slots": {"thread_instr_per_particle_step": prof["instr_per_pstep"], "source": "ncu SASS count, " + prof["file"],
+                            "frac": (per_gpu * prof["instr_per_pstep"] / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6))
+                            if (clocks.get("sm_mhz") and prof["instr_per_pstep"]) else None,
                             "note": "what actually binds K1 (DESIGN.md section 5): 4 warp-instructions per SM per clock"},
             "peak_source": "measured in-run (ssme_b200_measure_fp64_fma_rate); "
             "MEASURED_PEAKS.json has no FP64 entry",
-            "traffic": 258048 if (P_PROPOSALS == 4096 and T_STEPS == 4096) else None,
-            "traffic_note": "HBM bytes per launch, ncu --set full: dram__bytes_read.sum 258048 + dram__bytes_write.sum 0 (profiles/r1_k1_v2_L8_NT128.txt)",
+            "traffic": prof["traffic"] if (P_PROPOSALS == 4096) else None,
+            "traffic_note": "HBM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, %s; that "
+                            "capture ran T = %s, the observation stream is the only T-dependent part)" % (prof["file"], prof["T"]),
             "hbm_note": "resident kernel: HBM traffic per launch is the observation stream + theta + outputs (~0.2 MB); not HBM-bound",
         }
         # ---- SURVEY.md 8(d)'s op-mix roofline: t_roof = sum_k W_k / R_k, every R_k measured now, each class alone -----
@@ -517,6 +599,30 @@ def run_ours(args):
                 cpu["pmmh_config1_loglik_cpu"] = float(o1[0])
         except Exception as ex:  # the baseline is a reported extra; never let it sink the GPU line
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        def compact(d):
+            # numbers and booleans only (notes dropped): these keys close the line so that they land in a stdout tail
+            if not isinstance(d, dict):
+                return d
+            if "error" in d:
+                return {"error": d["error"]}
+            return {k: (compact(v) if isinstance(v, dict) else v) for k, v in d.items()
+                    if isinstance(v, (int, float, bool, dict)) or v is None}
+
+        legs = {"pmmh": pmmh, "spilled_filter": spilled, "liu_west": liu_west, "fp32_mode": fp32_mode, "parity_sample": parity_sample}
+
+        def leg_ok(d):
+            if d is None:
+                return True
+            if "error" in d:
+                return False
+            return all(leg_ok(v) for v in d.values() if isinstance(v, dict))
+        legs_ok = all(leg_ok(v) for v in legs.values())
+        if parity_sample and "error" not in parity_sample:
+            legs_ok = legs_ok and parity_sample["bit_identical"] == parity_sample["checked"]
+        if spilled and "cross_check" in spilled:
+            legs_ok = legs_ok and bool(spilled["cross_check"]["bit_identical_to_1gpu"])
+        if pmmh and "config3" in pmmh and "sharded_equals_local" in pmmh["config3"]:
+            legs_ok = legs_ok and bool(pmmh["config3"]["sharded_equals_local"])
         line = {
             "metric": "sv_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -526,9 +632,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(P_PROPOSALS * 8)},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "pmmh": pmmh, "spilled_filter": spilled, "liu_west": liu_west, "fp32_mode": fp32_mode,
             "layout": layout, "wall_s_timed_region": t_wall, "checksum": checksum,
-            "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-10); all filter arithmetic f64",
+            "normal_draws": "float32 Box-Muller widened to f64 (Philox4x32-7); all filter arithmetic f64",
+            "legs_detail": {"pmmh": pmmh, "spilled_filter": spilled, "liu_west": liu_west, "fp32_mode": fp32_mode},
+            # compact copies, last on the line
+            "legs_ok": legs_ok, "parity_sample": parity_sample, "fp32_mode": compact(fp32_mode), "liu_west": compact(liu_west),
+            "pmmh": compact(pmmh), "spilled_filter": compact(spilled),
         }
         print(json.dumps(line))
     if dist is not None:

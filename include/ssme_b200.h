@@ -308,6 +308,12 @@ int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_p
  * (3) descent steps over a 1024-entry breadth-first CDF in shared memory -- each written as the filter kernel writes it. */
 int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4]);
 
+/* Diagnostic (parity tests): the device's float32 Box-Muller (ssme_b200/csrc/det_math.cuh) on the radius words
+ * first_word + i * stride, i < count, with one angle word; z0/z1 receive the two variates of each pair.  The reference draws
+ * its normals from pf::rvsamp::UnivNormSampler (std::normal_distribution); this is the generator that replaces it. */
+int ssme_b200_box_muller_words(int32_t device, uint32_t first_word, uint32_t count, uint32_t stride, uint32_t angle_word, float* z0_host,
+                               float* z1_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,7 +114,10 @@ static inline void dm_box_muller(uint32_t a, uint32_t b, float* z0, float* z1)
     for (int i = 7; i >= 0; --i) P = fmaf(P, f, DM_FLOG_P[i]);
     float lnm = fmaf(f * f, P, f);
     float lnu = fmaf((float)e, DM_LN2_F, lnm);
-    float r = sqrtf(-2.0f * lnu);
+    /* u = 1 (one radius word in 2^24) gives -2 ln u = -0: clamped to 2^-100, radius 2^-50 instead of 0 (the kernel's
+     * branch-free square root is correctly rounded on [2^-100, 2^100]) */
+    float v2 = -2.0f * lnu;
+    float r = sqrtf(v2 > 0x1p-100f ? v2 : 0x1p-100f);
     /* angle: quadrant from the top two bits, 24-bit fraction of a quarter turn below them */
     uint32_t quad = b >> 30;
     float t = (float)((b >> 6) & 0x00ffffffu) * 0x1p-24f;

@@ -24,6 +24,10 @@
 double ssme_oracle_dexp(double x) { return dm_exp(x); }
 double ssme_oracle_dlog(double x) { return dm_log(x); }
 void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1) { dm_box_muller(a, b, z0, z1); }
+void ssme_oracle_box_muller_words(uint32_t first, uint32_t count, uint32_t stride, uint32_t b, float* z0, float* z1)
+{
+    for (uint32_t i = 0; i < count; ++i) dm_box_muller(first + i * stride, b, &z0[i], &z1[i]);
+}
 double ssme_oracle_uniform53(uint32_t hi, uint32_t lo) { return dm_uniform53(hi, lo); }
 void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {

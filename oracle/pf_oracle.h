@@ -95,6 +95,9 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
  * (example/main.cpp:13), canonical float arithmetic, resampling at every step, Philox streams; x_trace is widened to double. */
 int ssme_oracle_filter_f32(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T, const double* cov,
                            double* loglik, double* cond_like, int32_t* ancestors, double* x_trace);
+/* the Box-Muller of det_math.h on the radius words first + i * stride, i < count, with one angle word (exhaustive parity of the
+ * kernel's branch-free square root with sqrtf: tests/test_gpu_parity.py) */
+void ssme_oracle_box_muller_words(uint32_t first, uint32_t count, uint32_t stride, uint32_t b, float* z0, float* z1);
 float ssme_oracle_fexp(float x);
 
 /*

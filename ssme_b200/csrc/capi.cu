@@ -963,6 +963,35 @@ int ssme_b200_measure_fp64_fma_rate(int32_t device, int32_t iters, double* fma_p
     return SSME_B200_OK;
 }
 
+// diagnostic: the device Box-Muller on a range of radius words (parity of the branch-free square root with sqrtf)
+__global__ void box_muller_words_kernel(uint32_t first, uint32_t count, uint32_t stride, uint32_t b, float* z0, float* z1)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float a0, a1;
+    box_muller(first + i * stride, b, a0, a1);
+    z0[i] = a0;
+    z1[i] = a1;
+}
+
+int ssme_b200_box_muller_words(int32_t device, uint32_t first_word, uint32_t count, uint32_t stride, uint32_t angle_word, float* z0_host,
+                               float* z1_host)
+{
+    if (!z0_host || !z1_host || count == 0) return fail(SSME_B200_EINVAL, "bad argument");
+    SSME_CUDA(cudaSetDevice(device));
+    float *d0 = nullptr, *d1 = nullptr;
+    SSME_CUDA(cudaMalloc(&d0, (size_t)count * sizeof(float)));
+    SSME_CUDA(cudaMalloc(&d1, (size_t)count * sizeof(float)));
+    box_muller_words_kernel<<<(count + 255) / 256, 256>>>(first_word, count, stride, angle_word, d0, d1);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaMemcpy(z0_host, d0, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(z1_host, d1, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d0);
+    cudaFree(d1);
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "box_muller_words failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4])
 {
     if (!rates || iters < 1) return fail(SSME_B200_EINVAL, "bad argument");

@@ -1,7 +1,9 @@
 // ssme_b200/csrc/spill_capi.cu -- host driver of K3 (spill_kernel.cuh) and of its multi-GPU form K5:
-// a single filter whose particles are sharded over the ranks by tiles, with, per time step, one NCCL
-// all-reduce (max of the log-weights) and one NCCL all-gather (tile weight sums, from which every rank
-// derives the global CDF offsets), and peer reads of the ancestors' states over NVLink (CUDA IPC).
+// a single filter whose particles are sharded over the ranks by tiles.  Per time step every rank writes the (maximum, total,
+// largest CDF entry) triples of its tiles into every peer's HBM (CUDA IPC, stores over NVLink) and raises a step-numbered flag
+// there; every rank then scans all tile totals itself (identical on all ranks), and the resampling kernel writes the offspring
+// into the slot owners' HBM and raises a second flag.  No collective library call on the data path (the sorted-multinomial
+// resampler still all-gathers the tile totals of its exponential spacings with NCCL).
 #include "capi_internal.h"
 
 #include <cstring>
@@ -19,14 +21,22 @@ struct SpillState {
     double* x_anc = nullptr;
     double* x_cur[2] = {nullptr, nullptr};
     double* lwc[2] = {nullptr, nullptr};
-    double *tmax = nullptr, *ttot = nullptr, *tclmax = nullptr, *carry = nullptr, *E = nullptr, *scal = nullptr, *sync_word = nullptr;
+    double *tmax = nullptr, *ttot = nullptr, *tclmax = nullptr, *carry = nullptr, *E = nullptr, *scal = nullptr, *sb = nullptr;
+    // exchange block (one allocation, exported over CUDA IPC): tmax [4 nb] | ttot [nb] | tclmax [nb] | flags [16 u64] | counters
+    unsigned char* xchg = nullptr;
+    size_t xchg_bytes = 0;
+    unsigned long long* flags = nullptr;
+    unsigned int* done_ctr = nullptr;
+    unsigned long long epoch = 0;  // launches of spill_step_kernel so far (the same on every rank)
+    unsigned char* peer_xchg[kMaxPeers] = {};
+    bool loopback = false;  // the "ranks" are handles of ONE process on one device, driven in lockstep on one stream
     double* scan2 = nullptr;  // two-launch tile scan: lanepref[1024], lanetot[1024], wtot[32], cmax[32]
     // sorted-multinomial resampling: scan of the exponential spacings (allocated on first use)
     double *ecdf = nullptr, *ettot = nullptr, *eE = nullptr, *ecarry = nullptr;
     const double* peer_x[2][kMaxPeers] = {};
     const double* peer_lwc[2][kMaxPeers] = {};
     double* peer_x_anc[kMaxPeers] = {};
-    void* opened[kMaxPeers][5] = {};
+    void* opened[kMaxPeers][6] = {};
     bool prepared = false, peers_ready = false;
     // Liu-West extras (allocated on first use)
     double* th_anc[4] = {};
@@ -77,16 +87,26 @@ static int prepare(ssme_b200_handle h)
         SSME_CUDA(cudaMalloc(&s->x_cur[i], s->local * sizeof(double)));
         SSME_CUDA(cudaMalloc(&s->lwc[i], s->local * sizeof(double)));
     }
-    SSME_CUDA(cudaMalloc(&s->tmax, (size_t)s->nb * 4 * sizeof(double)));  // K4 keeps 4 partial maxima per tile
-    SSME_CUDA(cudaMalloc(&s->ttot, (size_t)s->nb * sizeof(double)));
-    SSME_CUDA(cudaMalloc(&s->tclmax, (size_t)s->nb * sizeof(double)));
+    // exchange block: at least 2 MiB so that it is an allocation of its own (one IPC handle maps exactly this block)
+    {
+        const size_t doubles = (size_t)s->nb * 6;  // K4 keeps 4 partial maxima per tile in tmax
+        s->xchg_bytes = doubles * sizeof(double) + 16 * sizeof(unsigned long long) + 64;
+        if (s->xchg_bytes < ((size_t)2 << 20)) s->xchg_bytes = (size_t)2 << 20;
+        SSME_CUDA(cudaMalloc(&s->xchg, s->xchg_bytes));
+        SSME_CUDA(cudaMemset(s->xchg, 0, s->xchg_bytes));
+        s->tmax = reinterpret_cast<double*>(s->xchg);
+        s->ttot = s->tmax + (size_t)s->nb * 4;
+        s->tclmax = s->ttot + s->nb;
+        s->flags = reinterpret_cast<unsigned long long*>(s->tclmax + s->nb);
+        s->done_ctr = reinterpret_cast<unsigned int*>(s->flags + 16);
+        s->peer_xchg[s->rank] = s->xchg;
+    }
+    SSME_CUDA(cudaMalloc(&s->sb, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
     // per device: the two-launch tile scan stages up to 2 x 256 x 33 doubles
     SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 33 * (int)sizeof(double)));
     SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * (int)sizeof(double)));
-    SSME_CUDA(cudaMalloc(&s->sync_word, sizeof(double)));
-    SSME_CUDA(cudaMemset(s->sync_word, 0, sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->E, (size_t)s->NBP * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scal, 8 * sizeof(double)));
     for (int i = 0; i < 2; ++i) {
@@ -111,11 +131,11 @@ void spill_destroy(ssme_b200_handle h)
     SpillState* s = h->spill_state;
     if (!s) return;
     for (int r = 0; r < kMaxPeers; ++r)
-        for (int i = 0; i < 5; ++i)
+        for (int i = 0; i < 6; ++i)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->tmax); cudaFree(s->ttot); cudaFree(s->tclmax); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal); cudaFree(s->sync_word);
+    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->xchg); cudaFree(s->sb); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
@@ -173,16 +193,90 @@ static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& 
     return SSME_B200_OK;
 }
 
-static bool launch_propagate(int model, const SpillArgs& a, int tiles, cudaStream_t st)
+static bool launch_step(int model, const SpillArgs& a, int tiles, cudaStream_t st)
 {
-#define SSME_SPILL_MODEL(M)                                        \
-    if (model == M::kId) {                                          \
-        spill_propagate_kernel<M><<<tiles, kTileNT, 0, st>>>(a);    \
-        return true;                                                \
+#define SSME_SPILL_MODEL(M)                                   \
+    if (model == M::kId) {                                     \
+        spill_step_kernel<M><<<tiles, kTileNT, 0, st>>>(a);    \
+        return true;                                           \
     }
     SSME_FOR_EACH_MODEL(SSME_SPILL_MODEL)
 #undef SSME_SPILL_MODEL
     return false;
+}
+
+// Arguments of one bootstrap filter of the tile-relative order (K3; K5 when the handle has peers).
+static void bootstrap_args(ssme_b200_handle h, SpillState* s, SpillArgs& a, const double* theta_dev, uint64_t fid, double* cond_like, int* ancestors)
+{
+    memset(&a, 0, sizeof(a));
+    a.theta = theta_dev;
+    a.obs = h->d_obs;
+    a.N = s->N; a.nb = s->nb; a.Lp = s->Lp; a.NBP = s->NBP;
+    a.tile0 = s->tile0; a.tile1 = s->tile1; a.tiles_per_rank = s->tiles_per_rank;
+    a.T = (int)h->T;
+    a.seed = h->cfg.seed;
+    a.rk = philox_round_keys(h->cfg.seed);
+    a.fid = fid;
+    a.x_anc = s->x_anc;
+    a.tmax = s->tmax; a.ttot = s->ttot; a.tclmax = s->tclmax; a.carry = s->carry; a.E = s->E; a.scal = s->scal;
+    a.rel = 1;
+    a.sb = s->sb;
+    a.world = s->world;
+    a.rank = s->rank;
+    a.flags = s->flags;
+    a.done_ctr = s->done_ctr;
+    for (int r = 0; r < s->world; ++r) {
+        a.peer_x_anc[r] = s->peer_x_anc[r];
+        double* base = reinterpret_cast<double*>(s->peer_xchg[r]);
+        a.peer_tmax[r] = base;
+        a.peer_ttot[r] = base + (size_t)s->nb * 4;
+        a.peer_tclmax[r] = base + (size_t)s->nb * 5;
+        a.peer_flags[r] = reinterpret_cast<unsigned long long*>(base + (size_t)s->nb * 6);
+    }
+    a.cond_like = cond_like;
+    a.ancestors = ancestors;
+}
+
+// The three phases of one time step.  A: fused propagate / weight / tile scan (raises flag 0 in the peers).  B: scan of all tile
+// totals (waits for the peers' flag 0).  C: resampling (raises flag 1 in the peers; phase A of the next step waits for it).
+static int phase_a(ssme_b200_handle h, SpillState* s, SpillArgs& a, int t, cudaStream_t st)
+{
+    const int cur = t & 1;
+    a.t = t;
+    a.epoch = ++s->epoch;
+    a.x_cur = s->x_cur[cur];
+    a.lwc = s->lwc[cur];
+    for (int r = 0; r < s->world; ++r) { a.peer_x[r] = s->peer_x[cur][r]; a.peer_lwc[r] = s->peer_lwc[cur][r]; }
+    if (!launch_step(h->cfg.model, a, s->tiles_per_rank, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
+    count_launch(1);
+    return SSME_B200_OK;
+}
+static int phase_b(SpillState* s, SpillArgs& a, cudaStream_t st)
+{
+    launch_tile_scan(s, a, st);
+    count_launch(1);
+    return SSME_B200_OK;
+}
+static int phase_c(ssme_b200_handle h, SpillState* s, SpillArgs& a, bool resample, cudaStream_t st)
+{
+    const int tiles = s->tiles_per_rank;
+    if (!resample) {
+        if (s->world > 1) {  // the peers must still learn that this rank is done with the step's tile arrays
+            k5_signal_kernel<<<1, 1, 0, st>>>(a, 1);
+            count_launch(1);
+        }
+        return SSME_B200_OK;
+    }
+    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
+        spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a);
+    } else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
+        int rc = launch_sorted_resample(h, s, a, tiles, st);
+        if (rc) return rc;
+    } else {
+        spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a);
+    }
+    count_launch(1);
+    return SSME_B200_OK;
 }
 
 int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, unsigned R, uint64_t stream_base, double* per_filter_dev,
@@ -192,66 +286,49 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
     if (rc) return rc;
     SpillState* s = h->spill_state;
     if (!s->peers_ready) return fail(SSME_B200_ERUNTIME, "multi-rank spilled filter: exchange the IPC handles first (ssme_b200_spill_ipc_export/import)");
-    // NCCL is looked up only when there are peers: loading it in a single-GPU process could shadow the NCCL a host
-    // application (e.g. torch) brings along and loads later
-    NcclApi* nccl = (s->world > 1) ? nccl_api() : nullptr;
+    if (s->loopback) return fail(SSME_B200_ERUNTIME, "this handle is a loopback rank: run it through ssme_b200_spill_loopback_run");
     const int T = (int)h->T;
-    const int tiles = s->tiles_per_rank;
     cudaStream_t st = h->stream;
     for (size_t f = 0; f < F; ++f) {
         SpillArgs a;
-        memset(&a, 0, sizeof(a));
-        a.theta = theta_dev + (f / R) * (size_t)h->num_params;
-        a.obs = h->d_obs;
-        a.N = s->N; a.nb = s->nb; a.Lp = s->Lp; a.NBP = s->NBP;
-        a.tile0 = s->tile0; a.tile1 = s->tile1; a.tiles_per_rank = s->tiles_per_rank;
-        a.T = T;
-        a.seed = h->cfg.seed;
-        a.rk = philox_round_keys(h->cfg.seed);
-        a.fid = stream_base + f;
-        a.x_anc = s->x_anc;
-        a.tmax = s->tmax; a.ttot = s->ttot; a.tclmax = s->tclmax; a.carry = s->carry; a.E = s->E; a.scal = s->scal;
-        for (int r = 0; r < s->world; ++r) a.peer_x_anc[r] = s->peer_x_anc[r];
-        a.cond_like = cond_like_dev ? cond_like_dev + f * (size_t)T : nullptr;
-        a.ancestors = ancestors_dev ? ancestors_dev + f * (size_t)T * (size_t)s->N : nullptr;
+        bootstrap_args(h, s, a, theta_dev + (f / R) * (size_t)h->num_params, stream_base + f, cond_like_dev ? cond_like_dev + f * (size_t)T : nullptr,
+                       ancestors_dev ? ancestors_dev + f * (size_t)T * (size_t)s->N : nullptr);
         spill_init_kernel<<<1, 1, 0, st>>>(s->scal, s->N);
         for (int t = 0; t < T; ++t) {
-            const int cur = t & 1;
-            a.t = t;
-            a.x_cur = s->x_cur[cur];
-            a.lwc = s->lwc[cur];
-            for (int r = 0; r < s->world; ++r) { a.peer_x[r] = s->peer_x[cur][r]; a.peer_lwc[r] = s->peer_lwc[cur][r]; }
-            launch_propagate(h->cfg.model, a, tiles, st);
-            spill_reduce_max_kernel<<<1, 1024, 0, st>>>(a);
-            if (s->world > 1) {
-                int nrc = nccl->AllReduce(s->scal, s->scal, 1, kNcclFloat64, kNcclMax, h->nccl_comm, st);
-                if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllReduce failed: %s", nccl->GetErrorString(nrc));
-            }
-            spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a);
-            if (s->world > 1) {
-                int nrc = nccl->AllGather(s->ttot + s->tile0, s->ttot, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
-                if (nrc == 0) nrc = nccl->AllGather(s->tclmax + s->tile0, s->tclmax, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
-                if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", nccl->GetErrorString(nrc));
-            }
-            launch_tile_scan(s, a, st);
-            count_launch(4);
-            if (t + 1 < T || a.ancestors) {
-                if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
-                    spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a);
-                    if (s->world > 1) {
-                        // offspring are written into the slot owners' HBM: nobody may propagate before everybody has expanded
-                        int nrc = nccl->AllReduce(s->sync_word, s->sync_word, 1, kNcclFloat64, kNcclMax, h->nccl_comm, st);
-                        if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllReduce failed: %s", nccl->GetErrorString(nrc));
-                    }
-                } else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
-                    if ((rc = launch_sorted_resample(h, s, a, tiles, st))) return rc;
-                } else {
-                    spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a);
-                }
-                count_launch(1);
-            }
+            if ((rc = phase_a(h, s, a, t, st))) return rc;
+            if ((rc = phase_b(s, a, st))) return rc;
+            if ((rc = phase_c(h, s, a, t + 1 < T || a.ancestors, st))) return rc;
         }
         spill_store_kernel<<<1, 1, 0, st>>>(s->scal, per_filter_dev + f);
+        SSME_CUDA(cudaGetLastError());
+    }
+    return SSME_B200_OK;
+}
+
+// Loopback form of K5 (tests, single-GPU boxes): the n handles are the ranks of ONE sharded filter, all on the same device and
+// in this process; every phase is launched for all ranks on one stream before the next phase, so every flag a kernel waits
+// for has been raised by the time it runs.  Exercises the tile ranges, the peer pointers and the flag protocol of the
+// multi-GPU data plane without a second GPU.
+int spill_loopback_run(ssme_b200_handle* hs, int n, const double* theta_dev, size_t F, unsigned R, uint64_t stream_base, double* per_filter_dev)
+{
+    cudaStream_t st = hs[0]->stream;
+    const int T = (int)hs[0]->T;
+    for (size_t f = 0; f < F; ++f) {
+        SpillArgs a[kMaxPeers];
+        for (int r = 0; r < n; ++r) {
+            bootstrap_args(hs[r], hs[r]->spill_state, a[r], theta_dev + (f / R) * (size_t)hs[r]->num_params, stream_base + f, nullptr, nullptr);
+            spill_init_kernel<<<1, 1, 0, st>>>(hs[r]->spill_state->scal, hs[r]->spill_state->N);
+        }
+        int rc;
+        for (int t = 0; t < T; ++t) {
+            for (int r = 0; r < n; ++r)
+                if ((rc = phase_a(hs[r], hs[r]->spill_state, a[r], t, st))) return rc;
+            for (int r = 0; r < n; ++r)
+                if ((rc = phase_b(hs[r]->spill_state, a[r], st))) return rc;
+            for (int r = 0; r < n; ++r)
+                if ((rc = phase_c(hs[r], hs[r]->spill_state, a[r], t + 1 < T, st))) return rc;
+        }
+        for (int r = 0; r < n; ++r) spill_store_kernel<<<1, 1, 0, st>>>(hs[r]->spill_state->scal, per_filter_dev + (size_t)r * F + f);
         SSME_CUDA(cudaGetLastError());
     }
     return SSME_B200_OK;

@@ -1,11 +1,15 @@
 // ssme_b200/csrc/spill_kernel.cuh -- K3: the bootstrap filter for particle counts beyond one CTA
 // (BASELINE.json configs 4/5 sizes: 2^20 .. 2^28 particles).  Particles live in HBM; one time step is
-// five launches over tiles of kTile = 4096 particles (512 threads x 8):
-//   K3a propagate_kernel      x' = f(x_anc, z), lw = log g(y | x'), tile max          (reads 8 B, writes 16 B / particle)
-//   K3b reduce_max_kernel     M = max over tile maxima
-//   K3c weights_scan_kernel   w = exp(lw - M), tile-local inclusive scan in place     (reads 8 B, writes 8 B)
-//   K3d tile_scan_kernel      one CTA scans the tile totals -> tile ends E, total S, log p(y_t | y_{1:t-1})
-//   K3e resample_kernel       two-level descent (tiles, then inside the tile) + gather (reads ~16 B, writes 8 B)
+// THREE launches over tiles of kTile = 4096 particles (512 threads x 8) -- the "tile-relative" order:
+//   K3a spill_step_kernel     x' = f(x_anc, z), lw = log g(y | x'), tile max m_b, w = exp(lw - m_b), tile-local inclusive
+//                             scan cl, tile total T_b                                   (reads 8 B, writes 16 B / particle)
+//   K3d tile_scan_kernel      M = max_b m_b, s_b = exp(m_b - M), scan of T_b s_b -> tile ends E, total S, log p(y_t | y_{1:t-1})
+//   K3e expand / resample     global CDF C_i = E_{b-1} + cl_i s_b; systematic: offspring counts, no search; multinomial: two-level
+//                             descent + gather                                          (reads 16 B, writes 8 B / particle)
+// Weighting every tile relative to ITS OWN maximum removes the global maximum from the per-particle path: the log-weights never
+// travel through HBM (48 -> 32 bytes per particle-step of traffic) and a rank of the multi-GPU form (K5) needs nothing from
+// its peers until the tile totals are scanned -- one exchange of (m_b, T_b, max cl) per step.  The Liu-West kernels (K4) keep
+// the earlier five-launch order (propagate / reduce_max / weights_scan with the global maximum / tile scan / resample):
 // Same per-particle arithmetic and Philox streams as K1; the scan / search order is the oracle's "tiled"
 // order (oracle/pf_oracle.c: tiled_build / tiled_search), so results are bit-identical to it -- and
 // independent of how many GPUs the tiles are spread over (K5).
@@ -70,7 +74,56 @@ struct SpillArgs {
     // streaming use (one observation per call): row of `obs`, `cond_like` and `theta_bar_out` that belongs to step t is
     // t - row0; the whole-series entry points leave row0 = 0
     int row0;
+    // tile-relative order (bootstrap filter K3 / K5): tmax[b] = m_b is the tile's own maximum, lwc holds cl relative to it,
+    // sb[b] = exp(m_b - M) is formed by the tile scan.  rel = 0: the K4 order (global maximum in scal[0], sb unused).
+    int rel;
+    double* sb;  // [nb]
+    // K5 (one filter sharded over ranks): every rank keeps ALL tile triples; a rank writes its tiles' (m_b, T_b, max cl) into
+    // every peer's arrays and then raises its flag there (release at system scope); consumers spin on their local flags.
+    int world, rank;
+    unsigned long long epoch;            // launch number of this step's spill_step_kernel (same on every rank)
+    double* peer_tmax[kMaxPeers];        // per-rank base pointers of tmax / ttot / tclmax (own rank included)
+    double* peer_ttot[kMaxPeers];
+    double* peer_tclmax[kMaxPeers];
+    unsigned long long* peer_flags[kMaxPeers];  // per rank: [0..7] "triples of step e written" by source rank, [8..15] "resampling
+                                                // of step e done" by source rank
+    unsigned long long* flags;           // this rank's flag block
+    unsigned int* done_ctr;              // [2] CTA counters (last CTA of a launch raises the flags)
 };
+
+// ---- K5 flag protocol -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread per CTA: wait until every peer has raised flag `which` (0 = triples, 1 = resampling done) to at least `e`
+__device__ __forceinline__ void k5_wait(const SpillArgs& a, int which, unsigned long long e)
+{
+    for (int r = 0; r < a.world; ++r) {
+        if (r == a.rank) continue;
+        while (ld_acquire_sys(a.flags + which * 8 + r) < e) __nanosleep(64);
+    }
+}
+// called by thread 0 of every CTA after its last (possibly remote) store: the last CTA of the launch raises this rank's flag
+// `which` in every peer's block
+__device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which, unsigned int nctas)
+{
+    __threadfence_system();
+    const unsigned int old = atomicAdd(a.done_ctr + which, 1u);
+    if (old == nctas - 1u) {
+        a.done_ctr[which] = 0u;
+        __threadfence_system();
+        for (int r = 0; r < a.world; ++r)
+            if (r != a.rank) st_release_sys(a.peer_flags[r] + which * 8 + a.rank, a.epoch);
+    }
+}
+__global__ void k5_signal_kernel(const SpillArgs a, int which) { k5_signal_last_cta(a, which, 1u); }
 
 template <typename MODEL>
 __global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const SpillArgs a)
@@ -134,7 +187,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const Spill
     }
 }
 
-// M = max over the tile maxima of this rank's tiles (the ranks' maxima are then max-reduced by NCCL)
+// M = max over the tile maxima of this rank's tiles (K4 order)
 __global__ void __launch_bounds__(1024) spill_reduce_max_kernel(const SpillArgs a)
 {
     __shared__ double red[32];
@@ -192,7 +245,103 @@ __device__ __forceinline__ double tile_scan_finish(double (&sc)[kTileL], double*
     return total;
 }
 
-// w = exp(lw - M) and the CTA scan of K1 (lane-local sequential, Kogge-Stone over lanes, Kogge-Stone over warps)
+// K3a, tile-relative order: propagate + log-weight + tile maximum + weights relative to it + tile-local scan, one pass.
+// HBM: reads x_anc (8 B), writes x' and cl (16 B) per particle; the log-weights stay in registers.
+template <typename MODEL>
+__global__ void __launch_bounds__(kTileNT, 2) spill_step_kernel(const SpillArgs a)
+{
+    constexpr int NW = kTileNT / 32;
+    __shared__ double red[NW];
+    __shared__ double red_sum[32];
+    __shared__ double red_max[32];
+    constexpr int OS = MODEL::kObsStride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = a.tile0 + blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;                      // global particle index
+    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;  // index into this rank's arrays
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    // K5: the ancestors of this step were written by the peers' resampling kernels of the previous one
+    if (a.world > 1 && a.epoch > 1) {
+        if (tid == 0) k5_wait(a, 1, a.epoch - 1);
+        __syncthreads();
+    }
+    const typename MODEL::Params mc = MODEL::init(a.theta);
+    const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)(a.t - a.row0) * OS);
+    const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
+    double z[kTileL];
+#pragma unroll
+    for (int q = 0; q < kTileL / 4; ++q) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
+        float z0, z1, z2, z3;
+        box_muller(r.x, r.y, z0, z1);
+        box_muller(r.z, r.w, z2, z3);
+        z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
+    }
+    double x[kTileL];
+    if (a.t > 0) {
+#pragma unroll
+        for (int k = 0; k < kTileL; k += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(a.x_anc + l0 + k);
+            x[k] = v.x; x[k + 1] = v.y;
+        }
+    }
+    double lw[kTileL];
+    double mloc = ninf;
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) {
+        x[k] = (a.t == 0) ? MODEL::q1(mc, ms, z[k]) : MODEL::f(mc, ms, x[k], z[k]);
+        double v = MODEL::logg(mc, ms, x[k]);
+        v = (i0 + k < a.N) ? v : ninf;
+        lw[k] = v;
+        mloc = (v > mloc) ? v : mloc;
+    }
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.x_cur + l0 + k) = make_double2(x[k], x[k + 1]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(mloc, d);
+        mloc = (other > mloc) ? other : mloc;
+    }
+    if (lane == 0) red[warp] = mloc;
+    __syncthreads();
+    double mb = (lane < NW) ? red[lane] : ninf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(mb, d);
+        mb = (other > mb) ? other : mb;
+    }
+    const double mref = (mb == ninf) ? 0.0 : mb;  // a tile without a finite log-weight: every weight is exp(-inf - 0) = 0
+    double sc[kTileL];
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) {
+        const double w = dexp_nonpos(__dsub_rn(lw[k], mref));
+        sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
+    }
+    const double Tb = tile_scan_finish(sc, red_sum, lane, warp);
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(sc[k], sc[k + 1]);
+    double cmax = sc[kTileL - 1];  // non-decreasing inside a thread
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(cmax, d);
+        cmax = (other > cmax) ? other : cmax;
+    }
+    if (lane == 0) red_max[warp] = cmax;
+    if (a.world > 1) __threadfence_system();  // x' and cl of this tile are read by the peers' resampling kernels
+    __syncthreads();
+    if (tid == 0) {
+        double m = red_max[0];
+        for (int g = 1; g < NW; ++g) m = (red_max[g] > m) ? red_max[g] : m;
+        for (int r = 0; r < a.world; ++r) {  // own arrays and, sharded, every peer's (remote stores over NVLink)
+            a.peer_tmax[r][tile] = mb;
+            a.peer_ttot[r][tile] = Tb;
+            a.peer_tclmax[r][tile] = m;
+        }
+        if (a.world > 1) k5_signal_last_cta(a, 0, gridDim.x);
+    }
+}
+
+// w = exp(lw - M) and the CTA scan of K1, K4 order (lane-local sequential, Kogge-Stone over lanes, Kogge-Stone over warps)
 __global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const SpillArgs a)
 {
     constexpr int NW = kTileNT / 32;
@@ -263,12 +412,65 @@ __global__ void __launch_bounds__(kTileNT) spill_expo_scan_kernel(const SpillArg
     if (tid == 0) a.ettot[tile] = tot;
 }
 
+// Tile-relative order: M = max_b m_b over ALL tiles of the filter, by the whole CTA; the result lands in *out (shared memory).
+__device__ __forceinline__ void tile_relative_max(const SpillArgs& a, int tid, int nthreads, double* out)
+{
+    __shared__ double pro_red[32];
+    const int lane = tid & 31, warp = tid >> 5;
+    double m = __longlong_as_double(0xfff0000000000000ll);
+    for (int b = tid; b < a.nb; b += nthreads) {
+        const double v = a.tmax[b];
+        m = (v > m) ? v : m;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(m, d);
+        m = (other > m) ? other : m;
+    }
+    if (lane == 0) pro_red[warp] = m;
+    __syncthreads();
+    if (warp == 0) {
+        m = (lane < nthreads / 32) ? pro_red[lane] : __longlong_as_double(0xfff0000000000000ll);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(m, d);
+            m = (other > m) ? other : m;
+        }
+        if (lane == 0) *out = m;
+    }
+    __syncthreads();
+}
+
+// ... then, for the tiles [b_lo, b_hi) of this thread, s_b = exp(m_b - M), and the tile total and the largest tile-local CDF
+// entry are rescaled in place (multiplication by s_b >= 0 is monotone, so the largest entry stays the largest).  A thread only
+// ever re-reads the tiles it rescaled itself.
+__device__ __forceinline__ void tile_relative_prologue(const SpillArgs& a, int b_lo, int b_hi, int tid, int nthreads, bool store_M)
+{
+    __shared__ double pro_M;
+    tile_relative_max(a, tid, nthreads, &pro_M);
+    const double M = pro_M;
+    if (store_M) a.scal[0] = M;
+    for (int b = b_lo; b < b_hi && b < a.nb; ++b) {
+        const double s = dexp_nonpos(__dsub_rn(a.tmax[b], M));
+        a.sb[b] = s;
+        a.ttot[b] = __dmul_rn(a.ttot[b], s);
+        a.tclmax[b] = __dmul_rn(a.tclmax[b], s);
+    }
+}
+
 // one CTA: canonical scan of the nb tile totals with Lp items per lane; E[b] for all NBP padded entries
 __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const SpillArgs a)
 {
     __shared__ double red_sum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = tid * a.Lp;
+    if (a.rel) {
+        if (a.world > 1 && a.cl_mode != 3) {  // K5: the peers' tile triples of this step
+            if (tid == 0) k5_wait(a, 0, a.epoch);
+            __syncthreads();
+        }
+        if (a.cl_mode != 3) tile_relative_prologue(a, b0, b0 + a.Lp, tid, kTileScanNT, tid == 0);
+    }
     double tot = 0.0;
 #pragma unroll 8
     for (int k = 0; k < a.Lp; ++k) {
@@ -342,7 +544,7 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
         }
     }
     if (tid == 0) {
-        const double M = a.scal[0], logN = a.scal[3];
+        const double M = a.scal[0], logN = a.scal[3];  // (tile-relative order: written by this thread in the prologue)
         if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
             a.scal[5] = S;
             return;
@@ -371,6 +573,26 @@ __global__ void __launch_bounds__(kScan2NT) spill_tile_scan_a_kernel(const Spill
     extern __shared__ double sh2[];  // [Lp][33]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = blockIdx.x, Lp = a.Lp, per = 32 * Lp, first = w * per;
+    if (a.rel && a.cl_mode != 3) {
+        if (a.world > 1) {  // K5: the peers' tile triples of this step
+            if (tid == 0) k5_wait(a, 0, a.epoch);
+            __syncthreads();
+        }
+        // thread tid rescales the tiles first + tid, first + tid + 256, ... that it stages below
+        __shared__ double proM;
+        tile_relative_max(a, tid, kScan2NT, &proM);
+        const double M = proM;
+        if (w == 0 && tid == 0) a.scal[0] = M;
+        for (int i = tid; i < per; i += kScan2NT) {
+            const int b = first + i;
+            if (b < a.nb) {
+                const double s = dexp_nonpos(__dsub_rn(a.tmax[b], M));
+                a.sb[b] = s;
+                a.ttot[b] = __dmul_rn(a.ttot[b], s);
+                a.tclmax[b] = __dmul_rn(a.tclmax[b], s);
+            }
+        }
+    }
     for (int i = tid; i < per; i += kScan2NT) {
         const int b = first + i;
         sh2[(i % Lp) * 33 + i / Lp] = (b < a.nb) ? a.ttot[b] : 0.0;
@@ -578,6 +800,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
         sh_range[1] = 0;
     }
     const double O = (tile > 0) ? a.E[tile - 1] : 0.0;
+    const double sbv = a.rel ? a.sb[tile] : 1.0;  // tile-relative order: C_i = O_b + cl_i s_b  (times 1.0 is exact: K4 order unchanged)
     double c[kTileL];
 #pragma unroll
     for (int k = 0; k < kTileL; k += 2) {
@@ -587,7 +810,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
     double m = ninf;
 #pragma unroll
     for (int k = 0; k < kTileL; ++k) {
-        const double v = __dadd_rn(O, c[k]);
+        const double v = __dadd_rn(O, __dmul_rn(c[k], sbv));
         m = (v > m) ? v : m;
         c[k] = m;  // running maximum inside the thread
     }
@@ -721,6 +944,11 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
         for (int k = 0; k < kTileL; ++k)
             for (int sl = A[k]; sl < A[k + 1]; ++sl) a.ancestors[(size_t)a.t * a.N + sl] = i0 + k;
     }
+    if (a.world > 1) {  // K5: the offspring went into the slot owners' HBM; tell every peer when this rank is done
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x);
+    }
 }
 
 // Multinomial resampling: slot j draws its own target (i.i.d.), finds its tile by the descent over E and its position
@@ -756,12 +984,13 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
         for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;
         b = min(b, a.nb - 1);
         const double O = (b > 0) ? a.E[b - 1] : 0.0;
+        const double sbv = a.rel ? a.sb[b] : 1.0;
         const int owner = b / a.tiles_per_rank;
         const size_t lbase = (size_t)(b - owner * a.tiles_per_rank) * kTile;
         const double* cl = a.peer_lwc[owner] + lbase;
         int idx = 0;
 #pragma unroll
-        for (int s = kTile / 2; s >= 1; s >>= 1) idx += (__dadd_rn(O, cl[idx + s - 1]) < tau) ? s : 0;
+        for (int s = kTile / 2; s >= 1; s >>= 1) idx += (__dadd_rn(O, __dmul_rn(cl[idx + s - 1], sbv)) < tau) ? s : 0;
         long long i = (long long)b * kTile + idx;
         if (i > (long long)a.N - 1) {  // clamp to the last real particle (it lives in the last tile)
             i = (long long)a.N - 1;
@@ -770,6 +999,10 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
         a.x_anc[(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid] = a.peer_x[owner][lbase + idx];
         for (int e = 0; e < a.nextra; ++e) a.extra_anc[e][(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid] = a.extra_cur[e][i];
         if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
+    }
+    if (a.world > 1) {  // K5: this rank has finished reading the peers' x' and cl of this step
+        __syncthreads();
+        if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x);
     }
 }
 

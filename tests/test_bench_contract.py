@@ -39,3 +39,7 @@ def test_gpu_arm_contract():
     assert 0 < d["roofline"]["frac"] < 1.2
     assert d["cpu_baseline"]["value"] > 1e5 and d["cpu_baseline"]["cores"] >= 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the bench checks itself: a sample of the timed filters against the oracle, and no leg may have failed
+    assert d["parity_sample"]["checked"] == 4 and d["parity_sample"]["bit_identical"] == 4
+    assert d["legs_ok"] is True
+    assert list(d)[-2:] == ["pmmh", "spilled_filter"]

@@ -282,3 +282,23 @@ def test_opmix_micro_benchmarks_run():
     assert set(r) == {"exp", "normal", "uniform", "search_step"}
     assert all(v > 1e10 for v in r.values())
     assert sb.measure_fp64_fma_rate(0, 1 << 12) > 1e12
+
+
+def test_box_muller_all_radius_words(oracle):
+    """The device Box-Muller (branch-free correctly rounded square root, det_math.cuh: fsqrt_rn_normal) against the oracle's
+    (sqrtf) on ALL 2^24 radius values (the generator uses the top 24 bits of the first word), for three angle words."""
+    import ctypes as C
+    import ssme_b200 as sb
+    lib = sb.load_library()
+    fp = C.POINTER(C.c_float)
+    lib.ssme_b200_box_muller_words.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, fp, fp]
+    L = oracle.lib()
+    L.ssme_oracle_box_muller_words.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, fp, fp]
+    L.ssme_oracle_box_muller_words.restype = None
+    n = 1 << 24
+    g0, g1, o0, o1 = (np.empty(n, dtype=np.float32) for _ in range(4))
+    p = lambda a: a.ctypes.data_as(fp)
+    for first, stride, b in [(0, 256, 0x12345678), (0xFF, 256, 0xC0000040), (0, 256, 0x7FFFFFC0)]:
+        assert lib.ssme_b200_box_muller_words(0, first, n, stride, b, p(g0), p(g1)) == 0
+        L.ssme_oracle_box_muller_words(first, n, stride, b, p(o0), p(o1))
+        assert np.array_equal(g0.view(np.uint32), o0.view(np.uint32)) and np.array_equal(g1.view(np.uint32), o1.view(np.uint32))
