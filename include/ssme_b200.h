@@ -271,14 +271,25 @@ int32_t ssme_b200_model(ssme_b200_handle h);
 /* ---- one filter sharded by particles over the ranks (N > 8192, "spilled" mode) --------------------------
  * The reference keeps a filter's particles in std::array members of one object on one thread
  * (univ_svol_bootstrap_filter.h:18 -> pf BSFilter); nothing there shards a filter.  Here rank r owns a
- * contiguous range of 4096-particle tiles; per time step the ranks all-reduce the weight maximum and
- * all-gather the tile weight sums (NCCL), and read ancestors' states from each other's HBM over NVLink.
- * After ssme_b200_comm_init, every rank exports five CUDA-IPC handles (320 bytes), the launcher gathers
- * them ([world][320], rank order) and every rank imports the lot.  All ranks then call the same
- * ssme_b200_loglike_batch / ssme_b200_filter_trace with the same arguments and get the same results,
- * which are bit-identical to the single-GPU run. */
-int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t handles_out[320]);
+ * contiguous range of 4096-particle tiles.  Per time step every rank writes the (maximum, weight total, largest
+ * CDF entry) of its tiles straight into every peer's HBM and raises a step-numbered flag there; every rank then scans
+ * all tile totals itself; the resampling kernel writes offspring into the slot owners' HBM (systematic) or reads the
+ * ancestors from the owners' HBM (multinomial) over NVLink and raises a second flag.  No collective call on that path.
+ * After ssme_b200_comm_init (which fixes rank and world), every rank exports six CUDA-IPC handles (384 bytes), the
+ * launcher gathers them ([world][384], rank order) and every rank imports the lot.  All ranks then call the same
+ * ssme_b200_loglike_batch / ssme_b200_filter_trace with the same arguments and get the same results, which are
+ * bit-identical to the single-GPU run (the summation order is defined on tiles, not on ranks). */
+int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t handles_out[384]);
 int ssme_b200_spill_ipc_import(ssme_b200_handle h, const uint8_t* all_handles);
+
+/* The same sharded filter with all n "ranks" (2..8 handles, same device, same config and series, not yet used) inside ONE
+ * process: connect wires the handles to each other's buffers directly; run launches every phase of a time step for all ranks
+ * on one stream before the next phase.  per_rank_loglik_host [n][num_proposals * R]: every rank's copy of the result (all
+ * equal, and equal to the single-handle run).  For tests and single-GPU boxes: it exercises the tile ranges, the peer
+ * stores and the flag protocol of the multi-GPU data plane without a second GPU. */
+int ssme_b200_spill_loopback_connect(ssme_b200_handle* handles, int32_t n);
+int ssme_b200_spill_loopback_run(ssme_b200_handle* handles, int32_t n, const double* theta_host, size_t num_proposals, uint32_t R,
+                                 uint64_t stream_base, double* per_rank_loglik_host);
 
 /* Replaces: the reduction at the end of thread_pool::worker_thread (thread_pool.h:263-268) on its own:
  * out[p] = log-mean-exp of values[p*R .. p*R+R).  HOST buffers; runs kernel K6 on `device`. */

@@ -184,6 +184,7 @@ typedef struct {
     int32_t N, TS, L, nb, Lp, NBP;
     double* cl;  /* [nb*TS] tile-local inclusive prefixes */
     double* E;   /* [NBP] inclusive tile ends (padded) */
+    double* sb;  /* [nb] tile scale: 1 in the global-maximum order, exp(m_b - M) in the tile-relative order */
     double S;
 } tiled_cdf_t;
 
@@ -196,8 +197,10 @@ static void tiled_alloc(tiled_cdf_t* c, int32_t N, int32_t TS, int32_t L)
     c->Lp = Lp; c->NBP = 1024 * Lp;
     c->cl = (double*)malloc(sizeof(double) * (size_t)c->nb * (size_t)TS);
     c->E = (double*)malloc(sizeof(double) * (size_t)c->NBP);
+    c->sb = (double*)malloc(sizeof(double) * (size_t)c->nb);
+    for (int32_t b = 0; b < c->nb; ++b) c->sb[b] = 1.0;
 }
-static void tiled_free(tiled_cdf_t* c) { free(c->cl); free(c->E); }
+static void tiled_free(tiled_cdf_t* c) { free(c->cl); free(c->E); free(c->sb); }
 static int injected_mode(const ssme_oracle_cfg* cfg) { return cfg->rng_mode == SSME_OR_RNG_INJECTED; }
 
 static void tiled_build(tiled_cdf_t* c, const double* w)
@@ -211,6 +214,37 @@ static void tiled_build(tiled_cdf_t* c, const double* w)
     free(tt);
 }
 
+/* Tile-relative order (cfg->tiled == 3; spill_step_kernel): every tile is weighted relative to ITS OWN maximum m_b,
+ * w_i = exp(lw_i - m_b) (m_b = -inf, a tile without a finite log-weight, counts as 0: all its weights are exp(-inf) = 0), scanned
+ * inside the tile as above (cl_i, total T_b).  Then M = max_b m_b, s_b = exp(m_b - M), the tile totals T_b s_b are scanned as
+ * above (E_b, S) and C_i = O_b + cl_i s_b.  Returns M. */
+static double tiled_build_rel(tiled_cdf_t* c, const double* lw, double* w_out)
+{
+    double* tt = (double*)calloc((size_t)c->nb, sizeof(double));
+    double* mb = (double*)calloc((size_t)c->nb, sizeof(double));
+    double* w = (double*)calloc((size_t)c->TS, sizeof(double));
+    double M = -INFINITY;
+    for (int32_t b = 0; b < c->nb; ++b) {
+        int32_t n_b = c->N - b * c->TS < c->TS ? c->N - b * c->TS : c->TS;
+        double m = -INFINITY;
+        for (int32_t i = 0; i < n_b; ++i) if (lw[(size_t)b * c->TS + i] > m) m = lw[(size_t)b * c->TS + i];
+        mb[b] = m;
+        if (m > M) M = m;
+        const double mref = (m == -INFINITY) ? 0.0 : m;
+        for (int32_t i = 0; i < n_b; ++i) w[i] = dm_exp(lw[(size_t)b * c->TS + i] - mref);
+        ssme_oracle_canonical_scan(w, n_b, c->L, c->TS, c->cl + (size_t)b * c->TS, &tt[b]);
+    }
+    for (int32_t b = 0; b < c->nb; ++b) {
+        c->sb[b] = dm_exp(mb[b] - M);
+        tt[b] = tt[b] * c->sb[b];
+    }
+    ssme_oracle_canonical_scan(tt, c->nb, c->Lp, c->NBP, c->E, &c->S);
+    if (w_out) /* weights relative to the global maximum, for reporting only */
+        for (int32_t i = 0; i < c->N; ++i) w_out[i] = dm_exp(lw[i] - M);
+    free(tt); free(mb); free(w);
+    return M;
+}
+
 static int32_t tiled_search(const tiled_cdf_t* c, double tau)
 {
     int32_t b = 0;
@@ -219,9 +253,10 @@ static int32_t tiled_search(const tiled_cdf_t* c, double tau)
     if (b > c->nb - 1) b = c->nb - 1;
     const double O = (b > 0) ? c->E[b - 1] : 0.0;
     const double* cl = c->cl + (size_t)b * c->TS;
+    const double sb = c->sb[b]; /* times 1.0 is exact: the global-maximum order is unchanged */
     int32_t idx = 0;
     for (int32_t s = c->TS / 2; s >= 1; s >>= 1)
-        if (O + cl[idx + s - 1] < tau) idx += s;
+        if (O + cl[idx + s - 1] * sb < tau) idx += s;
     int64_t i = (int64_t)b * c->TS + idx;
     return (int32_t)(i < c->N - 1 ? i : c->N - 1);
 }
@@ -259,7 +294,7 @@ static void systematic_by_counts(const tiled_cdf_t* c, int32_t N, double u0, dou
 static double tiled_value(const tiled_cdf_t* c, int32_t i)
 {
     int32_t b = i / c->TS;
-    return ((b > 0) ? c->E[b - 1] : 0.0) + c->cl[i];
+    return ((b > 0) ? c->E[b - 1] : 0.0) + c->cl[i] * c->sb[b];
 }
 
 /* ---------------------------------------------------------------- densities ------------------ */
@@ -422,7 +457,7 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
     }
     const int tiled = canonical && cfg->tiled;
     tiled_cdf_t tc, te; /* weights; exponential spacings of the sorted-multinomial resampler */
-    te.cl = NULL; te.E = NULL;
+    te.cl = NULL; te.E = NULL; te.sb = NULL;
     if (tiled) {
         if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL && injected_mode(cfg)) return -8;
         int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
@@ -489,7 +524,11 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         double M = -INFINITY;
         for (int32_t i = 0; i < N; ++i) if (lw[i] > M) M = lw[i];
         double S;
-        if (canonical) {
+        if (tiled && cfg->tiled == 3) {
+            M = tiled_build_rel(&tc, lw, w);
+            S = tc.S;
+            for (int32_t i = 0; i < N; ++i) C[i] = tiled_value(&tc, i);
+        } else if (canonical) {
             for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lw[i] - M);
             if (tiled) {
                 tiled_build(&tc, w);
@@ -606,7 +645,7 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
             } else { /* systematic: u_j = (j + u0)/N, spec'd by us (not in the reference tree) */
                 double u0 = injected ? ut[0] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
                 double sN = S / (double)N;
-                if (tiled && cfg->tiled == 2) systematic_by_counts(&tc, N, u0, sN, anc);
+                if (tiled && cfg->tiled >= 2) systematic_by_counts(&tc, N, u0, sN, anc);
                 else
                 for (int32_t j = 0; j < N; ++j) {
                     double tau = canonical ? ((double)j + u0) * sN : ((double)j + u0) / (double)N;
@@ -748,7 +787,7 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
     if (st && (!st->u_prior || !st->z_state || !st->z_jitter || !st->u_resamp || (form == 1 && !st->u_aux))) return -6;
     const double a = (3.0 * delta - 1.0) / (2.0 * delta), h2 = 1.0 - a * a, oma = 1.0 - a;
     tiled_cdf_t tc, te; /* weights; exponential spacings of the sorted-multinomial resampler (mn_resamp_states_and_params) */
-    te.cl = NULL; te.E = NULL;
+    te.cl = NULL; te.E = NULL; te.sb = NULL;
     if (canonical) tiled_alloc(&tc, N, nt * L, L);
     const int sorted = (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL);
     if (canonical && sorted) tiled_alloc(&te, N, nt * L, L);

@@ -59,7 +59,10 @@ typedef struct {
     int32_t tiled;               /* 1 = the order of the global-memory ("spilled") kernels: tiles of NT*L particles scanned
                                     as above, tile totals scanned by one CTA of 1024 lanes, two-level search (CANONICAL only);
                                     2 = the same, and SYSTEMATIC resampling by offspring counts on the running maximum of
-                                    the CDF (no search): what spill_expand_kernel does */
+                                    the CDF (no search): what spill_expand_kernel does (the order of the Liu-West kernels K4);
+                                    3 = the TILE-RELATIVE order of the bootstrap global-memory kernels K3 / K5: each tile is
+                                    weighted relative to its own maximum, the tile totals are rescaled by exp(m_b - M) before
+                                    their scan (pf_oracle.c: tiled_build_rel); systematic resampling by counts as in 2 */
     int32_t reserved2;
 } ssme_oracle_cfg;
 

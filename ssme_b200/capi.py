@@ -289,13 +289,33 @@ class ParticleFilterBackend:
         _check(self._lib.ssme_b200_comm_init(self._h, buf, rank, world))
 
     def spill_ipc_export(self) -> bytes:
-        buf = (C.c_uint8 * 320)()
+        buf = (C.c_uint8 * 384)()
         _check(self._lib.ssme_b200_spill_ipc_export(self._h, buf))
         return bytes(buf)
 
     def spill_ipc_import(self, all_handles: bytes):
         buf = (C.c_uint8 * len(all_handles))(*all_handles)
         _check(self._lib.ssme_b200_spill_ipc_import(self._h, buf))
+
+    @staticmethod
+    def spill_loopback_run(backends, theta, R: int = 1, stream_base: int = 0):
+        """K5 with all ranks in this process (same device): backends are the ranks, in order.  Connects them on first use.
+        Returns [n_ranks, P * R]: every rank's copy of the per-filter log-likelihoods."""
+        lib = backends[0]._lib
+        n = len(backends)
+        arr = (C.c_void_p * n)(*[b._h for b in backends])
+        if not getattr(backends[0], "_loopback", False):
+            lib.ssme_b200_spill_loopback_connect.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+            _check(lib.ssme_b200_spill_loopback_connect(arr, n))
+            for b in backends:
+                b._loopback = True
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, backends[0].num_params)
+        P = theta.shape[0]
+        out = np.empty((n, P * R))
+        lib.ssme_b200_spill_loopback_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_double), C.c_size_t, C.c_uint32, C.c_uint64,
+                                                     C.POINTER(C.c_double)]
+        _check(lib.ssme_b200_spill_loopback_run(arr, n, _dptr(theta), P, R, stream_base, _dptr(out)))
+        return out
 
     def work_batch_sharded(self, theta, R: int = 1, stream_base: int = 0):
         """Multi-rank thread_pool::work: returns (lme[P], per_filter[P, R]), identical on every rank."""

@@ -174,6 +174,7 @@ static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& 
     a.eE = s->eE;
     spill_expo_scan_kernel<<<tiles, kTileNT, 0, st>>>(a);
     if (s->world > 1) {  // every rank scans all tile totals of the spacings, as it does for the weights
+        if (s->loopback) return fail(SSME_B200_EUNSUPPORTED, "the loopback form of the sharded filter has no sorted-multinomial resampler (it all-gathers with NCCL)");
         NcclApi* nccl = nccl_api();
         int nrc = nccl->AllGather(s->ettot + s->tile0, s->ettot, (size_t)tiles, kNcclFloat64, h->nccl_comm, st);
         if (nrc != 0) return fail(SSME_B200_ERUNTIME, "ncclAllGather failed: %s", nccl->GetErrorString(nrc));
@@ -628,7 +629,7 @@ int ssme_b200_lw_state(ssme_b200_handle h, double* loglik_host, double* param_me
     return SSME_B200_OK;
 }
 
-int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[320])
+int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[384])
 {
     if (!h || !out) return fail(SSME_B200_EINVAL, "null argument");
     if (!h->spill) return fail(SSME_B200_EINVAL, "handle is not in global-memory (spilled) mode");
@@ -637,13 +638,14 @@ int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[320])
     if ((rc = prepare(h))) return rc;
     SpillState* s = h->spill_state;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    cudaIpcMemHandle_t hd[5];
+    cudaIpcMemHandle_t hd[6];
     SSME_CUDA(cudaIpcGetMemHandle(&hd[0], s->x_cur[0]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[1], s->x_cur[1]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[2], s->lwc[0]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[3], s->lwc[1]));
     SSME_CUDA(cudaIpcGetMemHandle(&hd[4], s->x_anc));
-    memcpy(out, hd, 320);
+    SSME_CUDA(cudaIpcGetMemHandle(&hd[5], s->xchg));
+    memcpy(out, hd, 384);
     return SSME_B200_OK;
 }
 
@@ -657,17 +659,80 @@ int ssme_b200_spill_ipc_import(ssme_b200_handle h, const uint8_t* all_handles)
     SpillState* s = h->spill_state;
     for (int r = 0; r < s->world; ++r) {
         if (r == s->rank) continue;
-        cudaIpcMemHandle_t hd[5];
-        memcpy(hd, all_handles + (size_t)r * 320, 320);
-        for (int i = 0; i < 5; ++i) SSME_CUDA(cudaIpcOpenMemHandle(&s->opened[r][i], hd[i], cudaIpcMemLazyEnablePeerAccess));
+        cudaIpcMemHandle_t hd[6];
+        memcpy(hd, all_handles + (size_t)r * 384, 384);
+        for (int i = 0; i < 6; ++i) SSME_CUDA(cudaIpcOpenMemHandle(&s->opened[r][i], hd[i], cudaIpcMemLazyEnablePeerAccess));
         s->peer_x_anc[r] = (double*)s->opened[r][4];
         s->peer_x[0][r] = (const double*)s->opened[r][0];
         s->peer_x[1][r] = (const double*)s->opened[r][1];
         s->peer_lwc[0][r] = (const double*)s->opened[r][2];
         s->peer_lwc[1][r] = (const double*)s->opened[r][3];
+        s->peer_xchg[r] = (unsigned char*)s->opened[r][5];
     }
     s->peers_ready = true;
     return SSME_B200_OK;
+}
+
+int ssme_b200_spill_loopback_connect(ssme_b200_handle* handles, int32_t n)
+{
+    if (!handles || n < 2 || n > kMaxPeers) return fail(SSME_B200_EINVAL, "loopback needs 2..%d handles", kMaxPeers);
+    for (int r = 0; r < n; ++r) {
+        ssme_b200_handle h = handles[r];
+        if (!h || !h->spill) return fail(SSME_B200_EINVAL, "handle %d is not in global-memory (spilled) mode", r);
+        if (h->cfg.device != handles[0]->cfg.device || h->cfg.num_particles != handles[0]->cfg.num_particles || h->T != handles[0]->T)
+            return fail(SSME_B200_EINVAL, "loopback ranks must share device, particle count and series");
+        if (h->spill_state->prepared) return fail(SSME_B200_ERUNTIME, "handle %d has already run a filter", r);
+        h->world = n;
+        h->rank = r;
+        int rc = set_device(h);
+        if (rc) return rc;
+        if ((rc = prepare(h))) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+        SpillState* s = handles[r]->spill_state;
+        for (int q = 0; q < n; ++q) {
+            SpillState* o = handles[q]->spill_state;
+            s->peer_x_anc[q] = o->x_anc;
+            for (int i = 0; i < 2; ++i) { s->peer_x[i][q] = o->x_cur[i]; s->peer_lwc[i][q] = o->lwc[i]; }
+            s->peer_xchg[q] = o->xchg;
+        }
+        s->peers_ready = true;
+        s->loopback = true;
+    }
+    return SSME_B200_OK;
+}
+
+int ssme_b200_spill_loopback_run(ssme_b200_handle* handles, int32_t n, const double* theta_host, size_t num_proposals, uint32_t R,
+                                 uint64_t stream_base, double* per_rank_loglik_host)
+{
+    if (!handles || n < 2 || n > kMaxPeers || !theta_host || !per_rank_loglik_host || R < 1 || num_proposals < 1)
+        return fail(SSME_B200_EINVAL, "bad argument");
+    const size_t F = num_proposals * R;
+    if (int src = check_stream_ids(stream_base, F)) return src;
+    for (int r = 0; r < n; ++r) {
+        if (!handles[r] || !handles[r]->spill || !handles[r]->spill_state->loopback) return fail(SSME_B200_ERUNTIME, "call ssme_b200_spill_loopback_connect first");
+        if (!handles[r]->have_obs) return fail(SSME_B200_ERUNTIME, "must add observed data before calculating anything");
+    }
+    ssme_b200_handle h0 = handles[0];
+    int rc = set_device(h0);
+    if (rc) return rc;
+    double *d_theta = nullptr, *d_out = nullptr;
+    const size_t np = (size_t)h0->num_params;
+    cudaError_t e = cudaMalloc(&d_theta, num_proposals * np * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * F * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_theta, theta_host, num_proposals * np * sizeof(double), cudaMemcpyHostToDevice, h0->stream);
+    if (e != cudaSuccess) { cudaFree(d_theta); cudaFree(d_out); return fail(SSME_B200_ECUDA, "loopback setup failed: %s", cudaGetErrorString(e)); }
+    // every rank's stream must be idle before the shared stream takes over
+    for (int r = 1; r < n; ++r) cudaStreamSynchronize(handles[r]->stream);
+    rc = spill_loopback_run(handles, n, d_theta, F, R, stream_base, d_out);
+    if (rc == SSME_B200_OK) {
+        e = cudaStreamSynchronize(h0->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(per_rank_loglik_host, d_out, (size_t)n * F * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(SSME_B200_ECUDA, "loopback run failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_theta);
+    cudaFree(d_out);
+    return rc;
 }
 
 }  // extern "C"

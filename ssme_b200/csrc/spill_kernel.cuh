@@ -125,68 +125,6 @@ __device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which
 }
 __global__ void k5_signal_kernel(const SpillArgs a, int which) { k5_signal_last_cta(a, which, 1u); }
 
-template <typename MODEL>
-__global__ void __launch_bounds__(kTileNT, 3) spill_propagate_kernel(const SpillArgs a)
-{
-    __shared__ double red[kTileNT / 32];
-    constexpr int OS = MODEL::kObsStride;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = a.tile0 + blockIdx.x;
-    const int i0 = tile * kTile + tid * kTileL;                      // global particle index
-    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;  // index into this rank's arrays
-    const typename MODEL::Params mc = MODEL::init(a.theta);
-    const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)(a.t - a.row0) * OS);
-    const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    double z[kTileL];
-#pragma unroll
-    for (int q = 0; q < kTileL / 4; ++q) {
-        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
-        float z0, z1, z2, z3;
-        box_muller(r.x, r.y, z0, z1);
-        box_muller(r.z, r.w, z2, z3);
-        z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
-    }
-    double x[kTileL];
-    if (a.t > 0) {
-#pragma unroll
-        for (int k = 0; k < kTileL; k += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(a.x_anc + l0 + k);
-            x[k] = v.x; x[k + 1] = v.y;
-        }
-    }
-    double lw[kTileL];
-    double mloc = __longlong_as_double(0xfff0000000000000ll);
-#pragma unroll
-    for (int k = 0; k < kTileL; ++k) {
-        x[k] = (a.t == 0) ? MODEL::q1(mc, ms, z[k]) : MODEL::f(mc, ms, x[k], z[k]);
-        double v = MODEL::logg(mc, ms, x[k]);
-        v = (i0 + k < a.N) ? v : __longlong_as_double(0xfff0000000000000ll);
-        lw[k] = v;
-        mloc = (v > mloc) ? v : mloc;
-    }
-#pragma unroll
-    for (int k = 0; k < kTileL; k += 2) {
-        *reinterpret_cast<double2*>(a.x_cur + l0 + k) = make_double2(x[k], x[k + 1]);
-        *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(lw[k], lw[k + 1]);
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(mloc, d);
-        mloc = (other > mloc) ? other : mloc;
-    }
-    if (lane == 0) red[warp] = mloc;
-    __syncthreads();
-    if (warp == 0) {
-        double m = (lane < kTileNT / 32) ? red[lane] : __longlong_as_double(0xfff0000000000000ll);
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const double other = shfl_xor_d(m, d);
-            m = (other > m) ? other : m;
-        }
-        if (lane == 0) a.tmax[tile] = m;
-    }
-}
-
 // M = max over the tile maxima of this rank's tiles (K4 order)
 __global__ void __launch_bounds__(1024) spill_reduce_max_kernel(const SpillArgs a)
 {

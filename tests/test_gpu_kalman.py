@@ -71,7 +71,7 @@ def test_linear_gaussian_cluster_and_global_memory_kernels(oracle, gpu_backend_f
     be3 = gpu_backend_factory(model=sb.MODEL_LINEAR_GAUSSIAN, num_particles=9000, resampler=sb.RESAMP_SYSTEMATIC, seed=5, force_global_memory=1)
     be3.add_observed_data(y)
     got3 = be3.work_batch(LG_THETA[None, :], R=1, stream_base=4, return_per_filter=True)[1][0, 0]
-    assert got3 == oracle.filter_run(LG_THETA, y, 9000, model=2, resampler=2, L=8, NT=512, tiled=2, seed=5, filter_id=4, trace=False)["loglik"]
+    assert got3 == oracle.filter_run(LG_THETA, y, 9000, model=2, resampler=2, L=8, NT=512, tiled=3, seed=5, filter_id=4, trace=False)["loglik"]
 
 
 @pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])

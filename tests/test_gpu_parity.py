@@ -266,7 +266,7 @@ def test_tiny_particle_counts(oracle, sv_series, gpu_backend_factory, N, resampl
     got = be.trace(SV_THETA[None, :], stream_base=6, want=("loglik", "cond_like", "ancestors"))
     lay = be.layout
     if force_global:
-        ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=43, filter_id=6)
+        ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=43, filter_id=6)
     else:
         ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=lay["scan_items_per_lane"], NT=lay["threads_per_filter"], seed=43, filter_id=6)
     assert np.array_equal(got["ancestors"][0], ref["ancestors"])

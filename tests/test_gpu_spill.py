@@ -20,7 +20,7 @@ def test_spilled_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, seed=8, force_global_memory=1)
     be.add_observed_data(y)
     got = be.trace(th[None, :], stream_base=3, want=("loglik", "cond_like", "ancestors"))
-    ref = oracle.filter_run(th, y, N, model=model, resampler=resampler, L=8, NT=512, tiled=2, seed=8, filter_id=3)
+    ref = oracle.filter_run(th, y, N, model=model, resampler=resampler, L=8, NT=512, tiled=3, seed=8, filter_id=3)
     assert np.array_equal(got["ancestors"][0], ref["ancestors"])
     assert np.array_equal(got["cond_like"][0], ref["cond_like"])
     assert got["loglik"][0] == ref["loglik"]
@@ -67,7 +67,7 @@ def test_spilled_filter_many_tiles_two_launch_scan(oracle, sv_series, gpu_backen
     be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=10)
     be.add_observed_data(y)
     got = be.trace(SV_THETA[None, :], stream_base=1, want=("loglik", "cond_like", "ancestors"))
-    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=10, filter_id=1)
+    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=10, filter_id=1)
     assert np.array_equal(got["cond_like"][0], ref["cond_like"])
     assert got["loglik"][0] == ref["loglik"]
     assert np.array_equal(got["ancestors"][0], ref["ancestors"])
@@ -83,10 +83,39 @@ def test_spilled_filter_degenerate_weights_and_invalid_parameters(oracle, sv_ser
     be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=12, force_global_memory=1)
     be.add_observed_data(y)
     got = be.trace(SV_THETA[None, :], stream_base=2, want=("loglik", "cond_like", "ancestors"))
-    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=12, filter_id=2)
+    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=12, filter_id=2)
     counts = np.bincount(ref["ancestors"][2], minlength=N)
     assert counts.max() > 8192      # the degenerate step really exceeds the staging buffer
     assert np.array_equal(got["ancestors"][0], ref["ancestors"])
     assert np.array_equal(got["cond_like"][0], ref["cond_like"]) and got["loglik"][0] == ref["loglik"]
     bad = be.work_batch(np.array([[1.0, 1.5, 0.0625]]), R=1)
     assert np.isnan(bad[0])
+
+
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("ranks,N", [(2, 4096 * 6), (4, 4096 * 8 - 100), (8, 4096 * 8)])
+def test_sharded_filter_loopback_on_one_gpu(oracle, sv_series, gpu_backend_factory, resampler, ranks, N):
+    """K5's data plane without a second GPU: the ranks are handles of this process on one device, wired to each other's HBM
+    directly and launched phase by phase on one stream (ssme_b200_spill_loopback_*).  Every rank owns a contiguous range of
+    tiles, pushes its tile triples into every peer, scans all tile totals itself and resamples across ranks (systematic:
+    offspring stored into the slot owner's array; multinomial: ancestors read from the owner's arrays).  The result is the
+    single-handle run's and the oracle's, bit for bit, on every rank -- the order of the sums is defined on tiles, not ranks."""
+    T = 14
+    y = sv_series(T, seed=35).copy()
+    y[5] = 25.0  # degenerate weights at one step: offspring runs cross rank boundaries
+    th = np.stack([SV_THETA, SV_THETA * np.array([1.1, 0.9, 1.3])])
+    bes = [gpu_backend_factory(num_particles=N, resampler=resampler, seed=13, force_global_memory=1) for _ in range(ranks)]
+    for b in bes:
+        b.add_observed_data(y)
+    got = sb.ParticleFilterBackend.spill_loopback_run(bes, th, R=2, stream_base=7)   # [ranks][2 * 2]
+    single = gpu_backend_factory(num_particles=N, resampler=resampler, seed=13, force_global_memory=1)
+    single.add_observed_data(y)
+    _, pf = single.work_batch(th, R=2, stream_base=7, return_per_filter=True)
+    for r in range(ranks):
+        assert np.array_equal(got[r], pf.ravel()), r
+    ref = [oracle.filter_run(th[f // 2], y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=13, filter_id=7 + f, trace=False)["loglik"]
+           for f in range(4)]
+    assert got[0].tolist() == ref
+    # a second call on the same (connected) handles continues the flag epochs
+    again = sb.ParticleFilterBackend.spill_loopback_run(bes, th[:1], R=1, stream_base=7)
+    assert again[ranks - 1, 0] == ref[0]

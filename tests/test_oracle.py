@@ -217,6 +217,25 @@ def test_tiled_sorted_multinomial_follows_the_in_tree_resampler(oracle, sv_serie
     assert np.array_equal(c["ancestors"], d["ancestors"]) and abs(c["loglik"] - d["loglik"]) <= 1e-9 * abs(d["loglik"])
 
 
+@pytest.mark.parametrize("resampler", [0, 1, 2])
+def test_tile_relative_order_agrees_with_faithful(oracle, sv_series, resampler):
+    """The tile-relative order of the bootstrap global-memory kernels (tiled = 3: every tile weighted relative to its own
+    maximum, tile totals rescaled by exp(m_b - M)) against the reference's sequential arithmetic on the same Philox draws:
+    same ancestors, log-likelihood within 1e-12; and against the global-maximum tiled order (tiled = 2)."""
+    from oracle import binding as ob
+    y = sv_series(20, seed=71)
+    y[7] = 9.0  # an outlying observation spreads the tile maxima apart
+    th = np.array([1.0, 0.95, 0.0625])
+    for N in (100, 4096 + 3, 3 * 4096, 20000):
+        a = ob.filter_run(th, y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=9, filter_id=3)
+        b = ob.filter_run(th, y, N, resampler=resampler, arithmetic=ob.ARITH_FAITHFUL, seed=9, filter_id=3)
+        c = ob.filter_run(th, y, N, resampler=resampler, L=8, NT=512, tiled=2, seed=9, filter_id=3)
+        assert a["margin"] > 1e-13
+        assert np.array_equal(a["ancestors"], b["ancestors"]) and np.array_equal(a["ancestors"], c["ancestors"])
+        assert abs(a["loglik"] - b["loglik"]) <= 1e-12 * abs(b["loglik"])
+        assert np.max(np.abs(a["cond_like"] - b["cond_like"])) <= 1e-11
+
+
 def test_liu_west_expectations_oracle(oracle, sv_series):
     """E[h | y_{1:t}] before resampling: canonical (tiled sums) vs the reference's sequential numer / denom; constants come back."""
     from oracle import binding as ob
