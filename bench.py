@@ -164,7 +164,7 @@ def run_reference(args):
                          "dispatcher": "reference include/ssme/thread_pool.h" if L.ssme_refcpu_pool_kind() else "local API-identical pool"},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 K1_PROFILE = os.path.join("profiles", "r2_k1_final_L8_NT128.txt")
@@ -639,7 +639,7 @@ def run_ours(args):
             "legs_ok": legs_ok, "parity_sample": parity_sample, "fp32_mode": compact(fp32_mode), "liu_west": compact(liu_west),
             "pmmh": compact(pmmh), "spilled_filter": compact(spilled),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -29,6 +29,7 @@ struct SpillState {
     unsigned int* done_ctr = nullptr;
     unsigned long long epoch = 0;  // launches of spill_step_kernel so far (the same on every rank)
     unsigned char* peer_xchg[kMaxPeers] = {};
+    void* params = nullptr;  // [256 B] MODEL::Params of the filter being run
     bool loopback = false;  // the "ranks" are handles of ONE process on one device, driven in lockstep on one stream
     double* scan2 = nullptr;  // two-launch tile scan: lanepref[1024], lanetot[1024], wtot[32], cmax[32]
     // sorted-multinomial resampling: scan of the exponential spacings (allocated on first use)
@@ -102,6 +103,7 @@ static int prepare(ssme_b200_handle h)
         s->peer_xchg[s->rank] = s->xchg;
     }
     SSME_CUDA(cudaMalloc(&s->sb, (size_t)s->nb * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->params, 256));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
     // per device: the two-launch tile scan stages up to 2 x 256 x 33 doubles
@@ -114,7 +116,7 @@ static int prepare(ssme_b200_handle h)
         s->peer_lwc[i][s->rank] = s->lwc[i];
     }
     s->peer_x_anc[s->rank] = s->x_anc;
-    SSME_CUDA(cudaFuncSetAttribute(spill_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandBuf * sizeof(double))));
+    SSME_CUDA(cudaFuncSetAttribute(spill_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandSmem * sizeof(double))));
     s->peers_ready = (s->world == 1);
     s->prepared = true;
     return SSME_B200_OK;
@@ -135,7 +137,7 @@ void spill_destroy(ssme_b200_handle h)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->xchg); cudaFree(s->sb); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal);
+    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->xchg); cudaFree(s->sb); cudaFree(s->params); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
@@ -194,6 +196,19 @@ static int launch_sorted_resample(ssme_b200_handle h, SpillState* s, SpillArgs& 
     return SSME_B200_OK;
 }
 
+static bool launch_params(int model, const double* theta, void* out, cudaStream_t st)
+{
+#define SSME_SPILL_MODEL(M)                                \
+    if (model == M::kId) {                                  \
+        static_assert(sizeof(typename M::Params) <= 256, "params buffer");  \
+        spill_params_kernel<M><<<1, 1, 0, st>>>(theta, out); \
+        return true;                                        \
+    }
+    SSME_FOR_EACH_MODEL(SSME_SPILL_MODEL)
+#undef SSME_SPILL_MODEL
+    return false;
+}
+
 static bool launch_step(int model, const SpillArgs& a, int tiles, cudaStream_t st)
 {
 #define SSME_SPILL_MODEL(M)                                   \
@@ -236,6 +251,7 @@ static void bootstrap_args(ssme_b200_handle h, SpillState* s, SpillArgs& a, cons
     }
     a.cond_like = cond_like;
     a.ancestors = ancestors;
+    a.params = s->params;
 }
 
 // The three phases of one time step.  A: fused propagate / weight / tile scan (raises flag 0 in the peers).  B: scan of all tile
@@ -248,6 +264,10 @@ static int phase_a(ssme_b200_handle h, SpillState* s, SpillArgs& a, int t, cudaS
     a.x_cur = s->x_cur[cur];
     a.lwc = s->lwc[cur];
     for (int r = 0; r < s->world; ++r) { a.peer_x[r] = s->peer_x[cur][r]; a.peer_lwc[r] = s->peer_lwc[cur][r]; }
+    if (s->world > 1 && a.epoch > 1) {  // the peers have finished writing this step's ancestors into this rank's HBM
+        k5_wait_kernel<<<1, 1, 0, st>>>(a, 1, a.epoch - 1);
+        count_launch(1);
+    }
     if (!launch_step(h->cfg.model, a, s->tiles_per_rank, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
     count_launch(1);
     return SSME_B200_OK;
@@ -269,7 +289,7 @@ static int phase_c(ssme_b200_handle h, SpillState* s, SpillArgs& a, bool resampl
         return SSME_B200_OK;
     }
     if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
-        spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a);
+        spill_expand_kernel<<<tiles, kTileNT, kExpandSmem * sizeof(double), st>>>(a);
     } else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
         int rc = launch_sorted_resample(h, s, a, tiles, st);
         if (rc) return rc;
@@ -295,6 +315,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
         bootstrap_args(h, s, a, theta_dev + (f / R) * (size_t)h->num_params, stream_base + f, cond_like_dev ? cond_like_dev + f * (size_t)T : nullptr,
                        ancestors_dev ? ancestors_dev + f * (size_t)T * (size_t)s->N : nullptr);
         spill_init_kernel<<<1, 1, 0, st>>>(s->scal, s->N);
+        launch_params(h->cfg.model, a.theta, s->params, st);
         for (int t = 0; t < T; ++t) {
             if ((rc = phase_a(h, s, a, t, st))) return rc;
             if ((rc = phase_b(s, a, st))) return rc;
@@ -319,6 +340,7 @@ int spill_loopback_run(ssme_b200_handle* hs, int n, const double* theta_dev, siz
         for (int r = 0; r < n; ++r) {
             bootstrap_args(hs[r], hs[r]->spill_state, a[r], theta_dev + (f / R) * (size_t)hs[r]->num_params, stream_base + f, nullptr, nullptr);
             spill_init_kernel<<<1, 1, 0, st>>>(hs[r]->spill_state->scal, hs[r]->spill_state->N);
+            launch_params(hs[r]->cfg.model, a[r].theta, hs[r]->spill_state->params, st);
         }
         int rc;
         for (int t = 0; t < T; ++t) {
@@ -435,7 +457,7 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
         count_launch(1);
     }
-    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandBuf * sizeof(double), st>>>(a.s);
+    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandSmem * sizeof(double), st>>>(a.s);
     else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
         int rc = launch_sorted_resample(h, s, a.s, tiles, st);
         if (rc) return rc;

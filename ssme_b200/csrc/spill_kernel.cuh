@@ -89,6 +89,7 @@ struct SpillArgs {
                                                 // of step e done" by source rank
     unsigned long long* flags;           // this rank's flag block
     unsigned int* done_ctr;              // [2] CTA counters (last CTA of a launch raises the flags)
+    const void* params;                  // MODEL::Params of the filter being run (spill_params_kernel)
 };
 
 // ---- K5 flag protocol -------------------------------------------------------------------------------------------------------
@@ -105,9 +106,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // one thread per CTA: wait until every peer has raised flag `which` (0 = triples, 1 = resampling done) to at least `e`
 __device__ __forceinline__ void k5_wait(const SpillArgs& a, int which, unsigned long long e)
 {
+    unsigned long long t0 = 0;
     for (int r = 0; r < a.world; ++r) {
         if (r == a.rank) continue;
-        while (ld_acquire_sys(a.flags + which * 8 + r) < e) __nanosleep(64);
+        while (ld_acquire_sys(a.flags + which * 8 + r) < e) {
+            __nanosleep(64);
+            // a peer that died or fell out of step must not hang this GPU: give up loudly after 20 s
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 20000000000ull) __trap();
+        }
     }
 }
 // called by thread 0 of every CTA after its last (possibly remote) store: the last CTA of the launch raises this rank's flag
@@ -124,6 +133,7 @@ __device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which
     }
 }
 __global__ void k5_signal_kernel(const SpillArgs a, int which) { k5_signal_last_cta(a, which, 1u); }
+__global__ void k5_wait_kernel(const SpillArgs a, int which, unsigned long long e) { k5_wait(a, which, e); }
 
 // M = max over the tile maxima of this rank's tiles (K4 order)
 __global__ void __launch_bounds__(1024) spill_reduce_max_kernel(const SpillArgs a)
@@ -183,10 +193,19 @@ __device__ __forceinline__ double tile_scan_finish(double (&sc)[kTileL], double*
     return total;
 }
 
+template <typename MODEL>
+__global__ void spill_params_kernel(const double* theta, void* out)
+{
+    *reinterpret_cast<typename MODEL::Params*>(out) = MODEL::init(theta);
+}
+
 // K3a, tile-relative order: propagate + log-weight + tile maximum + weights relative to it + tile-local scan, one pass.
 // HBM: reads x_anc (8 B), writes x' and cl (16 B) per particle; the log-weights stay in registers.
+#ifndef SSME_STEP_MINB
+#define SSME_STEP_MINB 3
+#endif
 template <typename MODEL>
-__global__ void __launch_bounds__(kTileNT, 2) spill_step_kernel(const SpillArgs a)
+__global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(const SpillArgs a)
 {
     constexpr int NW = kTileNT / 32;
     __shared__ double red[NW];
@@ -198,43 +217,41 @@ __global__ void __launch_bounds__(kTileNT, 2) spill_step_kernel(const SpillArgs 
     const int i0 = tile * kTile + tid * kTileL;                      // global particle index
     const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;  // index into this rank's arrays
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
-    // K5: the ancestors of this step were written by the peers' resampling kernels of the previous one
-    if (a.world > 1 && a.epoch > 1) {
-        if (tid == 0) k5_wait(a, 1, a.epoch - 1);
-        __syncthreads();
-    }
-    const typename MODEL::Params mc = MODEL::init(a.theta);
+    // (K5: the ancestors of this step were written by the peers' resampling kernels of the previous one; the one-thread
+    // k5_wait_kernel launched ahead of this kernel has seen their flags -- 32768 CTAs each paying a system-scope acquire
+    // would cost more than one 3 us launch)
+    // the model's per-filter constants (a log, two square roots, two divides for SV) were derived once per filter by
+    // spill_params_kernel: ~25 instructions per particle-step when every thread of every step repeats them
+    const typename MODEL::Params mc = *reinterpret_cast<const typename MODEL::Params*>(a.params);
     const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)(a.t - a.row0) * OS);
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    double z[kTileL];
-#pragma unroll
-    for (int q = 0; q < kTileL / 4; ++q) {
-        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
-        float z0, z1, z2, z3;
-        box_muller(r.x, r.y, z0, z1);
-        box_muller(r.z, r.w, z2, z3);
-        z[4 * q + 0] = (double)z0; z[4 * q + 1] = (double)z1; z[4 * q + 2] = (double)z2; z[4 * q + 3] = (double)z3;
-    }
-    double x[kTileL];
-    if (a.t > 0) {
-#pragma unroll
-        for (int k = 0; k < kTileL; k += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(a.x_anc + l0 + k);
-            x[k] = v.x; x[k + 1] = v.y;
-        }
-    }
+    // four particles at a time (one Philox block): draw, propagate, weigh, store the state -- only the log-weights stay live
     double lw[kTileL];
     double mloc = ninf;
 #pragma unroll
-    for (int k = 0; k < kTileL; ++k) {
-        x[k] = (a.t == 0) ? MODEL::q1(mc, ms, z[k]) : MODEL::f(mc, ms, x[k], z[k]);
-        double v = MODEL::logg(mc, ms, x[k]);
-        v = (i0 + k < a.N) ? v : ninf;
-        lw[k] = v;
-        mloc = (v > mloc) ? v : mloc;
-    }
+    for (int q = 0; q < kTileL / 4; ++q) {
+        double x[4];
+        if (a.t > 0) {
+            const double2 v0 = *reinterpret_cast<const double2*>(a.x_anc + l0 + 4 * q);
+            const double2 v1 = *reinterpret_cast<const double2*>(a.x_anc + l0 + 4 * q + 2);
+            x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y;
+        }
+        const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
+        float zf[4];
+        box_muller(r.x, r.y, zf[0], zf[1]);
+        box_muller(r.z, r.w, zf[2], zf[3]);
 #pragma unroll
-    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.x_cur + l0 + k) = make_double2(x[k], x[k + 1]);
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * q + j;
+            x[j] = (a.t == 0) ? MODEL::q1(mc, ms, (double)zf[j]) : MODEL::f(mc, ms, x[j], (double)zf[j]);
+            double v = MODEL::logg(mc, ms, x[j]);
+            v = (i0 + k < a.N) ? v : ninf;
+            lw[k] = v;
+            mloc = (v > mloc) ? v : mloc;
+        }
+        *reinterpret_cast<double2*>(a.x_cur + l0 + 4 * q) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2*>(a.x_cur + l0 + 4 * q + 2) = make_double2(x[2], x[3]);
+    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         const double other = shfl_xor_d(mloc, d);
@@ -265,8 +282,7 @@ __global__ void __launch_bounds__(kTileNT, 2) spill_step_kernel(const SpillArgs 
         cmax = (other > cmax) ? other : cmax;
     }
     if (lane == 0) red_max[warp] = cmax;
-    if (a.world > 1) __threadfence_system();  // x' and cl of this tile are read by the peers' resampling kernels
-    __syncthreads();
+    __syncthreads();  // (K5: every thread's x' and cl stores happen before thread 0's system-scope fence and flag below)
     if (tid == 0) {
         double m = red_max[0];
         for (int g = 1; g < NW; ++g) m = (red_max[g] > m) ? red_max[g] : m;
@@ -697,6 +713,7 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
 }
 
 constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wider slot ranges (degenerate weights) are written directly
+constexpr int kExpandSmem = kExpandBuf;
 
 // Systematic resampling WITHOUT a search (oracle: systematic_by_counts).  Each CTA takes a tile of PARTICLES: it forms
 // the running maximum Ct of the global CDF over its tile (carry-in from earlier tiles in a.carry; a parallel scan is
@@ -883,8 +900,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
             for (int sl = A[k]; sl < A[k + 1]; ++sl) a.ancestors[(size_t)a.t * a.N + sl] = i0 + k;
     }
     if (a.world > 1) {  // K5: the offspring went into the slot owners' HBM; tell every peer when this rank is done
-        __threadfence_system();
-        __syncthreads();
+        __syncthreads();  // all stores of the CTA happen before thread 0's system-scope fence (cumulativity through the barrier)
         if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x);
     }
 }

@@ -185,8 +185,9 @@ def _spill_worker(rank, world, port, q, N, T, resampler):
 @pytest.mark.gpu
 @pytest.mark.parametrize("resampler", [2, 0, 1])
 def test_particle_sharded_filter_matches_single_gpu(resampler):
-    """Config-5 shape at test size: ONE filter whose particles are sharded over 2 GPUs (per step: NCCL all-reduce of
-    the weight maximum, all-gather of the tile sums, peer reads of ancestors) == the single-GPU run, bit for bit."""
+    """Config-5 shape at test size: ONE filter whose particles are sharded over 2 GPUs (per step: tile triples stored into
+    the peer's HBM + flag, every rank scans all tile totals, offspring written to / ancestors read from the owner's HBM)
+    == the single-GPU run, bit for bit.  (tests/test_gpu_spill.py runs the same data plane on ONE GPU in loopback.)"""
     import torch
     import torch.multiprocessing as mp
     import ssme_b200 as sb
