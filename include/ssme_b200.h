@@ -70,12 +70,15 @@ typedef struct {
     uint64_t seed;               /* Philox key; the reference seeds mt19937 from the clock (liu_west_filter.h:75-76) */
     int32_t scan_items_per_lane; /* L of the canonical scan order; 0 = library default */
     int32_t threads_per_filter;  /* CTA size; 0 = library default */
-    int32_t filters_per_sm;      /* resident CTAs per SM; 0 = library default */
+    int32_t filters_per_sm;      /* must be 0: the resident CTAs per SM follow from the kernel's registers and shared memory
+                                    (read the value in use from ssme_b200_get_layout) */
     int32_t force_global_memory; /* 1 = use the global-memory ("spilled") kernels even when N fits one CTA (parity runs);
                                     they are selected automatically for N > 8192 */
-    int32_t use_cluster;         /* 1 = one filter per thread-block cluster: tiles of 4*threads_per_filter particles
-                                    (threads 256 by default, or 128), one tile per SM, up to 16 tiles (N <= 16384):
-                                    2-3x lower time-step latency when a GPU runs fewer filters than it has SMs */
+    int32_t use_cluster;         /* 1 = one filter per thread-block cluster: tiles of scan_items_per_lane (4 or 8) x
+                                    threads_per_filter (256 by default; 128 .. 1024) particles, one tile per SM, up to 16
+                                    tiles: 2-3x lower time-step latency when a GPU runs fewer filters than it has SMs.
+                                    Philox streams, resample_every = 1, fp64.  A particle count that does not fit 16 tiles
+                                    is refused (SSME_B200_EUNSUPPORTED), never silently run by another kernel */
     int32_t reserved;
 } ssme_b200_config;
 
@@ -100,6 +103,11 @@ int ssme_b200_destroy(ssme_b200_handle h);
  * leverage model.  Copied to the device once; may be called once per handle (as the reference:
  * a second call fails with SSME_B200_ERUNTIME). */
 int ssme_b200_set_observations(ssme_b200_handle h, const double* y_host, size_t T, size_t dimy);
+
+/* The same for an object that filters one series after another (the host mirrors Swarm::update_series and the Liu-West
+ * filter_series of the headers under include/ssme_b200/ may be called repeatedly, as a reference filter object may be fed any number of
+ * observations): waits for queued work, drops the old series and any streaming run on it, stores the new one. */
+int ssme_b200_replace_observations(ssme_b200_handle h, const double* y_host, size_t T, size_t dimy);
 
 /* The launch layout chosen for this handle (valid after create). */
 int ssme_b200_get_layout(ssme_b200_handle h, ssme_b200_layout* out);

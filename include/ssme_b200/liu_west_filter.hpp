@@ -76,7 +76,7 @@ public:
         if (obs.empty() || obs.size() != cov.size()) throw std::length_error("observations and covariates must be non-empty and of equal length");
         std::vector<double> rows(2 * obs.size());
         for (size_t t = 0; t < obs.size(); ++t) { rows[2 * t] = (double)obs[t]; rows[2 * t + 1] = (double)cov[t]; }
-        throw_on_error(ssme_b200_set_observations(m_h, rows.data(), obs.size(), 2));
+        throw_on_error(ssme_b200_replace_observations(m_h, rows.data(), obs.size(), 2));
         m_streaming = false;
         m_cond_like.assign(obs.size(), 0.0);
         m_theta_bar.assign(obs.size() * 4, 0.0);
@@ -93,7 +93,7 @@ public:
         if (obs.empty() || obs.size() != cov.size()) throw std::length_error("observations and covariates must be non-empty and of equal length");
         std::vector<double> rows(2 * obs.size());
         for (size_t t = 0; t < obs.size(); ++t) { rows[2 * t] = (double)obs[t]; rows[2 * t + 1] = (double)cov[t]; }
-        throw_on_error(ssme_b200_set_observations(m_h, rows.data(), obs.size(), 2));
+        throw_on_error(ssme_b200_replace_observations(m_h, rows.data(), obs.size(), 2));
         m_streaming = false;
         m_cond_like.assign(obs.size(), 0.0);
         m_expect.assign(obs.size() * 5, 0.0);

@@ -58,7 +58,7 @@ public:
             const psv p = samp_untrans_params();
             for (size_t k = 0; k < dimparam; ++k) theta[j * dimparam + k] = (double)p(k);
         }
-        throw_on_error(ssme_b200_set_observations(m_h, obs.data(), T, dimy));
+        throw_on_error(ssme_b200_replace_observations(m_h, obs.data(), T, dimy));
         m_log_cond_like.assign(T, 0.0);
         if (with_expectations) {
             m_expectations.assign(2 * T, 0.0);

@@ -165,12 +165,14 @@ __global__ void fp64_fma_rate_kernel(double* out, int iters, double a, double b)
 
 void count_launch(unsigned n) { g_launches.fetch_add(n); }
 
+static char g_nccl_load_error[256] = "symbols missing";
+
 NcclApi* nccl_api()
 {
-    static NcclApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // a function-local static initialised by a lambda: the C++11 runtime runs it exactly once, also when several handles
+    // set up their communicators from different host threads
+    static NcclApi api = [] {
+        NcclApi api;
         // prefer the NCCL the host process already loaded (torch ships its own); never export its symbols globally
         void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
@@ -183,8 +185,11 @@ NcclApi* nccl_api()
             api.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
             api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
             api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy && api.GetErrorString;
+        } else if (const char* e = dlerror()) {
+            snprintf(g_nccl_load_error, sizeof(g_nccl_load_error), "%s", e);
         }
-    }
+        return api;
+    }();
     return &api;
 }
 
@@ -276,11 +281,14 @@ int launch_filters(ssme_b200_handle h, const KernelEntry* ke, const FilterArgs& 
         const void* fn = cluster_kernel_fn(h->cfg.model, h->cfg.resampler, h->NT, h->L);
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
+        if (F * (size_t)h->cluster_size > 0x7fffffffull) return fail(SSME_B200_EINVAL, "too many CTAs in one cluster launch: %zu filters x %d tiles", F, h->cluster_size);
         lc.gridDim = dim3((unsigned)(F * (size_t)h->cluster_size));
         lc.blockDim = dim3((unsigned)h->NT);
         lc.dynamicSmemBytes = cluster_smem_bytes(h->L * h->NT, h->cluster_size);
         lc.stream = st;
-        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, F * (size_t)(kClMax * h->L * h->NT));
+        // L2-resident staging of the CDF tiles the larger clusters multicast; two-tile (DSMEM) clusters never touch it
+        const size_t scratch_need = (h->cluster_size <= kClDsmemMax) ? 1 : F * (size_t)h->cluster_size * (size_t)(h->L * h->NT);
+        int rc2 = ensure_dev(&h->d_cluster_scratch, &h->cap_cluster_scratch, scratch_need);
         if (rc2) return rc2;
         double* scratch = h->d_cluster_scratch;
         cudaLaunchAttribute attr[1];
@@ -366,8 +374,16 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     const int cl_L = (cfg->scan_items_per_lane == 8) ? 8 : 4;
     const int cl_tile = cl_L * cl_nt;
     const int cl_size = (cfg->num_particles + cl_tile - 1) / cl_tile;
-    const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0 && cl_size <= kClMax &&
-                             cluster_smem_bytes(cl_tile, cl_size) <= (size_t)227 * 1024;
+    if (cfg->use_cluster != 0 && cfg->force_global_memory == 0 &&
+        (cl_size > kClMax || cluster_smem_bytes(cl_tile, cl_size) > (size_t)227 * 1024))
+        return fail(SSME_B200_EUNSUPPORTED,
+                    "use_cluster: %d particles in tiles of %d need %d CTAs per cluster (at most %d, and every tile's CDF must fit one CTA's "
+                    "shared memory); use larger tiles (threads_per_filter x scan_items_per_lane) or drop use_cluster",
+                    cfg->num_particles, cl_tile, cl_size, kClMax);
+    if (cfg->filters_per_sm != 0)
+        return fail(SSME_B200_EUNSUPPORTED, "filters_per_sm is chosen by the library (registers and shared memory of the kernel fix it); leave it 0 "
+                                            "and read the value in use from ssme_b200_get_layout");
+    const bool use_cluster = cfg->use_cluster != 0 && cfg->force_global_memory == 0;
     const bool spill = !use_cluster && (cfg->force_global_memory != 0 || cfg->num_particles > 8192);
     int L = 0, NT = 0;
     const KernelEntry *fast = nullptr, *dbg = nullptr;
@@ -504,6 +520,24 @@ int ssme_b200_set_observations(ssme_b200_handle h, const double* y_host, size_t 
     h->T = T;
     h->have_obs = true;
     return SSME_B200_OK;
+}
+
+int ssme_b200_replace_observations(ssme_b200_handle h, const double* y_host, size_t T, size_t dimy)
+{
+    if (!h) return fail(SSME_B200_EINVAL, "null handle");
+    if (!y_host || T == 0) return fail(SSME_B200_ELENGTH, "can't read in data");
+    int rc = set_device(h);
+    if (rc) return rc;
+    if (h->have_obs) {
+        SSME_CUDA(cudaStreamSynchronize(h->stream));  // nothing queued may still read the old series
+        cudaFree(h->d_obs);
+        h->d_obs = nullptr;
+        h->have_obs = false;
+        h->T = 0;
+        h->sw_t = -1;  // a streaming swarm / Liu-West run in progress belongs to the old series
+        if (h->spill) spill_reset_streaming(h);
+    }
+    return ssme_b200_set_observations(h, y_host, T, dimy);
 }
 
 static FilterArgs base_args(ssme_b200_handle h, const double* theta_dev, unsigned R, uint64_t stream_base, double* loglik_dev)
@@ -821,7 +855,7 @@ int ssme_b200_comm_unique_id(uint8_t id_out[128])
 {
     if (!id_out) return fail(SSME_B200_EINVAL, "null argument");
     NcclApi* n = nccl_api();
-    if (!n->ok) return fail(SSME_B200_ERUNTIME, "NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbols missing");
+    if (!n->ok) return fail(SSME_B200_ERUNTIME, "NCCL (libnccl.so.2) could not be loaded: %s", g_nccl_load_error);
     NcclApi::unique_id id;
     int rc = n->GetUniqueId(&id);
     if (rc != 0) return fail(SSME_B200_ERUNTIME, "ncclGetUniqueId failed: %s", n->GetErrorString(rc));

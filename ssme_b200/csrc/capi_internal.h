@@ -90,6 +90,7 @@ int ensure_pinned(ssme_b200_handle h, size_t bytes);
 // spill_capi.cu
 int spill_create(ssme_b200_handle h);
 void spill_destroy(ssme_b200_handle h);
+void spill_reset_streaming(ssme_b200_handle h);  // forget a streaming Liu-West run (its series was replaced)
 int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, unsigned R, uint64_t stream_base, double* per_filter_dev,
                       double* cond_like_dev, int* ancestors_dev);
 int spill_loopback_run(ssme_b200_handle* hs, int n, const double* theta_dev, size_t F, unsigned R, uint64_t stream_base, double* per_filter_dev);

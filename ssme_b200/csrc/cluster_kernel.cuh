@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
     const int N = a.N, T = a.T;
     const int i0 = rank * kClTile + tid * kClL;  // first particle of this thread (index within the filter)
     const int l0 = tid * kClL;                   // ... within the tile
-    // L2-resident scratch of this filter: [CS][512] CDF tiles (the source of the multicast)
-    double* gC = scratch + floc * (size_t)(kClMax * kClTile) + (size_t)rank * kClTile;
+    // L2-resident scratch of this filter: [CS][tile] CDF tiles (the source of the multicast; unused by DSMEM clusters)
+    double* gC = dsmem ? scratch : scratch + floc * (size_t)(CS * kClTile) + (size_t)rank * kClTile;
     const uint32_t x_base = smem_u32(shX);
 
     uint32_t eoff[kClL];

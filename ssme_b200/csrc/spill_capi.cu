@@ -128,6 +128,11 @@ int spill_create(ssme_b200_handle h)
     return SSME_B200_OK;
 }
 
+void spill_reset_streaming(ssme_b200_handle h)
+{
+    if (h->spill_state) h->spill_state->lw_t = -1;
+}
+
 void spill_destroy(ssme_b200_handle h)
 {
     SpillState* s = h->spill_state;

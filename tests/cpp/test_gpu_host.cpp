@@ -130,6 +130,13 @@ int main(int argc, char** argv)
         const auto pm = big.getParamMeans();
         REQUIRE(pm(0) > .8 && pm(0) < .99 && pm(2) > .01 && pm(2) < .3 && pm(3) > -.5 && pm(3) < -.01);
         REQUIRE(std::isfinite(big.getLogLike()));
+        // the object filters a second series (ssme_b200_replace_observations): same stream id, same series -> the same bits
+        const double first = big.getLogLike();
+        big.filter_series(y, cov);
+        REQUIRE(big.getLogLike() == first);
+        std::vector<double> y2(y.begin(), y.begin() + y.size() / 2), cov2(cov.begin(), cov.begin() + y.size() / 2);
+        big.filter_series(y2, cov2);
+        REQUIRE((std::isfinite(big.getLogLike()) && big.getLogLike() != first));
     }
     TEST_CASE("test filter without funcs for type 1 filters with covariates [filter method]")  // test_liu_west.cpp:163-173
     {
