@@ -32,9 +32,12 @@ sys.path.insert(0, ROOT)
 
 P_PROPOSALS, N_PARTICLES, T_STEPS, R_REPL = 4096, 1024, 4096, 1
 SEED_SERIES, SEED_THETA, SEED_FILTER = 20260101, 20260102, 20260103
-# algorithmic FP64-pipe work per particle-step of the canonical SV / multinomial / rs=1 step at L = 4
-# (DESIGN.md "Roofline"): fused multiply-adds, other adds/muls/converts, compares (binary search, max).
+# FP64 work per particle-step of the reference's algorithm (SV / multinomial / rs = 1; DESIGN.md "Roofline"): fused
+# multiply-adds, other adds/muls/converts, compares (10 levels of lower_bound on doubles + the max).  Fixed by the algorithm
+# and therefore the same count as in round 1; the kernel itself now runs the ten search compares on integer keys, so only
+# FP64_ON_PIPE of them occupy the FP64 pipe (reported next to the fraction).
 FP64_FMA, FP64_OTHER, FP64_CMP = 31.0, 13.0, 12.0
+FP64_ON_PIPE = 46.0
 
 
 def synthetic_sv_series(T, seed=SEED_SERIES, beta=1.0, phi=0.95, sigma=0.25):
@@ -536,13 +539,17 @@ def run_ours(args):
         roofline = {
             "bound": "fp64", "kernel": "bootstrap_filter_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": per_gpu * pipe_instr / fma_rate,
-            "frac_definition": "FP64-pipe issue slots: (31 FMA + 13 add/mul/cvt + 12 compare) per particle-step x particle-steps/s "
-                               "/ measured FP64 FMA instruction rate (micro-benchmark in this run)",
+            "frac_definition": "FP64 work of the reference's algorithm: (31 FMA + 13 add/mul/cvt + 12 compare) = 56 per particle-step x "
+                               "particle-steps/s / measured FP64 FMA instruction rate (micro-benchmark in this run); same count as round 1",
+            "fp64_pipe_instr_per_particle_step": FP64_ON_PIPE,
+            "fp64_pipe_utilisation": per_gpu * FP64_ON_PIPE / fma_rate,
+            "fp64_pipe_note": "the kernel runs the 10 search compares on 32-bit integer keys: 46 of the 56 occupy the FP64 pipe",
             "frac_flops": achieved_tflops / peak_tflops,
             "issue_slots": {"thread_instr_per_particle_step": prof["instr_per_pstep"], "source": "ncu SASS count, " + prof["file"],
                             "frac": (per_gpu * prof["instr_per_pstep"] / (layout["num_sms"] * 128.0 * clocks["sm_mhz"] * 1e6))
                             if (clocks.get("sm_mhz") and prof["instr_per_pstep"]) else None,
-                            "note": "what actually binds K1 (DESIGN.md section 5): 4 warp-instructions per SM per clock"},
+                            "note": "issue-slot utilisation (all issued instructions): what actually binds K1 (DESIGN.md section 5): "
+                                    "4 warp-instructions per SM per clock, with the FP64, ALU and IMAD pipes half-rate"},
             "peak_source": "measured in-run (ssme_b200_measure_fp64_fma_rate); "
             "MEASURED_PEAKS.json has no FP64 entry",
             "traffic": prof["traffic"] if (P_PROPOSALS == 4096) else None,
@@ -562,9 +569,9 @@ def run_ours(args):
                                  "frac_if_classes_overlapped_perfectly": per_gpu * max(terms.values()),
                                  "seconds_per_particle_step_by_class": terms,
                                  "rates_per_sec": dict(om, fp64_other=fma_rate),
-                                 "note": "op classes of the canonical step (N = 1024: 10 search levels; 18 = 3 FMA outside the two exps "
-                                         "+ 13 add/mul/convert + 2 compares), each class timed alone on the whole GPU in this run and "
-                                         "their times ADDED (no overlap between classes assumed)"}
+                                 "note": "NOT a roofline: op classes of the canonical step (N = 1024: 10 search levels; 18 = 3 FMA outside the "
+                                         "two exps + 13 add/mul/convert + 2 compares), each class timed alone on the whole GPU in this run and "
+                                         "their times ADDED (no overlap between classes assumed; the search class is timed on 8-byte keys)"}
         except Exception as ex:  # noqa: BLE001
             roofline["opmix"] = {"error": repr(ex)[:200]}
         # ---- CPU baseline: the reference's thread_pool path on this box's host cores -------------

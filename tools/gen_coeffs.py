@@ -7,7 +7,7 @@ reproducible on the other side, so both sides evaluate the SAME polynomials with
 SAME sequence of IEEE-754 operations.  This script derives those polynomials from
 scratch (Chebyshev-node interpolation in 60-digit arithmetic, then rounding to the
 target format) and prints them as C initialisers.  Output is pasted into
-oracle/det_math.h and ssme_b200/csrc/det_math.cuh; tests/test_detmath.py re-checks
+oracle/det_math.h and ssme_b200/csrc/det_math.cuh; tests/test_oracle.py (test_det_exp_log_within_ulps_of_libm) re-checks
 accuracy against libm.
 
 Usage: python tools/gen_coeffs.py
