@@ -43,6 +43,9 @@ extern "C" {
 #define SSME_B200_MODEL_SV 0          /* example/univ_svol_bootstrap_filter.h:17-103; theta = (beta, phi, sigma^2) */
 #define SSME_B200_MODEL_SV_LEVERAGE 1 /* test/test_liu_west.cpp:83-157; theta = (phi, mu, sigma, rho); z_t = y_{t-1} */
 #define SSME_B200_MODEL_LINEAR_GAUSSIAN 2 /* AR(1) + Gaussian noise, theta = (phi, sigma, tau): exact likelihood known (Kalman) */
+#define SSME_B200_MODEL_LINEAR_GAUSSIAN_OPTIMAL 3 /* the same model with the optimal proposal q(x_t | x_{t-1}, y_t): a model that
+                                                     brings its own proposal and incremental weights (general SISR: the reference's
+                                                     qSamp / logQEv / logFEv hooks, liu_west_filter.h:1495-1516) */
 
 /* resamplers */
 #define SSME_B200_RESAMP_MULTINOMIAL 0        /* pf::resamplers::mn_resampler (estimate_univ_svol.h:119) */

@@ -316,7 +316,10 @@ typedef struct {
     double inv2b2;  /* 0.5 / beta^2 */
     double rho_sigma, sdv; /* leverage: rho*sigma, sigma*sqrt(1-rho^2) */
     double tau, lg_h;      /* linear-Gaussian: observation sd, 0.5 / tau^2 */
+    /* linear-Gaussian with the optimal proposal (ssme_b200/csrc/models/linear_gaussian_optimal.cuh) */
+    double o_s, o_ax, o_ay, o_hw, o_cw, o_s0, o_ay0, o_hw0, o_cw0;
 } model_t;
+static int is_lg(int model) { return model == SSME_OR_MODEL_LINEAR_GAUSSIAN || model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL; }
 
 static void model_init(model_t* m, int model, const double* theta)
 {
@@ -325,26 +328,48 @@ static void model_init(model_t* m, int model, const double* theta)
         /* svol_bs(const pack&): beta = theta0, phi = theta1, sigma = sqrt(theta2) (:54-61) */
         m->beta = theta[0]; m->phi = theta[1]; m->sigma = sqrt(theta[2]);
         m->mu = 0.0; m->rho = 0.0;
-    } else if (model == SSME_OR_MODEL_LINEAR_GAUSSIAN) {
+    } else if (is_lg(model)) {
         /* phi, sigma, tau (ssme_b200/csrc/models/linear_gaussian.cuh) */
         m->beta = 1.0; m->phi = theta[0]; m->sigma = theta[1]; m->mu = 0.0; m->rho = 0.0;
     } else {
         /* phi, mu, sigma, rho (test_liu_west.cpp:70 transform order logit,null,log,twice_fisher) */
         m->beta = 1.0; m->phi = theta[0]; m->mu = theta[1]; m->sigma = theta[2]; m->rho = theta[3];
     }
-    m->tau = (model == SSME_OR_MODEL_LINEAR_GAUSSIAN) ? theta[2] : 1.0;
+    m->tau = is_lg(model) ? theta[2] : 1.0;
     m->lg_h = 0.5 / (m->tau * m->tau);
     m->sd0 = m->sigma / sqrt(1.0 - m->phi * m->phi);
-    m->c0 = -dm_log(model == SSME_OR_MODEL_LINEAR_GAUSSIAN ? m->tau : m->beta) - DM_HALF_LOG_2PI;
+    m->c0 = -dm_log(is_lg(model) ? m->tau : m->beta) - DM_HALF_LOG_2PI;
     m->inv2b2 = 0.5 / (m->beta * m->beta);
     m->rho_sigma = m->rho * m->sigma;
     m->sdv = m->sigma * sqrt(1.0 - m->rho * m->rho);
+    if (model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) { /* same operations, same order as LinearGaussianOptimalModel::init */
+        const double sig2 = m->sigma * m->sigma, tau2 = m->tau * m->tau;
+        const double s2 = 1.0 / (1.0 / sig2 + 1.0 / tau2);
+        m->o_s = sqrt(s2);
+        m->o_ax = (s2 * m->phi) / sig2;
+        m->o_ay = s2 / tau2;
+        const double v = sig2 + tau2;
+        m->o_hw = 0.5 / v;
+        m->o_cw = -0.5 * dm_log(v) - DM_HALF_LOG_2PI;
+        const double p0 = sig2 / (1.0 - m->phi * m->phi);
+        const double s02 = 1.0 / (1.0 / p0 + 1.0 / tau2);
+        m->o_s0 = sqrt(s02);
+        m->o_ay0 = s02 / tau2;
+        const double v0 = p0 + tau2;
+        m->o_hw0 = 0.5 / v0;
+        m->o_cw0 = -0.5 * dm_log(v0) - DM_HALF_LOG_2PI;
+    }
 }
 
 /* canonical: time-1 draw, transition and log-observation density */
-static double can_q1(const model_t* m, double z) { return z * m->sd0; }
-static double can_f(const model_t* m, double xa, double z, double cov)
+static double can_q1(const model_t* m, double z, double y)
 {
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) return fma(m->o_s0, z, m->o_ay0 * y);
+    return z * m->sd0;
+}
+static double can_f(const model_t* m, double xa, double z, double cov, double y)
+{
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) return fma(m->o_s, z, fma(m->o_ax, xa, m->o_ay * y));
     if (m->model != SSME_OR_MODEL_SV_LEVERAGE) return fma(m->phi, xa, m->sigma * z);
     double e2 = dm_exp(-0.5 * xa);
     double cz = m->rho_sigma * cov;
@@ -360,10 +385,32 @@ static double can_logg(const model_t* m, double y, double x)
     return fma(-h, e, fma(-0.5, x, m->c0));
 }
 
-/* faithful: the reference's expressions, operand order preserved */
-static double fai_q1(const model_t* m, double z) { return z * m->sigma / sqrt(1. - m->phi * m->phi); }
-static double fai_f(const model_t* m, double xa, double z, double cov)
+/* canonical incremental log-weight of a particle moved from xp to x: log g for the bootstrap models, the closed form of
+ * log g + log f - log q for the model with its own proposal (first: the time-1 draw, log mu + log g - log q1) */
+static double can_logw(const model_t* m, double y, double x, double xp, int first)
 {
+    if (m->model != SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) return can_logg(m, y, x);
+    if (first) return fma(-m->o_hw0, y * y, m->o_cw0);
+    const double d = y - m->phi * xp;
+    return fma(-m->o_hw, d * d, m->o_cw);
+}
+
+/* faithful: the reference's expressions, operand order preserved */
+static double fai_q1(const model_t* m, double z, double y)
+{
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) {
+        const double p0 = m->sigma * m->sigma / (1. - m->phi * m->phi), t2 = m->tau * m->tau;
+        const double s02 = 1. / (1. / p0 + 1. / t2);
+        return s02 / t2 * y + sqrt(s02) * z;
+    }
+    return z * m->sigma / sqrt(1. - m->phi * m->phi);
+}
+static double fai_f(const model_t* m, double xa, double z, double cov, double y)
+{
+    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) { /* qSamp: the optimal proposal */
+        const double s2 = 1. / (1. / (m->sigma * m->sigma) + 1. / (m->tau * m->tau));
+        return s2 * (m->phi * xa / (m->sigma * m->sigma) + y / (m->tau * m->tau)) + sqrt(s2) * z;
+    }
     if (m->model != SSME_OR_MODEL_SV_LEVERAGE) return m->phi * xa + z * m->sigma; /* univ_svol_bootstrap_filter.h:77 */
     double xt = m->mu + m->phi * (xa - m->mu) + cov * m->rho * m->sigma * exp(-.5 * xa); /* test_liu_west.cpp:116 */
     xt += z * m->sigma * sqrt(1.0 - m->rho * m->rho);                                  /* :118 */
@@ -371,12 +418,26 @@ static double fai_f(const model_t* m, double xa, double z, double cov)
 }
 static double fai_logg(const model_t* m, double y, double x)
 {
-    if (m->model == SSME_OR_MODEL_LINEAR_GAUSSIAN) return faithful_log_norm(y, x, m->tau);
+    if (is_lg(m->model)) return faithful_log_norm(y, x, m->tau);
     return faithful_log_norm(y, 0.0, m->beta * exp(.5 * x)); /* :85 ; leverage: beta = 1 */
 }
 static double fai_logmu(const model_t* m, double x)
 {
     return faithful_log_norm(x, 0.0, m->sigma / sqrt(1.0 - m->phi * m->phi)); /* :92-95 == :102 */
+}
+
+/* general SISR pieces of the model with its own proposal: logFEv, logQEv, logQ1Ev (liu_west_filter.h:1634-1636, :1706-1708) */
+static double fai_logf(const model_t* m, double x, double xp) { return faithful_log_norm(x, m->phi * xp, m->sigma); }
+static double fai_logq(const model_t* m, double x, double xp, double y)
+{
+    const double s2 = 1. / (1. / (m->sigma * m->sigma) + 1. / (m->tau * m->tau));
+    return faithful_log_norm(x, s2 * (m->phi * xp / (m->sigma * m->sigma) + y / (m->tau * m->tau)), sqrt(s2));
+}
+static double fai_logq1(const model_t* m, double x, double y)
+{
+    const double p0 = m->sigma * m->sigma / (1. - m->phi * m->phi), t2 = m->tau * m->tau;
+    const double s02 = 1. / (1. / p0 + 1. / t2);
+    return faithful_log_norm(x, s02 / t2 * y, sqrt(s02));
 }
 
 /* first i in [0,n) with !(C[i] < tau); n-1 if none (the reference pins cp[n-1] = 1.0 instead) */
@@ -466,7 +527,7 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         if (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL) tiled_alloc(&te, N, nt * L, L);
         NP = N; /* C below holds the global values O_b + cl_i, for the margin report only */
     }
-    if (cfg->model < SSME_OR_MODEL_SV || cfg->model > SSME_OR_MODEL_LINEAR_GAUSSIAN) return -3;
+    if (cfg->model < SSME_OR_MODEL_SV || cfg->model > SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL) return -3;
     if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
     const int injected = (cfg->rng_mode == SSME_OR_RNG_INJECTED);
     if (injected && !z_inj) return -5;
@@ -498,24 +559,28 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         for (int32_t i = 0; i < N; ++i) {
             double z = injected ? z_inj[t * N + i]
                                 : ssme_oracle_draw_normal(cfg->seed, cfg->filter_id, (uint32_t)t, (uint32_t)i);
+            const int own_q = (cfg->model == SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL); /* the model brings its own proposal */
             if (t == 0) {
                 if (canonical) {
-                    x[i] = can_q1(&mod, z);
-                    lw[i] = can_logg(&mod, yt, x[i]); /* logMu - logQ1 cancels analytically */
+                    x[i] = can_q1(&mod, z, yt);
+                    lw[i] = can_logw(&mod, yt, x[i], 0.0, 1); /* bootstrap models: logMu - logQ1 cancels analytically */
                 } else {
-                    x[i] = fai_q1(&mod, z);
-                    double v = fai_logmu(&mod, x[i]);  /* liu_west_filter.h:1703-1705 order */
+                    x[i] = fai_q1(&mod, z, yt);
+                    double v = fai_logmu(&mod, x[i]);  /* liu_west_filter.h:1706-1708 order */
                     v += fai_logg(&mod, yt, x[i]);
-                    v -= fai_logmu(&mod, x[i]);
+                    v -= own_q ? fai_logq1(&mod, x[i], yt) : fai_logmu(&mod, x[i]);
                     lw[i] = v;
                 }
             } else {
+                const double xp = x[i];
                 if (canonical) {
-                    x[i] = can_f(&mod, x[i], z, ct);
-                    lw[i] = lw[i] + can_logg(&mod, yt, x[i]);
+                    x[i] = can_f(&mod, xp, z, ct, yt);
+                    lw[i] = lw[i] + can_logw(&mod, yt, x[i], xp, 0);
                 } else {
-                    x[i] = fai_f(&mod, x[i], z, ct);
+                    x[i] = fai_f(&mod, xp, z, ct, yt);
+                    if (own_q) lw[i] += fai_logf(&mod, x[i], xp); /* liu_west_filter.h:1634-1636 order */
                     lw[i] += fai_logg(&mod, yt, x[i]);
+                    if (own_q) lw[i] -= fai_logq(&mod, x[i], xp, yt);
                 }
             }
             if (x_trace) x_trace[t * N + i] = x[i];

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1, SSME_OR_MODEL_LINEAR_GAUSSIAN = 2 };
+enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1, SSME_OR_MODEL_LINEAR_GAUSSIAN = 2, SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL = 3 };
 enum { SSME_OR_RESAMP_MULTINOMIAL = 0, SSME_OR_RESAMP_SORTED_MULTINOMIAL = 1, SSME_OR_RESAMP_SYSTEMATIC = 2 };
 enum { SSME_OR_ARITH_CANONICAL = 0, SSME_OR_ARITH_FAITHFUL = 1 };
 enum { SSME_OR_RNG_PHILOX = 0, SSME_OR_RNG_INJECTED = 1 };
@@ -72,6 +72,9 @@ typedef struct {
  *              SV_LEVERAGE (phi, mu, sigma, rho)                  [test/test_liu_west.cpp:83-157]
  *              LINEAR_GAUSSIAN (phi, sigma, tau): x_t = phi x_{t-1} + sigma z, y_t ~ N(x_t, tau^2)  [not a reference model:
  *              its exact likelihood is known (Kalman), ssme_b200/csrc/models/linear_gaussian.cuh]
+ *              LINEAR_GAUSSIAN_OPTIMAL: the same model and theta, filtered with the optimal proposal q(x_t | x_{t-1}, y_t)
+ *              (general SISR weights log g + log f - log q; FAITHFUL evaluates the three densities separately as the
+ *              reference's LWFilter2::filter does, liu_west_filter.h:1731-1736, CANONICAL their closed form)
  *   cov        covariate series z_t (leverage only); NULL means z_t = y_{t-1}, z_0 unused
  *   z_inj      injected N(0,1) stream [T][N]              (rng_mode INJECTED)
  *   u_inj      injected U[0,1) stream [T][stride_u]       (rng_mode INJECTED); stride_u = N

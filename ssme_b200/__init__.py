@@ -20,6 +20,7 @@ from .capi import (  # noqa: F401
     MODEL_SV,
     MODEL_SV_LEVERAGE,
     MODEL_LINEAR_GAUSSIAN,
+    MODEL_LINEAR_GAUSSIAN_OPTIMAL,
     RESAMP_MULTINOMIAL,
     RESAMP_SORTED_MULTINOMIAL,
     RESAMP_SYSTEMATIC,

@@ -12,8 +12,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-MODEL_SV, MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN = 0, 1, 2
-_NUM_PARAMS = {MODEL_SV: 3, MODEL_SV_LEVERAGE: 4, MODEL_LINEAR_GAUSSIAN: 3}
+MODEL_SV, MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN, MODEL_LINEAR_GAUSSIAN_OPTIMAL = 0, 1, 2, 3
+_NUM_PARAMS = {MODEL_SV: 3, MODEL_SV_LEVERAGE: 4, MODEL_LINEAR_GAUSSIAN: 3, MODEL_LINEAR_GAUSSIAN_OPTIMAL: 3}
 RESAMP_MULTINOMIAL, RESAMP_SORTED_MULTINOMIAL, RESAMP_SYSTEMATIC = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
 RNG_PHILOX, RNG_INJECTED = 0, 1

@@ -180,16 +180,17 @@ __global__ void __launch_bounds__(NT) cluster_filter_kernel(const FilterArgs a, 
         }
         double lw[kClL];
         double mloc = ninf;
+        double xo[kClL];  // the states before the move: only a model with its own proposal (logw) reads them
         if (t == 0) {
 #pragma unroll
-            for (int k = 0; k < kClL; ++k) x[k] = MODEL::q1(mc, ms, z[k]);
+            for (int k = 0; k < kClL; ++k) { xo[k] = 0.0; x[k] = MODEL::q1(mc, ms, z[k]); }
         } else {
 #pragma unroll
-            for (int k = 0; k < kClL; ++k) x[k] = MODEL::f(mc, ms, x[k], z[k]);
+            for (int k = 0; k < kClL; ++k) { xo[k] = x[k]; x[k] = MODEL::f(mc, ms, x[k], z[k]); }
         }
 #pragma unroll
         for (int k = 0; k < kClL; ++k) {
-            double v = MODEL::logg(mc, ms, x[k]);
+            double v = model_log_weight<MODEL>(mc, ms, x[k], xo[k], t == 0);
             v = (i0 + k < N) ? v : ninf;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;

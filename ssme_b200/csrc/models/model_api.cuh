@@ -19,10 +19,16 @@
 //       static __device__ double f   (const Params&, const Step&, double x, double z);  // x_t | x_{t-1} from one draw   (fSamp)
 //       static __device__ double logg(const Params&, const Step&, double x);            // log g(y_t | x_t)              (logGEv)
 //       // kHasF32: ParamsF, StepF, init_f32, step_f32, q1_f32, f_f32, logg_f32 with float states
+//       // OPTIONAL, for a proposal other than the transition density (general SISR, the qSamp / logQEv / logFEv hooks of
+//       // liu_west_filter.h:1495-1516 and of pf's SISR filters): f and q1 then SAMPLE THE PROPOSAL (they see the observation
+//       // through Step), and the model supplies the incremental log-weights
+//       static __device__ double logw (const Params&, const Step&, double x, double x_prev);  // log g + log f - log q
+//       static __device__ double logw1(const Params&, const Step&, double x);                 // log mu + log g - log q1
 //   };
 //
-// Contract.  The bootstrap proposal is built in (q = f, q1 = mu), so the time-1 weight is logg alone: logMuEv - logQ1Ev
-// cancels exactly (univ_svol_bootstrap_filter.h:92-95 vs :102).  One N(0,1) variate per particle per step (scalar state).
+// Contract.  Without logw / logw1 the bootstrap proposal is meant (q = f, q1 = mu), so the weight is logg alone: logMuEv -
+// logQ1Ev cancels exactly (univ_svol_bootstrap_filter.h:92-95 vs :102).  models/linear_gaussian_optimal.cuh is a model with
+// the optimal proposal p(x_t | x_{t-1}, y_t).  One N(0,1) variate per particle per step (scalar state).
 // Every arithmetic operation must be an explicit round-to-nearest intrinsic (__fma_rn, __dmul_rn, ...) or a det_math.cuh
 // function, because the same sequence is restated in oracle/pf_oracle.c (can_q1 / can_f / can_logg) and the two are tested
 // bit for bit.
@@ -31,4 +37,24 @@
 // include/ssme_b200.h; plus, for the parity tests, its restatement in oracle/pf_oracle.c.  No kernel changes
 // (models/linear_gaussian.cuh was added that way).
 #pragma once
+#include <type_traits>
+
 #include "../det_math.cuh"
+
+namespace ssme {
+
+template <typename M, typename = void>
+struct model_has_logw : std::false_type {};
+template <typename M>
+struct model_has_logw<M, std::void_t<decltype(&M::logw), decltype(&M::logw1)>> : std::true_type {};
+
+// incremental log-weight of a particle that moved from x_prev to x (first: the time-1 draw): log g for a bootstrap model
+// (identical code to calling logg directly), log g + log f - log q for a model that brings its own proposal
+template <typename M>
+__device__ __forceinline__ double model_log_weight(const typename M::Params& mc, const typename M::Step& ms, double x, double x_prev, bool first)
+{
+    if constexpr (model_has_logw<M>::value) return first ? M::logw1(mc, ms, x) : M::logw(mc, ms, x, x_prev);
+    else return M::logg(mc, ms, x);
+}
+
+}  // namespace ssme

@@ -2,6 +2,7 @@
 // Adding a model: write models/<name>.cuh, include it here and add one X(...) line; give it an id in include/ssme_b200.h.
 #pragma once
 #include "linear_gaussian.cuh"
+#include "linear_gaussian_optimal.cuh"
 #include "sv.cuh"
 #include "sv_leverage.cuh"
 
@@ -10,7 +11,8 @@
 #define SSME_FOR_EACH_MODEL(X) \
     X(SvModel)                 \
     X(SvLeverageModel)         \
-    X(LinearGaussianModel)
+    X(LinearGaussianModel)     \
+    X(LinearGaussianOptimalModel)
 
 namespace ssme {
 

@@ -262,16 +262,17 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         double lw[L];
         double mloc = __longlong_as_double(0xfff0000000000000ll);
         // one uniform branch per step (inside the particle loop the compiler keeps a test per particle)
+        double xo[L];  // the states before the move: only a model with its own proposal (logw) reads them
         if (tg == 0) {
 #pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = MODEL::q1(mc, ms, z[k]);
+            for (int k = 0; k < L; ++k) { xo[k] = 0.0; x[k] = MODEL::q1(mc, ms, z[k]); }
         } else {
 #pragma unroll
-            for (int k = 0; k < L; ++k) x[k] = MODEL::f(mc, ms, x[k], z[k]);
+            for (int k = 0; k < L; ++k) { xo[k] = x[k]; x[k] = MODEL::f(mc, ms, x[k], z[k]); }
         }
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            const double g = MODEL::logg(mc, ms, x[k]);
+            const double g = model_log_weight<MODEL>(mc, ms, x[k], xo[k], tg == 0);
             const double v = DEBUG ? __dadd_rn(lwacc[k], g) : g;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;

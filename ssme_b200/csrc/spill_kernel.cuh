@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = 4 * q + j;
+            const double xo = (a.t == 0) ? 0.0 : x[j];
             x[j] = (a.t == 0) ? MODEL::q1(mc, ms, (double)zf[j]) : MODEL::f(mc, ms, x[j], (double)zf[j]);
-            double v = MODEL::logg(mc, ms, x[j]);
+            double v = model_log_weight<MODEL>(mc, ms, x[j], xo, a.t == 0);
             v = (i0 + k < a.N) ? v : ninf;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;

@@ -236,6 +236,39 @@ def test_tile_relative_order_agrees_with_faithful(oracle, sv_series, resampler):
         assert np.max(np.abs(a["cond_like"] - b["cond_like"])) <= 1e-11
 
 
+@pytest.mark.parametrize("resampler", [0, 1, 2])
+def test_model_with_its_own_proposal_general_sisr(oracle, resampler):
+    """Model 3 (linear-Gaussian with the optimal proposal): CANONICAL (closed-form incremental weight) against FAITHFUL
+    (log f + log g - log q evaluated separately, in the order of liu_west_filter.h:1634-1636 / :1706-1708) on the same Philox
+    draws: same ancestors, log-likelihood within 1e-9; and the estimate is consistent with the exact Kalman likelihood."""
+    from oracle import binding as ob
+    th = np.array([0.9, 0.5, 0.7])
+    rng = np.random.default_rng(5)
+    T = 60
+    x, y = 0.0, np.empty(T)
+    x = rng.standard_normal() * th[1] / np.sqrt(1 - th[0] ** 2)
+    for t in range(T):
+        if t > 0:
+            x = th[0] * x + th[1] * rng.standard_normal()
+        y[t] = x + th[2] * rng.standard_normal()
+    m, P, exact = 0.0, th[1] ** 2 / (1 - th[0] ** 2), 0.0
+    for t, yt in enumerate(y):
+        if t > 0:
+            m, P = th[0] * m, th[0] ** 2 * P + th[1] ** 2
+        S = P + th[2] ** 2
+        exact += -0.5 * np.log(2 * np.pi * S) - 0.5 * (yt - m) ** 2 / S
+        m, P = m + P / S * (yt - m), (1 - P / S) * P
+    lls = []
+    for fid in range(6):
+        a = ob.filter_run(th, y, 300, model=3, resampler=resampler, L=4, seed=4, filter_id=fid)
+        b = ob.filter_run(th, y, 300, model=3, resampler=resampler, arithmetic=ob.ARITH_FAITHFUL, seed=4, filter_id=fid)
+        if a["margin"] > 1e-12:
+            assert np.array_equal(a["ancestors"], b["ancestors"])
+        assert abs(a["loglik"] - b["loglik"]) <= 1e-9 * abs(b["loglik"])
+        lls.append(a["loglik"])
+    assert abs(np.mean(lls) - exact) < 0.6 and np.std(lls) < 0.8
+
+
 def test_liu_west_expectations_oracle(oracle, sv_series):
     """E[h | y_{1:t}] before resampling: canonical (tiled sums) vs the reference's sequential numer / denom; constants come back."""
     from oracle import binding as ob
