@@ -119,11 +119,18 @@ __device__ __forceinline__ void k5_wait(const SpillArgs& a, int which, unsigned 
         }
     }
 }
-// called by thread 0 of every CTA after its last (possibly remote) store: the last CTA of the launch raises this rank's flag
-// `which` in every peer's block
-__device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which, unsigned int nctas)
+// called by thread 0 of every CTA after a CTA barrier that follows the CTA's last store: the last CTA of the launch raises this
+// rank's flag `which` in every peer's block.  A CTA that stored into a peer's HBM fences at system scope itself before it is
+// counted in; a CTA whose stores were all local needs the device-scope fence only.
+__device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which, unsigned int nctas, bool wrote_remote = true)
 {
+#ifdef SSME_K5_ALWAYS_SYSFENCE
+    (void)wrote_remote;
     __threadfence_system();
+#else
+    if (wrote_remote) __threadfence_system();
+    else __threadfence();
+#endif
     const unsigned int old = atomicAdd(a.done_ctr + which, 1u);
     if (old == nctas - 1u) {
         a.done_ctr[which] = 0u;
@@ -819,6 +826,17 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
     const bool staged = (s_hi - s_lo) <= kExpandBuf;
     const bool single = (a.tiles_per_rank == a.nb);
     const long long per_rank = (long long)a.tiles_per_rank * kTile;
+    // owner of a slot without a 64-bit division per slot: the slots of this tile start at s_lo, whose owner is found once;
+    // later slots cross into the next rank(s) at multiples of per_rank
+    static_assert(kTile == 4096, "the shift below is log2(kTile)");
+    const int owner0 = single ? 0 : (int)((unsigned)(s_lo >> 12) / (unsigned)a.tiles_per_rank);
+    const long long bound0 = (long long)(owner0 + 1) * per_rank;
+    auto store_slot = [&](long long sl, double val) {
+        int owner = owner0;
+        long long bnd = bound0;
+        while (sl >= bnd) { ++owner; bnd += per_rank; }
+        a.peer_x_anc[owner][sl - (bnd - per_rank)] = val;
+    };
     const int nfields = 1 + a.nextra;
     for (int fld = 0; fld < nfields; ++fld) {
         const double* src = (fld == 0) ? a.x_cur + l0 : a.extra_cur[fld - 1] + i0;  // extras are single-rank: global index
@@ -844,8 +862,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
                 if (single || fld > 0) {
                     dst_local[sl] = ebuf[q];
                 } else {
-                    const int owner = (int)(sl / per_rank);
-                    a.peer_x_anc[owner][sl - (long long)owner * per_rank] = ebuf[q];
+                    store_slot(sl, ebuf[q]);
                 }
             }
             __syncthreads();
@@ -873,8 +890,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
                         if (single || fld > 0) {
                             dst_local[sl] = v[k];
                         } else {
-                            const int owner = (int)(sl / per_rank);
-                            a.peer_x_anc[owner][sl - (long long)owner * per_rank] = v[k];
+                            store_slot(sl, v[k]);
                         }
                     }
                 }
@@ -887,8 +903,7 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
                     if (single || fld > 0) {
                         dst_local[sl] = val;
                     } else {
-                        const int owner = (int)(sl / per_rank);
-                        a.peer_x_anc[owner][sl - (long long)owner * per_rank] = val;
+                        store_slot(sl, val);
                     }
                 }
             }
@@ -901,8 +916,14 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
             for (int sl = A[k]; sl < A[k + 1]; ++sl) a.ancestors[(size_t)a.t * a.N + sl] = i0 + k;
     }
     if (a.world > 1) {  // K5: the offspring went into the slot owners' HBM; tell every peer when this rank is done
-        __syncthreads();  // all stores of the CTA happen before thread 0's system-scope fence (cumulativity through the barrier)
-        if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x);
+        __syncthreads();  // all stores of the CTA happen before thread 0's fence (cumulativity through the barrier)
+        if (tid == 0) {
+            int owner_hi = owner0;  // owner of the last slot this tile fathered
+            long long bnd = bound0;
+            while ((long long)s_hi - 1 >= bnd) { ++owner_hi; bnd += per_rank; }
+            const bool wrote_remote = (s_hi > s_lo) && (owner0 != a.rank || owner_hi != a.rank);
+            k5_signal_last_cta(a, 1, gridDim.x, wrote_remote);
+        }
     }
 }
 
@@ -955,9 +976,9 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
         for (int e = 0; e < a.nextra; ++e) a.extra_anc[e][(size_t)blockIdx.x * kTile + (size_t)k * kTileNT + tid] = a.extra_cur[e][i];
         if (a.ancestors) a.ancestors[(size_t)a.t * a.N + j] = (int)i;
     }
-    if (a.world > 1) {  // K5: this rank has finished reading the peers' x' and cl of this step
+    if (a.world > 1) {  // K5: this rank has finished reading the peers' x' and cl of this step (its stores are all local)
         __syncthreads();
-        if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x);
+        if (tid == 0) k5_signal_last_cta(a, 1, gridDim.x, false);
     }
 }
 
