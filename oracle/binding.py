@@ -126,7 +126,7 @@ class _LwStreams(C.Structure):
 
 
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
-                  cov=None, trace=True, tiled=2, form="sisr", streams=None):
+                  cov=None, trace=True, tiled=3, form="sisr", streams=None):
     """Liu-West filter on the SV-with-leverage model; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary
     particle filter).  streams: optional dict(u_prior [N][4], z_state [T][N], z_jitter [T][N][4], u_resamp [T][s], u_aux [T][N])
     of pre-generated draws replacing the Philox streams.

@@ -218,7 +218,7 @@ static void tiled_build(tiled_cdf_t* c, const double* w)
  * w_i = exp(lw_i - m_b) (m_b = -inf, a tile without a finite log-weight, counts as 0: all its weights are exp(-inf) = 0), scanned
  * inside the tile as above (cl_i, total T_b).  Then M = max_b m_b, s_b = exp(m_b - M), the tile totals T_b s_b are scanned as
  * above (E_b, S) and C_i = O_b + cl_i s_b.  Returns M. */
-static double tiled_build_rel(tiled_cdf_t* c, const double* lw, double* w_out)
+static double tiled_build_rel2(tiled_cdf_t* c, const double* lw, double* w_out, double* wrel_out)
 {
     double* tt = (double*)calloc((size_t)c->nb, sizeof(double));
     double* mb = (double*)calloc((size_t)c->nb, sizeof(double));
@@ -232,6 +232,8 @@ static double tiled_build_rel(tiled_cdf_t* c, const double* lw, double* w_out)
         if (m > M) M = m;
         const double mref = (m == -INFINITY) ? 0.0 : m;
         for (int32_t i = 0; i < n_b; ++i) w[i] = dm_exp(lw[(size_t)b * c->TS + i] - mref);
+        if (wrel_out) /* weights relative to the tile's own maximum (the Liu-West expectations sum these) */
+            for (int32_t i = 0; i < n_b; ++i) wrel_out[(size_t)b * c->TS + i] = w[i];
         ssme_oracle_canonical_scan(w, n_b, c->L, c->TS, c->cl + (size_t)b * c->TS, &tt[b]);
     }
     for (int32_t b = 0; b < c->nb; ++b) {
@@ -244,6 +246,7 @@ static double tiled_build_rel(tiled_cdf_t* c, const double* lw, double* w_out)
     free(tt); free(mb); free(w);
     return M;
 }
+static double tiled_build_rel(tiled_cdf_t* c, const double* lw, double* w_out) { return tiled_build_rel2(c, lw, w_out, NULL); }
 
 static int32_t tiled_search(const tiled_cdf_t* c, double tau)
 {
@@ -856,6 +859,15 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
     if (canonical) tiled_alloc(&tc, N, nt * L, L);
     const int sorted = (cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL);
     if (canonical && sorted) tiled_alloc(&te, N, nt * L, L);
+    /* tiled == 3 (what lw_kernel.cuh runs since round 2): the weights of both stages in the tile-relative order of
+     * tiled_build_rel; expectations as tile sums of h exp(lw - m_b), rescaled by s_b when the tiles are added; and, with
+     * systematic resampling, the moments of the RESAMPLED parameters summed by the kernel that writes the offspring, in ITS
+     * order: the slots fathered by tile b of particles form a contiguous range [lo_b, hi_b) (the ancestors are monotone); lane l
+     * of the 512 takes the slots lo_b + l, lo_b + l + 512, ... in order; the lanes are added as in block_sum; the tiles as usual. */
+    const int rel = canonical && cfg->tiled == 3;
+    const int by_counts = rel && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC;
+    double pend_s1[4] = {0, 0, 0, 0}, pend_s2[4][4] = {{0}};
+    double* wrel = rel ? (double*)malloc(sizeof(double) * (size_t)N) : NULL;
     double* Ex = sorted ? (double*)malloc(sizeof(double) * (size_t)(N + 1)) : NULL;
     double* x = (double*)malloc(sizeof(double) * (size_t)N);
     double* th = (double*)malloc(sizeof(double) * (size_t)N * 4); /* SoA: th[k*N + i], transformed */
@@ -878,7 +890,15 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
         if (t > 0) {
             /* update_parameter_proposal_components: thetaBar, V_t, cov = h^2 V_t, factor */
             double V[4][4];
-            if (canonical) {
+            if (by_counts) {
+                double s2[4][4];
+                for (int k = 0; k < 4; ++k) tb[k] = pend_s1[k] / (double)N;
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l <= k; ++l) {
+                        s2[k][l] = pend_s2[k][l] / (double)N;
+                        V[k][l] = h2 * (s2[k][l] - tb[k] * tb[l]);
+                    }
+            } else if (canonical) {
                 double s2[4][4];
                 for (int k = 0; k < 4; ++k) tb[k] = ssme_oracle_canonical_sum(th + (size_t)k * N, N, L, nt) / (double)N;
                 for (int k = 0; k < 4; ++k)
@@ -928,7 +948,11 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
                 if (lfs[i] > M2) M2 = lfs[i];
             }
             double S2;
-            if (canonical) {
+            if (rel) {
+                M2 = tiled_build_rel(&tc, lfs, NULL);
+                S2 = tc.S;
+                fs_M2 = M2; fs_logS2 = dm_log(S2);
+            } else if (canonical) {
                 for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lfs[i] - M2);
                 tiled_build(&tc, w);
                 S2 = tc.S;
@@ -1014,7 +1038,11 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
         double M = -INFINITY;
         for (int32_t i = 0; i < N; ++i) if (lw[i] > M) M = lw[i];
         double S;
-        if (canonical) {
+        if (rel) {
+            M = tiled_build_rel2(&tc, lw, w, wrel);
+            S = tc.S;
+            for (int32_t i = 0; i < N; ++i) C[i] = tiled_value(&tc, i);
+        } else if (canonical) {
             for (int32_t i = 0; i < N; ++i) w[i] = dm_exp(lw[i] - M);
             tiled_build(&tc, w);
             S = tc.S;
@@ -1028,7 +1056,19 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
         }
         if (expect) {
             for (int q = 0; q < 5; ++q) {
-                if (canonical) {
+                if (rel) {
+                    double* pb = (double*)calloc((size_t)tc.nb, sizeof(double));
+                    for (int32_t i = 0; i < N; ++i) {
+                        double hv = (q == 0) ? x[i] : lw_inv_trans(TT[q - 1], th[(size_t)(q - 1) * N + i], 1);
+                        tmp[i] = wrel[i] * hv;
+                    }
+                    for (int32_t b = 0; b < tc.nb; ++b) {
+                        int32_t n_b = N - b * tc.TS < tc.TS ? N - b * tc.TS : tc.TS;
+                        pb[b] = block_sum(tmp + (size_t)b * tc.TS, n_b, L, nt) * tc.sb[b];
+                    }
+                    expect[t * 5 + q] = block_sum(pb, tc.nb, tc.Lp, 1024) / S;
+                    free(pb);
+                } else if (canonical) {
                     for (int32_t i = 0; i < N; ++i) {
                         double hv = (q == 0) ? x[i] : lw_inv_trans(TT[q - 1], th[(size_t)(q - 1) * N + i], 1);
                         tmp[i] = w[i] * hv;
@@ -1054,7 +1094,7 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
         double u0 = 0.0, sN = S / (double)N;
         if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC)
             u0 = st ? st->u_resamp[t * stride_u] : ssme_oracle_draw_uniform(cfg->seed, cfg->filter_id, (uint32_t)t, 0u, utag);
-        if (canonical && cfg->tiled == 2 && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) systematic_by_counts(&tc, N, u0, sN, anc);
+        if (canonical && cfg->tiled >= 2 && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC) systematic_by_counts(&tc, N, u0, sN, anc);
         else if (sorted) {
             /* liu_west_filter.h:104-139: N+1 exponential spacings -> uniform order statistics */
             for (int32_t j = 0; j <= N; ++j) {
@@ -1095,6 +1135,51 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
             anc[j] = canonical ? tiled_search(&tc, tau) : lower_bound_idx(C, N, tau);
             upd_margin(&margin, C, anc[j], tau, total);
         }
+        if (by_counts) {
+            const int32_t TS = tc.TS, nb = tc.nb, lanes = nt;
+            double* partq = (double*)calloc((size_t)nb * 14, sizeof(double));
+            double* tl = (double*)malloc(sizeof(double) * (size_t)lanes);
+            int32_t lo = 0;
+            for (int32_t b = 0; b < nb; ++b) {
+                int32_t hi = lo;
+                while (hi < N && anc[hi] / TS == b) ++hi;
+                for (int q = 0; q < 14; ++q) {
+                    int k = 0, l = -1;
+                    if (q < 4) k = q;
+                    else { int slot = 4; for (int kk = 0; kk < 4; ++kk) for (int ll = 0; ll <= kk; ++ll) { if (slot == q) { k = kk; l = ll; } ++slot; } }
+                    for (int32_t ln = 0; ln < lanes; ++ln) {
+                        double acc = 0.0;
+                        int first = 1;
+                        for (int32_t j = lo + ln; j < hi; j += lanes) {
+                            const double vk = th[(size_t)k * N + anc[j]];
+                            const double val = (l < 0) ? vk : vk * th[(size_t)l * N + anc[j]];
+                            acc = first ? val : acc + val;
+                            first = 0;
+                        }
+                        tl[ln] = acc;
+                    }
+                    double accw = 0.0;
+                    for (int32_t g = 0; g < lanes / 32; ++g) {
+                        double* wv = tl + g * 32;
+                        for (int32_t d = 16; d >= 1; d >>= 1) {
+                            double t2[32];
+                            for (int32_t ln = 0; ln < 32; ++ln) t2[ln] = wv[ln] + wv[ln ^ d];
+                            for (int32_t ln = 0; ln < 32; ++ln) wv[ln] = t2[ln];
+                        }
+                        accw = (g == 0) ? wv[0] : accw + wv[0];
+                    }
+                    partq[(size_t)q * nb + b] = accw;
+                }
+                lo = hi;
+            }
+            {
+                int slot = 4;
+                for (int k = 0; k < 4; ++k) pend_s1[k] = block_sum(partq + (size_t)k * nb, nb, tc.Lp, 1024);
+                for (int k = 0; k < 4; ++k)
+                    for (int l = 0; l <= k; ++l) pend_s2[k][l] = block_sum(partq + (size_t)(slot++) * nb, nb, tc.Lp, 1024);
+            }
+            free(partq); free(tl);
+        }
         for (int32_t j = 0; j < N; ++j) {
             xn[j] = x[anc[j]];
             for (int k = 0; k < 4; ++k) xn[(size_t)(k + 1) * N + j] = th[(size_t)k * N + anc[j]];
@@ -1116,7 +1201,7 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
     free(Ex);
     if (loglik_out) *loglik_out = loglik;
     if (tie_margin) *tie_margin = margin;
-    free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc); free(lfs); free(ks);
+    free(x); free(th); free(xn); free(lw); free(w); free(C); free(tmp); free(anc); free(lfs); free(ks); free(wrel);
     return 0;
 }
 

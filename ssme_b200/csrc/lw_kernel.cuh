@@ -2,19 +2,25 @@
 //
 // Replaces LWFilter2WithCovs::filter (include/ssme/liu_west_filter.h:2191-2343) and
 // update_parameter_proposal_components (:2346-2360) for the SV-with-leverage model svol_lw_2_par
-// (test/test_liu_west.cpp:213-358): per step
-//   lw_moments_kernel + lw_moments_final_kernel   thetaBar, V_t over all particles, chol(h^2 V_t)        (:2346-2360)
-//   lw_propagate_kernel    theta' = a theta + (1-a) thetaBar + L z, untransform, x' ~ f(.|x, theta'), log g  (:2210-2224)
-//   spill_reduce_max / weights_scan / tile_scan   log-sum-exp of :2238-2245 (K3 kernels, unchanged)
-//   spill_resample_kernel  states and the 4 parameters resampled together (mn_resamp_states_and_params, :91-145)
+// (test/test_liu_west.cpp:213-358).  Round 2: THREE launches per time step in the tile-relative order of K3 (round 1: seven):
+//   lw_step_kernel<0>      theta' = a theta + (1-a) thetaBar + L z, untransform, x' ~ f(.|x, theta'), log g (:2210-2224), then in
+//                          the same pass the tile maximum m_b, w = exp(lw - m_b), the tile-local scan cl and the tile triple
+//                          (the log-weights never reach HBM); optionally the tile sums of h exp(lw - m_b) for the expectations
+//   spill_tile_scan_kernel M = max_b m_b, s_b = exp(m_b - M), scan of T_b s_b, log p(y_t | y_{1:t-1})      (:2238-2245)
+//   lw_expand_kernel       systematic resampling of the states and the 4 parameters together by offspring counts
+//                          (mn_resamp_states_and_params, :91-145, is the reference's resampler; systematic is ours), the
+//                          moments of the RESAMPLED parameters summed while the offspring are written, and -- in the last
+//                          CTA to finish -- thetaBar, V_t and chol(h^2 V_t) for the next step (:2346-2360)
+// (multinomial / sorted-multinomial resampling: spill_resample_kernel, then lw_moments_kernel over the resampled parameters,
+// whose last CTA finishes the moments the same way.)
 // and LWFilterWithCovs::filter (:971-1159, the auxiliary-particle form, on svol_lw_1_par, test/test_liu_west.cpp:83-157):
-//   lw_apf_first_kernel    lfs_i = log g(y_t | propMu(x_i, z_t, theta_i))                                   (:985-1000)
-//   K3b/K3c/K3d            its max, tile CDFs and tile ends (first stage: log S kept, no likelihood term yet)
-//   lw_propagate_kernel<1> slot j draws k_j by the two-level descent (k_gen::sample, :1012), gathers particle k_j,
-//                          jitters and propagates it, lw_j = log g(y_t | x'_j) - lfs_k                         (:1025-1042)
-//   then K3b..K3e as in the SISR form; log p(y_t | y_{1:t-1}) joins both stages (:1056-1058)
+//   lw_first_kernel        lfs_i = log g(y_t | propMu(x_i, z_t, theta_i)) (:985-1000), its tile maximum, weights, tile scan
+//   spill_tile_scan_kernel first stage: M2 + log S2 kept
+//   lw_step_kernel<1>      slot j draws k_j by the two-level descent (k_gen::sample, :1012), gathers particle k_j,
+//                          jitters and propagates it, lw_j = log g(y_t | x'_j) - lfs_k (:1025-1042); tail as above
+//   then the tile scan and the resampling as in the SISR form; log p(y_t | y_{1:t-1}) joins both stages (:1056-1058)
 // The reference builds 2-3 param::pack objects (heap, string-keyed factory) per particle per step (:2214, parameters.h:290-313);
-// here a particle is five doubles in five SoA arrays.  Arithmetic = oracle's ssme_oracle_lw_filter, CANONICAL.
+// here a particle is five doubles in five SoA arrays.  Arithmetic = oracle's ssme_oracle_lw_filter_streams, CANONICAL, tiled = 3.
 #pragma once
 #include "spill_kernel.cuh"
 
@@ -24,17 +30,17 @@ struct LwArgs {
     SpillArgs s;
     const double* th_anc[4];  // transformed parameters entering the step (after resampling)
     double* th_cur[4];        // jittered parameters of this step
-    double* part;             // [14][nb] tile partial sums
+    double* part;             // [14][nb] tile partial sums (moments; expectations use the first 5 rows)
     double* mom;              // [0..3] thetaBar, [4..19] chol factor row-major, [20..23] scratch means
+    unsigned int* ctr;        // arrival counter: the last CTA of a launch finishes the sums
     double* theta_bar_out;    // [T][4] or null
     double lo[4], hi[4];      // uniform prior box (untransformed)
     double a, oma, h2;
-    int mode;                 // moments kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values,
-                              // 2 = 5 weighted sums  sum_i exp(lw_i - M) h(x_i, theta_i)  for the expectations (h = x, phi, mu, sigma, rho)
-    double* expect_out;       // [T][5] E[h | y_{1:t}] formed before resampling, or null
+    int mode;                 // lw_moments_kernel: 0 = 4 sums + 10 products of transformed values, 1 = 4 sums of untransformed values
+    double* expect_out;       // [T][5] E[h | y_{1:t}] (h = x, phi, mu, sigma, rho) formed before resampling, or null
     // auxiliary-particle form (LWFilterWithCovs, liu_west_filter.h:971-1159)
     double* lfs;              // [N] first-stage log-weights log g(y_t | propMu(x_i, z_t, theta_i))
-    double* cdf1;             // [N] first-stage buffer: log-weights, then their tile-local CDF (K3c/K3d run on it)
+    const double* cdf1;       // [N] tile-local CDF of the first-stage weights
     int* aux_out;             // [T][N] first-stage indices k_j, or null
 };
 
@@ -80,77 +86,113 @@ __device__ __forceinline__ void block_sums(double (&v)[NQ], double* red /*[NW][N
     __syncthreads();
 }
 
-// thetaBar, V_t, cholesky(h^2 V_t) (or the plain means / the expectations) from the 14 totals; one thread
-__device__ __forceinline__ void lw_finalize(const LwArgs& a, const double* tot)
+// Totals of the tile partials part[q][0..nb) in the canonical 1024-lane order (oracle: block_sum(part, nb, Lp, 1024)) by a CTA
+// of NT threads: thread tid plays the virtual lanes tid, tid + NT, ...  With `scale` the partial of tile b is multiplied by
+// scale[b] first (expectations: s_b).  tot[0..nq) in shared memory on return.
+template <int NT>
+__device__ __forceinline__ void lw_final_sums(const double* part, const double* scale, int nb, int Lp, int nq, double* red /*[32*14]*/,
+                                              double* tot /*[14]*/, int tid)
 {
-    const double dN = (double)a.s.N;
-    if (a.mode == 1) {
-        for (int k = 0; k < 4; ++k) a.mom[20 + k] = __ddiv_rn(tot[k], dN);
-        return;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+    for (int v = 0; v < 1024 / NT; ++v) {
+        const int b0 = (v * NT + tid) * Lp;
+        double s[14];
+#pragma unroll
+        for (int q = 0; q < 14; ++q) s[q] = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            const bool in = b0 + k < nb;
+            const double sc = (in && scale) ? __ldcg(scale + b0 + k) : 1.0;
+#pragma unroll
+            for (int q = 0; q < 14; ++q) {
+                if (q < nq) {
+                    double val = in ? __ldcg(part + (size_t)q * nb + b0 + k) : 0.0;
+                    if (scale) val = in ? __dmul_rn(val, sc) : 0.0;
+                    s[q] = (k == 0) ? val : __dadd_rn(s[q], val);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 14; ++q) {
+            if (q < nq) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) s[q] = __dadd_rn(s[q], shfl_xor_d(s[q], d));
+                if (lane == 0) red[(v * (NT / 32) + warp) * 14 + q] = s[q];
+            }
+        }
     }
-    if (a.mode == 2) {  // runs after the scan of the tile totals: scal[1] = S
-        const double S = a.s.scal[1];
-        for (int k = 0; k < 5; ++k) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + k] = __ddiv_rn(tot[k], S);
-        return;
+    __syncthreads();
+    if (tid < nq) {
+        double acc = red[tid];
+        for (int g = 1; g < 32; ++g) acc = __dadd_rn(acc, red[g * 14 + tid]);
+        tot[tid] = acc;
     }
+    __syncthreads();
+}
+
+// thetaBar, V_t, cholesky(h^2 V_t) from the 14 totals; thread 0 of the finishing CTA (the totals' divisions by N run in
+// parallel in the callers' threads 0..13 first: tot[] holds the MEANS on entry)
+__device__ __forceinline__ void lw_finalize_moments(const LwArgs& a, const double* mean)
+{
     double tb[4], V[4][4], Lc[4][4];
-    for (int k = 0; k < 4; ++k) tb[k] = __ddiv_rn(tot[k], dN);
+    for (int k = 0; k < 4; ++k) tb[k] = mean[k];
     int slot = 4;
     for (int k = 0; k < 4; ++k)
-        for (int l = 0; l <= k; ++l) {
-            const double s2 = __ddiv_rn(tot[slot++], dN);
-            V[k][l] = __dmul_rn(a.h2, __dsub_rn(s2, __dmul_rn(tb[k], tb[l])));
-        }
+        for (int l = 0; l <= k; ++l) V[k][l] = __dmul_rn(a.h2, __dsub_rn(mean[slot++], __dmul_rn(tb[k], tb[l])));
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) Lc[i][j] = 0.0;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j <= i; ++j) {
             double sacc = V[i][j];
             for (int k = 0; k < j; ++k) sacc = __dsub_rn(sacc, __dmul_rn(Lc[i][k], Lc[j][k]));
-            Lc[i][j] = (i == j) ? __dsqrt_rn(sacc) : __ddiv_rn(sacc, Lc[j][j]);
+            // a non-positive pivot zeroes its column, so a zero covariance (delta = 1) draws the mean exactly (as the oracle)
+            if (i == j) Lc[i][j] = (sacc > 0.0) ? __dsqrt_rn(sacc) : 0.0;
+            else Lc[i][j] = (Lc[j][j] > 0.0) ? __ddiv_rn(sacc, Lc[j][j]) : 0.0;
         }
     for (int k = 0; k < 4; ++k) a.mom[k] = tb[k];
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) a.mom[4 + 4 * i + j] = Lc[i][j];
-    if (a.theta_bar_out)
-        for (int k = 0; k < 4; ++k) a.theta_bar_out[(size_t)(a.s.t - a.s.row0) * 4 + k] = tb[k];
 }
 
+// Called by every thread of a CTA after the CTA's tile partials have been stored (and fenced) by their writers: counts the CTA
+// in; the last CTA of the launch adds the partials up and finishes them (mode 0: moments -> mom[0..19]; mode 1: means of the
+// untransformed parameters -> mom[20..23]).  red [32*14], tot [14], flag [1] are shared scratch.
+template <int NT>
+__device__ __forceinline__ void lw_last_cta_finish(const LwArgs& a, int mode, double* red, double* tot, int* flag, int tid)
+{
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int old = atomicAdd(a.ctr, 1u);
+        *flag = (old == gridDim.x - 1u);
+        if (*flag) *a.ctr = 0u;
+    }
+    __syncthreads();
+    if (!*flag) return;
+    __threadfence();
+    const int nq = (mode == 1) ? 4 : 14;
+    lw_final_sums<NT>(a.part, nullptr, a.s.nb, a.s.Lp, nq, red, tot, tid);
+    if (tid < nq) tot[tid] = __ddiv_rn(tot[tid], (double)a.s.N);
+    __syncthreads();
+    if (mode == 1) {
+        if (tid < 4) a.mom[20 + tid] = tot[tid];
+    } else if (tid == 0) {
+        lw_finalize_moments(a, tot);
+    }
+}
+
+// Tile sums over PARTICLES of the resampled parameters (multinomial / sorted-multinomial resampling; and mode 1, the means of
+// the untransformed parameters at the end of a run); the last CTA finishes them.
 __global__ void __launch_bounds__(kTileNT, 2) lw_moments_kernel(const LwArgs a)
 {
     constexpr int NW = kTileNT / 32;
-    __shared__ double red[NW * 14];
+    __shared__ double red[32 * 14];
     __shared__ double tot[14];
+    __shared__ int flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
     double s[14];
-    if (a.mode == 2) {
-        // expectations before resampling (liu_west_filter.h:1087-1101 / :2263-2276): numer += h(x_i, theta_i) exp(lw_i - m);
-        // the denominator is the weight total S of the scan that follows.  Runs between the max and the weights/scan kernels.
-        const double M = a.s.scal[0];
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < kTileL; ++k) {
-            const size_t i = (size_t)i0 + k;
-            const bool valid = i0 + k < a.s.N;
-            const double w = valid ? dexp_nonpos(__dsub_rn(a.s.lwc[i], M)) : 0.0;
-            double hv[5];
-            hv[0] = valid ? a.s.x_cur[i] : 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hv[1 + q] = valid ? lw_inv_trans(q, a.th_cur[q][i]) : 0.0;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const double p = __dmul_rn(w, hv[q]);
-                acc[q] = (k == 0) ? p : __dadd_rn(acc[q], p);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 14; ++q) s[q] = (q < 5) ? acc[q] : 0.0;
-        block_sums<14, NW>(s, red, 5, lane, warp, tid, tot);
-        if (tid < 5) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
-        return;
-    }
     // two particles at a time (16-byte loads), the 14 running sums updated in particle order: the same additions in the same
     // order as summing each quantity over the thread's 8 particles, with 8 + 14 live doubles instead of 32 + 14 (2 CTAs per SM)
 #pragma unroll
@@ -198,78 +240,33 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_moments_kernel(const LwArgs a)
     }
     const int nq = (a.mode == 1) ? 4 : 14;
     block_sums<14, NW>(s, red, nq, lane, warp, tid, tot);
-    if (tid < nq) a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
+    if (tid < nq) {
+        a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
+        __threadfence();
+    }
+    lw_last_cta_finish<kTileNT>(a, a.mode, red, tot, &flag, tid);
 }
 
-// one CTA: totals of the tile partials, thetaBar, V_t, cholesky(h^2 V_t)
-__global__ void __launch_bounds__(kTileScanNT) lw_moments_final_kernel(const LwArgs a)
+// one CTA, after the scan of the tile totals (scal[1] = S): E[h | y_{1:t}] = sum_b s_b P_b / S from the tile sums
+// P_b = sum_{i in b} h_i exp(lw_i - m_b) that lw_step_kernel left in part[0..4]
+__global__ void __launch_bounds__(kTileScanNT) lw_expect_final_kernel(const LwArgs a)
 {
     __shared__ double red[32 * 14];
     __shared__ double tot[14];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nq = (a.mode == 1) ? 4 : (a.mode == 2) ? 5 : 14;
-    const int b0 = tid * a.s.Lp;
-    double s[14];
-#pragma unroll
-    for (int q = 0; q < 14; ++q) {
-        s[q] = 0.0;
-        if (q < nq) {
-            const double* p = a.part + (size_t)q * a.s.nb;
-            for (int k = 0; k < a.s.Lp; ++k) {
-                const double v = (b0 + k < a.s.nb) ? p[b0 + k] : 0.0;
-                s[q] = (k == 0) ? v : __dadd_rn(s[q], v);
-            }
-        }
-    }
-    block_sums<14, 32>(s, red, nq, lane, warp, tid, tot);
-    if (tid == 0) lw_finalize(a, tot);
+    const int tid = threadIdx.x;
+    lw_final_sums<kTileScanNT>(a.part, a.s.sb, a.s.nb, a.s.Lp, 5, red, tot, tid);
+    if (tid < 5) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + tid] = __ddiv_rn(tot[tid], a.s.scal[1]);
 }
 
-constexpr int kLwNT = 256;                 // threads of the propagation CTA
-constexpr int kLwIters = 4;                // particles per thread, one at a time
-constexpr int kLwSub = kLwNT * kLwIters;   // 1024 particles per CTA: kTile / kLwSub partial maxima per tile
-static_assert(kTile % kLwSub == 0, "sub-tiles nest in the tiles");
-
-// state normal of particle (warp base + q*32 + lane): lane l of the warp holds the Philox block of particles
-// warp base + 4l .. 4l+3 (same blocks as K1/K3: block index = particle / 4), so each block is computed once
-__device__ __forceinline__ double lw_state_normal(const float (&zs)[4], int q, int lane)
+// ---- the fused tile pass ----------------------------------------------------------------------------------------------------
+// Tail of a fused tile pass (the same steps as spill_step_kernel's): lws[k * kTileNT + tid] holds the log-weight of this
+// thread's k-th particle (thread-private slots) and mloc their maximum.  Forms the tile maximum m_b, the weights relative to it
+// (left in lws), the tile-local inclusive scan (stored to cl) and the tile triple (m_b, T_b, max cl).
+__device__ __forceinline__ void lw_tile_tail(const SpillArgs& s, double* lws, double mloc, double* cl /*this thread's 8 entries*/, int tile,
+                                             double* red /*[16]*/, double* red_sum /*[32]*/, double* red_max /*[32]*/, int tid, int lane, int warp)
 {
-    const int src = q * 8 + (lane >> 2);
-    const float z0 = __shfl_sync(0xffffffffu, zs[0], src), z1 = __shfl_sync(0xffffffffu, zs[1], src);
-    const float z2 = __shfl_sync(0xffffffffu, zs[2], src), z3 = __shfl_sync(0xffffffffu, zs[3], src);
-    const int c = lane & 3;
-    return (double)((c == 0) ? z0 : (c == 1) ? z1 : (c == 2) ? z2 : z3);
-}
-
-// First stage of the auxiliary form: the log-weight of the predicted state propMu(x_i) under particle i's own parameters.
-__global__ void __launch_bounds__(kLwNT, 4) lw_apf_first_kernel(const LwArgs a)
-{
-    __shared__ double red[kLwNT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = a.s.t;
-    const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
-    const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
-    const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
+    constexpr int NW = kTileNT / 32;
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
-    const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);
-    double mloc = ninf;
-#pragma unroll 1
-    for (int q = 0; q < kLwIters; ++q) {
-        const int i = wbase + q * 32 + lane;
-        const bool valid = i < a.s.N;
-        double p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = lw_inv_trans(k, valid ? a.th_anc[k][i] : 0.0);
-        const double xa = valid ? a.s.x_anc[i] : 0.0;
-        const double e2 = dexp(__dmul_rn(-0.5, xa));
-        const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
-        const double mu = __fma_rn(cz, e2, __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]));
-        double v = __fma_rn(-hh, dexp(-mu), __fma_rn(-0.5, mu, -SSME_DM_HALF_LOG_2PI));
-        v = valid ? v : ninf;
-        a.lfs[i] = v;   // whole tiles are allocated
-        a.cdf1[i] = v;
-        mloc = (v > mloc) ? v : mloc;
-    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         const double other = shfl_xor_d(mloc, d);
@@ -277,63 +274,144 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_apf_first_kernel(const LwArgs a)
     }
     if (lane == 0) red[warp] = mloc;
     __syncthreads();
-    if (tid == 0) {
-        double m = red[0];
+    double mb = (lane < NW) ? red[lane] : ninf;
 #pragma unroll
-        for (int g = 1; g < kLwNT / 32; ++g) m = (red[g] > m) ? red[g] : m;
-        a.s.tmax[blockIdx.x] = m;
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(mb, d);
+        mb = (other > mb) ? other : mb;
+    }
+    const double mref = (mb == ninf) ? 0.0 : mb;  // a tile without a finite log-weight: every weight is exp(-inf - 0) = 0
+    double sc[kTileL];
+#pragma unroll
+    for (int k = 0; k < kTileL; ++k) {
+        const double w = dexp_nonpos(__dsub_rn(lws[k * kTileNT + tid], mref));
+        lws[k * kTileNT + tid] = w;
+        sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
+    }
+    const double Tb = tile_scan_finish(sc, red_sum, lane, warp);
+#pragma unroll
+    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(cl + k) = make_double2(sc[k], sc[k + 1]);
+    double cmax = sc[kTileL - 1];  // non-decreasing inside a thread
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(cmax, d);
+        cmax = (other > cmax) ? other : cmax;
+    }
+    if (lane == 0) red_max[warp] = cmax;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red_max[0];
+        for (int g = 1; g < NW; ++g) m = (red_max[g] > m) ? red_max[g] : m;
+        s.tmax[tile] = mb;
+        s.ttot[tile] = Tb;
+        s.tclmax[tile] = m;
     }
 }
 
-// One particle per thread at a time (coalesced 8-byte accesses, ~64 registers, 4 CTAs per SM).  Nothing depends on which
-// thread owns a particle: the maximum is order-free and every other value is per particle.  Writes the maximum of its
-// 1024 particles to tmax[blockIdx.x] (spill_reduce_max_kernel is then run over N/1024 entries).
-// FORM 0: slot i continues particle i (SISR).  FORM 1: slot i continues particle k_i drawn from the first-stage weights.
-template <int FORM>
-__global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
+// First stage of the auxiliary form: the log-weight of the predicted state propMu(x_i) under particle i's own parameters, and
+// in the same pass its tile-relative weights and their tile scan (into a.s.lwc, which the host points at the first-stage buffer).
+__global__ void __launch_bounds__(kTileNT, 2) lw_first_kernel(const LwArgs a)
 {
-    __shared__ double red[kLwNT / 32];
+    __shared__ double lws[kTile];
+    __shared__ double red[kTileNT / 32], red_sum[32], red_max[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
+    const int t = a.s.t;
+    const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
+    const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
+    const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    double mloc = ninf;
+#pragma unroll 1
+    for (int k = 0; k < kTileL; ++k) {
+        const int i = i0 + k;
+        const bool valid = i < a.s.N;
+        double p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p[q] = lw_inv_trans(q, valid ? a.th_anc[q][i] : 0.0);
+        const double xa = valid ? a.s.x_anc[i] : 0.0;
+        const double e2 = dexp(__dmul_rn(-0.5, xa));
+        const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
+        const double mu = __fma_rn(cz, e2, __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]));
+        double v = __fma_rn(-hh, dexp(-mu), __fma_rn(-0.5, mu, -SSME_DM_HALF_LOG_2PI));
+        v = valid ? v : ninf;
+        a.lfs[i] = v;  // whole tiles are allocated
+        lws[k * kTileNT + tid] = v;
+        mloc = (v > mloc) ? v : mloc;
+    }
+    lw_tile_tail(a.s, lws, mloc, a.s.lwc + i0, tile, red, red_sum, red_max, tid, lane, warp);
+}
+
+// The fused time step.  FORM 0: slot i continues particle i (SISR).  FORM 1: slot i continues particle k_i drawn from the
+// first-stage weights.  Thread tid owns the tile's particles 8 tid .. 8 tid + 7 (the scan's ownership), one at a time.
+template <int FORM>
+__global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
+{
+    constexpr int NW = kTileNT / 32;
+    __shared__ double lws[kTile];
+    __shared__ double red[NW], red_sum[32], red_max[32];
     __shared__ double smom[20];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
     const int t = a.s.t;
     if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
     __syncthreads();
+    if (tile == 0 && tid < 4 && t > 0 && a.theta_bar_out) a.theta_bar_out[(size_t)(t - a.s.row0) * 4 + tid] = smom[tid];
     const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
     const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
     const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
     const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
-    const int wbase = blockIdx.x * kLwSub + warp * (32 * kLwIters);  // this warp's 128 consecutive particles
-    float zs[4];
-    {
-        const uint4 rz = philox4x32(make_uint4((uint32_t)(wbase / 4 + lane), (uint32_t)t, ctr2, ctr3), a.s.rk);
-        box_muller(rz.x, rz.y, zs[0], zs[1]);
-        box_muller(rz.z, rz.w, zs[2], zs[3]);
-    }
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
     double mloc = ninf;
+    // SISR form: the inputs of the next particle are requested before the current one is worked on (the loop is not unrolled:
+    // ~570 instructions per particle; without this every iteration exposes an L2 round trip)
+    double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (FORM == 0 && t > 0 && i0 < a.s.N) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nx[q] = a.th_anc[q][i0];
+        nx[4] = a.s.x_anc[i0];
+    }
 #pragma unroll 1
-    for (int q = 0; q < kLwIters; ++q) {
-        const int i = wbase + q * 32 + lane;
-        const double z = lw_state_normal(zs, q, lane);
+    for (int k = 0; k < kTileL; ++k) {
+        const int i = i0 + k;
+        double in[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) in[q] = nx[q];
+        if (FORM == 0 && t > 0 && k + 1 < kTileL && i + 1 < a.s.N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nx[q] = a.th_anc[q][i + 1];
+            nx[4] = a.s.x_anc[i + 1];
+        }
+        if ((k & 3) == 0) {  // state normals: one Philox block per four particles (the blocks of K1 / K3)
+            const uint4 rz = philox4x32(make_uint4((uint32_t)(i >> 2), (uint32_t)t, ctr2, ctr3), a.s.rk);
+            box_muller(rz.x, rz.y, zs[0], zs[1]);
+            box_muller(rz.z, rz.w, zs[2], zs[3]);
+        }
+        const int c = k & 3;
+        const double z = (double)((c == 0) ? zs[0] : (c == 1) ? zs[1] : (c == 2) ? zs[2] : zs[3]);
         const bool valid = i < a.s.N;
         double p[4], nth[4], x;
         int src = i;          // the particle this slot continues
         double lfs_k = 0.0;
         if (FORM == 1 && t > 0 && valid) {
-            // k_i ~ discrete(first-stage weights): uniform of stream 6, two-level descent (spill_resample_kernel's)
+            // k_i ~ discrete(first-stage weights): uniform of stream 6, two-level descent over E and O_b + cl s_b (oracle: tiled_search)
             const uint4 r = philox4x32(make_uint4((uint32_t)(i >> 1), (uint32_t)t, ctr2, ctr3 | 6u), a.s.rk);
             const double tau = __dmul_rn((i & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), a.s.scal[1]);
             int b = 0;
             for (int s = a.s.NBP >> 1; s >= 1; s >>= 1) b += (a.s.E[b + s - 1] < tau) ? s : 0;
             b = min(b, a.s.nb - 1);
             const double O = (b > 0) ? a.s.E[b - 1] : 0.0;
+            const double sbv = a.s.sb[b];
             const double* cl = a.cdf1 + (size_t)b * kTile;
             int idx = 0;
 #pragma unroll
-            for (int s = kTile / 2; s >= 1; s >>= 1) idx += (__dadd_rn(O, cl[idx + s - 1]) < tau) ? s : 0;
-            long long k = (long long)b * kTile + idx;
-            k = (k > (long long)a.s.N - 1) ? (long long)a.s.N - 1 : k;
-            src = (int)k;
+            for (int s = kTile / 2; s >= 1; s >>= 1) idx += (__dadd_rn(O, __dmul_rn(cl[idx + s - 1], sbv)) < tau) ? s : 0;
+            long long kk = (long long)b * kTile + idx;
+            kk = (kk > (long long)a.s.N - 1) ? (long long)a.s.N - 1 : kk;
+            src = (int)kk;
             lfs_k = a.lfs[src];
             if (a.aux_out) a.aux_out[(size_t)t * a.s.N + i] = src;
         }
@@ -346,7 +424,7 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
                 p[2 * k2 + 1] = __fma_rn(ub, __dsub_rn(a.hi[2 * k2 + 1], a.lo[2 * k2 + 1]), a.lo[2 * k2 + 1]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) nth[k] = lw_trans(k, p[k]);
+            for (int q = 0; q < 4; ++q) nth[q] = lw_trans(q, p[q]);
             x = __dmul_rn(z, __ddiv_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[0], p[0])))));
         } else {
             const uint4 rp = philox4x32(make_uint4((uint32_t)i, (uint32_t)t, ctr2, ctr3 | 4u), a.s.rk);
@@ -354,15 +432,15 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
             box_muller(rp.x, rp.y, zf[0], zf[1]);
             box_muller(rp.z, rp.w, zf[2], zf[3]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double th = valid ? a.th_anc[k][src] : 0.0;
-                double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[k]));
+            for (int q = 0; q < 4; ++q) {
+                const double th = (FORM == 0) ? (valid ? in[q] : 0.0) : (valid ? a.th_anc[q][src] : 0.0);
+                double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[q]));
 #pragma unroll
-                for (int l = 0; l <= k; ++l) acc = __fma_rn(smom[4 + 4 * k + l], (double)zf[l], acc);
-                nth[k] = acc;
-                p[k] = lw_inv_trans(k, acc);
+                for (int l = 0; l <= q; ++l) acc = __fma_rn(smom[4 + 4 * q + l], (double)zf[l], acc);
+                nth[q] = acc;
+                p[q] = lw_inv_trans(q, acc);
             }
-            const double xa = valid ? a.s.x_anc[src] : 0.0;
+            const double xa = (FORM == 0) ? (valid ? in[4] : 0.0) : (valid ? a.s.x_anc[src] : 0.0);
             const double e2 = dexp(__dmul_rn(-0.5, xa));
             const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), cov);
             double mean = __fma_rn(p[0], __dsub_rn(xa, p[1]), p[1]);
@@ -374,26 +452,140 @@ __global__ void __launch_bounds__(kLwNT, 4) lw_propagate_kernel(const LwArgs a)
         if (valid) {
             a.s.x_cur[i] = x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a.th_cur[k][i] = nth[k];
+            for (int q = 0; q < 4; ++q) a.th_cur[q][i] = nth[q];
         } else {
             v = ninf;
         }
-        a.s.lwc[i] = v;  // the arrays are allocated in whole tiles
+        lws[k * kTileNT + tid] = v;
         mloc = (v > mloc) ? v : mloc;
     }
+    lw_tile_tail(a.s, lws, mloc, a.s.lwc + i0, tile, red, red_sum, red_max, tid, lane, warp);
+    if (a.expect_out) {
+        // expectations before resampling (liu_west_filter.h:1087-1101 / :2263-2276): tile sums of h(x_i, theta_i) exp(lw_i - m_b);
+        // lw_expect_final_kernel rescales them by s_b and divides by S once the tile totals are scanned
+        __shared__ double ered[NW * 5];
+        __shared__ double etot[5];
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int k = 0; k < kTileL; ++k) {
+            const int i = i0 + k;
+            const bool valid = i < a.s.N;
+            const double w = lws[k * kTileNT + tid];
+            double hv[5];
+            hv[0] = valid ? a.s.x_cur[i] : 0.0;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(mloc, d);
-        mloc = (other > mloc) ? other : mloc;
+            for (int q = 0; q < 4; ++q) hv[1 + q] = valid ? lw_inv_trans(q, a.th_cur[q][i]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const double pr = __dmul_rn(w, hv[q]);
+                acc[q] = (k == 0) ? pr : __dadd_rn(acc[q], pr);
+            }
+        }
+        block_sums<5, NW>(acc, ered, 5, lane, warp, tid, etot);
+        if (tid < 5) a.part[(size_t)tid * a.s.nb + tile] = etot[tid];
     }
-    if (lane == 0) red[warp] = mloc;
+}
+
+// ---- systematic resampling of states and parameters, with the moments of the resampled parameters -----------------------------
+constexpr int kLwStage = 2 * kTile;   // staged slots per CTA (2-byte local ancestor indices: 16 KB)
+
+// One CTA per tile of PARTICLES (spill_expand_kernel's counting): A_i = cumulative offspring counts.  The slots a tile fathers
+// are contiguous, [s_lo, s_hi): thread tid takes the slots s_lo + tid, s_lo + tid + 512, ...; a slot finds its ancestor in shared
+// memory -- from the staged 2-byte local indices when the range fits the staging buffer, by a 12-step descent over the tile's
+// cumulative counts otherwise (degenerate weights: one tile fathering up to all N slots; no capacity limit, the whole CTA writes)
+// -- gathers its five fields (x' and the four parameters; nearly coalesced, the ancestors of consecutive slots are non-decreasing)
+// and writes them out coalesced: one staging pass and no barrier between the fields (round 1 staged the VALUES field by field,
+// two barriers each).  The moments of the resampled parameters are summed over the same slots while their values are in
+// registers (oracle: by_slots): no second pass over the parameters (round 1: an 18 us kernel plus a 13 us one-CTA kernel).
+__global__ void __launch_bounds__(kTileNT, 2) lw_expand_kernel(const LwArgs a)
+{
+    constexpr int NW = kTileNT / 32;
+    __shared__ __align__(16) unsigned short eidx[kLwStage];
+    __shared__ double red[32 * 14];
+    __shared__ double tot[14];
+    __shared__ double sh_par[5];
+    __shared__ int sh_range[2];
+    __shared__ int flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int i0 = tile * kTile + tid * kTileL;
+    int s_lo, s_hi;
+    bool staged;
+    {
+        int A[kTileL + 1];
+        expand_counts(a.s, tile, tid, lane, warp, (size_t)i0, i0, red, sh_par, sh_range, A, s_lo, s_hi);
+        staged = (s_hi - s_lo) <= kLwStage;
+        if (staged) {
+#pragma unroll
+            for (int k = 0; k < kTileL; ++k) {
+                const int a0 = A[k] - s_lo, cnt = A[k + 1] - A[k];
+                const unsigned short me = (unsigned short)(tid * kTileL + k);
+                for (int j = 0; j < cnt; ++j) eidx[a0 + j] = me;
+            }
+        } else {
+            int* acum = reinterpret_cast<int*>(eidx);  // [kTile] slots fathered up to and including each particle of the tile
+#pragma unroll
+            for (int k = 0; k < kTileL; ++k) acum[tid * kTileL + k] = A[k + 1];
+        }
+    }
     __syncthreads();
-    if (tid == 0) {
-        double m = red[0];
+    const double* src[5] = {a.s.x_cur, a.th_cur[0], a.th_cur[1], a.th_cur[2], a.th_cur[3]};
+    double* dst[5] = {a.s.x_anc, a.s.extra_anc[0], a.s.extra_anc[1], a.s.extra_anc[2], a.s.extra_anc[3]};
+    const size_t tbase = (size_t)tile * kTile;
+    const int ns = s_hi - s_lo;
+    auto ancestor_of = [&](int q) -> int {  // local index of the particle that fathers slot s_lo + q
+        if (staged) return eidx[q];
+        const int* acum = reinterpret_cast<const int*>(eidx);
+        const int sl = s_lo + q;
+        int idx = 0;
 #pragma unroll
-        for (int g = 1; g < kLwNT / 32; ++g) m = (red[g] > m) ? red[g] : m;
-        a.s.tmax[blockIdx.x] = m;
+        for (int st = kTile / 2; st >= 1; st >>= 1) idx += (acum[idx + st - 1] <= sl) ? st : 0;
+        return idx;
+    };
+    double s[14];
+#pragma unroll
+    for (int q = 0; q < 14; ++q) s[q] = 0.0;
+    auto accumulate = [&](const double (&v)[5], bool first) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] = first ? v[1 + q] : __dadd_rn(s[q], v[1 + q]);
+        int slot = 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int l = 0; l <= q; ++l) {
+                const double p = __dmul_rn(v[1 + q], v[1 + l]);
+                s[slot] = first ? p : __dadd_rn(s[slot], p);
+                ++slot;
+            }
+    };
+    // two slots per iteration: ten gathers in flight per thread; the sums stay in slot order
+    for (int q = tid; q < ns; q += 2 * kTileNT) {
+        const bool two = q + kTileNT < ns;
+        const size_t from0 = tbase + ancestor_of(q);
+        const size_t from1 = two ? tbase + ancestor_of(q + kTileNT) : from0;
+        double v0[5], v1[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) v0[f] = __ldg(src[f] + from0);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) v1[f] = __ldg(src[f] + from1);
+        const size_t sl = (size_t)s_lo + q;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) dst[f][sl] = v0[f];
+        if (a.s.ancestors) a.s.ancestors[(size_t)a.s.t * a.s.N + sl] = (int)from0;
+        accumulate(v0, q == tid);
+        if (two) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) dst[f][sl + kTileNT] = v1[f];
+            if (a.s.ancestors) a.s.ancestors[(size_t)a.s.t * a.s.N + sl + kTileNT] = (int)from1;
+            accumulate(v1, false);
+        }
     }
+    block_sums<14, NW>(s, red, 14, lane, warp, tid, tot);
+    if (tid < 14) {
+        a.part[(size_t)tid * a.s.nb + tile] = tot[tid];
+        __threadfence();
+    }
+    lw_last_cta_finish<kTileNT>(a, 0, red, tot, &flag, tid);
 }
 
 }  // namespace ssme

@@ -163,7 +163,8 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         count_launch(1);
     } else {
         a.cmax = nullptr;
-        spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        if (s->Lp == 1) spill_tile_scan_small_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        else spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
     }
 }
 
@@ -376,7 +377,8 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
             SSME_CUDA(cudaMalloc(&s->th_cur[k], s->local * sizeof(double)));
         }
         SSME_CUDA(cudaMalloc(&s->part, (size_t)14 * s->nb * sizeof(double)));
-        SSME_CUDA(cudaMalloc(&s->mom, 32 * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&s->mom, 40 * sizeof(double)));  // [0..31] moments, [32] the arrival counter of the finishing CTA
+        SSME_CUDA(cudaMemset(s->mom, 0, 40 * sizeof(double)));
     }
     if (form == 1 && !s->lfs) SSME_CUDA(cudaMalloc(&s->lfs, s->local * sizeof(double)));
     LwArgs& a = *out;
@@ -404,8 +406,12 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
         a.lo[k] = lo[k];
         a.hi[k] = hi[k];
     }
+    a.s.rel = 1;
+    a.s.sb = s->sb;
+    a.s.world = 1;
     a.part = s->part;
     a.mom = s->mom;
+    a.ctr = reinterpret_cast<unsigned int*>(s->mom + 32);
     a.lfs = s->lfs;
     a.cdf1 = s->lwc[1];
     a.a = (3.0 * delta - 1.0) / (2.0 * delta);
@@ -416,58 +422,45 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     return SSME_B200_OK;
 }
 
-// One time step of the Liu-West filter (both forms); `a` carries the output pointers and row0.
+// One time step of the Liu-West filter (both forms); `a` carries the output pointers and row0.  SISR form with systematic
+// resampling: three launches (fused step, scan of the tile totals, expansion + moments of the next step).
 static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
 {
     SpillState* s = h->spill_state;
     const int tiles = s->nb;
     cudaStream_t st = h->stream;
     a.s.t = t;
-    if (t > 0) {
-        a.mode = 0;
-        lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
-        lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
-        count_launch(2);
-    }
-    const int subs = tiles * (kTile / kLwSub);
-    SpillArgs m = a.s;  // K4's kernels leave one partial maximum per 1024 particles
-    m.tile0 = 0;
-    m.tile1 = subs;
     const bool apf = (form == 1 && t > 0);
     if (apf) {
-        // first stage: weights of the predicted states, their CDF (in lwc[1]) and M2 + log S2
-        SpillArgs f = a.s;
-        f.lwc = s->lwc[1];
-        f.cl_mode = 1;
-        lw_apf_first_kernel<<<subs, kLwNT, 0, st>>>(a);
-        spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
-        spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(f);
-        launch_tile_scan(s, f, st);
-        lw_propagate_kernel<1><<<subs, kLwNT, 0, st>>>(a);
-        count_launch(4);
+        // first stage: weights of the predicted states, their tile-relative CDF (in lwc[1]) and M2 + log S2
+        LwArgs f = a;
+        f.s.lwc = s->lwc[1];
+        f.s.cl_mode = 1;
+        lw_first_kernel<<<tiles, kTileNT, 0, st>>>(f);
+        launch_tile_scan(s, f.s, st);
+        lw_step_kernel<1><<<tiles, kTileNT, 0, st>>>(a);
+        count_launch(2);
     } else {
-        lw_propagate_kernel<0><<<subs, kLwNT, 0, st>>>(a);
+        lw_step_kernel<0><<<tiles, kTileNT, 0, st>>>(a);
     }
     a.s.cl_mode = apf ? 2 : 0;
-    spill_reduce_max_kernel<<<1, 1024, 0, st>>>(m);
-    if (a.expect_out) {  // weighted sums of h(x, theta) while the log-weights are still in lwc
-        a.mode = 2;
+    launch_tile_scan(s, a.s, st);
+    if (a.expect_out) {
+        lw_expect_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        count_launch(1);
+    }
+    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
+        lw_expand_kernel<<<tiles, kTileNT, 0, st>>>(a);
+    } else {
+        if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
+            int rc = launch_sorted_resample(h, s, a.s, tiles, st);
+            if (rc) return rc;
+        } else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+        a.mode = 0;  // moments of the resampled parameters for the next step (the systematic expansion forms them itself)
         lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
         count_launch(1);
     }
-    spill_weights_scan_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
-    launch_tile_scan(s, a.s, st);
-    if (a.expect_out) {
-        a.mode = 2;
-        lw_moments_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
-        count_launch(1);
-    }
-    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) spill_expand_kernel<<<tiles, kTileNT, kExpandSmem * sizeof(double), st>>>(a.s);
-    else if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
-        int rc = launch_sorted_resample(h, s, a.s, tiles, st);
-        if (rc) return rc;
-    } else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
-    count_launch(5);
+    count_launch(3);
     SSME_CUDA(cudaGetLastError());
     return SSME_B200_OK;
 }
@@ -478,9 +471,8 @@ static int lw_means(ssme_b200_handle h, LwArgs& a, double* d_mean)
     SpillState* s = h->spill_state;
     a.mode = 1;
     lw_moments_kernel<<<s->nb, kTileNT, 0, h->stream>>>(a);
-    lw_moments_final_kernel<<<1, kTileScanNT, 0, h->stream>>>(a);
     SSME_CUDA(cudaMemcpyAsync(d_mean, s->mom + 20, 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    count_launch(2);
+    count_launch(1);
     return SSME_B200_OK;
 }
 

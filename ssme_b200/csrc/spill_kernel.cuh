@@ -524,6 +524,118 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
     }
 }
 
+// The same scan for at most 1024 tiles (Lp = 1: one tile per lane) with every intermediate value in registers or shared memory:
+// one round trip to global memory instead of six (the kernel above re-reads through L2 what it has just stored: rescaled totals,
+// tile ends, largest entries).  Same operations in the same order, bit for bit; 8.8 -> ~3 us at 256 tiles.
+__global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_small_kernel(const SpillArgs a)
+{
+    __shared__ double red_sum[32];
+    __shared__ double red_max[32];
+    __shared__ double shE[kTileScanNT];
+    __shared__ double shM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = tid;
+    const bool in = b < a.nb;
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    const bool rescale = a.rel && a.cl_mode != 3;
+    if (rescale && a.world > 1) {  // K5: the peers' tile triples of this step
+        if (tid == 0) k5_wait(a, 0, a.epoch);
+        __syncthreads();
+    }
+    double tm = in ? a.tmax[b] : ninf;
+    double v = in ? a.ttot[b] : 0.0;
+    double tc = in ? a.tclmax[b] : 0.0;
+    if (rescale) {
+        double m = tm;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(m, d);
+            m = (other > m) ? other : m;
+        }
+        if (lane == 0) red_max[warp] = m;
+        __syncthreads();
+        if (warp == 0) {
+            m = red_max[lane];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double other = shfl_xor_d(m, d);
+                m = (other > m) ? other : m;
+            }
+            if (lane == 0) shM = m;
+        }
+        __syncthreads();
+        const double M = shM;
+        if (tid == 0) a.scal[0] = M;
+        if (in) {
+            const double sbv = dexp_nonpos(__dsub_rn(tm, M));
+            a.sb[b] = sbv;
+            v = __dmul_rn(v, sbv);
+            tc = __dmul_rn(tc, sbv);
+        }
+    }
+    double incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(incl, d);
+        incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+    }
+    if (lane == 31) red_sum[warp] = incl;
+    __syncthreads();
+    double wv = red_sum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(wv, d);
+        wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+    }
+    const double S = shfl_d(wv, 31);
+    double wex = shfl_d(wv, (warp > 0) ? warp - 1 : 0);
+    wex = (warp > 0) ? wex : 0.0;
+    double lex = shfl_up_d(incl, 1);
+    lex = (lane > 0) ? lex : 0.0;
+    const double Eb = __dadd_rn(__dadd_rn(wex, lex), v);
+    a.E[b] = Eb;
+    shE[b] = Eb;
+    __syncthreads();
+    // exclusive running maximum over tiles of (O_b + largest local entry): exact, order-free
+    const double O = (b > 0) ? shE[b - 1] : 0.0;
+    const double loc = in ? __dadd_rn(O, tc) : ninf;
+    double inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double other = shfl_up_d(inc, d);
+        inc = (lane >= d && other > inc) ? other : inc;
+    }
+    __syncthreads();  // red_max is reused
+    if (lane == 31) red_max[warp] = inc;
+    __syncthreads();
+    double wprev = (lane < warp) ? red_max[lane] : ninf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double other = shfl_xor_d(wprev, d);
+        wprev = (other > wprev) ? other : wprev;
+    }
+    double excl = shfl_up_d(inc, 1);
+    excl = (lane > 0) ? excl : ninf;
+    if (in) a.carry[b] = (wprev > excl) ? wprev : excl;
+    if (tid == 0) {
+        const double M = a.scal[0], logN = a.scal[3];
+        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
+            a.scal[5] = S;
+            return;
+        }
+        const double logS = dlog(S);
+        a.scal[1] = S;
+        if (a.cl_mode == 1) {
+            a.scal[4] = __dadd_rn(M, logS);
+        } else {
+            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
+            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
+            a.scal[2] = __dadd_rn(a.scal[2], cl);
+            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
+        }
+    }
+}
+
 // ---- the same scan of the tile totals in two launches of 32 CTAs (one per virtual warp of the canonical 1024-lane scan) ----
 // Used when there are thousands of tiles (Lp >= 4): the single CTA above walks its Lp items per lane with strided,
 // uncoalesced loads through one SM (329 us at 65536 tiles); here every virtual warp stages its 32*Lp totals through
@@ -720,25 +832,12 @@ __device__ __forceinline__ double warp_max_nonneg(double v)
     return __hiloint2double((int)mh, (int)ml);
 }
 
-constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wider slot ranges (degenerate weights) are written directly
-constexpr int kExpandSmem = kExpandBuf;
-
-// Systematic resampling WITHOUT a search (oracle: systematic_by_counts).  Each CTA takes a tile of PARTICLES: it forms
-// the running maximum Ct of the global CDF over its tile (carry-in from earlier tiles in a.carry; a parallel scan is
-// sorted only up to rounding, its running maximum exactly), turns it into cumulative offspring counts
-// A_i = #{targets <= Ct_i} in O(1) per particle; particle i fathers the slots A_{i-1} .. A_i - 1, which are contiguous
-// over the CTA: they are staged in shared memory and written out coalesced (to the slot owner's HBM when the filter is
-// sharded over ranks).  HBM traffic: read CDF 8 + read x' 8 + write 8 B per particle.
-__global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArgs a)
+// The counting half of the systematic expansion (shared by spill_expand_kernel and the Liu-West lw_expand_kernel): the running
+// maximum of the global CDF over the tile, the cumulative offspring counts A[0..kTileL] of this thread's particles and the slot
+// range [s_lo, s_hi) the whole tile fathers.  red [kTileNT/32], sh_par [5], sh_range [2] are the CTA's shared scratch.
+__device__ __forceinline__ void expand_counts(const SpillArgs& a, int tile, int tid, int lane, int warp, size_t l0, int i0, double* red,
+                                              double* sh_par, int* sh_range, int (&A)[kTileL + 1], int& s_lo, int& s_hi)
 {
-    extern __shared__ __align__(16) double ebuf[];  // [kExpandBuf]
-    __shared__ double red[kTileNT / 32];
-    __shared__ double sh_par[5];
-    __shared__ int sh_range[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = a.tile0 + blockIdx.x;
-    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
-    const int i0 = tile * kTile + tid * kTileL;
     const int N = a.N;
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
     if (tid == 0) {  // one thread draws the offset and forms the grid constants for the CTA
@@ -795,7 +894,6 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
     excl = (lane > 0) ? excl : ninf;
     prevmax = (excl > prevmax) ? excl : prevmax;
     // cumulative offspring counts of this thread's particles
-    int A[kTileL + 1];
     A[0] = (i0 == 0 || i0 >= N) ? 0 : count_targets_fast(prevmax, tau0, u0, sN, inv_sN, N, Nm1);
     if (i0 + kTileL < N) {  // every particle of this thread is real and none is the last one
 #pragma unroll
@@ -822,7 +920,32 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
     if (tid == 0) sh_range[0] = A[0];
     if (i0 <= tile_last && tile_last < i0 + kTileL) sh_range[1] = A[tile_last - i0 + 1];
     __syncthreads();
-    const int s_lo = sh_range[0], s_hi = sh_range[1];
+    s_lo = sh_range[0];
+    s_hi = sh_range[1];
+}
+
+constexpr int kExpandBuf = 2 * kTile;  // offspring staged per CTA (64 KB); wider slot ranges (degenerate weights) are written directly
+constexpr int kExpandSmem = kExpandBuf;
+
+// Systematic resampling WITHOUT a search (oracle: systematic_by_counts).  Each CTA takes a tile of PARTICLES: it forms
+// the running maximum Ct of the global CDF over its tile (carry-in from earlier tiles in a.carry; a parallel scan is
+// sorted only up to rounding, its running maximum exactly), turns it into cumulative offspring counts
+// A_i = #{targets <= Ct_i} in O(1) per particle; particle i fathers the slots A_{i-1} .. A_i - 1, which are contiguous
+// over the CTA: they are staged in shared memory and written out coalesced (to the slot owner's HBM when the filter is
+// sharded over ranks).  HBM traffic: read CDF 8 + read x' 8 + write 8 B per particle.
+__global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArgs a)
+{
+    extern __shared__ __align__(16) double ebuf[];  // [kExpandBuf]
+    __shared__ double red[kTileNT / 32];
+    __shared__ double sh_par[5];
+    __shared__ int sh_range[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = a.tile0 + blockIdx.x;
+    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
+    const int i0 = tile * kTile + tid * kTileL;
+    int A[kTileL + 1];
+    int s_lo, s_hi;
+    expand_counts(a, tile, tid, lane, warp, l0, i0, red, sh_par, sh_range, A, s_lo, s_hi);
     const bool staged = (s_hi - s_lo) <= kExpandBuf;
     const bool single = (a.tiles_per_rank == a.nb);
     const long long per_rank = (long long)a.tiles_per_rank * kTile;
