@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_moments_kernel(const LwArgs a)
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
     double s[14];
+    pdl_trigger();
+    pdl_wait();
     // two particles at a time (16-byte loads), the 14 running sums updated in particle order: the same additions in the same
     // order as summing each quantity over the thread's 8 particles, with 8 + 14 live doubles instead of 32 + 14 (2 CTAs per SM)
 #pragma unroll
@@ -254,6 +256,8 @@ __global__ void __launch_bounds__(kTileScanNT) lw_expect_final_kernel(const LwAr
     __shared__ double red[32 * 14];
     __shared__ double tot[14];
     const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     lw_final_sums<kTileScanNT>(a.part, a.s.sb, a.s.nb, a.s.Lp, 5, red, tot, tid);
     if (tid < 5) a.expect_out[(size_t)(a.s.t - a.s.row0) * 5 + tid] = __ddiv_rn(tot[tid], a.s.scal[1]);
 }
@@ -318,6 +322,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_first_kernel(const LwArgs a)
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
     const int t = a.s.t;
+    pdl_trigger();
+    pdl_wait();
     const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
     const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
     const double hh = __dmul_rn(__dmul_rn(y, y), 0.5);
@@ -356,6 +362,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
     const int t = a.s.t;
+    pdl_trigger();
+    pdl_wait();
     if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
     __syncthreads();
     if (tile == 0 && tid < 4 && t > 0 && a.theta_bar_out) a.theta_bar_out[(size_t)(t - a.s.row0) * 4 + tid] = smom[tid];
@@ -511,6 +519,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_expand_kernel(const LwArgs a)
     const int i0 = tile * kTile + tid * kTileL;
     int s_lo, s_hi;
     bool staged;
+    pdl_trigger();
+    pdl_wait();
     {
         int A[kTileL + 1];
         expand_counts(a.s, tile, tid, lane, warp, (size_t)i0, i0, red, sh_par, sh_range, A, s_lo, s_hi);

@@ -149,6 +149,24 @@ void spill_destroy(ssme_b200_handle h)
     h->spill_state = nullptr;
 }
 
+// Launch with programmatic stream serialization: the kernel's CTAs may be scheduled while the preceding kernel on the stream is
+// still draining; every kernel launched this way calls pdl_wait() before it touches global memory (spill_kernel.cuh).
+template <typename Args>
+static cudaError_t launch_pdl(void (*kernel)(const Args), int grid, int block, cudaStream_t st, const Args& args)
+{
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3((unsigned)block);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, kernel, args);
+}
+
 // Scan of the tile totals: one CTA for a few tiles, two launches of 32 CTAs beyond 4096 tiles (same result, bit for bit).
 static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
 {
@@ -163,7 +181,7 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         count_launch(1);
     } else {
         a.cmax = nullptr;
-        if (s->Lp == 1) spill_tile_scan_small_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        if (s->Lp == 1) (void)launch_pdl(spill_tile_scan_small_kernel, 1, kTileScanNT, st, a);  // errors surface in the caller's cudaGetLastError
         else spill_tile_scan_kernel<<<1, kTileScanNT, 0, st>>>(a);
     }
 }
@@ -436,28 +454,28 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         LwArgs f = a;
         f.s.lwc = s->lwc[1];
         f.s.cl_mode = 1;
-        lw_first_kernel<<<tiles, kTileNT, 0, st>>>(f);
+        SSME_CUDA(launch_pdl(lw_first_kernel, tiles, kTileNT, st, f));
         launch_tile_scan(s, f.s, st);
-        lw_step_kernel<1><<<tiles, kTileNT, 0, st>>>(a);
+        SSME_CUDA(launch_pdl(lw_step_kernel<1>, tiles, kTileNT, st, a));
         count_launch(2);
     } else {
-        lw_step_kernel<0><<<tiles, kTileNT, 0, st>>>(a);
+        SSME_CUDA(launch_pdl(lw_step_kernel<0>, tiles, kTileNT, st, a));
     }
     a.s.cl_mode = apf ? 2 : 0;
     launch_tile_scan(s, a.s, st);
     if (a.expect_out) {
-        lw_expect_final_kernel<<<1, kTileScanNT, 0, st>>>(a);
+        SSME_CUDA(launch_pdl(lw_expect_final_kernel, 1, kTileScanNT, st, a));
         count_launch(1);
     }
     if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
-        lw_expand_kernel<<<tiles, kTileNT, 0, st>>>(a);
+        SSME_CUDA(launch_pdl(lw_expand_kernel, tiles, kTileNT, st, a));
     } else {
         if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
             int rc = launch_sorted_resample(h, s, a.s, tiles, st);
             if (rc) return rc;
         } else spill_resample_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
         a.mode = 0;  // moments of the resampled parameters for the next step (the systematic expansion forms them itself)
-        lw_moments_kernel<<<tiles, kTileNT, 0, st>>>(a);
+        SSME_CUDA(launch_pdl(lw_moments_kernel, tiles, kTileNT, st, a));
         count_launch(1);
     }
     count_launch(3);

@@ -92,6 +92,14 @@ struct SpillArgs {
     const void* params;                  // MODEL::Params of the filter being run (spill_params_kernel)
 };
 
+// ---- programmatic dependent launch (the Liu-West step: three short kernels per time step) ------------------------------------
+// pdl_wait(): everything the preceding kernel on the stream wrote is visible after it (a no-op when the kernel was launched
+// without the programmatic-serialization attribute).  pdl_trigger(): the next kernel's CTAs may be scheduled as soon as every
+// CTA of this grid has called it (or exited); they then sit in pdl_wait() until this grid has completed, so the next kernel
+// starts without a launch gap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- K5 flag protocol -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
@@ -538,6 +546,8 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_small_kernel(cons
     const bool in = b < a.nb;
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
     const bool rescale = a.rel && a.cl_mode != 3;
+    pdl_trigger();
+    pdl_wait();
     if (rescale && a.world > 1) {  // K5: the peers' tile triples of this step
         if (tid == 0) k5_wait(a, 0, a.epoch);
         __syncthreads();

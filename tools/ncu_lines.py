@@ -16,6 +16,8 @@ for r in csv.reader(io.StringIO(out)):
         hdr = r; ix = {h: i for i, h in enumerate(hdr)}; continue
     if hdr is None or len(r) < len(hdr) or r[0] == "" or not r[0].isdigit():
         continue
+    if r[ix["# Samples"]] in ("-", ""):
+        continue
     s = float(r[ix["# Samples"]] or 0)
     key = "%s:%s  %s" % (fname, r[0], r[1].strip()[:100])
     agg[key] += s; inst[key] += float(r[ix["Instructions Executed"]] or 0); tot += s
