@@ -368,12 +368,18 @@ def run_liu_west_leg(sb, local_rank, hbm_gbs):
     dt = time.perf_counter() - t0
     be.close()
     rate = N * T / dt
+    # SISR form, systematic resampling, three launches per time step (lw_kernel.cuh): fused step reads x 8 + theta 32 and writes
+    # x' 8 + theta' 32 + cl 8; expansion reads cl 8, gathers 40 and writes 40 -> 176 B per particle-step.  SURVEY.md 8(d) quotes
+    # 288 B for the auxiliary-particle form with separate passes; both fractions are reported.  The 2^20-particle working set
+    # (11 arrays, 92 MB) mostly stays in the 126 MB L2: ncu sees 156 B per particle-step at the DRAM (profiles/r2_k4_liu_west.md).
     return {"particle_steps_per_sec": rate, "particles": N, "T_timed": T, "seconds": dt, "us_per_time_step": 1e6 * dt / T,
+            "launches_per_time_step": 3,
             "loglik": float(r["loglik"]), "posterior_mean_phi_mu_sigma_rho": [float(v) for v in r["final_mean"]],
-            "roofline": {"bound": "hbm", "achieved": rate * 184 / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": rate * 184 / 1e9 / hbm_gbs,
-                         "algorithmic_bytes_per_particle_step": 184,
-                         "note": "moments read 32 + propagate read 40 write 48 + scan read 8 write 8 + resample read 8+40 (the 2^20-particle "
-                                 "working set, 59 MB, is L2-resident on B200, so HBM is not what binds here: launch latency of 7 kernels per step is)"}}
+            "roofline": {"bound": "hbm", "achieved": rate * 176 / 1e9, "peak": hbm_gbs, "unit": "GB/s", "frac": rate * 176 / 1e9 / hbm_gbs,
+                         "algorithmic_bytes_per_particle_step": 176, "frac_on_survey_288_bytes": rate * 288 / 1e9 / hbm_gbs,
+                         "note": "step: read x 8 + theta 32, write x' 8 + theta' 32 + cl 8; expansion: read cl 8 + gather 40, write 40. "
+                                 "At 2^20 particles the step is bound by instruction latency in a GPU that is 43 % occupied "
+                                 "(256 tiles on 148 SMs), not by HBM"}}
 
 
 def run_ours(args):

@@ -46,15 +46,17 @@ struct LwArgs {
 
 __device__ __forceinline__ double lw_inv_trans(int k, double t)
 {
-    // parameter order phi (logit), mu (null), sigma (log), rho (twice_fisher): parameters.h:403-413, 441-443, 361-372
+    // parameter order phi (logit), mu (null), sigma (log), rho (twice_fisher): parameters.h:403-413, 441-443, 361-372.
+    // Both branches of the reference's logit / twice-Fisher inverses evaluate exp(-|t|): written branch-free (same operations,
+    // same bits), so the exponentials of the four parameters and of the state are independent chains the scheduler interleaves.
     if (k == 1) return t;
     if (k == 2) return dexp(t);
-    if (k == 0) {
-        if (t >= 0.0) return __ddiv_rn(1.0, __dadd_rn(1.0, dexp(-t)));
-        const double e = dexp(t);
-        return __ddiv_rn(e, __dadd_rn(1.0, e));
-    }
-    return (t >= 0.0) ? __dsub_rn(__ddiv_rn(2.0, __dadd_rn(1.0, dexp(-t))), 1.0) : __dsub_rn(1.0, __ddiv_rn(2.0, __dadd_rn(1.0, dexp(t))));
+    const bool pos = t >= 0.0;
+    const double e = dexp(pos ? -t : t);
+    const double den = __dadd_rn(1.0, e);
+    if (k == 0) return __ddiv_rn(pos ? 1.0 : e, den);
+    const double r = __ddiv_rn(2.0, den);
+    return pos ? __dsub_rn(r, 1.0) : __dsub_rn(1.0, r);
 }
 __device__ __forceinline__ double lw_trans(int k, double p)
 {
@@ -357,16 +359,19 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
     constexpr int NW = kTileNT / 32;
     __shared__ double lws[kTile];
     __shared__ double red[NW], red_sum[32], red_max[32];
-    __shared__ double smom[20];
+    __shared__ __align__(16) double smom[20];  // [0..3] (1 - a) thetaBar, [4..19] chol(h^2 V_t) row-major
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int i0 = tile * kTile + tid * kTileL;
     const int t = a.s.t;
     pdl_trigger();
     pdl_wait();
-    if (tid < 20) smom[tid] = (t > 0) ? a.mom[tid] : 0.0;
+    if (tid < 20) {
+        const double m = (t > 0) ? a.mom[tid] : 0.0;
+        if (tile == 0 && tid < 4 && t > 0 && a.theta_bar_out) a.theta_bar_out[(size_t)(t - a.s.row0) * 4 + tid] = m;
+        smom[tid] = (tid < 4) ? __dmul_rn(a.oma, m) : m;
+    }
     __syncthreads();
-    if (tile == 0 && tid < 4 && t > 0 && a.theta_bar_out) a.theta_bar_out[(size_t)(t - a.s.row0) * 4 + tid] = smom[tid];
     const double y = a.s.obs[(size_t)(t - a.s.row0) * 2];
     const double cov = a.s.obs[(size_t)(t - a.s.row0) * 2 + 1];
     const uint32_t ctr2 = (uint32_t)a.s.fid, ctr3 = ((uint32_t)(a.s.fid >> 32)) << 4;
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const double th = (FORM == 0) ? (valid ? in[q] : 0.0) : (valid ? a.th_anc[q][src] : 0.0);
-                double acc = __fma_rn(a.a, th, __dmul_rn(a.oma, smom[q]));
+                double acc = __fma_rn(a.a, th, smom[q]);
 #pragma unroll
                 for (int l = 0; l <= q; ++l) acc = __fma_rn(smom[4 + 4 * q + l], (double)zf[l], acc);
                 nth[q] = acc;
