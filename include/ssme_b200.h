@@ -46,6 +46,7 @@ extern "C" {
 #define SSME_B200_MODEL_LINEAR_GAUSSIAN_OPTIMAL 3 /* the same model with the optimal proposal q(x_t | x_{t-1}, y_t): a model that
                                                      brings its own proposal and incremental weights (general SISR: the reference's
                                                      qSamp / logQEv / logFEv hooks, liu_west_filter.h:1495-1516) */
+#define SSME_B200_MODEL_SV_VOLATILITY 4 /* MODEL_SV with expectation functions of its own: h = x, x^2, exp(x/2) (csrc/models/sv_volatility.cuh) */
 
 /* resamplers */
 #define SSME_B200_RESAMP_MULTINOMIAL 0        /* pf::resamplers::mn_resampler (estimate_univ_svol.h:119) */
@@ -186,17 +187,22 @@ int ssme_b200_swarm_filter(ssme_b200_handle h, const double* theta_host, size_t 
 
 /* Replaces: the expectation outputs of the same call -- Swarm::getExpectations after each update
  * (pswarm_filter.h:96-160: per filter numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m) before resampling, in-tree
- * twin liu_west_filter.h:1662-1683; then the mean over the parameter particles) for the two functions h(x) = x and
- * h(x) = x^2 (the reference takes std::function callbacks; a device kernel cannot call host lambdas, so the filtering
- * mean and second moment of the log-volatility are built in).  expectations_host [T][2]; per_filter [P][T][2] and
- * log_cond_like_host [T] may be NULL.  Runs the tracing instantiation of the resident kernel. */
+ * twin liu_west_filter.h:1662-1683; then the mean over the parameter particles).  The reference takes std::function
+ * callbacks (pswarm_filter.h:47, 340); a device kernel cannot call host lambdas, so the functions h_k are members of the
+ * device model type (csrc/models/model_api.cuh: kNumExpect, expect_fn; SSME_B200_MODEL_SV_VOLATILITY brings x, x^2 and
+ * exp(x/2)); a model without them gets the two built-in ones h(x) = x and h(x) = x^2.  K = ssme_b200_num_expectations(h);
+ * expectations_host [T][K]; per_filter [P][T][K] and log_cond_like_host [T] may be NULL.  Runs the tracing instantiation
+ * of the resident kernel. */
 int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base,
                                  double* log_cond_like_host, double* expectations_host, double* per_filter_expectations_host);
+/* Number K of expectation functions of the handle's model (the size of the reference's std::vector<func>, pswarm_filter.h:47):
+ * 2 unless the model type brings its own; -1 for a null handle. */
+int ssme_b200_num_expectations(ssme_b200_handle h);
 
 /* Streaming form: Swarm::update(y_t) once per observation (pswarm_filter.h:223-239).  _begin fixes the P parameter
  * particles (untransformed, [P][numparams]) and the random streams; each _step advances all P filters by one
  * observation row ([1] = y_t, or [2] = (y_t, z_t) for the leverage model) and returns the swarm's log cond-like of that
- * step and, if expectations_host != NULL, the two expectations.  T steps == the whole-series calls above, bit for bit.
+ * step and, if expectations_host != NULL, the K expectations [K].  T steps == the whole-series calls above, bit for bit.
  * The resampled states wait in HBM between calls; no ssme_b200_set_observations needed. */
 int ssme_b200_swarm_begin(ssme_b200_handle h, const double* theta_host, size_t P, uint64_t stream_base);
 int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_cond_like_host, double* expectations_host);

@@ -47,8 +47,9 @@ public:
     virtual psv samp_untrans_params() = 0;
 
     // update(y_t) for t = 0 .. T-1 in one call; obs is row-major [T][dimy], dimy = 1 or 2 (y_t, z_t)
-    // with_expectations: also form E[x_t | y_{1:t}] and E[x_t^2 | y_{1:t}] averaged over the parameter particles
-    // (Swarm::update(yt, fs) + getExpectations, pswarm_filter.h:223-239, 96-160, for h(x) = x and h(x) = x^2)
+    // with_expectations: also form E[h_k(x_t) | y_{1:t}] averaged over the parameter particles (Swarm::update(yt, fs) +
+    // getExpectations, pswarm_filter.h:223-239, 96-160).  The functions h_k are members of the device model type
+    // (csrc/models/model_api.cuh); num_expectations() of them, h(x) = x and h(x) = x^2 unless the model brings its own.
     void update_series(const std::vector<double>& obs, size_t dimy, std::uint64_t stream_base = 0, bool with_expectations = false)
     {
         if (obs.empty() || obs.size() % dimy != 0) throw std::length_error("bad observation array");
@@ -61,7 +62,7 @@ public:
         throw_on_error(ssme_b200_replace_observations(m_h, obs.data(), T, dimy));
         m_log_cond_like.assign(T, 0.0);
         if (with_expectations) {
-            m_expectations.assign(2 * T, 0.0);
+            m_expectations.assign(num_expectations() * T, 0.0);
             throw_on_error(ssme_b200_swarm_expectations(m_h, theta.data(), nparamparts, stream_base, m_log_cond_like.data(),
                                                         m_expectations.data(), nullptr));
         } else {
@@ -87,18 +88,20 @@ public:
             m_num_obs = 0;
             m_streaming = true;
         }
-        double cl = 0.0, ex[2] = {0.0, 0.0};
+        double cl = 0.0, ex[8] = {0.0};
         throw_on_error(ssme_b200_swarm_step(m_h, row.data(), &cl, with_expectations ? ex : nullptr));
         m_log_cond_like.push_back(cl);
-        if (with_expectations) m_expectations.insert(m_expectations.end(), ex, ex + 2);
+        if (with_expectations) m_expectations.insert(m_expectations.end(), ex, ex + num_expectations());
         m_num_obs += 1;
     }
 
     float_t getLogCondLike(size_t t) const { return (float_t)m_log_cond_like.at(t); }
     float_t getLogCondLike() const { return (float_t)m_log_cond_like.back(); }
     unsigned num_obs() const { return m_num_obs; }
-    // getExpectations()[which] at step t: which = 0 -> E[x_t | y_{1:t}], 1 -> E[x_t^2 | y_{1:t}]
-    float_t getExpectation(size_t t, size_t which) const { return (float_t)m_expectations.at(2 * t + which); }
+    // size of the reference's std::vector<func> of expectation callbacks (pswarm_filter.h:47): fixed by the device model type
+    size_t num_expectations() const { return (size_t)ssme_b200_num_expectations(m_h); }
+    // getExpectations()[which] at step t: E[h_which(x_t) | y_{1:t}] (default functions: which = 0 -> x_t, 1 -> x_t^2)
+    float_t getExpectation(size_t t, size_t which) const { return (float_t)m_expectations.at(num_expectations() * t + which); }
 
 private:
     ssme_b200_handle m_h = nullptr;

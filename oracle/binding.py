@@ -81,7 +81,7 @@ def filter_run(theta, y, N, model=0, resampler=0, rs=1, arithmetic=ARITH_CANONIC
     cl = np.empty(T) if trace else None
     anc = np.empty((T, N), dtype=np.int32) if trace else None
     xs = np.empty((T, N)) if trace else None
-    ex = np.empty((T, 2)) if (trace and not (tiled and arithmetic == ARITH_CANONICAL)) else None
+    ex = np.empty((T, 3 if model == 4 else 2)) if (trace and not (tiled and arithmetic == ARITH_CANONICAL)) else None
     fn = lib().ssme_oracle_filter_expect
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 9

@@ -464,6 +464,16 @@ static void upd_margin(double* margin, const double* C, int32_t a, double tau, d
 
 /* sum_i w_i x_i^p (p = 1, 2) in the resident kernel's order: lane l owns items lL .. lL+L-1 and accumulates them with
  * fma from zero, butterfly over the 32 lanes of each warp, warps added in order */
+/* expectation function k of a model that brings its own (SvVolatilityModel::expect_fn): x, x^2, exp(x/2) */
+static double model_expect_fn(int k, double x, int canonical)
+{
+    if (k == 0) return x;
+    if (k == 1) return x * x;
+    return canonical ? dm_exp(0.5 * x) : exp(0.5 * x);
+}
+int32_t ssme_oracle_num_expect(int32_t model) { return model == SSME_OR_MODEL_SV_VOLATILITY ? 3 : 2; }
+
+/* power = 1, 2: the built-in moments; power = -1 - k: the model's own function k, s = fma(w, h_k(x), s) */
 static double block_sum_wx(const double* w, const double* x, int32_t n, int32_t L, int32_t lanes, int power)
 {
     double* t = (double*)calloc((size_t)lanes, sizeof(double));
@@ -471,7 +481,10 @@ static double block_sum_wx(const double* w, const double* x, int32_t n, int32_t 
         double s = 0.0;
         for (int32_t k = 0; k < L; ++k) {
             int64_t i = (int64_t)l * L + k;
-            if (i < n) s = (power == 1) ? fma(w[i], x[i], s) : fma(w[i] * x[i], x[i], s);
+            if (i < n) {
+                if (power < 0) s = fma(w[i], model_expect_fn(-1 - power, x[i], 1), s);
+                else s = (power == 1) ? fma(w[i], x[i], s) : fma(w[i] * x[i], x[i], s);
+            }
         }
         t[l] = s;
     }
@@ -500,12 +513,17 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
 /* as ssme_oracle_filter, plus expect[T][2] = E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}]: the weighted means the reference
  * forms before resampling, numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m) (pswarm / BSFilter expectations;
  * in-tree twin liu_west_filter.h:1662-1683), with h(x) = x and h(x) = x^2 */
-int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
+int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg_in, const double* theta, const double* y, int64_t T,
                               const double* cov, const double* z_inj, const double* u_inj,
                               double* loglik_out, double* cond_like, int32_t* ancestors, double* x_trace,
                               double* tie_margin, double* expect)
 {
-    if (!cfg || !theta || !y || T < 0) return -1;
+    if (!cfg_in || !theta || !y || T < 0) return -1;
+    /* SV_VOLATILITY is the SV model with three expectation functions of its own: same densities, same filter */
+    ssme_oracle_cfg cfg_local = *cfg_in;
+    const int own_expect = (cfg_in->model == SSME_OR_MODEL_SV_VOLATILITY);
+    if (own_expect) cfg_local.model = SSME_OR_MODEL_SV;
+    const ssme_oracle_cfg* cfg = &cfg_local;
     const int32_t N = cfg->num_particles;
     const int canonical = (cfg->arithmetic == SSME_OR_ARITH_CANONICAL);
     const int32_t L = cfg->scan_items_per_lane;
@@ -620,7 +638,19 @@ int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, c
         }
         if (cond_like) cond_like[t] = cl;
         loglik += cl; /* estimate_univ_svol.h:125 */
-        if (expect) {
+        if (expect && own_expect) {
+            if (canonical) {
+                if (tiled) return -9; /* expectations are an output of the resident kernel */
+                for (int k = 0; k < 3; ++k) expect[3 * t + k] = block_sum_wx(w, x, N, L, NP / L, -1 - k) / S;
+            } else {
+                double nk[3] = {0.0, 0.0, 0.0}, den = 0.0;
+                for (int32_t i = 0; i < N; ++i) {
+                    for (int k = 0; k < 3; ++k) nk[k] += model_expect_fn(k, x[i], 0) * w[i];
+                    den += w[i];
+                }
+                for (int k = 0; k < 3; ++k) expect[3 * t + k] = nk[k] / den;
+            }
+        } else if (expect) {
             if (canonical) {
                 if (tiled) return -9; /* expectations are an output of the resident kernel */
                 expect[2 * t + 0] = block_sum_wx(w, x, N, L, NP / L, 1) / S;

@@ -40,7 +40,8 @@
 extern "C" {
 #endif
 
-enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1, SSME_OR_MODEL_LINEAR_GAUSSIAN = 2, SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL = 3 };
+enum { SSME_OR_MODEL_SV = 0, SSME_OR_MODEL_SV_LEVERAGE = 1, SSME_OR_MODEL_LINEAR_GAUSSIAN = 2, SSME_OR_MODEL_LINEAR_GAUSSIAN_OPTIMAL = 3,
+       SSME_OR_MODEL_SV_VOLATILITY = 4 /* the SV model with its own expectation functions h = x, x^2, exp(x/2) (models/sv_volatility.cuh) */ };
 enum { SSME_OR_RESAMP_MULTINOMIAL = 0, SSME_OR_RESAMP_SORTED_MULTINOMIAL = 1, SSME_OR_RESAMP_SYSTEMATIC = 2 };
 enum { SSME_OR_ARITH_CANONICAL = 0, SSME_OR_ARITH_FAITHFUL = 1 };
 enum { SSME_OR_RNG_PHILOX = 0, SSME_OR_RNG_INJECTED = 1 };
@@ -90,7 +91,9 @@ int ssme_oracle_filter(const ssme_oracle_cfg* cfg, const double* theta, const do
                        double* loglik, double* cond_like, int32_t* ancestors, double* x_trace,
                        double* tie_margin);
 
-/* the same, plus expect[T][2] = E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] formed before resampling (reference:
+/* number of expectation functions of a model: 2 (h = x, x^2) unless the model brings its own */
+int32_t ssme_oracle_num_expect(int32_t model);
+/* the same, plus expect[T][K] (K = ssme_oracle_num_expect(model); E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] by default) formed before resampling (reference:
  * expectation callbacks of the filters, in-tree twin liu_west_filter.h:1662-1683; swarm average pswarm_filter.h:96-160) */
 int ssme_oracle_filter_expect(const ssme_oracle_cfg* cfg, const double* theta, const double* y, int64_t T,
                               const double* cov, const double* z_inj, const double* u_inj,

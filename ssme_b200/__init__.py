@@ -21,6 +21,7 @@ from .capi import (  # noqa: F401
     MODEL_SV_LEVERAGE,
     MODEL_LINEAR_GAUSSIAN,
     MODEL_LINEAR_GAUSSIAN_OPTIMAL,
+    MODEL_SV_VOLATILITY,
     RESAMP_MULTINOMIAL,
     RESAMP_SORTED_MULTINOMIAL,
     RESAMP_SYSTEMATIC,

@@ -12,8 +12,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-MODEL_SV, MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN, MODEL_LINEAR_GAUSSIAN_OPTIMAL = 0, 1, 2, 3
-_NUM_PARAMS = {MODEL_SV: 3, MODEL_SV_LEVERAGE: 4, MODEL_LINEAR_GAUSSIAN: 3, MODEL_LINEAR_GAUSSIAN_OPTIMAL: 3}
+MODEL_SV, MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN, MODEL_LINEAR_GAUSSIAN_OPTIMAL, MODEL_SV_VOLATILITY = 0, 1, 2, 3, 4
+_NUM_PARAMS = {MODEL_SV: 3, MODEL_SV_LEVERAGE: 4, MODEL_LINEAR_GAUSSIAN: 3, MODEL_LINEAR_GAUSSIAN_OPTIMAL: 3, MODEL_SV_VOLATILITY: 3}
 RESAMP_MULTINOMIAL, RESAMP_SORTED_MULTINOMIAL, RESAMP_SYSTEMATIC = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
 RNG_PHILOX, RNG_INJECTED = 0, 1
@@ -107,6 +107,8 @@ def load_library():
     lib.ssme_b200_lw_step.argtypes = [H, C.c_double, C.c_double, dp, dp]
     lib.ssme_b200_lw_state.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
     lib.ssme_b200_swarm_expectations.argtypes = [H, dp, C.c_size_t, C.c_uint64, dp, dp, dp]
+    lib.ssme_b200_num_expectations.argtypes = [H]
+    lib.ssme_b200_num_expectations.restype = C.c_int
     lib.ssme_b200_pmmh_run.argtypes = [H, C.POINTER(_PmmhConfig), dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_pmmh_run_custom.argtypes = [C.c_int32, C.POINTER(_PmmhConfig), EVALUATOR_FN, C.c_void_p, dp, dp, dp, dp, dp, dp]
     lib.ssme_b200_model.argtypes = [H]
@@ -339,6 +341,11 @@ class ParticleFilterBackend:
                                                   _dptr(fm), ip(anc), ip(aux)))
         return {"loglik": ll.value, "cond_like": cl, "theta_bar": tb, "final_mean": fm, "ancestors": anc, "aux_index": aux}
 
+    @property
+    def num_expectations(self) -> int:
+        """Number of expectation functions of the handle's model (the size of the reference's vector of callbacks)."""
+        return int(self._lib.ssme_b200_num_expectations(self._h))
+
     def swarm_begin(self, theta, stream_base: int = 0):
         """Start a streaming swarm (Swarm::update once per observation)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
@@ -347,7 +354,7 @@ class ParticleFilterBackend:
     def swarm_step(self, obs_row, want_expectations: bool = False):
         row = np.ascontiguousarray(np.atleast_1d(obs_row), dtype=np.float64)
         cl = C.c_double()
-        ex = np.zeros(2) if want_expectations else None
+        ex = np.zeros(self.num_expectations) if want_expectations else None
         _check(self._lib.ssme_b200_swarm_step(self._h, _dptr(row), C.byref(cl), _dptr(ex)))
         return (cl.value, ex) if want_expectations else cl.value
 
@@ -390,11 +397,13 @@ class ParticleFilterBackend:
         return (out, pf) if return_per_filter else out
 
     def swarm_expectations(self, theta, stream_base: int = 0, return_per_filter: bool = False):
-        """Swarm::getExpectations over the whole series for h(x) = x, x^2: dict(log_cond_like[T], expectations[T,2], per_filter[P,T,2])."""
+        """Swarm::getExpectations over the whole series for the model's K expectation functions (h(x) = x, x^2 unless the model type
+        brings its own): dict(log_cond_like[T], expectations[T,K], per_filter[P,T,K])."""
         theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.num_params)
         P = theta.shape[0]
-        cl, ex = np.empty(self.T), np.empty((self.T, 2))
-        pf = np.empty((P, self.T, 2)) if return_per_filter else None
+        K = self.num_expectations
+        cl, ex = np.empty(self.T), np.empty((self.T, K))
+        pf = np.empty((P, self.T, K)) if return_per_filter else None
         _check(self._lib.ssme_b200_swarm_expectations(self._h, _dptr(theta), P, stream_base, _dptr(cl), _dptr(ex), _dptr(pf)))
         return {"log_cond_like": cl, "expectations": ex, "per_filter": pf}
 

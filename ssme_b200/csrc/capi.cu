@@ -436,6 +436,7 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
     h->NT = NT;
     h->num_params = mi.num_params;
     h->obs_stride = mi.obs_stride;
+    h->num_expect = mi.num_expect;
     h->num_sms = prop.multiProcessorCount;
     h->fast = fast;
     h->debug = dbg;
@@ -743,14 +744,14 @@ int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, s
     if (rc) return rc;
     rc = set_device(h);
     if (rc) return rc;
-    const size_t np = (size_t)h->num_params, T = h->T;
+    const size_t np = (size_t)h->num_params, T = h->T, KE = (size_t)h->num_expect;
     double *d_theta = nullptr, *d_ll = nullptr, *d_cl = nullptr, *d_ex = nullptr, *d_mean = nullptr;
     auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_ll); cudaFree(d_cl); cudaFree(d_ex); cudaFree(d_mean); };
     cudaError_t e = cudaMalloc(&d_theta, P * np * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&d_ll, P * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&d_cl, P * T * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_ex, P * T * 2 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_mean, T * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ex, P * T * KE * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mean, T * (1 + KE) * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_theta, theta_host, P * np * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (e != cudaSuccess) { cleanup(); return fail(SSME_B200_ECUDA, "swarm setup failed: %s", cudaGetErrorString(e)); }
     FilterArgs a = base_args(h, d_theta, 1u, stream_base, d_ll);
@@ -759,13 +760,13 @@ int ssme_b200_swarm_expectations(ssme_b200_handle h, const double* theta_host, s
     rc = launch_filters(h, h->debug, a, P, h->stream);  // the tracing instantiation carries the extra reduction
     if (rc) { cleanup(); return rc; }
     swarm_mean_kernel<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(d_cl, P, (int)T, d_mean);
-    swarm_mean_kernel<<<(unsigned)((2 * T + 127) / 128), 128, 0, h->stream>>>(d_ex, P, (int)(2 * T), d_mean + T);
+    swarm_mean_kernel<<<(unsigned)((KE * T + 127) / 128), 128, 0, h->stream>>>(d_ex, P, (int)(KE * T), d_mean + T);
     g_launches.fetch_add(2);
     e = cudaGetLastError();
     if (e == cudaSuccess && log_cond_like_host) e = cudaMemcpyAsync(log_cond_like_host, d_mean, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(expectations_host, d_mean + T, 2 * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(expectations_host, d_mean + T, KE * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && per_filter_expectations_host)
-        e = cudaMemcpyAsync(per_filter_expectations_host, d_ex, P * T * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        e = cudaMemcpyAsync(per_filter_expectations_host, d_ex, P * T * KE * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cleanup();
     if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "swarm expectations failed: %s", cudaGetErrorString(e));
@@ -793,7 +794,7 @@ int ssme_b200_swarm_begin(ssme_b200_handle h, const double* theta_host, size_t P
         h->sw_P = 0;
         SSME_CUDA(cudaMalloc(&h->d_sw_theta, P * np * sizeof(double)));
         SSME_CUDA(cudaMalloc(&h->d_sw_x, P * N * sizeof(double)));
-        SSME_CUDA(cudaMalloc(&h->d_sw_buf, (128 + 4 * P + 4) * sizeof(double)));
+        SSME_CUDA(cudaMalloc(&h->d_sw_buf, (128 + (2 + (size_t)h->num_expect) * P + 1 + (size_t)h->num_expect) * sizeof(double)));
         h->sw_P = P;
     }
     SSME_CUDA(cudaMemcpyAsync(h->d_sw_theta, theta_host, P * np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -815,8 +816,9 @@ int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_
     double* d_row = h->d_sw_buf;                 // a whole 64-step chunk is what the kernel's bulk copy reads
     double* d_ll = h->d_sw_buf + 128;            // [P]
     double* d_cl = d_ll + P;                     // [P][1]
-    double* d_ex = d_cl + P;                     // [P][1][2]
-    double* d_mean = d_ex + 2 * P;               // [0] mean cond-like, [1..2] mean expectations
+    const int KE = h->num_expect;
+    double* d_ex = d_cl + P;                     // [P][1][KE]
+    double* d_mean = d_ex + (size_t)KE * P;      // [0] mean cond-like, [1..KE] mean expectations
     SSME_CUDA(cudaMemcpyAsync(d_row, obs_row, (size_t)OS * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     FilterArgs a = base_args(h, h->d_sw_theta, 1u, h->sw_base, d_ll);
     a.obs = d_row;
@@ -827,16 +829,27 @@ int ssme_b200_swarm_step(ssme_b200_handle h, const double* obs_row, double* log_
     a.expect = expectations_host ? d_ex : nullptr;
     if ((rc = launch_filters(h, h->debug, a, P, h->stream))) return rc;
     swarm_mean_kernel<<<1, 128, 0, h->stream>>>(d_cl, P, 1, d_mean);
-    if (expectations_host) swarm_mean_kernel<<<1, 128, 0, h->stream>>>(d_ex, P, 2, d_mean + 1);
+    if (expectations_host) swarm_mean_kernel<<<1, 128, 0, h->stream>>>(d_ex, P, KE, d_mean + 1);
     g_launches.fetch_add(expectations_host ? 2 : 1);
     SSME_CUDA(cudaGetLastError());
-    double out[3] = {0, 0, 0};
-    SSME_CUDA(cudaMemcpyAsync(out, d_mean, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    double out[1 + 8] = {0};
+    static_assert(8 >= 1, "models bring at most 8 expectation functions");
+    SSME_CUDA(cudaMemcpyAsync(out, d_mean, (size_t)(1 + KE) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     SSME_CUDA(cudaStreamSynchronize(h->stream));
     if (log_cond_like_host) *log_cond_like_host = out[0];
-    if (expectations_host) { expectations_host[0] = out[1]; expectations_host[1] = out[2]; }
+    if (expectations_host)
+        for (int k = 0; k < KE; ++k) expectations_host[k] = out[1 + k];
     h->sw_t += 1;
     return SSME_B200_OK;
+}
+
+int ssme_b200_num_expectations(ssme_b200_handle h)
+{
+    if (!h) {
+        fail(SSME_B200_EINVAL, "null handle");
+        return -1;
+    }
+    return h->num_expect;
 }
 
 int ssme_b200_shard_range(uint64_t F, int32_t world, int32_t rank, uint64_t* first, uint64_t* count, uint64_t* chunk)

@@ -48,6 +48,7 @@ struct ssme_b200_filter_s {
     int L = 0, NT = 0;
     int num_params = 0;
     int obs_stride = 1;  // doubles per observation row of the model (models/model_api.cuh: kObsStride)
+    int num_expect = 2;  // expectation functions of the model (models/model_api.cuh: kNumExpect; 2 built-in ones by default)
     int num_sms = 0;
     int filters_per_sm = 0;
     const ssme::KernelEntry* fast = nullptr;

@@ -24,6 +24,11 @@
 //       // through Step), and the model supplies the incremental log-weights
 //       static __device__ double logw (const Params&, const Step&, double x, double x_prev);  // log g + log f - log q
 //       static __device__ double logw1(const Params&, const Step&, double x);                 // log mu + log g - log q1
+//       // OPTIONAL, expectation functions E[h_k(x_t) | y_{1:t}] formed before resampling -- the device counterpart of the
+//       // std::function callbacks the reference's filter() / Swarm take (pswarm_filter.h:47, 340; liu_west_filter.h:1662-1683).
+//       // Without them the two built-in functions h = x, x^2 are used.
+//       static constexpr int kNumExpect;                                                        // 1 .. 8
+//       static __device__ double expect_fn(const Params&, const Step&, double x, int k);        // h_k(x_t), k < kNumExpect
 //   };
 //
 // Contract.  Without logw / logw1 the bootstrap proposal is meant (q = f, q1 = mu), so the weight is logg alone: logMuEv -
@@ -47,6 +52,21 @@ template <typename M, typename = void>
 struct model_has_logw : std::false_type {};
 template <typename M>
 struct model_has_logw<M, std::void_t<decltype(&M::logw), decltype(&M::logw1)>> : std::true_type {};
+
+template <typename M, typename = void>
+struct model_has_expect : std::false_type {};
+template <typename M>
+struct model_has_expect<M, std::void_t<decltype(&M::expect_fn), decltype(M::kNumExpect)>> : std::true_type {};
+// number of expectation functions of a model (2 built-in ones, h = x and x^2, unless the model brings its own)
+template <typename M, bool = model_has_expect<M>::value>
+struct model_num_expect {
+    static constexpr int value = 2;
+};
+template <typename M>
+struct model_num_expect<M, true> {
+    static constexpr int value = M::kNumExpect;
+    static_assert(M::kNumExpect >= 1 && M::kNumExpect <= 8, "1 .. 8 expectation functions");
+};
 
 // incremental log-weight of a particle that moved from x_prev to x (first: the time-1 draw): log g for a bootstrap model
 // (identical code to calling logg directly), log g + log f - log q for a model that brings its own proposal

@@ -57,7 +57,7 @@ struct FilterArgs {
     int t_begin;
     double* x_state;
     int k2_dsmem_max;    // cluster kernel: largest cluster size that exchanges the CDF tiles by DSMEM bulk copies
-    double* expect;      // [F][T][2] filtering moments E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] (DEBUG kernels), or null      // [F][T][N]
+    double* expect;      // [F][T][K] E[h_k(x_t) | y_{1:t}], K = model_num_expect (x, x^2 by default) (DEBUG kernels), or null      // [F][T][N]
 };
 
 // The gather table X keeps two doubles of padding after every eight (xslot): thread tid stores its L = 8 states as four
@@ -395,36 +395,40 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         const bool do_resample = DEBUG ? ((t + 1) % a.rs == 0) : true;
 
         if (DEBUG && a.expect) {
-            // E[x_t | y_{1:t}], E[x_t^2 | y_{1:t}] before resampling: numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m)
+            // E[h_k(x_t) | y_{1:t}] before resampling: numer += h(x_i) exp(lw_i - m), denom += exp(lw_i - m)
             // (the filters' expectation callbacks; in-tree twin liu_west_filter.h:1662-1683).  Order = oracle block_sum_wx.
-            double n1 = 0.0, n2 = 0.0;
+            // h_k: the model's own expect_fn (model_api.cuh), or the two built-in moments x, x^2.
+            constexpr int KE = model_num_expect<MODEL>::value;
+            double nk[KE];
+#pragma unroll
+            for (int e = 0; e < KE; ++e) nk[e] = 0.0;
 #pragma unroll
             for (int k = 0; k < L; ++k) {
                 if (i0 + k < N) {
                     const double w = dexp_nonpos(__dsub_rn(lw[k], M));
-                    n1 = __fma_rn(w, x[k], n1);
-                    n2 = __fma_rn(__dmul_rn(w, x[k]), x[k], n2);
+                    if constexpr (model_has_expect<MODEL>::value) {
+#pragma unroll
+                        for (int e = 0; e < KE; ++e) nk[e] = __fma_rn(w, MODEL::expect_fn(mc, ms, x[k], e), nk[e]);
+                    } else {
+                        nk[0] = __fma_rn(w, x[k], nk[0]);
+                        nk[1] = __fma_rn(__dmul_rn(w, x[k]), x[k], nk[1]);
+                    }
                 }
             }
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                n1 = __dadd_rn(n1, shfl_xor_d(n1, d));
-                n2 = __dadd_rn(n2, shfl_xor_d(n2, d));
-            }
-            if (lane == 0) {  // clM / clS only buffer cond-likes in the fast path
-                clM[warp] = n1;
-                clS[warp] = n2;
+            for (int e = 0; e < KE; ++e) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) nk[e] = __dadd_rn(nk[e], shfl_xor_d(nk[e], d));
+                __syncthreads();  // clM only buffers cond-likes in the fast path; the previous function's total has been read
+                if (lane == 0) clM[warp] = nk[e];
+                __syncthreads();
+                if (tid == 0) {
+                    double acc = clM[0];
+                    for (int g = 1; g < NW; ++g) acc = __dadd_rn(acc, clM[g]);
+                    a.expect[((size_t)f * T + t) * KE + e] = __ddiv_rn(acc, S);
+                }
             }
             __syncthreads();
-            if (tid == 0) {
-                double a1 = clM[0], a2 = clS[0];
-                for (int g = 1; g < NW; ++g) {
-                    a1 = __dadd_rn(a1, clM[g]);
-                    a2 = __dadd_rn(a2, clS[g]);
-                }
-                a.expect[((size_t)f * T + t) * 2 + 0] = __ddiv_rn(a1, S);
-                a.expect[((size_t)f * T + t) * 2 + 1] = __ddiv_rn(a2, S);
-            }
         }
 
         if (DEBUG) {

@@ -193,6 +193,51 @@ def test_swarm_expectations_bit_exact(oracle, sv_series, gpu_backend_factory, mo
     assert np.all(got["expectations"][:, 1] >= got["expectations"][:, 0] ** 2 - 1e-12)
 
 
+@pytest.mark.parametrize("N,L", [(500, 4), (1024, 8), (37, 1)])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
+def test_model_supplied_expectation_functions(oracle, sv_series, gpu_backend_factory, N, L, resampler):
+    """The reference's filters take a vector of std::function callbacks h(x_t) (pswarm_filter.h:47, 340; liu_west_filter.h:1662-1683).
+    On the device they are members of the model type (models/model_api.cuh: kNumExpect, expect_fn).  MODEL_SV_VOLATILITY is the SV
+    model with three of its own (x, x^2, exp(x/2)): same likelihood as MODEL_SV bit for bit, K = 3 expectations bit-exact
+    against the oracle, the first one equal to MODEL_SV's built-in mean, streaming == whole series."""
+    T, P = 70, 3
+    y = sv_series(T, seed=79)
+    theta = np.stack([np.array([1.0, 0.95, 0.0625]) * (1 + 0.01 * p) for p in range(P)])
+    be = gpu_backend_factory(model=sb.MODEL_SV_VOLATILITY, num_particles=N, resampler=resampler, seed=22, scan_items_per_lane=L)
+    be.add_observed_data(y)
+    assert be.num_expectations == 3
+    got = be.swarm_expectations(theta, stream_base=3, return_per_filter=True)
+    assert got["expectations"].shape == (T, 3) and got["per_filter"].shape == (P, T, 3)
+    lay = be.layout
+    refs = [oracle.filter_run(theta[p], y, N, model=sb.MODEL_SV_VOLATILITY, resampler=resampler, L=lay["scan_items_per_lane"],
+                              NT=lay["threads_per_filter"], seed=22, filter_id=3 + p) for p in range(P)]
+    acc = np.zeros((T, 3))
+    for p in range(P):
+        assert np.array_equal(got["per_filter"][p], refs[p]["expect"])
+        acc = acc + refs[p]["expect"]
+    assert np.array_equal(got["expectations"], acc / P)
+    # the same filter as MODEL_SV: identical likelihoods, and h_0 = x is MODEL_SV's first built-in function
+    sv = gpu_backend_factory(model=sb.MODEL_SV, num_particles=N, resampler=resampler, seed=22, scan_items_per_lane=L)
+    sv.add_observed_data(y)
+    assert sv.num_expectations == 2
+    base = sv.swarm_expectations(theta, stream_base=3, return_per_filter=True)
+    assert np.array_equal(base["log_cond_like"], got["log_cond_like"])
+    assert np.array_equal(base["per_filter"][:, :, 0], got["per_filter"][:, :, 0])
+    assert np.allclose(base["per_filter"][:, :, 1], got["per_filter"][:, :, 1], rtol=1e-13)   # fma(w x, x, .) vs fma(w, x x, .)
+    assert be.work_batch(theta, R=1, stream_base=3).tolist() == sv.work_batch(theta, R=1, stream_base=3).tolist()
+    # Jensen: E[exp(x/2)] >= exp(E[x]/2); reference-order (libm, sequential) weighted means to 1e-9
+    assert np.all(got["expectations"][:, 2] >= np.exp(0.5 * got["expectations"][:, 0]) * (1 - 1e-12))
+    fai = oracle.filter_run(theta[0], y, N, model=sb.MODEL_SV_VOLATILITY, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=22, filter_id=3)
+    if np.array_equal(fai["ancestors"], refs[0]["ancestors"]):
+        assert np.allclose(got["per_filter"][0], fai["expect"], rtol=1e-9, atol=1e-12)
+    # streaming: Swarm::update(y_t, fs) once per observation
+    be2 = gpu_backend_factory(model=sb.MODEL_SV_VOLATILITY, num_particles=N, resampler=resampler, seed=22, scan_items_per_lane=L)
+    be2.swarm_begin(theta, stream_base=3)
+    for t in range(T):
+        cl, ex = be2.swarm_step([y[t]], want_expectations=True)
+        assert cl == got["log_cond_like"][t] and np.array_equal(ex, got["expectations"][t])
+
+
 @pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
 @pytest.mark.parametrize("resampler", [sb.RESAMP_MULTINOMIAL, sb.RESAMP_SYSTEMATIC])
 @pytest.mark.parametrize("N,T,L,rs", [(500, 70, 1, 1), (500, 70, 2, 1), (33, 20, 1, 1), (1000, 40, 2, 3), (1024, 33, 1, 1), (63, 9, 2, 1)])

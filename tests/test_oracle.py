@@ -330,3 +330,21 @@ def test_detmath_v2_streams(oracle):
     # equidistribution of the uniforms over 64 cells (chi-square, 63 degrees of freedom: mean 63, sd 11.2)
     cnt = np.bincount((u * 64).astype(int), minlength=64)
     assert ((cnt - n / 64) ** 2 / (n / 64)).sum() < 63 + 5 * 11.3
+
+
+def test_model_supplied_expectation_functions_restated(oracle, sv_series):
+    """MODEL_SV_VOLATILITY = MODEL_SV plus three expectation functions of its own (x, x^2, exp(x/2)): same filter, and the
+    canonical weighted means agree with the reference-order ones (numer += h w, denom += w; pswarm_filter.h:96-160)."""
+    ob = oracle
+    y = sv_series(40, seed=3)
+    th = np.array([1.0, 0.95, 0.0625])
+    assert ob.lib().ssme_oracle_num_expect(4) == 3 and ob.lib().ssme_oracle_num_expect(0) == 2
+    a = ob.filter_run(th, y, 500, model=4, L=4, seed=8, filter_id=1)
+    b = ob.filter_run(th, y, 500, model=0, L=4, seed=8, filter_id=1)
+    f = ob.filter_run(th, y, 500, model=4, arithmetic=ob.ARITH_FAITHFUL, seed=8, filter_id=1)
+    assert a["expect"].shape == (40, 3) and b["expect"].shape == (40, 2)
+    assert a["loglik"] == b["loglik"] and np.array_equal(a["ancestors"], b["ancestors"])
+    assert np.array_equal(a["expect"][:, 0], b["expect"][:, 0])
+    assert np.array_equal(a["ancestors"], f["ancestors"])
+    assert np.allclose(a["expect"], f["expect"], rtol=1e-12, atol=1e-14)
+    assert np.all(a["expect"][:, 2] > 0)
