@@ -8,8 +8,8 @@
 //                             descent + gather                                          (reads 16 B, writes 8 B / particle)
 // Weighting every tile relative to ITS OWN maximum removes the global maximum from the per-particle path: the log-weights never
 // travel through HBM (48 -> 32 bytes per particle-step of traffic) and a rank of the multi-GPU form (K5) needs nothing from
-// its peers until the tile totals are scanned -- one exchange of (m_b, T_b, max cl) per step.  The Liu-West kernels (K4) keep
-// the earlier five-launch order (propagate / reduce_max / weights_scan with the global maximum / tile scan / resample):
+// its peers until the tile totals are scanned -- one exchange of (m_b, T_b, max cl) per step.  The Liu-West kernels (K4,
+// lw_kernel.cuh) use the same order, the tile scan, the resamplers and expand_counts() of this file.
 // Same per-particle arithmetic and Philox streams as K1; the scan / search order is the oracle's "tiled"
 // order (oracle/pf_oracle.c: tiled_build / tiled_search), so results are bit-identical to it -- and
 // independent of how many GPUs the tiles are spread over (K5).
@@ -75,7 +75,8 @@ struct SpillArgs {
     // t - row0; the whole-series entry points leave row0 = 0
     int row0;
     // tile-relative order (bootstrap filter K3 / K5): tmax[b] = m_b is the tile's own maximum, lwc holds cl relative to it,
-    // sb[b] = exp(m_b - M) is formed by the tile scan.  rel = 0: the K4 order (global maximum in scal[0], sb unused).
+    // sb[b] = exp(m_b - M) is formed by the tile scan.  rel = 0 (global maximum in scal[0], sb unused) is the round-1 order:
+    // no kernel of the library launches it any more.
     int rel;
     double* sb;  // [nb]
     // K5 (one filter sharded over ranks): every rank keeps ALL tile triples; a rank writes its tiles' (m_b, T_b, max cl) into
@@ -149,34 +150,6 @@ __device__ __forceinline__ void k5_signal_last_cta(const SpillArgs& a, int which
 }
 __global__ void k5_signal_kernel(const SpillArgs a, int which) { k5_signal_last_cta(a, which, 1u); }
 __global__ void k5_wait_kernel(const SpillArgs a, int which, unsigned long long e) { k5_wait(a, which, e); }
-
-// M = max over the tile maxima of this rank's tiles (K4 order)
-__global__ void __launch_bounds__(1024) spill_reduce_max_kernel(const SpillArgs a)
-{
-    __shared__ double red[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double m = __longlong_as_double(0xfff0000000000000ll);
-    for (int b = a.tile0 + tid; b < a.tile1; b += 1024) {
-        const double v = a.tmax[b];
-        m = (v > m) ? v : m;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(m, d);
-        m = (other > m) ? other : m;
-    }
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    if (warp == 0) {
-        m = red[lane];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const double other = shfl_xor_d(m, d);
-            m = (other > m) ? other : m;
-        }
-        if (lane == 0) a.scal[0] = m;
-    }
-}
 
 // The tile scan of the canonical order: sc holds a thread's lane-local inclusive prefix sums on entry and the tile-local
 // inclusive prefix sums on exit (Kogge-Stone over the 32 lanes, then over the warps; one block barrier).  Returns the tile total.
@@ -308,48 +281,6 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
             a.peer_tclmax[r][tile] = m;
         }
         if (a.world > 1) k5_signal_last_cta(a, 0, gridDim.x);
-    }
-}
-
-// w = exp(lw - M) and the CTA scan of K1, K4 order (lane-local sequential, Kogge-Stone over lanes, Kogge-Stone over warps)
-__global__ void __launch_bounds__(kTileNT) spill_weights_scan_kernel(const SpillArgs a)
-{
-    constexpr int NW = kTileNT / 32;
-    __shared__ double red_sum[32];
-    __shared__ double red_max[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = a.tile0 + blockIdx.x;
-    const size_t l0 = (size_t)blockIdx.x * kTile + (size_t)tid * kTileL;
-    const double M = a.scal[0];
-    double sc[kTileL];
-#pragma unroll
-    for (int k = 0; k < kTileL; k += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(a.lwc + l0 + k);
-        sc[k] = v.x; sc[k + 1] = v.y;
-    }
-#pragma unroll
-    for (int k = 0; k < kTileL; ++k) {
-        const double w = dexp_nonpos(__dsub_rn(sc[k], M));
-        sc[k] = (k == 0) ? w : __dadd_rn(sc[k - 1], w);
-    }
-    const double S = tile_scan_finish(sc, red_sum, lane, warp);
-#pragma unroll
-    for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(a.lwc + l0 + k) = make_double2(sc[k], sc[k + 1]);
-    // largest tile-local CDF entry (feeds the running maximum used by the systematic expansion).  Inside a thread the
-    // entries are non-decreasing (floating-point addition of non-negative terms is monotone), so its last one is its largest.
-    double cmax = sc[kTileL - 1];
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(cmax, d);
-        cmax = (other > cmax) ? other : cmax;
-    }
-    if (lane == 0) red_max[warp] = cmax;
-    __syncthreads();
-    if (tid == 0) {
-        double m = red_max[0];
-        for (int g = 1; g < NW; ++g) m = (red_max[g] > m) ? red_max[g] : m;
-        a.ttot[tile] = S;
-        a.tclmax[tile] = m;
     }
 }
 
@@ -872,7 +803,7 @@ __device__ __forceinline__ void expand_counts(const SpillArgs& a, int tile, int 
         sh_range[1] = 0;
     }
     const double O = (tile > 0) ? a.E[tile - 1] : 0.0;
-    const double sbv = a.rel ? a.sb[tile] : 1.0;  // tile-relative order: C_i = O_b + cl_i s_b  (times 1.0 is exact: K4 order unchanged)
+    const double sbv = a.rel ? a.sb[tile] : 1.0;  // tile-relative order: C_i = O_b + cl_i s_b  (rel = 0: times 1.0 is exact)
     double c[kTileL];
 #pragma unroll
     for (int k = 0; k < kTileL; k += 2) {
