@@ -176,6 +176,10 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         a.wtot = s->scan2 + 2048;
         a.cmax = s->scan2 + 2048 + 32;
         const size_t smem_b = (size_t)2 * s->Lp * 33 * sizeof(double);
+        if (a.rel && a.cl_mode != 3) {
+            spill_tile_max_kernel<<<1, kTileScanNT, 0, st>>>(a);
+            count_launch(1);
+        }
         spill_tile_scan_a_kernel<<<32, kScan2NT, (size_t)s->Lp * 33 * sizeof(double), st>>>(a);
         spill_tile_scan_b_kernel<<<32, kScan2NT, smem_b, st>>>(a);
         count_launch(1);

@@ -583,21 +583,29 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_small_kernel(cons
 // shared memory (transposed, conflict-free) and the 32 CTAs run on 32 SMs.  Same additions in the same order.
 constexpr int kScan2NT = 256;
 
+// one CTA ahead of the two-launch scan: waits for the peers' tile triples (K5) and forms M = max over ALL tile maxima
+__global__ void __launch_bounds__(kTileScanNT) spill_tile_max_kernel(const SpillArgs a)
+{
+    __shared__ double sM;
+    const int tid = threadIdx.x;
+    if (a.world > 1) {
+        if (tid == 0) k5_wait(a, 0, a.epoch);
+        __syncthreads();
+    }
+    tile_relative_max(a, tid, kTileScanNT, &sM);
+    if (tid == 0) a.scal[0] = sM;
+}
+
 __global__ void __launch_bounds__(kScan2NT) spill_tile_scan_a_kernel(const SpillArgs a)
 {
     extern __shared__ double sh2[];  // [Lp][33]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = blockIdx.x, Lp = a.Lp, per = 32 * Lp, first = w * per;
     if (a.rel && a.cl_mode != 3) {
-        if (a.world > 1) {  // K5: the peers' tile triples of this step
-            if (tid == 0) k5_wait(a, 0, a.epoch);
-            __syncthreads();
-        }
+        // M = max_b m_b was formed by spill_tile_max_kernel (which also waited for the peers' tile triples, K5): every one of
+        // the 32 CTAs reading all the tile maxima itself cost 30 us at 65536 tiles
+        const double M = a.scal[0];
         // thread tid rescales the tiles first + tid, first + tid + 256, ... that it stages below
-        __shared__ double proM;
-        tile_relative_max(a, tid, kScan2NT, &proM);
-        const double M = proM;
-        if (w == 0 && tid == 0) a.scal[0] = M;
         for (int i = tid; i < per; i += kScan2NT) {
             const int b = first + i;
             if (b < a.nb) {

@@ -71,6 +71,28 @@ def test_liu_west_apf_bit_exact(oracle, gpu_backend_factory, resampler, N, T):
         assert N >= 5000  # index ties between the tiled and the sequential CDF need many particles
 
 
+@pytest.mark.parametrize("form", ["sisr", "apf"])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+def test_liu_west_degenerate_weights(oracle, gpu_backend_factory, form, resampler):
+    """Two outlying observations collapse the weights onto one or two particles: one tile of particles then fathers every slot
+    (16389 > the 8192 staged slots of lw_expand_kernel, so the expansion finds ancestors by its descent over the tile's
+    cumulative offspring counts), and the moments of the next step are sums of one repeated parameter vector."""
+    N, T = 4096 * 4 + 5, 8
+    y = leverage_series(T, seed=5)
+    y[3], y[6] = 40.0, -60.0
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=6, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.lw_filter(LO, HI, delta=0.99, stream_id=2, want_ancestors=True, form=form)
+    ref = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, seed=6, filter_id=2, form=form)
+    assert np.unique(ref["ancestors"][3]).size <= 4                 # the collapse happened
+    assert np.bincount(ref["ancestors"][3] // 4096).max() > 8192    # one tile fathers more than the staging buffer holds
+    assert np.array_equal(got["ancestors"], ref["ancestors"])
+    assert np.array_equal(got["cond_like"], ref["cond_like"])
+    assert np.array_equal(got["theta_bar"], ref["theta_bar"])
+    assert np.array_equal(got["final_mean"], ref["final_mean"])
+    assert got["loglik"] == ref["loglik"] and np.isfinite(got["loglik"])
+
+
 def test_liu_west_forms_agree_statistically(gpu_backend_factory):
     y = leverage_series(60, seed=12, sigma=0.05)
     be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=1 << 17, resampler=sb.RESAMP_SYSTEMATIC, seed=3)

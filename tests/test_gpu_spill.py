@@ -35,6 +35,20 @@ def test_spilled_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     assert pf[0, 0] == ref["loglik"] and out[0] == ref["loglik"]
 
 
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+def test_many_tiles_two_launch_scan_bit_exact(oracle, gpu_backend_factory, resampler):
+    """2^23 + 12293 particles = 2052 tiles: the tile totals are scanned by the two-launch form (Lp = 4: spill_tile_max_kernel,
+    spill_tile_scan_a / _b with per-virtual-warp carries, the expansion's cmax look-up) -- the path the 2^28-particle filter of
+    BASELINE.json config 5 runs.  Three steps against the oracle, bit for bit (the second and third depend on the ancestors)."""
+    N, T = (1 << 23) + 4096 * 3 + 5, 3
+    y = np.random.default_rng(1).standard_normal(T)
+    be = gpu_backend_factory(num_particles=N, resampler=resampler, seed=9)
+    be.add_observed_data(y)
+    got = be.work_batch(SV_THETA[None, :], R=1, stream_base=3)[0]
+    ref = oracle.filter_run(SV_THETA, y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=9, filter_id=3, trace=False)["loglik"]
+    assert got == ref
+
+
 def test_spilled_filter_selected_automatically_and_agrees_statistically(sv_series, gpu_backend_factory):
     """N = 2^20 (the Liu-West config's size): selected without the force flag; the estimate agrees with the
     resident kernel at N = 8192 within Monte Carlo error, and repeated runs with the same stream id are identical."""
