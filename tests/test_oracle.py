@@ -348,3 +348,30 @@ def test_model_supplied_expectation_functions_restated(oracle, sv_series):
     assert np.array_equal(a["ancestors"], f["ancestors"])
     assert np.allclose(a["expect"], f["expect"], rtol=1e-12, atol=1e-14)
     assert np.all(a["expect"][:, 2] > 0)
+
+
+def test_cpu_baseline_filter_agrees_with_the_oracle_statistically(oracle, sv_series):
+    """bench.py's CPU arm (oracle/ref_cpu.cpp: the reference's own thread_pool.h dispatching a restated filter on libstdc++'s
+    mt19937 / normal_distribution / discrete_distribution) and the oracle's FAITHFUL filter (Philox streams) are two
+    restatements of the same algorithm with independent random numbers: their log-likelihood estimates of the same series must
+    agree within Monte Carlo error.  R = 1 per call, so out[p] is one filter's estimate."""
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libssme_refcpu.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libssme_refcpu.so not built (make -C oracle ref)")
+    L = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    L.ssme_refcpu_loglike_batch.argtypes = [C.c_int, C.c_int, dp, C.c_int64, dp, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint64,
+                                            dp, dp, C.POINTER(C.c_uint)]
+    N, T, F = 300, 60, 96
+    y = np.ascontiguousarray(sv_series(T, seed=11))
+    th = np.array([1.0, 0.95, 0.0625])
+    thetas = np.ascontiguousarray(np.tile(th, (F, 1)))
+    out = np.zeros(F)
+    sec, used = C.c_double(), C.c_uint()
+    assert L.ssme_refcpu_loglike_batch(0, N, y.ctypes.data_as(dp), T, thetas.ctypes.data_as(dp), 3, F, 1, 1, 12345,
+                                       out.ctypes.data_as(dp), C.byref(sec), C.byref(used)) == 0
+    ref = np.array([oracle.filter_run(th, y, N, arithmetic=oracle.ARITH_FAITHFUL, seed=77, filter_id=f, trace=False)["loglik"] for f in range(F)])
+    assert np.all(np.isfinite(out)) and np.unique(out).size == F       # independent streams per call
+    se = np.sqrt(out.var(ddof=1) / F + ref.var(ddof=1) / F)
+    assert abs(out.mean() - ref.mean()) < 4 * se, (out.mean(), ref.mean(), se)
+    assert 0.5 < out.std(ddof=1) / ref.std(ddof=1) < 2.0
