@@ -77,12 +77,12 @@ typedef struct {
     int32_t filters_per_sm;      /* must be 0: the resident CTAs per SM follow from the kernel's registers and shared memory
                                     (read the value in use from ssme_b200_get_layout) */
     int32_t force_global_memory; /* 1 = use the global-memory ("spilled") kernels even when N fits one CTA (parity runs);
-                                    they are selected automatically for N > 8192.  These kernels (and the Liu-West entry
-                                    points built on them) resample at every step (resample_every = 1), draw from the
-                                    on-device Philox streams only (no injected streams) and compute in fp64; any other
-                                    setting is refused with SSME_B200_EUNSUPPORTED.  The reference takes the resampling
-                                    schedule as a constructor argument (liu_west_filter.h:1686,1754); its tests and example
-                                    use 1 */
+                                    they are selected automatically for N > 8192.  The bootstrap filter on these kernels
+                                    (one GPU or sharded by particles) honours resample_every like the resident kernels
+                                    (the reference's constructor argument rs, liu_west_filter.h:1686,1754); the Liu-West
+                                    entry points built on them resample at every step (rs = 1, what the reference's tests
+                                    use).  Both draw from the on-device Philox streams only (no injected streams) and
+                                    compute in fp64; any other setting is refused with SSME_B200_EUNSUPPORTED */
     int32_t use_cluster;         /* 1 = one filter per thread-block cluster: tiles of scan_items_per_lane (4 or 8) x
                                     threads_per_filter (256 by default; 128 .. 1024) particles, one tile per SM, up to 16
                                     tiles: 2-3x lower time-step latency when a GPU runs fewer filters than it has SMs.

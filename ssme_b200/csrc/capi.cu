@@ -402,7 +402,6 @@ int ssme_b200_create(const ssme_b200_config* cfg, ssme_b200_handle* out)
         NT = cl_nt;
     } else if (spill) {
         // K3: particles in HBM, tiles of 4096 (spill_kernel.cuh)
-        if (cfg->resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels resample at every step (resample_every = 1)");
         if (cfg->rng_mode != SSME_B200_RNG_PHILOX) return fail(SSME_B200_EUNSUPPORTED, "the global-memory kernels use the on-device Philox streams");
         L = 8;
         NT = 512;

@@ -29,6 +29,7 @@ struct SpillState {
     unsigned int* done_ctr = nullptr;
     unsigned long long epoch = 0;  // launches of spill_step_kernel so far (the same on every rank)
     unsigned char* peer_xchg[kMaxPeers] = {};
+    double* lwacc = nullptr;  // [local] accumulated log-weights (resample_every > 1)
     void* params = nullptr;  // [256 B] MODEL::Params of the filter being run
     bool loopback = false;  // the "ranks" are handles of ONE process on one device, driven in lockstep on one stream
     double* scan2 = nullptr;  // two-launch tile scan: lanepref[1024], lanetot[1024], wtot[32], cmax[32]
@@ -59,6 +60,13 @@ __global__ void spill_init_kernel(double* scal, int N)
 }
 
 __global__ void spill_store_kernel(const double* scal, double* out) { *out = scal[2]; }
+
+__global__ void spill_identity_kernel(const SpillArgs a)
+{
+    const long long base = (long long)(a.tile0 + blockIdx.x) * kTile;
+    for (int k = threadIdx.x; k < kTile; k += blockDim.x)
+        if (base + k < a.N) a.ancestors[(size_t)a.t * a.N + base + k] = (int)(base + k);
+}
 
 static int prepare(ssme_b200_handle h)
 {
@@ -103,6 +111,7 @@ static int prepare(ssme_b200_handle h)
         s->peer_xchg[s->rank] = s->xchg;
     }
     SSME_CUDA(cudaMalloc(&s->sb, (size_t)s->nb * sizeof(double)));
+    if (h->cfg.resample_every > 1) SSME_CUDA(cudaMalloc(&s->lwacc, s->local * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->params, 256));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
@@ -142,7 +151,7 @@ void spill_destroy(ssme_b200_handle h)
             if (s->opened[r][i]) cudaIpcCloseMemHandle(s->opened[r][i]);
     cudaFree(s->x_anc);
     for (int i = 0; i < 2; ++i) { cudaFree(s->x_cur[i]); cudaFree(s->lwc[i]); }
-    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->xchg); cudaFree(s->sb); cudaFree(s->params); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal);
+    cudaFree(s->ecdf); cudaFree(s->ettot); cudaFree(s->eE); cudaFree(s->ecarry); cudaFree(s->scan2); cudaFree(s->xchg); cudaFree(s->sb); cudaFree(s->lwacc); cudaFree(s->params); cudaFree(s->carry); cudaFree(s->E); cudaFree(s->scal);
     for (int k = 0; k < 4; ++k) { cudaFree(s->th_anc[k]); cudaFree(s->th_cur[k]); }
     cudaFree(s->part); cudaFree(s->mom); cudaFree(s->lfs); cudaFree(s->lw_row);
     delete s;
@@ -237,12 +246,13 @@ static bool launch_params(int model, const double* theta, void* out, cudaStream_
     return false;
 }
 
-static bool launch_step(int model, const SpillArgs& a, int tiles, cudaStream_t st)
+static bool launch_step(int model, const SpillArgs& a, int tiles, bool schedule, cudaStream_t st)
 {
-#define SSME_SPILL_MODEL(M)                                   \
-    if (model == M::kId) {                                     \
-        spill_step_kernel<M><<<tiles, kTileNT, 0, st>>>(a);    \
-        return true;                                           \
+#define SSME_SPILL_MODEL(M)                                                      \
+    if (model == M::kId) {                                                        \
+        if (schedule) spill_step_kernel<M, true><<<tiles, kTileNT, 0, st>>>(a);   \
+        else spill_step_kernel<M, false><<<tiles, kTileNT, 0, st>>>(a);           \
+        return true;                                                              \
     }
     SSME_FOR_EACH_MODEL(SSME_SPILL_MODEL)
 #undef SSME_SPILL_MODEL
@@ -280,10 +290,15 @@ static void bootstrap_args(ssme_b200_handle h, SpillState* s, SpillArgs& a, cons
     a.cond_like = cond_like;
     a.ancestors = ancestors;
     a.params = s->params;
+    a.lwacc = s->lwacc;
+    a.prev_resampled = 1;
 }
 
 // The three phases of one time step.  A: fused propagate / weight / tile scan (raises flag 0 in the peers).  B: scan of all tile
 // totals (waits for the peers' flag 0).  C: resampling (raises flag 1 in the peers; phase A of the next step waits for it).
+// resampling schedule of the reference's filters: resample after step t when (t + 1) % rs == 0 (liu_west_filter.h:1686, 1754)
+static bool resamples_after(ssme_b200_handle h, int t) { return (t + 1) % h->cfg.resample_every == 0; }
+
 static int phase_a(ssme_b200_handle h, SpillState* s, SpillArgs& a, int t, cudaStream_t st)
 {
     const int cur = t & 1;
@@ -291,12 +306,17 @@ static int phase_a(ssme_b200_handle h, SpillState* s, SpillArgs& a, int t, cudaS
     a.epoch = ++s->epoch;
     a.x_cur = s->x_cur[cur];
     a.lwc = s->lwc[cur];
+    const bool schedule = h->cfg.resample_every > 1;
+    a.prev_resampled = (t == 0 || resamples_after(h, t - 1)) ? 1 : 0;
+    a.lw_carry = a.prev_resampled ? 0 : 1;
+    a.lw_store = (schedule && !resamples_after(h, t)) ? 1 : 0;
+    a.x_in = a.prev_resampled ? s->x_anc : s->x_cur[cur ^ 1];  // no resampling after step t-1: its states are this step's ancestors
     for (int r = 0; r < s->world; ++r) { a.peer_x[r] = s->peer_x[cur][r]; a.peer_lwc[r] = s->peer_lwc[cur][r]; }
     if (s->world > 1 && a.epoch > 1) {  // the peers have finished writing this step's ancestors into this rank's HBM
         k5_wait_kernel<<<1, 1, 0, st>>>(a, 1, a.epoch - 1);
         count_launch(1);
     }
-    if (!launch_step(h->cfg.model, a, s->tiles_per_rank, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
+    if (!launch_step(h->cfg.model, a, s->tiles_per_rank, schedule, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
     count_launch(1);
     return SSME_B200_OK;
 }
@@ -310,6 +330,10 @@ static int phase_c(ssme_b200_handle h, SpillState* s, SpillArgs& a, bool resampl
 {
     const int tiles = s->tiles_per_rank;
     if (!resample) {
+        if (a.ancestors) {  // a step without resampling: every particle continues itself (the oracle traces the identity)
+            spill_identity_kernel<<<tiles, kTileNT, 0, st>>>(a);
+            count_launch(1);
+        }
         if (s->world > 1) {  // the peers must still learn that this rank is done with the step's tile arrays
             k5_signal_kernel<<<1, 1, 0, st>>>(a, 1);
             count_launch(1);
@@ -347,7 +371,7 @@ int spill_run_filters(ssme_b200_handle h, const double* theta_dev, size_t F, uns
         for (int t = 0; t < T; ++t) {
             if ((rc = phase_a(h, s, a, t, st))) return rc;
             if ((rc = phase_b(s, a, st))) return rc;
-            if ((rc = phase_c(h, s, a, t + 1 < T || a.ancestors, st))) return rc;
+            if ((rc = phase_c(h, s, a, resamples_after(h, t) && (t + 1 < T || a.ancestors), st))) return rc;
         }
         spill_store_kernel<<<1, 1, 0, st>>>(s->scal, per_filter_dev + f);
         SSME_CUDA(cudaGetLastError());
@@ -377,7 +401,7 @@ int spill_loopback_run(ssme_b200_handle* hs, int n, const double* theta_dev, siz
             for (int r = 0; r < n; ++r)
                 if ((rc = phase_b(hs[r]->spill_state, a[r], st))) return rc;
             for (int r = 0; r < n; ++r)
-                if ((rc = phase_c(hs[r], hs[r]->spill_state, a[r], t + 1 < T, st))) return rc;
+                if ((rc = phase_c(hs[r], hs[r]->spill_state, a[r], resamples_after(hs[r], t) && t + 1 < T, st))) return rc;
         }
         for (int r = 0; r < n; ++r) spill_store_kernel<<<1, 1, 0, st>>>(hs[r]->spill_state->scal, per_filter_dev + (size_t)r * F + f);
         SSME_CUDA(cudaGetLastError());
@@ -393,6 +417,7 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     if (rc) return rc;
     SpillState* s = h->spill_state;
     if (s->world != 1) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter runs on one GPU");
+    if (h->cfg.resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West kernels resample at every step (resample_every = 1)");
     if (!s->part) {
         for (int k = 0; k < 4; ++k) {
             SSME_CUDA(cudaMalloc(&s->th_anc[k], s->local * sizeof(double)));
@@ -431,6 +456,7 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     a.s.rel = 1;
     a.s.sb = s->sb;
     a.s.world = 1;
+    a.s.prev_resampled = 1;  // the Liu-West filters resample at every step
     a.part = s->part;
     a.mom = s->mom;
     a.ctr = reinterpret_cast<unsigned int*>(s->mom + 32);

@@ -91,6 +91,14 @@ struct SpillArgs {
     unsigned long long* flags;           // this rank's flag block
     unsigned int* done_ctr;              // [2] CTA counters (last CTA of a launch raises the flags)
     const void* params;                  // MODEL::Params of the filter being run (spill_params_kernel)
+    // resampling schedule (the reference's constructor argument rs, liu_west_filter.h:1686, 1754: resample when (t + 1) % rs == 0).
+    // Between resampling steps the log-weights accumulate: lw_t = lw_{t-1} + log g (spill_step_kernel<MODEL, true>), and
+    // log p(y_t | y_{1:t-1}) = (M + log S) - (M_prev + log S_prev) with the previous step's scal[6], scal[7].
+    const double* x_in;   // [local] states entering spill_step_kernel: x_anc after a resampling step, else the previous step's x'
+    double* lwacc;        // [local] accumulated log-weights (allocated when resample_every > 1)
+    int lw_carry;         // the previous step did not resample: this step's log-weights start from lwacc
+    int lw_store;         // this step does not resample: leave the log-weights in lwacc
+    int prev_resampled;   // 1: (M_prev, S_prev) = (0, N)
 };
 
 // ---- programmatic dependent launch (the Liu-West step: three short kernels per time step) ------------------------------------
@@ -192,7 +200,7 @@ __global__ void spill_params_kernel(const double* theta, void* out)
 #ifndef SSME_STEP_MINB
 #define SSME_STEP_MINB 3
 #endif
-template <typename MODEL>
+template <typename MODEL, bool RS = false>
 __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(const SpillArgs a)
 {
     constexpr int NW = kTileNT / 32;
@@ -220,8 +228,8 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
     for (int q = 0; q < kTileL / 4; ++q) {
         double x[4];
         if (a.t > 0) {
-            const double2 v0 = *reinterpret_cast<const double2*>(a.x_anc + l0 + 4 * q);
-            const double2 v1 = *reinterpret_cast<const double2*>(a.x_anc + l0 + 4 * q + 2);
+            const double2 v0 = *reinterpret_cast<const double2*>(a.x_in + l0 + 4 * q);
+            const double2 v1 = *reinterpret_cast<const double2*>(a.x_in + l0 + 4 * q + 2);
             x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y;
         }
         const uint4 r = philox4x32(make_uint4((uint32_t)(i0 / 4 + q), (uint32_t)a.t, ctr2, ctr3), a.rk);
@@ -234,6 +242,10 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
             const double xo = (a.t == 0) ? 0.0 : x[j];
             x[j] = (a.t == 0) ? MODEL::q1(mc, ms, (double)zf[j]) : MODEL::f(mc, ms, x[j], (double)zf[j]);
             double v = model_log_weight<MODEL>(mc, ms, x[j], xo, a.t == 0);
+            if (RS) {  // resampling every rs > 1 steps: the weights of the steps since the last resampling accumulate
+                if (a.lw_carry) v = __dadd_rn(a.lwacc[l0 + k], v);
+                if (a.lw_store) a.lwacc[l0 + k] = v;
+            }
             v = (i0 + k < a.N) ? v : ninf;
             lw[k] = v;
             mloc = (v > mloc) ? v : mloc;
@@ -359,6 +371,31 @@ __device__ __forceinline__ void tile_relative_prologue(const SpillArgs& a, int b
     }
 }
 
+// thread 0 of the kernel that finishes the scan of the tile totals: what to do with (M, S), see SpillArgs::cl_mode
+__device__ __forceinline__ void spill_finish_scan(const SpillArgs& a, double S)
+{
+    const double M = a.scal[0], logN = a.scal[3];  // (tile-relative order: M was written earlier in this launch / by spill_tile_max_kernel)
+    if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
+        a.scal[5] = S;
+        return;
+    }
+    const double logS = dlog(S);
+    a.scal[1] = S;
+    if (a.cl_mode == 1) {
+        a.scal[4] = __dadd_rn(M, logS);
+    } else {
+        // liu_west_filter.h:1651-1659: (M + log S) - (M_old + log S_old); after a resampling step the old weights are all zero
+        const double Mo = a.prev_resampled ? 0.0 : a.scal[6];
+        const double logS2 = a.prev_resampled ? logN : dlog(a.scal[7]);
+        double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), Mo), logS2);
+        if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
+        a.scal[2] = __dadd_rn(a.scal[2], cl);
+        a.scal[6] = M;
+        a.scal[7] = S;
+        if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
+    }
+}
+
 // one CTA: canonical scan of the nb tile totals with Lp items per lane; E[b] for all NBP padded entries
 __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const SpillArgs a)
 {
@@ -444,23 +481,7 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_kernel(const Spil
             }
         }
     }
-    if (tid == 0) {
-        const double M = a.scal[0], logN = a.scal[3];  // (tile-relative order: written by this thread in the prologue)
-        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
-            a.scal[5] = S;
-            return;
-        }
-        const double logS = dlog(S);
-        a.scal[1] = S;
-        if (a.cl_mode == 1) {
-            a.scal[4] = __dadd_rn(M, logS);
-        } else {
-            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
-            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
-            a.scal[2] = __dadd_rn(a.scal[2], cl);
-            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
-        }
-    }
+    if (tid == 0) spill_finish_scan(a, S);
 }
 
 // The same scan for at most 1024 tiles (Lp = 1: one tile per lane) with every intermediate value in registers or shared memory:
@@ -559,21 +580,7 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_small_kernel(cons
     excl = (lane > 0) ? excl : ninf;
     if (in) a.carry[b] = (wprev > excl) ? wprev : excl;
     if (tid == 0) {
-        const double M = a.scal[0], logN = a.scal[3];
-        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
-            a.scal[5] = S;
-            return;
-        }
-        const double logS = dlog(S);
-        a.scal[1] = S;
-        if (a.cl_mode == 1) {
-            a.scal[4] = __dadd_rn(M, logS);
-        } else {
-            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
-            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
-            a.scal[2] = __dadd_rn(a.scal[2], cl);
-            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
-        }
+        spill_finish_scan(a, S);
     }
 }
 
@@ -716,21 +723,7 @@ __global__ void __launch_bounds__(kScan2NT) spill_tile_scan_b_kernel(const Spill
         if (b < a.nb) a.carry[b] = shT[(i % Lp) * 33 + i / Lp];
     }
     if (w == 0 && tid == 0) {
-        const double M = a.scal[0], logN = a.scal[3];
-        if (a.cl_mode == 3) {  // scan of the exponential spacings: only their total is wanted
-            a.scal[5] = S;
-            return;
-        }
-        const double logS = dlog(S);
-        a.scal[1] = S;
-        if (a.cl_mode == 1) {
-            a.scal[4] = __dadd_rn(M, logS);
-        } else {
-            double cl = (a.t == 0) ? __dadd_rn(__dadd_rn(-logN, M), logS) : __dsub_rn(__dsub_rn(__dadd_rn(M, logS), 0.0), logN);
-            if (a.cl_mode == 2) cl = __dsub_rn(__dadd_rn(__dadd_rn(M, logS), a.scal[4]), __dmul_rn(2.0, logN));
-            a.scal[2] = __dadd_rn(a.scal[2], cl);
-            if (a.cond_like) a.cond_like[a.t - a.row0] = cl;
-        }
+        spill_finish_scan(a, S);
     }
 }
 

@@ -35,6 +35,30 @@ def test_spilled_filter_bit_exact(oracle, sv_series, gpu_backend_factory, model,
     assert pf[0, 0] == ref["loglik"] and out[0] == ref["loglik"]
 
 
+@pytest.mark.parametrize("model", [sb.MODEL_SV, sb.MODEL_SV_LEVERAGE])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
+@pytest.mark.parametrize("N,T,rs", [(5000, 20, 2), (4096 * 3 + 17, 13, 3), (100, 9, 5), (16384, 7, 2), (4096, 6, 7)])
+def test_spilled_filter_resampling_schedule(oracle, sv_series, gpu_backend_factory, model, resampler, N, T, rs):
+    """The reference's filters take the resampling schedule as a constructor argument (resample when (t + 1) % rs == 0,
+    liu_west_filter.h:1686, 1754): between resampling steps the log-weights accumulate and log p(y_t | y_{1:t-1}) =
+    (M + log S) - (M_prev + log S_prev) (:1651-1659).  Global-memory kernels, bit for bit against the oracle."""
+    y = sv_series(T, seed=33)
+    th = SV_THETA if model == sb.MODEL_SV else LEV_THETA
+    be = gpu_backend_factory(model=model, num_particles=N, resampler=resampler, resample_every=rs, seed=8, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.trace(th[None, :], stream_base=3, want=("loglik", "cond_like", "ancestors"))
+    ref = oracle.filter_run(th, y, N, model=model, resampler=resampler, rs=rs, L=8, NT=512, tiled=3, seed=8, filter_id=3)
+    assert np.array_equal(got["ancestors"][0], ref["ancestors"])
+    assert np.array_equal(got["cond_like"][0], ref["cond_like"])
+    assert got["loglik"][0] == ref["loglik"]
+    fai = oracle.filter_run(th, y, N, model=model, resampler=resampler, rs=rs, arithmetic=oracle.ARITH_FAITHFUL, seed=8, filter_id=3)
+    if ref["margin"] > 1e-12:
+        assert np.array_equal(got["ancestors"][0], fai["ancestors"])
+    assert abs(got["loglik"][0] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+    out, pf = be.work_batch(np.stack([th, th]), R=1, stream_base=3, return_per_filter=True)   # untraced: no last-step resampling
+    assert pf[0, 0] == ref["loglik"] and out[0] == ref["loglik"]
+
+
 @pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
 def test_many_tiles_two_launch_scan_bit_exact(oracle, gpu_backend_factory, resampler):
     """2^23 + 12293 particles = 2052 tiles: the tile totals are scanned by the two-launch form (Lp = 4: spill_tile_max_kernel,
@@ -66,8 +90,11 @@ def test_spilled_filter_selected_automatically_and_agrees_statistically(sv_serie
 
 
 def test_spilled_mode_argument_checks():
-    with pytest.raises(sb.SsmeB200Error):
-        sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, resample_every=2))
+    lw = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV_LEVERAGE, num_particles=10000, resample_every=2))
+    lw.add_observed_data(np.ones(4))
+    with pytest.raises(sb.SsmeB200Error):   # the bootstrap filter takes a schedule, the Liu-West kernels do not
+        lw.lw_filter(np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01]))
+    lw.close()
     with pytest.raises(sb.SsmeB200Error):
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, rng_mode=sb.RNG_INJECTED))
 
@@ -108,7 +135,8 @@ def test_spilled_filter_degenerate_weights_and_invalid_parameters(oracle, sv_ser
 
 @pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
 @pytest.mark.parametrize("ranks,N", [(2, 4096 * 6), (4, 4096 * 8 - 100), (8, 4096 * 8)])
-def test_sharded_filter_loopback_on_one_gpu(oracle, sv_series, gpu_backend_factory, resampler, ranks, N):
+@pytest.mark.parametrize("rs", [1, 3])
+def test_sharded_filter_loopback_on_one_gpu(oracle, sv_series, gpu_backend_factory, resampler, ranks, N, rs):
     """K5's data plane without a second GPU: the ranks are handles of this process on one device, wired to each other's HBM
     directly and launched phase by phase on one stream (ssme_b200_spill_loopback_*).  Every rank owns a contiguous range of
     tiles, pushes its tile triples into every peer, scans all tile totals itself and resamples across ranks (systematic:
@@ -118,16 +146,16 @@ def test_sharded_filter_loopback_on_one_gpu(oracle, sv_series, gpu_backend_facto
     y = sv_series(T, seed=35).copy()
     y[5] = 25.0  # degenerate weights at one step: offspring runs cross rank boundaries
     th = np.stack([SV_THETA, SV_THETA * np.array([1.1, 0.9, 1.3])])
-    bes = [gpu_backend_factory(num_particles=N, resampler=resampler, seed=13, force_global_memory=1) for _ in range(ranks)]
+    bes = [gpu_backend_factory(num_particles=N, resampler=resampler, resample_every=rs, seed=13, force_global_memory=1) for _ in range(ranks)]
     for b in bes:
         b.add_observed_data(y)
     got = sb.ParticleFilterBackend.spill_loopback_run(bes, th, R=2, stream_base=7)   # [ranks][2 * 2]
-    single = gpu_backend_factory(num_particles=N, resampler=resampler, seed=13, force_global_memory=1)
+    single = gpu_backend_factory(num_particles=N, resampler=resampler, resample_every=rs, seed=13, force_global_memory=1)
     single.add_observed_data(y)
     _, pf = single.work_batch(th, R=2, stream_base=7, return_per_filter=True)
     for r in range(ranks):
         assert np.array_equal(got[r], pf.ravel()), r
-    ref = [oracle.filter_run(th[f // 2], y, N, resampler=resampler, L=8, NT=512, tiled=3, seed=13, filter_id=7 + f, trace=False)["loglik"]
+    ref = [oracle.filter_run(th[f // 2], y, N, resampler=resampler, rs=rs, L=8, NT=512, tiled=3, seed=13, filter_id=7 + f, trace=False)["loglik"]
            for f in range(4)]
     assert got[0].tolist() == ref
     # a second call on the same (connected) handles continues the flag epochs
