@@ -114,10 +114,12 @@ static int prepare(ssme_b200_handle h)
     if (h->cfg.resample_every > 1) SSME_CUDA(cudaMalloc(&s->lwacc, s->local * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->params, 256));
     SSME_CUDA(cudaMalloc(&s->carry, (size_t)s->nb * sizeof(double)));
-    SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32) * sizeof(double)));
+    SSME_CUDA(cudaMalloc(&s->scan2, (1024 + 1024 + 32 + 32 + 32 + 2) * sizeof(double)));
+    SSME_CUDA(cudaMemset(s->scan2, 0, (1024 + 1024 + 32 + 32 + 32 + 2) * sizeof(double)));  // the grid-barrier counter starts at 0
     // per device: the two-launch tile scan stages up to 2 x 256 x 33 doubles
     SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 33 * (int)sizeof(double)));
     SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * (int)sizeof(double)));
+    SSME_CUDA(cudaFuncSetAttribute(spill_tile_scan_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 128 * 33 * (int)sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->E, (size_t)s->NBP * sizeof(double)));
     SSME_CUDA(cudaMalloc(&s->scal, 8 * sizeof(double)));
     for (int i = 0; i < 2; ++i) {
@@ -184,6 +186,12 @@ static void launch_tile_scan(SpillState* s, SpillArgs& a, cudaStream_t st)
         a.lanetot = s->scan2 + 1024;
         a.wtot = s->scan2 + 2048;
         a.cmax = s->scan2 + 2048 + 32;
+        a.gmax = s->scan2 + 2048 + 64;
+        a.gbar = reinterpret_cast<unsigned long long*>(s->scan2 + 2048 + 96);
+        if (s->Lp <= 128) {  // one launch: three phases separated by grid barriers of the 32 co-resident CTAs
+            spill_tile_scan_merged_kernel<<<32, kScan2NT, (size_t)3 * s->Lp * 33 * sizeof(double), st>>>(a);
+            return;
+        }
         const size_t smem_b = (size_t)2 * s->Lp * 33 * sizeof(double);
         if (a.rel && a.cl_mode != 3) {
             spill_tile_max_kernel<<<1, kTileScanNT, 0, st>>>(a);

@@ -71,6 +71,8 @@ struct SpillArgs {
     double* lanetot;   // [1024]
     double* wtot;      // [32]
     double* cmax;      // [32] or null
+    double* gmax;      // [32] per-virtual-warp maxima of the tile maxima (one-launch form of the many-tile scan)
+    unsigned long long* gbar;  // arrival counter of its grid barrier (never reset: 32 arrivals per barrier)
     // streaming use (one observation per call): row of `obs`, `cond_like` and `theta_bar_out` that belongs to step t is
     // t - row0; the whole-series entry points leave row0 = 0
     int row0;
@@ -584,11 +586,189 @@ __global__ void __launch_bounds__(kTileScanNT) spill_tile_scan_small_kernel(cons
     }
 }
 
+// ---- the many-tile scan in ONE launch of 32 co-resident CTAs (one per virtual warp of the canonical 1024-lane scan) -------------
+// The two-launch form below (a: lane totals per virtual warp; b: tile ends, running maxima) plus the launch that forms the
+// global maximum cost three launch latencies per time step and re-read what the previous launch staged (50 us of 620 on eight
+// GPUs).  Here the three phases are separated by two grid barriers (32 CTAs: always co-resident), the rescaled totals and largest
+// entries stay in shared memory, and only the 32 x 3 per-lane values cross CTAs.  Same operations in the same order.
+__device__ __forceinline__ void scan_grid_barrier(unsigned long long* ctr, int tid)
+{
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(ctr, 1ull);
+        const unsigned long long target = (old / gridDim.x + 1ull) * gridDim.x;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int kScan2NT = 256;
+
+__global__ void __launch_bounds__(kScan2NT) spill_tile_scan_merged_kernel(const SpillArgs a)
+{
+    extern __shared__ double sh2[];  // totals [Lp][33] (later: carries), tile ends [Lp][33], largest entries [Lp][33]
+    __shared__ double red[kScan2NT / 32];
+    __shared__ double shM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x, Lp = a.Lp, per = 32 * Lp, first = w * per;
+    double* shT = sh2;
+    double* shE = sh2 + Lp * 33;
+    double* shC = sh2 + 2 * Lp * 33;
+    const double ninf = __longlong_as_double(0xfff0000000000000ll);
+    if (a.rel && a.cl_mode != 3) {
+        if (a.world > 1) {  // K5: the peers' tile triples of this step
+            if (tid == 0) k5_wait(a, 0, a.epoch);
+            __syncthreads();
+        }
+        // phase 1: maximum of this virtual warp's tile maxima; all 32 of them after the barrier (the maximum is order-free)
+        double m = ninf;
+        for (int i = tid; i < per; i += kScan2NT) {
+            const int b = first + i;
+            if (b < a.nb) {
+                const double v = a.tmax[b];
+                m = (v > m) ? v : m;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double other = shfl_xor_d(m, d);
+            m = (other > m) ? other : m;
+        }
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            for (int g = 1; g < kScan2NT / 32; ++g) m = (red[g] > m) ? red[g] : m;
+            a.gmax[w] = m;
+        }
+        scan_grid_barrier(a.gbar, tid);
+        if (warp == 0) {
+            double g = __ldcg(a.gmax + lane);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double other = shfl_xor_d(g, d);
+                g = (other > g) ? other : g;
+            }
+            if (lane == 0) {
+                shM = g;
+                if (w == 0) a.scal[0] = g;
+            }
+        }
+        __syncthreads();
+        const double M = shM;
+        for (int i = tid; i < per; i += kScan2NT) {
+            const int b = first + i;
+            double tot = 0.0, tc = 0.0;
+            if (b < a.nb) {
+                const double sv = dexp_nonpos(__dsub_rn(a.tmax[b], M));
+                a.sb[b] = sv;
+                tot = __dmul_rn(a.ttot[b], sv);
+                tc = __dmul_rn(a.tclmax[b], sv);
+            }
+            shT[(i % Lp) * 33 + i / Lp] = tot;
+            shC[(i % Lp) * 33 + i / Lp] = tc;
+        }
+    } else {
+        for (int i = tid; i < per; i += kScan2NT) {
+            const int b = first + i;
+            shT[(i % Lp) * 33 + i / Lp] = (b < a.nb) ? a.ttot[b] : 0.0;
+            shC[(i % Lp) * 33 + i / Lp] = (b < a.nb) ? a.tclmax[b] : 0.0;
+        }
+    }
+    __syncthreads();
+    // phase 2 (spill_tile_scan_a_kernel): this virtual warp's lane totals and their inclusive scan
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            const double v = shT[k * 33 + lane];
+            tot = (k == 0) ? v : __dadd_rn(tot, v);
+        }
+        double incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(incl, d);
+            incl = (lane >= d) ? __dadd_rn(other, incl) : incl;
+        }
+        a.lanetot[w * 32 + lane] = tot;
+        a.lanepref[w * 32 + lane] = incl;
+        if (lane == 31) a.wtot[w] = incl;
+    }
+    scan_grid_barrier(a.gbar, tid);
+    // phase 3 (spill_tile_scan_b_kernel): tile ends, running maxima
+    double S = 0.0, Eprev = 0.0;  // total; inclusive end of the tile before this virtual warp's first
+    if (warp == 0) {
+        double wv = __ldcg(a.wtot + lane);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(wv, d);
+            wv = (lane >= d) ? __dadd_rn(other, wv) : wv;
+        }
+        S = shfl_d(wv, 31);
+        double wex = shfl_d(wv, (w > 0) ? w - 1 : 0);
+        wex = (w > 0) ? wex : 0.0;
+        const double lex = (lane > 0) ? __ldcg(a.lanepref + w * 32 + lane - 1) : 0.0;
+        const double base = __dadd_rn(wex, lex);
+        double run = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            const double v = shT[k * 33 + lane];
+            run = (k == 0) ? v : __dadd_rn(run, v);
+            shE[k * 33 + lane] = __dadd_rn(base, run);
+        }
+        if (w > 0) {  // E of the last tile of virtual warp w-1, formed exactly as that warp's lane 31 forms it
+            double wex1 = shfl_d(wv, (w > 1) ? w - 2 : 0);
+            wex1 = (w > 1) ? wex1 : 0.0;
+            Eprev = __dadd_rn(__dadd_rn(wex1, __ldcg(a.lanepref + (w - 1) * 32 + 30)), __ldcg(a.lanetot + (w - 1) * 32 + 31));
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < per; i += kScan2NT) a.E[first + i] = shE[(i % Lp) * 33 + i / Lp];
+    // exclusive running maximum of v_b = O_b + tclmax_b (O_b = E_{b-1}) over the tiles of this virtual warp; exact, order-free
+    if (warp == 0) {
+        double loc = ninf;
+        for (int k = 0; k < Lp; ++k) {
+            const int b = first + lane * Lp + k;
+            if (b < a.nb) {
+                const double O = (k > 0) ? shE[(k - 1) * 33 + lane] : (lane > 0 ? shE[(Lp - 1) * 33 + lane - 1] : Eprev);
+                const double v = __dadd_rn((b > 0) ? O : 0.0, shC[k * 33 + lane]);
+                loc = (v > loc) ? v : loc;
+            }
+        }
+        double inc = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double other = shfl_up_d(inc, d);
+            inc = (lane >= d && other > inc) ? other : inc;
+        }
+        double run = shfl_up_d(inc, 1);
+        run = (lane > 0) ? run : ninf;
+        for (int k = 0; k < Lp; ++k) {
+            const int b = first + lane * Lp + k;
+            shT[k * 33 + lane] = run;  // carry of tile b within this virtual warp
+            if (b < a.nb) {
+                const double O = (k > 0) ? shE[(k - 1) * 33 + lane] : (lane > 0 ? shE[(Lp - 1) * 33 + lane - 1] : Eprev);
+                const double v = __dadd_rn((b > 0) ? O : 0.0, shC[k * 33 + lane]);
+                run = (v > run) ? v : run;
+            }
+        }
+        if (lane == 31) a.cmax[w] = inc;
+    }
+    __syncthreads();
+    for (int i = tid; i < per; i += kScan2NT) {
+        const int b = first + i;
+        if (b < a.nb) a.carry[b] = shT[(i % Lp) * 33 + i / Lp];
+    }
+    if (w == 0 && tid == 0) spill_finish_scan(a, S);
+}
+
 // ---- the same scan of the tile totals in two launches of 32 CTAs (one per virtual warp of the canonical 1024-lane scan) ----
 // Used when there are thousands of tiles (Lp >= 4): the single CTA above walks its Lp items per lane with strided,
 // uncoalesced loads through one SM (329 us at 65536 tiles); here every virtual warp stages its 32*Lp totals through
 // shared memory (transposed, conflict-free) and the 32 CTAs run on 32 SMs.  Same additions in the same order.
-constexpr int kScan2NT = 256;
+// (Kept for more than 128 tiles per lane, where three staged arrays no longer fit the shared memory of one SM.)
 
 // one CTA ahead of the two-launch scan: waits for the peers' tile triples (K5) and forms M = max over ALL tile maxima
 __global__ void __launch_bounds__(kTileScanNT) spill_tile_max_kernel(const SpillArgs a)
