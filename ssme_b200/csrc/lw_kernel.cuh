@@ -366,6 +366,14 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
     const int t = a.s.t;
     pdl_trigger();
     pdl_wait();
+    // auxiliary form: every slot walks the first-stage tile ends E (10 levels) before the tile's own CDF (12 levels), each level a
+    // dependent load; with at most 1024 tiles E fits in 8 KB of shared memory and the first ten stop being L2 round trips
+    __shared__ double sE[FORM == 1 ? 1024 : 1];
+    const double* Eb = a.s.E;
+    if (FORM == 1 && t > 0 && a.s.NBP == 1024) {
+        for (int i = tid; i < 1024; i += kTileNT) sE[i] = a.s.E[i];
+        Eb = sE;
+    }
     if (tid < 20) {
         const double m = (t > 0) ? a.mom[tid] : 0.0;
         if (tile == 0 && tid < 4 && t > 0 && a.theta_bar_out) a.theta_bar_out[(size_t)(t - a.s.row0) * 4 + tid] = m;
@@ -414,9 +422,9 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
             const uint4 r = philox4x32(make_uint4((uint32_t)(i >> 1), (uint32_t)t, ctr2, ctr3 | 6u), a.s.rk);
             const double tau = __dmul_rn((i & 1) ? uniform53(r.z, r.w) : uniform53(r.x, r.y), a.s.scal[1]);
             int b = 0;
-            for (int s = a.s.NBP >> 1; s >= 1; s >>= 1) b += (a.s.E[b + s - 1] < tau) ? s : 0;
+            for (int s = a.s.NBP >> 1; s >= 1; s >>= 1) b += (Eb[b + s - 1] < tau) ? s : 0;
             b = min(b, a.s.nb - 1);
-            const double O = (b > 0) ? a.s.E[b - 1] : 0.0;
+            const double O = (b > 0) ? Eb[b - 1] : 0.0;
             const double sbv = a.s.sb[b];
             const double* cl = a.cdf1 + (size_t)b * kTile;
             int idx = 0;

@@ -1181,8 +1181,16 @@ __global__ void __launch_bounds__(kTileNT, 3) spill_expand_kernel(const SpillArg
 // at large N by nature; systematic resampling uses spill_expand_kernel instead.
 __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs a)
 {
+    // the tile ends E are walked by every slot (log2 NBP dependent loads); up to 1024 tiles they are staged in shared memory
+    __shared__ double sE[1024];
     const int tid = threadIdx.x;
     const int tile = a.tile0 + blockIdx.x;
+    const double* Eb = a.E;
+    if (a.NBP == 1024) {
+        for (int i = tid; i < 1024; i += kTileNT) sE[i] = a.E[i];
+        __syncthreads();
+        Eb = sE;
+    }
     const double S = a.scal[1];
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
     double sg = 0.0, Oe = 0.0;
@@ -1206,9 +1214,9 @@ __global__ void __launch_bounds__(kTileNT) spill_resample_kernel(const SpillArgs
             tau = __dmul_rn(uniform32((j & 2) ? w23 : w01), S);
         }
         int b = 0;
-        for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (a.E[b + s - 1] < tau) ? s : 0;
+        for (int s = a.NBP >> 1; s >= 1; s >>= 1) b += (Eb[b + s - 1] < tau) ? s : 0;
         b = min(b, a.nb - 1);
-        const double O = (b > 0) ? a.E[b - 1] : 0.0;
+        const double O = (b > 0) ? Eb[b - 1] : 0.0;
         const double sbv = a.rel ? a.sb[b] : 1.0;
         const int owner = b / a.tiles_per_rank;
         const size_t lbase = (size_t)(b - owner * a.tiles_per_rank) * kTile;
