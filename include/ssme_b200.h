@@ -347,6 +347,11 @@ int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4]
 int ssme_b200_box_muller_words(int32_t device, uint32_t first_word, uint32_t count, uint32_t stride, uint32_t angle_word, float* z0_host,
                                float* z1_host);
 
+/* Diagnostic (parity tests): the device's canonical exp (det_math.cuh: dexp, and dexp_nonpos, the form used for the weights
+ * exp(lw - max)) on count caller-chosen arguments -- range ends, infinities, NaN -- to be compared bit for bit with the oracle's.
+ * The reference calls std::exp (univ_svol_bootstrap_filter.h:85; liu_west_filter.h:97-101). */
+int ssme_b200_dexp_values(int32_t device, const double* x_host, uint32_t count, double* exp_host, double* exp_nonpos_host);
+
 #ifdef __cplusplus
 }
 #endif

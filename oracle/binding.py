@@ -176,3 +176,14 @@ def canonical_scan(w, L, NP=None):
     out = np.empty(NP)
     lib().ssme_oracle_canonical_scan(_dp(w), w.size, L, NP, _dp(out), None)
     return out
+
+
+def dexp_array(x):
+    """The canonical exp (det_math.h: dm_exp) on an array."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    fn = lib().ssme_oracle_dexp_array
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    fn(x.ctypes.data_as(C.c_void_p), x.size, out.ctypes.data_as(C.c_void_p))
+    return out

@@ -23,6 +23,7 @@
 /* ---------------------------------------------------------------- exported raw pieces ------- */
 double ssme_oracle_dexp(double x) { return dm_exp(x); }
 double ssme_oracle_dlog(double x) { return dm_log(x); }
+void ssme_oracle_dexp_array(const double* x, int64_t n, double* out) { for (int64_t i = 0; i < n; ++i) out[i] = dm_exp(x[i]); }
 void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1) { dm_box_muller(a, b, z0, z1); }
 void ssme_oracle_box_muller_words(uint32_t first, uint32_t count, uint32_t stride, uint32_t b, float* z0, float* z1)
 {

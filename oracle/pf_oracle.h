@@ -162,6 +162,7 @@ double ssme_oracle_log_mean_exp(const double* v, int64_t n, int32_t arithmetic);
 /* raw pieces, exported so tests can pin them */
 double ssme_oracle_dexp(double x);
 double ssme_oracle_dlog(double x);
+void ssme_oracle_dexp_array(const double* x, int64_t n, double* out);
 void ssme_oracle_box_muller(uint32_t a, uint32_t b, float* z0, float* z1);
 double ssme_oracle_uniform53(uint32_t hi, uint32_t lo);
 void ssme_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -1038,6 +1038,33 @@ int ssme_b200_box_muller_words(int32_t device, uint32_t first_word, uint32_t cou
     return SSME_B200_OK;
 }
 
+// diagnostic: the device's canonical exp on caller-chosen arguments (range ends, NaN, infinities), bit for bit vs the oracle's
+__global__ void dexp_values_kernel(const double* x, uint32_t count, double* e, double* e_nonpos)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    e[i] = dexp(x[i]);
+    e_nonpos[i] = dexp_nonpos(x[i]);
+}
+
+int ssme_b200_dexp_values(int32_t device, const double* x_host, uint32_t count, double* exp_host, double* exp_nonpos_host)
+{
+    if (!x_host || !exp_host || !exp_nonpos_host || count == 0) return fail(SSME_B200_EINVAL, "bad argument");
+    SSME_CUDA(cudaSetDevice(device));
+    double* d = nullptr;
+    SSME_CUDA(cudaMalloc(&d, (size_t)count * 3 * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, x_host, (size_t)count * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        dexp_values_kernel<<<(count + 255) / 256, 256>>>(d, count, d + count, d + 2 * (size_t)count);
+        g_launches.fetch_add(1);
+        e = cudaMemcpy(exp_host, d + count, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(exp_nonpos_host, d + 2 * (size_t)count, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "dexp_values failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4])
 {
     if (!rates || iters < 1) return fail(SSME_B200_EINVAL, "bad argument");

@@ -5,6 +5,8 @@ particle states are compared with == because kernel and oracle evaluate the same
 operation sequence (canonical arithmetic).  The faithful (libm, reference-formula) oracle is
 compared at 1e-9 relative, the tolerance BASELINE.json's north_star states for fp64.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -347,3 +349,37 @@ def test_box_muller_all_radius_words(oracle):
         assert lib.ssme_b200_box_muller_words(0, first, n, stride, b, p(g0), p(g1)) == 0
         L.ssme_oracle_box_muller_words(first, n, stride, b, p(o0), p(o1))
         assert np.array_equal(g0.view(np.uint32), o0.view(np.uint32)) and np.array_equal(g1.view(np.uint32), o1.view(np.uint32))
+
+
+def test_device_exp_bit_exact_over_its_whole_domain(oracle):
+    """det_math.cuh's exp (14 fused multiply-adds, the power of two applied by adding to the exponent field) against the oracle's
+    dm_exp, bit for bit: 2^22 arguments spread over (-745, 710), every integer and half-integer, the range ends to the ulp,
+    infinities, NaN, +-0, subnormals.  exp_nonpos (the weights' form) on the non-positive ones."""
+    import ctypes as C
+    import ssme_b200 as sb
+    lib = sb.load_library()
+    dp = C.POINTER(C.c_double)
+    lib.ssme_b200_dexp_values.argtypes = [C.c_int32, dp, C.c_uint32, dp, dp]
+    rng = np.random.default_rng(5)
+    edges = [-708.0, 709.0, 0.0, -0.0, 1.0, -1.0, float("inf"), -float("inf"), float("nan"), 5e-324, -5e-324, 2.2250738585072014e-308,
+             1e-300, -1e-300, 709.782712893384, -745.1332191019411, 1e5, -1e5, 1e300, -1e300]
+    near = []
+    for c in (-708.0, 709.0, -707.5, 708.5, -1022 * math.log(2), 1023 * math.log(2), 0.5 * math.log(2), -0.5 * math.log(2)):
+        v = c
+        for _ in range(6):
+            near += [v, np.nextafter(v, np.inf), np.nextafter(v, -np.inf)]
+            v = np.nextafter(np.nextafter(v, np.inf), np.inf)
+    grid = np.arange(-745.0, 710.5, 0.5)
+    x = np.concatenate([np.array(edges), np.array(near), grid, rng.uniform(-745.0, 710.0, 1 << 22), rng.uniform(-40.0, 0.0, 1 << 20),
+                        rng.uniform(-1e-3, 1e-3, 1 << 16)])
+    x = np.ascontiguousarray(x)
+    g, gn = np.empty_like(x), np.empty_like(x)
+    assert lib.ssme_b200_dexp_values(0, x.ctypes.data_as(dp), x.size, g.ctypes.data_as(dp), gn.ctypes.data_as(dp)) == 0
+    ob = oracle.dexp_array(x)
+    same = (g.view(np.uint64) == ob.view(np.uint64)) | (np.isnan(g) & np.isnan(ob))
+    assert same.all(), x[~same][:5]
+    neg = (x <= 0) | np.isnan(x)
+    assert ((gn[neg].view(np.uint64) == ob[neg].view(np.uint64)) | (np.isnan(gn[neg]) & np.isnan(ob[neg]))).all()
+    ok = np.isfinite(x) & (x > -708.0) & (x <= 709.0)
+    rel = np.abs(g[ok] - np.exp(x[ok])) / np.exp(x[ok])
+    assert rel.max() < 3e-16
