@@ -347,6 +347,16 @@ int ssme_b200_measure_opmix_rates(int32_t device, int32_t iters, double rates[4]
 int ssme_b200_box_muller_words(int32_t device, uint32_t first_word, uint32_t count, uint32_t stride, uint32_t angle_word, float* z0_host,
                                float* z1_host);
 
+/* Replaces: LWFilterWithCovsFutureSimulator::sim_future_obs(num_steps, last_obs) (liu_west_filter.h:1315-1360; without
+ * covariates :693-738; the Liu-West-2 twins :1888, :2480 do not compile upstream) for the SV-with-leverage test models
+ * (gSamp: y = z e^{x/2}, test/test_liu_west.cpp:152-157, 353-358).  From the particles of the streaming run in progress (after at
+ * least one ssme_b200_lw_step; the filter's state is not modified): num_steps future observations per particle,
+ * theta' ~ N(a theta + (1-a) thetaBar, h^2 V_t) with the current particles' moments, x' = fSamp(x, predictor, theta'), y = gSamp(x');
+ * the first predictor (covariate) is last_obs, afterwards the particle's own simulated observation.
+ * obs_host [num_steps][num_particles] (the reference's vector over time of arrays over particles).  sim_stream selects the Philox
+ * streams of the draws (< 2^60): the same value reproduces the same simulation. */
+int ssme_b200_lw_sim_future(ssme_b200_handle h, uint32_t num_steps, double last_obs, uint64_t sim_stream, double* obs_host);
+
 /* Diagnostic (parity tests): the device's canonical exp (det_math.cuh: dexp, and dexp_nonpos, the form used for the weights
  * exp(lw - max)) on count caller-chosen arguments -- range ends, infinities, NaN -- to be compared bit for bit with the oracle's.
  * The reference calls std::exp (univ_svol_bootstrap_filter.h:85; liu_west_filter.h:97-101). */

@@ -123,6 +123,20 @@ public:
         throw_on_error(ssme_b200_lw_state(m_h, &m_loglik, m_final_mean.data(), nullptr));
     }
 
+    // *FutureSimulator::sim_future_obs(num_steps, last_obs) (liu_west_filter.h:1315-1360): from the particles of the streaming
+    // run, num_steps simulated observations per particle; result[time][particle] as the reference's obsSamples.  The filter's
+    // state is not modified.  Every call draws fresh randomness unless the same sim_stream is passed again.
+    std::vector<std::vector<float_t>> sim_future_obs(unsigned num_steps, float_t last_obs, std::uint64_t sim_stream = 0)
+    {
+        if (!m_streaming) throw std::runtime_error("sim_future_obs follows filter(y_t, z_t)");
+        std::vector<double> flat((size_t)num_steps * nparts);
+        throw_on_error(ssme_b200_lw_sim_future(m_h, num_steps, (double)last_obs, sim_stream ? sim_stream : ++m_sim_calls, flat.data()));
+        std::vector<std::vector<float_t>> out(num_steps, std::vector<float_t>(nparts));
+        for (size_t t = 0; t < num_steps; ++t)
+            for (size_t i = 0; i < nparts; ++i) out[t][i] = (float_t)flat[t * nparts + i];
+        return out;
+    }
+
     // log p(y_t | y_{1:t-1}) of step t (the reference returns the latest one; :2180-2184)
     float_t getLogCondLike(size_t t) const { return (float_t)m_cond_like.at(t); }
     float_t getLogCondLike() const { return (float_t)m_cond_like.back(); }
@@ -141,7 +155,7 @@ private:
     psv m_lo, m_hi;
     double m_loglik = 0.0;
     bool m_streaming = false;
-    std::uint64_t m_stream = 0;
+    std::uint64_t m_stream = 0, m_sim_calls = 0;
     std::vector<double> m_cond_like, m_theta_bar, m_expect;
     std::array<double, 4> m_final_mean{};
 };

@@ -187,3 +187,25 @@ def dexp_array(x):
     fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     fn(x.ctypes.data_as(C.c_void_p), x.size, out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def lw_sim_future(prior_lo, prior_hi, delta, y, N, steps, last_obs, sim_stream=0, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512,
+                  seed=20260101, filter_id=0, tiled=3, form="sisr"):
+    """The Liu-West filter over y, then `steps` future observations simulated from every particle it ends with
+    (*FutureSimulator::sim_future_obs, liu_west_filter.h:693-738, 1315-1360): dict(loglik, sim [steps][N])."""
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
+    hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
+    cfg = _Cfg(1, N, resampler, 1, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, int(tiled) if arithmetic == ARITH_CANONICAL else 0, 0)
+    ll = C.c_double(0)
+    out = np.empty((steps, N))
+    fn = lib().ssme_oracle_lw_filter_sim
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double,
+                   C.c_uint64, C.c_void_p, C.c_void_p]
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = fn(C.cast(C.byref(cfg), C.c_void_p), {"sisr": 0, "apf": 1}[form], vp(lo), vp(hi), delta, vp(y), y.size, None, steps, last_obs,
+            sim_stream, C.cast(C.byref(ll), C.c_void_p), vp(out))
+    if rc != 0:
+        raise ValueError("ssme_oracle_lw_filter_sim failed with %d" % rc)
+    return {"loglik": ll.value, "sim": out}

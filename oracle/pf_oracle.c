@@ -868,10 +868,48 @@ int ssme_oracle_lw_filter_expect(const ssme_oracle_cfg* cfg, int32_t form, const
 
 /* the same with every random draw optionally taken from pre-generated streams (st != NULL): the form in which the filter
  * is compared with the reference's own LWFilter2WithCovs / LWFilterWithCovs compiled from /root/reference (tests/test_refhdr.py) */
+/* simulation of future observations from the particles the filter ends with (the *FutureSimulator add-ons, liu_west_filter.h:
+ * 693-738 and, with covariates, :1315-1360): for s = 0 .. steps-1 and every particle, theta' ~ N(a theta + (1-a) thetaBar, h^2 V)
+ * with thetaBar, V of the filter's CURRENT particles (the reference calls update_parameter_proposal_components, which looks at
+ * m_param_particles, inside the loop: the same values every step), x' = fSamp(x, predictor, theta'), y = gSamp(x') = z e^{x'/2}
+ * (test/test_liu_west.cpp:152-157, 353-358); the predictor (covariate) of the first step is the last real observation, afterwards
+ * the particle's own simulated one.  Draws: Philox blocks (particle, s) of stream `stream`, tag 7 (four jitter normals) and tag 8
+ * (state normal, observation normal). */
+typedef struct {
+    int32_t steps;
+    double last_obs;
+    uint64_t stream;
+    double* out; /* [steps][N] */
+} lw_sim_t;
+
+static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                          const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
+                          double* loglik_out, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
+                          int32_t* aux_index, double* tie_margin, double* expect, const lw_sim_t* sim);
+
 int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
                                   const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
                                   double* loglik_out, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
                                   int32_t* aux_index, double* tie_margin, double* expect)
+{
+    return lw_filter_impl(cfg, form, prior_lo, prior_hi, delta, y, T, cov, st, loglik_out, cond_like, theta_bar, final_mean, ancestors,
+                          aux_index, tie_margin, expect, NULL);
+}
+
+/* the filter over y[0..T), then sim_steps simulated future observations per particle: sim_out [sim_steps][N] */
+int ssme_oracle_lw_filter_sim(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                              const double* y, int64_t T, const double* cov, int32_t sim_steps, double last_obs, uint64_t sim_stream,
+                              double* loglik_out, double* sim_out)
+{
+    lw_sim_t sim = {sim_steps, last_obs, sim_stream, sim_out};
+    if (sim_steps < 0 || (sim_steps > 0 && !sim_out) || T < 1) return -1;
+    return lw_filter_impl(cfg, form, prior_lo, prior_hi, delta, y, T, cov, NULL, loglik_out, NULL, NULL, NULL, NULL, NULL, NULL, NULL, &sim);
+}
+
+static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                          const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
+                          double* loglik_out, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
+                          int32_t* aux_index, double* tie_margin, double* expect, const lw_sim_t* sim)
 {
     static const int TT[4] = {2, 0, 3, 1}; /* logit, null, log, twice_fisher */
     if (!cfg || !prior_lo || !prior_hi || !y || T < 0) return -1;
@@ -914,9 +952,10 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
     const double logN = canonical ? dm_log((double)N) : log((double)N);
     const double c0 = -DM_HALF_LOG_2PI;
 
-    for (int64_t t = 0; t < T; ++t) {
-        const double yt = y[t];
-        const double ct = (t > 0) ? (cov ? cov[t] : y[t - 1]) : 0.0;
+    const int64_t Tend = (sim && sim->steps > 0) ? T + 1 : T; /* one more pass forms the moments the simulation uses */
+    for (int64_t t = 0; t < Tend; ++t) {
+        const double yt = (t < T) ? y[t] : 0.0;
+        const double ct = (t > 0 && t < T) ? (cov ? cov[t] : y[t - 1]) : 0.0;
         double Lc[4][4] = {{0}}, tb[4] = {0, 0, 0, 0};
         if (t > 0) {
             /* update_parameter_proposal_components: thetaBar, V_t, cov = h^2 V_t, factor */
@@ -957,7 +996,52 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
                     if (i == j) Lc[i][j] = (sacc > 0.0) ? sqrt(sacc) : 0.0;
                     else Lc[i][j] = (Lc[j][j] > 0.0) ? sacc / Lc[j][j] : 0.0;
                 }
-            if (theta_bar) for (int k = 0; k < 4; ++k) theta_bar[t * 4 + k] = tb[k];
+            if (theta_bar && t < T) for (int k = 0; k < 4; ++k) theta_bar[t * 4 + k] = tb[k];
+        }
+        if (t == T) { /* only with sim: the particles are those the filter ended with; they are not modified */
+            for (int32_t i = 0; i < N; ++i) {
+                double thp[4], xs = x[i], pred = sim->last_obs;
+                for (int k = 0; k < 4; ++k) thp[k] = th[(size_t)k * N + i];
+                for (int32_t sidx = 0; sidx < sim->steps; ++sidx) {
+                    uint32_t wd[4];
+                    float zf[4], zx, zy;
+                    philox_block(cfg->seed, sim->stream, (uint32_t)sidx, (uint32_t)i, 7u, wd);
+                    dm_box_muller(wd[0], wd[1], &zf[0], &zf[1]);
+                    dm_box_muller(wd[2], wd[3], &zf[2], &zf[3]);
+                    philox_block(cfg->seed, sim->stream, (uint32_t)sidx, (uint32_t)i, 8u, wd);
+                    dm_box_muller(wd[0], wd[1], &zx, &zy);
+                    double p[4], nth[4];
+                    for (int k = 0; k < 4; ++k) {
+                        if (canonical) {
+                            double acc = fma(a, thp[k], oma * tb[k]);
+                            for (int l = 0; l <= k; ++l) acc = fma(Lc[k][l], (double)zf[l], acc);
+                            nth[k] = acc;
+                        } else {
+                            double acc = 0.0;
+                            for (int l = 0; l < 4; ++l) acc += Lc[k][l] * (double)zf[l];
+                            nth[k] = a * thp[k] + oma * tb[k] + acc;
+                        }
+                        p[k] = lw_inv_trans(TT[k], nth[k], canonical);
+                    }
+                    double ysim;
+                    if (canonical) {
+                        double e2 = dm_exp(-0.5 * xs);
+                        double cz = (p[3] * p[2]) * pred;
+                        double mean = fma(p[0], xs - p[1], p[1]);
+                        mean = fma(cz, e2, mean);
+                        xs = fma(p[2] * sqrt(1.0 - p[3] * p[3]), (double)zx, mean);
+                        ysim = (double)zy * dm_exp(0.5 * xs);
+                    } else {
+                        double mean = p[1] + p[0] * (xs - p[1]) + pred * p[3] * p[2] * exp(-.5 * xs);
+                        xs = mean + (double)zx * p[2] * sqrt(1.0 - p[3] * p[3]);
+                        ysim = (double)zy * exp(.5 * xs);
+                    }
+                    sim->out[(size_t)sidx * N + i] = ysim;
+                    pred = ysim;
+                    for (int k = 0; k < 4; ++k) thp[k] = nth[k];
+                }
+            }
+            break;
         }
         double fs_M2 = 0.0, fs_logS2 = 0.0; /* first stage: max and log of the sum */
         if (form == 1 && t > 0) {

@@ -150,6 +150,11 @@ int ssme_oracle_lw_filter_streams(const ssme_oracle_cfg* cfg, int32_t form, cons
                                   const double* y, int64_t T, const double* cov, const ssme_oracle_lw_streams* st,
                                   double* loglik, double* cond_like, double* theta_bar, double* final_mean, int32_t* ancestors,
                                   int32_t* aux_index, double* tie_margin, double* expect);
+/* the filter over y[0..T), then sim_steps future observations simulated from every particle it ends with (the *FutureSimulator
+ * add-ons of liu_west_filter.h:693-738, 1315-1360): sim_out [sim_steps][N]; see lw_sim_t in pf_oracle.c */
+int ssme_oracle_lw_filter_sim(const ssme_oracle_cfg* cfg, int32_t form, const double* prior_lo, const double* prior_hi, double delta,
+                              const double* y, int64_t T, const double* cov, int32_t sim_steps, double last_obs, uint64_t sim_stream,
+                              double* loglik_out, double* sim_out);
 
 /* canonical sum of v[0..n): tile partials (lane-local sequential over L, butterfly over the 32 lanes, sequential
  * over the warps of the tile), then the tile partials by one CTA of 1024 lanes the same way */

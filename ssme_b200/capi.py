@@ -103,6 +103,7 @@ def load_library():
     lib.ssme_b200_swarm_begin.argtypes = [H, dp, C.c_size_t, C.c_uint64]
     lib.ssme_b200_swarm_step.argtypes = [H, dp, dp, dp]
     lib.ssme_b200_lw_expectations.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64, dp, dp, dp]
+    lib.ssme_b200_lw_sim_future.argtypes = [H, C.c_uint32, C.c_double, C.c_uint64, dp]
     lib.ssme_b200_lw_begin.argtypes = [H, C.c_int32, dp, dp, C.c_double, C.c_uint64]
     lib.ssme_b200_lw_step.argtypes = [H, C.c_double, C.c_double, dp, dp]
     lib.ssme_b200_lw_state.argtypes = [H, dp, dp, C.POINTER(C.c_int64)]
@@ -357,6 +358,12 @@ class ParticleFilterBackend:
         ex = np.zeros(self.num_expectations) if want_expectations else None
         _check(self._lib.ssme_b200_swarm_step(self._h, _dptr(row), C.byref(cl), _dptr(ex)))
         return (cl.value, ex) if want_expectations else cl.value
+
+    def lw_sim_future(self, num_steps: int, last_obs: float, sim_stream: int = 0):
+        """*FutureSimulator::sim_future_obs from the streaming Liu-West run in progress: simulated observations [num_steps, N]."""
+        out = np.empty((int(num_steps), self.cfg.num_particles))
+        _check(self._lib.ssme_b200_lw_sim_future(self._h, int(num_steps), float(last_obs), int(sim_stream), _dptr(out)))
+        return out
 
     def lw_expectations(self, prior_lo, prior_hi, delta: float = 0.99, stream_id: int = 0, form: str = "sisr"):
         """Liu-West filter with the expectations E[h | y_1:t], h = x_t, phi, mu, sigma, rho: dict(loglik, cond_like[T], expect[T,5])."""

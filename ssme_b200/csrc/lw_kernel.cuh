@@ -611,4 +611,55 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_expand_kernel(const LwArgs a)
     lw_last_cta_finish<kTileNT>(a, 0, red, tot, &flag, tid);
 }
 
+// ---- simulation of future observations ------------------------------------------------------------------------------------------
+// *FutureSimulator::sim_future_obs (liu_west_filter.h:693-738; with covariates :1315-1360; the Liu-West-2 twins :1888, :2480 --
+// which do not compile upstream: they use a member m_delta that does not exist, :719).  From the particles the filter holds
+// (read only): for s = 0 .. steps-1, theta' ~ N(a theta + (1-a) thetaBar, h^2 V) with the moments of the CURRENT particles
+// (the reference recomputes them from m_param_particles inside the loop: the same values at every step), x' = fSamp(x, predictor,
+// theta'), y = gSamp(x') = z e^{x'/2} (test/test_liu_west.cpp:152-157); the predictor of the first step is the last real
+// observation, afterwards the particle's own simulated one.  One particle per thread: the steps of a particle are a chain.
+// Draws: Philox blocks (particle, s) of stream `sid`, tag 7 (four jitter normals) and tag 8 (state normal, observation normal).
+__global__ void __launch_bounds__(256) lw_future_kernel(const LwArgs a, int steps, double last_obs, unsigned long long sid, double* out /*[steps][N]*/)
+{
+    __shared__ __align__(16) double smom[20];
+    const int tid = threadIdx.x;
+    if (tid < 20) {
+        const double m = a.mom[tid];
+        smom[tid] = (tid < 4) ? __dmul_rn(a.oma, m) : m;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + tid;
+    if (i >= a.s.N) return;
+    const uint32_t ctr2 = (uint32_t)sid, ctr3 = ((uint32_t)(sid >> 32)) << 4;
+    double th[4], xs = a.s.x_anc[i], pred = last_obs;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) th[q] = a.th_anc[q][i];
+#pragma unroll 1
+    for (int sidx = 0; sidx < steps; ++sidx) {
+        const uint4 rp = philox4x32(make_uint4((uint32_t)i, (uint32_t)sidx, ctr2, ctr3 | 7u), a.s.rk);
+        float zf[4], zx, zy;
+        box_muller(rp.x, rp.y, zf[0], zf[1]);
+        box_muller(rp.z, rp.w, zf[2], zf[3]);
+        const uint4 rz = philox4x32(make_uint4((uint32_t)i, (uint32_t)sidx, ctr2, ctr3 | 8u), a.s.rk);
+        box_muller(rz.x, rz.y, zx, zy);
+        double p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double acc = __fma_rn(a.a, th[q], smom[q]);
+#pragma unroll
+            for (int l = 0; l <= q; ++l) acc = __fma_rn(smom[4 + 4 * q + l], (double)zf[l], acc);
+            th[q] = acc;
+            p[q] = lw_inv_trans(q, acc);
+        }
+        const double e2 = dexp(__dmul_rn(-0.5, xs));
+        const double cz = __dmul_rn(__dmul_rn(p[3], p[2]), pred);
+        double mean = __fma_rn(p[0], __dsub_rn(xs, p[1]), p[1]);
+        mean = __fma_rn(cz, e2, mean);
+        xs = __fma_rn(__dmul_rn(p[2], __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(p[3], p[3])))), (double)zx, mean);
+        const double ysim = __dmul_rn((double)zy, dexp(__dmul_rn(0.5, xs)));
+        out[(size_t)sidx * a.s.N + i] = ysim;
+        pred = ysim;
+    }
+}
+
 }  // namespace ssme

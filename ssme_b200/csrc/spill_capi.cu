@@ -704,6 +704,29 @@ int ssme_b200_lw_state(ssme_b200_handle h, double* loglik_host, double* param_me
     return SSME_B200_OK;
 }
 
+int ssme_b200_lw_sim_future(ssme_b200_handle h, uint32_t num_steps, double last_obs, uint64_t sim_stream, double* obs_host)
+{
+    if (!h || !obs_host) return fail(SSME_B200_EINVAL, "null argument");
+    if (num_steps == 0) return fail(SSME_B200_EINVAL, "num_steps must be positive");
+    if (!h->spill || !h->spill_state || h->spill_state->lw_t < 1)
+        return fail(SSME_B200_ERUNTIME, "simulate from a streaming Liu-West run that has filtered at least one observation (ssme_b200_lw_begin / _step)");
+    if (int src = check_stream_ids(sim_stream, 1)) return src;
+    int rc = set_device(h);
+    if (rc) return rc;
+    SpillState* s = h->spill_state;
+    const size_t n = (size_t)num_steps * (size_t)s->N;
+    double* d_out = nullptr;
+    SSME_CUDA(cudaMalloc(&d_out, n * sizeof(double)));
+    lw_future_kernel<<<(s->N + 255) / 256, 256, 0, h->stream>>>(s->lw_args, (int)num_steps, last_obs, sim_stream, d_out);
+    count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(obs_host, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SSME_B200_ECUDA, "lw_sim_future failed: %s", cudaGetErrorString(e));
+    return SSME_B200_OK;
+}
+
 int ssme_b200_spill_ipc_export(ssme_b200_handle h, uint8_t out[384])
 {
     if (!h || !out) return fail(SSME_B200_EINVAL, "null argument");

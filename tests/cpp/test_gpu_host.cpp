@@ -164,6 +164,19 @@ int main(int argc, char** argv)
         REQUIRE(online.getLogLike() == big.getLogLike());
         REQUIRE(online.getLogCondLike() == big.getLogCondLike());
         REQUIRE(online.getParamMeans()(0) == big.getParamMeans()(0));
+        // LWFilterWithCovsFutureSimulator::sim_future_obs(num_steps, last_obs) (liu_west_filter.h:1315-1360): [time][particle]
+        const auto sim = online.sim_future_obs(5, y.back(), 77);
+        REQUIRE(sim.size() == 5);
+        REQUIRE(sim[0].size() == 20000);
+        double m1 = 0, m2 = 0;
+        for (const auto& row : sim)
+            for (double v : row) { REQUIRE(std::isfinite(v)); m1 += v; m2 += v * v; }
+        m1 /= 1e5; m2 /= 1e5;
+        REQUIRE(std::abs(m1) < 0.05);
+        REQUIRE(m2 > 0.05);
+        REQUIRE(online.sim_future_obs(5, y.back(), 77) == sim);   // same stream, same simulation; the filter is untouched:
+        online.filter(y[0], cov[0]);
+        REQUIRE(std::isfinite(online.getLogCondLike()));
         REQUIRE(std::abs(big.getLogLike() - big2.getLogLike()) < 0.02 * std::abs(big2.getLogLike()));
     }
     TEST_CASE("covariate-free Liu-West twins: filter(y_t)")

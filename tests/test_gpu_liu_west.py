@@ -184,3 +184,53 @@ def test_liu_west_argument_checks(gpu_backend_factory):
         be2.lw_filter(HI, LO)
     with pytest.raises(ValueError):
         be2.lw_filter(LO, HI, delta=0.2)
+
+
+@pytest.mark.parametrize("form", ["sisr", "apf"])
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL])
+@pytest.mark.parametrize("N,T,S", [(10, 3, 4), (5000, 9, 6), (4096 * 2 + 5, 5, 3)])
+def test_future_simulator_bit_exact(oracle, gpu_backend_factory, form, resampler, N, T, S):
+    """*FutureSimulator::sim_future_obs(num_steps, last_obs) (liu_west_filter.h:1315-1360, :693-738): from the particles of the
+    streaming run, S simulated observations per particle (jitter with the current particles' moments, fSamp with the previous
+    simulated observation as covariate, gSamp y = z e^{x/2}).  Bit-exact against the oracle; the filter's state is untouched."""
+    y = leverage_series(T + 2, seed=N + T + 7)
+    z = np.concatenate([[0.0], y[:-1]])
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, seed=12, force_global_memory=1)
+    with pytest.raises(RuntimeError):
+        be.lw_sim_future(2, 0.0)                       # no streaming run yet
+    be.lw_begin(LO, HI, delta=0.99, stream_id=6, form=form)
+    with pytest.raises(RuntimeError):
+        be.lw_sim_future(2, 0.0)                       # no observation filtered yet
+    for t in range(T):
+        be.lw_step(y[t], z[t])
+    got = be.lw_sim_future(S, y[T - 1], sim_stream=41)
+    ref = oracle.lw_sim_future(LO, HI, 0.99, y[:T], N, S, y[T - 1], sim_stream=41, resampler=resampler, seed=12, filter_id=6, form=form)
+    assert got.shape == (S, N) and np.array_equal(got, ref["sim"])
+    assert np.array_equal(be.lw_sim_future(S, y[T - 1], sim_stream=41), got)          # same stream, same simulation
+    assert not np.array_equal(be.lw_sim_future(S, y[T - 1], sim_stream=42), got)      # another stream, another one
+    fai = oracle.lw_sim_future(LO, HI, 0.99, y[:T], N, S, y[T - 1], sim_stream=41, resampler=resampler, seed=12, filter_id=6, form=form,
+                               arithmetic=oracle.ARITH_FAITHFUL)
+    chk = oracle.lw_filter_run(LO, HI, 0.99, y[:T], N, resampler=resampler, seed=12, filter_id=6, form=form)
+    cf = oracle.lw_filter_run(LO, HI, 0.99, y[:T], N, resampler=resampler, seed=12, filter_id=6, form=form, arithmetic=oracle.ARITH_FAITHFUL)
+    if np.array_equal(chk["ancestors"], cf["ancestors"]) and np.array_equal(chk["aux_index"], cf["aux_index"]):
+        assert np.allclose(got, fai["sim"], rtol=1e-9, atol=1e-12)
+    # the simulation read the filter's particles only: the run continues exactly as without it
+    cl, tb = be.lw_step(y[T], z[T])
+    cont = oracle.lw_filter_run(LO, HI, 0.99, y[:T + 1], N, resampler=resampler, seed=12, filter_id=6, form=form)
+    assert cl == cont["cond_like"][T] and np.array_equal(tb, cont["theta_bar"][T])
+
+
+def test_future_simulator_law(gpu_backend_factory):
+    """Simulated observations are N(0, e^{x}) mixtures: zero mean, variance of the order of the series', heavier tails than a normal."""
+    y = leverage_series(200, seed=3, sigma=0.3)
+    z = np.concatenate([[0.0], y[:-1]])
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=1 << 16, resampler=sb.RESAMP_SYSTEMATIC, seed=5)
+    be.lw_begin(LO, HI, delta=0.99, stream_id=1)
+    for t in range(200):
+        be.lw_step(y[t], z[t])
+    sim = be.lw_sim_future(20, y[-1], sim_stream=7)
+    assert np.all(np.isfinite(sim))
+    assert abs(sim.mean()) < 0.02
+    assert 0.3 < sim.var() / y.var() < 3.0
+    kurt = (sim ** 4).mean() / (sim ** 2).mean() ** 2
+    assert kurt > 3.0

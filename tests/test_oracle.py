@@ -375,3 +375,20 @@ def test_cpu_baseline_filter_agrees_with_the_oracle_statistically(oracle, sv_ser
     se = np.sqrt(out.var(ddof=1) / F + ref.var(ddof=1) / F)
     assert abs(out.mean() - ref.mean()) < 4 * se, (out.mean(), ref.mean(), se)
     assert 0.5 < out.std(ddof=1) / ref.std(ddof=1) < 2.0
+
+
+def test_future_simulator_restated(oracle):
+    """*FutureSimulator::sim_future_obs (liu_west_filter.h:693-738, 1315-1360): the canonical simulation agrees with the
+    reference-order one (libm, sequential) on the same draws; the filter's outputs are unchanged by asking for it."""
+    ob = oracle
+    lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
+    y = 0.5 * np.random.default_rng(3).standard_normal(12)
+    for form in ("sisr", "apf"):
+        a = ob.lw_sim_future(lo, hi, 0.99, y, 3000, 6, y[-1], sim_stream=9, seed=4, filter_id=1, form=form)
+        f = ob.lw_sim_future(lo, hi, 0.99, y, 3000, 6, y[-1], sim_stream=9, seed=4, filter_id=1, form=form, arithmetic=ob.ARITH_FAITHFUL)
+        b = ob.lw_filter_run(lo, hi, 0.99, y, 3000, seed=4, filter_id=1, form=form)
+        assert a["loglik"] == b["loglik"] and a["sim"].shape == (6, 3000)
+        assert np.abs(a["sim"] - f["sim"]).max() < 1e-12
+        assert 0.5 < a["sim"].std() < 2.0 and abs(a["sim"].mean()) < 0.1
+        other = ob.lw_sim_future(lo, hi, 0.99, y, 3000, 6, y[-1], sim_stream=10, seed=4, filter_id=1, form=form)
+        assert not np.array_equal(other["sim"], a["sim"])
