@@ -273,19 +273,10 @@ __device__ __forceinline__ void lw_tile_tail(const SpillArgs& s, double* lws, do
 {
     constexpr int NW = kTileNT / 32;
     const double ninf = __longlong_as_double(0xfff0000000000000ll);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(mloc, d);
-        mloc = (other > mloc) ? other : mloc;
-    }
+    mloc = warp_max_any(mloc);
     if (lane == 0) red[warp] = mloc;
     __syncthreads();
-    double mb = (lane < NW) ? red[lane] : ninf;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(mb, d);
-        mb = (other > mb) ? other : mb;
-    }
+    const double mb = warp_max_any((lane < NW) ? red[lane] : ninf);
     const double mref = (mb == ninf) ? 0.0 : mb;  // a tile without a finite log-weight: every weight is exp(-inf - 0) = 0
     double sc[kTileL];
 #pragma unroll
@@ -297,12 +288,7 @@ __device__ __forceinline__ void lw_tile_tail(const SpillArgs& s, double* lws, do
     const double Tb = tile_scan_finish(sc, red_sum, lane, warp);
 #pragma unroll
     for (int k = 0; k < kTileL; k += 2) *reinterpret_cast<double2*>(cl + k) = make_double2(sc[k], sc[k + 1]);
-    double cmax = sc[kTileL - 1];  // non-decreasing inside a thread
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const double other = shfl_xor_d(cmax, d);
-        cmax = (other > cmax) ? other : cmax;
-    }
+    const double cmax = warp_max_any(sc[kTileL - 1]);  // non-decreasing inside a thread
     if (lane == 0) red_max[warp] = cmax;
     __syncthreads();
     if (tid == 0) {

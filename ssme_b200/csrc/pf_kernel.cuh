@@ -127,6 +127,22 @@ __device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xo
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// Maximum over the 32 lanes of a warp of doubles (no NaN; -inf and either sign allowed) with the integer reduction unit: the
+// bit patterns are mapped to unsigned keys of the same order, the maximum of the high words is found by one REDUX, then the
+// maximum of the low words among the lanes that hold it.  Replaces the five-level butterfly (10 SHFL, 5 DSETP, 10 FSEL): the
+// maximum is exact and order-free, so the value is the same.  (Only the sign of a zero maximum can differ when +0 and -0 are both
+// present: the butterfly keeps whichever it meets first.)
+__device__ __forceinline__ double warp_max_any(double v)
+{
+    const long long b = __double_as_longlong(v);
+    const unsigned long long key = (b < 0) ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+    const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+    return __longlong_as_double((long long)((mk & 0x8000000000000000ull) ? (mk & 0x7fffffffffffffffull) : ~mk));
+}
+
 template <int L, int NT, typename MODEL, int RESAMP, bool DEBUG>
 __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a)
 {
@@ -300,11 +316,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
         }
 
         // ---- block max -----------------------------------------------------------------------
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const double other = shfl_xor_d(mloc, d);
-            mloc = (other > mloc) ? other : mloc;
-        }
+        mloc = warp_max_any(mloc);
         if (lane == 0) red_max[warp] = mloc;
         __syncthreads();  // B2
         if (tid == 0 && o == 0 && c >= 1 && c + 1 < nchunks) {
@@ -322,12 +334,7 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
                 M = (other > M) ? other : M;
             }
         } else {
-            M = (lane < NW) ? red_max[lane] : __longlong_as_double(0xfff0000000000000ll);
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const double other = shfl_xor_d(M, d);
-                M = (other > M) ? other : M;
-            }
+            M = warp_max_any((lane < NW) ? red_max[lane] : __longlong_as_double(0xfff0000000000000ll));
         }
 
         // ---- batched log p(y_t | y_{1:t-1}) for the previous 32 steps (fast path) -----------
