@@ -6,6 +6,7 @@
 // resampler still all-gathers the tile totals of its exponential spacings with NCCL).
 #include "capi_internal.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -254,31 +255,13 @@ static bool launch_params(int model, const double* theta, void* out, cudaStream_
     return false;
 }
 
-// The persistent bulk-copy form needs 64 KB of dynamic shared memory per CTA.
-template <typename M, bool RS>
-static cudaError_t launch_step_tma(const SpillArgs& a, int tiles, int resident, cudaStream_t st)
+static bool launch_step(int model, const SpillArgs& a, int tiles, bool schedule, cudaStream_t st)
 {
-    constexpr int smem = 2 * kTile * (int)sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(spill_step_kernel<M, RS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // per device
-    if (e != cudaSuccess) return e;
-    spill_step_kernel<M, RS, true><<<resident, kTileNT, smem, st>>>(a, tiles);
-    return cudaSuccess;
-}
-
-static bool launch_step(int model, const SpillArgs& a, int tiles, bool schedule, int num_sms, cudaStream_t st)
-{
-    // more tiles than resident CTAs (3 per SM): a persistent grid that streams the ancestor states in by bulk copies
-    const int resident = num_sms * SSME_STEP_MINB;
-    const bool tma = tiles > resident;
-#define SSME_SPILL_MODEL(M)                                                                   \
-    if (model == M::kId) {                                                                     \
-        if (tma) {                                                                             \
-            if (schedule) return launch_step_tma<M, true>(a, tiles, resident, st) == cudaSuccess;  \
-            return launch_step_tma<M, false>(a, tiles, resident, st) == cudaSuccess;           \
-        }                                                                                      \
-        if (schedule) spill_step_kernel<M, true, false><<<tiles, kTileNT, 0, st>>>(a, tiles);   \
-        else spill_step_kernel<M, false, false><<<tiles, kTileNT, 0, st>>>(a, tiles);           \
-        return true;                                                                           \
+#define SSME_SPILL_MODEL(M)                                                             \
+    if (model == M::kId) {                                                               \
+        if (schedule) spill_step_kernel<M, true><<<tiles, kTileNT, 0, st>>>(a, tiles);   \
+        else spill_step_kernel<M, false><<<tiles, kTileNT, 0, st>>>(a, tiles);           \
+        return true;                                                                     \
     }
     SSME_FOR_EACH_MODEL(SSME_SPILL_MODEL)
 #undef SSME_SPILL_MODEL
@@ -342,7 +325,7 @@ static int phase_a(ssme_b200_handle h, SpillState* s, SpillArgs& a, int t, cudaS
         k5_wait_kernel<<<1, 1, 0, st>>>(a, 1, a.epoch - 1);
         count_launch(1);
     }
-    if (!launch_step(h->cfg.model, a, s->tiles_per_rank, schedule, h->num_sms, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
+    if (!launch_step(h->cfg.model, a, s->tiles_per_rank, schedule, st)) return fail(SSME_B200_EUNSUPPORTED, "model %d has no global-memory kernel", h->cfg.model);
     count_launch(1);
     return SSME_B200_OK;
 }

@@ -202,18 +202,13 @@ __global__ void spill_params_kernel(const double* theta, void* out)
 #ifndef SSME_STEP_MINB
 #define SSME_STEP_MINB 3
 #endif
-// TMA = true (the launcher's choice when there are more tiles than resident CTAs): a PERSISTENT grid of 3 CTAs per SM walks the
-// tiles, and one thread streams the NEXT tile's 32 KB of ancestor states into shared memory with a 1-D bulk copy
-// (cp.async.bulk + mbarrier, as K1 streams its observations) while the CTA works on the current one.  The kernel spends ~125
-// instructions per particle between its loads; with the loads issued by the threads themselves only ~1/4 of the bytes the HBM
-// needs in flight were in flight (1.74 ms per step at 2^28 particles = 3.7 TB/s); the copy engine keeps 96 KB per SM in flight
-// whatever the threads are doing.  Same arithmetic, same tiles: bit-identical.
-template <typename MODEL, bool RS = false, bool TMA = false>
+// (Tried and dropped, profiles/r2_k3_k5.md: a persistent grid of 3 CTAs per SM that streams the next tile's ancestor states into
+// shared memory with 1-D bulk copies while it works on the current one -- bit-identical, 0.7 % slower at 2^28 particles: the kernel
+// is bound by instruction issue and the shuffle / shared-memory pipe, not by the bytes it keeps in flight.)
+template <typename MODEL, bool RS = false>
 __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(const SpillArgs a, const int ntiles)
 {
     constexpr int NW = kTileNT / 32;
-    extern __shared__ __align__(128) double xbuf[];  // TMA: [2][kTile] ancestor states of the current and the next tile
-    __shared__ __align__(8) uint64_t bars[2];
     __shared__ double red[NW];
     __shared__ double red_sum[32];
     __shared__ double red_max[32];
@@ -228,34 +223,10 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
     const typename MODEL::Params mc = *reinterpret_cast<const typename MODEL::Params*>(a.params);
     const typename MODEL::Step ms = MODEL::step(mc, a.obs + (size_t)(a.t - a.row0) * OS);
     const uint32_t ctr2 = (uint32_t)a.fid, ctr3 = ((uint32_t)(a.fid >> 32)) << 4;
-    const bool stream_in = TMA && a.t > 0;
-    constexpr uint32_t kTileBytes = kTile * sizeof(double);
-    if (TMA) {
-        if (tid == 0) {
-            mbar_init(&bars[0], 1);
-            mbar_init(&bars[1], 1);
-            mbar_fence_init();
-            if (stream_in) {
-                mbar_expect_tx(&bars[0], kTileBytes);
-                tma_load_1d(xbuf, a.x_in + (size_t)blockIdx.x * kTile, kTileBytes, &bars[0]);
-            }
-        }
-        __syncthreads();
-    }
-    int it = 0;
-    for (int bt = blockIdx.x; bt < ntiles; bt += gridDim.x, ++it) {
+    for (int bt = blockIdx.x; bt < ntiles; bt += gridDim.x) {  // one tile per CTA as launched (gridDim.x = ntiles)
     const int tile = a.tile0 + bt;
     const int i0 = tile * kTile + tid * kTileL;                      // global particle index
     const size_t l0 = (size_t)bt * kTile + (size_t)tid * kTileL;     // index into this rank's arrays
-    const double* xsm = xbuf + (it & 1) * kTile + tid * kTileL;
-    if (stream_in) {
-        // every thread has finished with the other buffer (two barriers of the previous tile lie in between): refill it
-        if (tid == 0 && bt + (int)gridDim.x < ntiles) {
-            mbar_expect_tx(&bars[(it & 1) ^ 1], kTileBytes);
-            tma_load_1d(xbuf + ((it & 1) ^ 1) * kTile, a.x_in + (size_t)(bt + gridDim.x) * kTile, kTileBytes, &bars[(it & 1) ^ 1]);
-        }
-        mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-    }
     // four particles at a time (one Philox block): draw, propagate, weigh, store the state -- only the log-weights stay live
     double lw[kTileL];
     double mloc = ninf;
@@ -263,7 +234,7 @@ __global__ void __launch_bounds__(kTileNT, SSME_STEP_MINB) spill_step_kernel(con
     for (int q = 0; q < kTileL / 4; ++q) {
         double x[4];
         if (a.t > 0) {
-            const double* xs = TMA ? xsm + 4 * q : a.x_in + l0 + 4 * q;
+            const double* xs = a.x_in + l0 + 4 * q;
             const double2 v0 = *reinterpret_cast<const double2*>(xs);
             const double2 v1 = *reinterpret_cast<const double2*>(xs + 2);
             x[0] = v0.x; x[1] = v0.y; x[2] = v1.x; x[3] = v1.y;
