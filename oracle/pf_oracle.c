@@ -934,7 +934,7 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
      * order: the slots fathered by tile b of particles form a contiguous range [lo_b, hi_b) (the ancestors are monotone); lane l
      * of the 512 takes the slots lo_b + l, lo_b + l + 512, ... in order; the lanes are added as in block_sum; the tiles as usual. */
     const int rel = canonical && cfg->tiled == 3;
-    const int by_counts = rel && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC;
+    const int by_slots = rel && cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC; /* moments summed in the expansion's slot order */
     double pend_s1[4] = {0, 0, 0, 0}, pend_s2[4][4] = {{0}};
     double* wrel = rel ? (double*)malloc(sizeof(double) * (size_t)N) : NULL;
     double* Ex = sorted ? (double*)malloc(sizeof(double) * (size_t)(N + 1)) : NULL;
@@ -960,7 +960,7 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
         if (t > 0) {
             /* update_parameter_proposal_components: thetaBar, V_t, cov = h^2 V_t, factor */
             double V[4][4];
-            if (by_counts) {
+            if (by_slots) {
                 double s2[4][4];
                 for (int k = 0; k < 4; ++k) tb[k] = pend_s1[k] / (double)N;
                 for (int k = 0; k < 4; ++k)
@@ -1250,7 +1250,7 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
             anc[j] = canonical ? tiled_search(&tc, tau) : lower_bound_idx(C, N, tau);
             upd_margin(&margin, C, anc[j], tau, total);
         }
-        if (by_counts) {
+        if (by_slots) {
             const int32_t TS = tc.TS, nb = tc.nb, lanes = nt;
             double* partq = (double*)calloc((size_t)nb * 14, sizeof(double));
             double* tl = (double*)malloc(sizeof(double) * (size_t)lanes);
