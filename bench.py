@@ -170,7 +170,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-K1_PROFILE = os.path.join("profiles", "r2_k1_final3_L8_NT128.txt")
+K1_PROFILE = os.path.join("profiles", "r2_k1_final4_L8_NT128.txt")
 
 
 def read_k1_profile():
