@@ -598,8 +598,30 @@ __global__ void __launch_bounds__(NT) bootstrap_filter_kernel(const FilterArgs a
 #pragma unroll
             for (int k = 0; k < L; ++k) { h[k] = 1u; ng[k] = ~tq[k]; }
             const uint32_t* Qm = reinterpret_cast<const uint32_t*>(Cb) - 1;
+            // The top five levels of the tree are 31 keys: lane l of every warp keeps node l in a register and a probe is a
+            // shuffle by the heap index (no address arithmetic, no bank conflicts) instead of LEA + LDS.  Same keys, same descent.
+            // (A sixth level, nodes 32 .. 63, costs one more register per lane: the shuffle takes the lane number h mod 32.)
+            constexpr int KT = (K < 5) ? K : 5;
+            constexpr int KT2 = (K >= 6) ? 6 : KT;
+            const uint32_t topkey = Qm[lane ? lane : 1];
+            const uint32_t topkey2 = (K >= 6) ? Qm[32 + lane] : 0u;
 #pragma unroll
-            for (int lvl = 0; lvl < K; ++lvl) {
+            for (int lvl = 0; lvl < KT; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, topkey, (int)h[k]);
+                    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(h[k]) : "r"(v), "r"(ng[k]));
+                }
+            }
+            if (K >= 6) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, topkey2, (int)h[k]);  // h in [32, 64): source lane = h mod 32
+                    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(h[k]) : "r"(v), "r"(ng[k]));
+                }
+            }
+#pragma unroll
+            for (int lvl = KT2; lvl < K; ++lvl) {
 #pragma unroll
                 for (int k = 0; k < L; ++k) {
                     const uint32_t v = Qm[h[k]];
