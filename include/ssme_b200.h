@@ -79,9 +79,10 @@ typedef struct {
     int32_t force_global_memory; /* 1 = use the global-memory ("spilled") kernels even when N fits one CTA (parity runs);
                                     they are selected automatically for N > 8192.  The bootstrap filter on these kernels
                                     (one GPU or sharded by particles) honours resample_every like the resident kernels
-                                    (the reference's constructor argument rs, liu_west_filter.h:1686,1754); the Liu-West
-                                    entry points built on them resample at every step (rs = 1, what the reference's tests
-                                    use).  Both draw from the on-device Philox streams only (no injected streams) and
+                                    (the reference's constructor argument rs, liu_west_filter.h:1686,1754), and so does the
+                                    SISR form of the Liu-West filter (LWFilter2WithCovs); its auxiliary-particle form and the
+                                    future-observation simulator need rs = 1 (what the reference's tests use).  All draw from
+                                    the on-device Philox streams only (no injected streams) and
                                     compute in fp64; any other setting is refused with SSME_B200_EUNSUPPORTED */
     int32_t use_cluster;         /* 1 = one filter per thread-block cluster: tiles of scan_items_per_lane (4 or 8) x
                                     threads_per_filter (256 by default; 128 .. 1024) particles, one tile per SM, up to 16

@@ -126,7 +126,7 @@ class _LwStreams(C.Structure):
 
 
 def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH_CANONICAL, L=8, NT=512, seed=20260101, filter_id=0,
-                  cov=None, trace=True, tiled=3, form="sisr", streams=None):
+                  cov=None, trace=True, tiled=3, form="sisr", streams=None, rs=1):
     """Liu-West filter on the SV-with-leverage model; form "sisr" = LWFilter2WithCovs, "apf" = LWFilterWithCovs (auxiliary
     particle filter).  streams: optional dict(u_prior [N][4], z_state [T][N], z_jitter [T][N][4], u_resamp [T][s], u_aux [T][N])
     of pre-generated draws replacing the Philox streams.
@@ -135,7 +135,7 @@ def lw_filter_run(prior_lo, prior_hi, delta, y, N, resampler=2, arithmetic=ARITH
     lo = np.ascontiguousarray(prior_lo, dtype=np.float64)
     hi = np.ascontiguousarray(prior_hi, dtype=np.float64)
     T = y.shape[0]
-    cfg = _Cfg(1, N, resampler, 1, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, int(tiled) if arithmetic == ARITH_CANONICAL else 0, 0)
+    cfg = _Cfg(1, N, resampler, rs, arithmetic, L, RNG_PHILOX, NT, seed, filter_id, int(tiled) if arithmetic == ARITH_CANONICAL else 0, 0)
     cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
     ll, mg = C.c_double(0), C.c_double(0)
     cl, tb, fm = np.empty(T), np.zeros((T, 4)), np.empty(4)

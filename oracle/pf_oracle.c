@@ -918,6 +918,14 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
     if (N < 1 || (canonical && (!cfg->tiled || L < 1))) return -2;
     if (cfg->resampler < 0 || cfg->resampler > 2) return -4;
     if (form != 0 && form != 1) return -5;
+    /* resampling schedule (the filters' constructor argument rs, liu_west_filter.h:1686, 1754): resample when (t + 1) % rs == 0;
+     * in between the log-weights accumulate (:1619-1640) and log p(y_t | y_{1:t-1}) uses the previous step's (max, sum)
+     * (:1651-1659).  The parameter moments stay unweighted (update_parameter_proposal_components looks at the particles only).
+     * SISR form only. */
+    const int32_t rs = cfg->resample_every < 1 ? 1 : cfg->resample_every;
+    if (rs > 1 && (form != 0 || st || sim)) return -7;
+    int prev_resampled = 1, have_pend = 0;
+    double M_prev = 0.0, S_prev = 0.0;
     const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;
     const uint32_t utag = 1u + (uint32_t)cfg->resampler;
     const int64_t stride_u = cfg->resampler == SSME_OR_RESAMP_MULTINOMIAL ? N : cfg->resampler == SSME_OR_RESAMP_SORTED_MULTINOMIAL ? N + 1 : 1;
@@ -960,7 +968,7 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
         if (t > 0) {
             /* update_parameter_proposal_components: thetaBar, V_t, cov = h^2 V_t, factor */
             double V[4][4];
-            if (by_slots) {
+            if (by_slots && have_pend) {
                 double s2[4][4];
                 for (int k = 0; k < 4; ++k) tb[k] = pend_s1[k] / (double)N;
                 for (int k = 0; k < 4; ++k)
@@ -1142,11 +1150,15 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
                     x[i] = mean + z * p[2] * sqrt(1.0 - p[3] * p[3]);
                 }
             }
-            if (canonical) {
-                double hh = (yt * yt) * 0.5;
-                lw[i] = fma(-hh, dm_exp(-x[i]), fma(-0.5, x[i], c0));
-            } else {
-                lw[i] = faithful_log_norm(yt, 0.0, exp(.5 * x[i]));
+            {
+                double g;
+                if (canonical) {
+                    double hh = (yt * yt) * 0.5;
+                    g = fma(-hh, dm_exp(-x[i]), fma(-0.5, x[i], c0));
+                } else {
+                    g = faithful_log_norm(yt, 0.0, exp(.5 * x[i]));
+                }
+                lw[i] = (rs > 1 && !prev_resampled) ? lw[i] + g : g;
             }
             if (form == 1 && t > 0) lw[i] = lw[i] - lfs[ks[i]];
         }
@@ -1202,9 +1214,17 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
         }
         const double logS = canonical ? dm_log(S) : log(S);
         double cl = (t == 0) ? -logN + M + logS : M + logS - 0.0 - logN;
+        if (rs > 1 && t > 0 && !prev_resampled) cl = M + logS - M_prev - (canonical ? dm_log(S_prev) : log(S_prev));
         if (form == 1 && t > 0) cl = canonical ? ((M + logS) + (fs_M2 + fs_logS2)) - 2.0 * logN : M + logS + fs_M2 + fs_logS2 - 2 * 0.0 - 2 * logN;
         if (cond_like) cond_like[t] = cl;
         loglik += cl;
+        if ((t + 1) % rs != 0) { /* no resampling after this step: the particles and their weights carry over */
+            if (ancestors) for (int32_t j = 0; j < N; ++j) ancestors[t * N + j] = j;
+            prev_resampled = 0; M_prev = M; S_prev = S; have_pend = 0;
+            continue;
+        }
+        prev_resampled = 1;
+        have_pend = by_slots;
         const double total = canonical ? S : 1.0;
         double u0 = 0.0, sN = S / (double)N;
         if (cfg->resampler == SSME_OR_RESAMP_SYSTEMATIC)

@@ -28,7 +28,9 @@ namespace ssme {
 
 struct LwArgs {
     SpillArgs s;
-    const double* th_anc[4];  // transformed parameters entering the step (after resampling)
+    const double* th_anc[4];  // transformed parameters after resampling (what the resampling kernels write, the moments kernel reads)
+    const double* th_in[4];   // transformed parameters ENTERING the step: th_anc after a resampling step, else the previous step's
+    const double* x_in;       //   th_cur / x' in place (resampling schedule rs > 1: no resampling after every step)
     double* th_cur[4];        // jittered parameters of this step
     double* part;             // [14][nb] tile partial sums (moments; expectations use the first 5 rows)
     double* mom;              // [0..3] thetaBar, [4..19] chol factor row-major, [20..23] scratch means
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_first_kernel(const LwArgs a)
 
 // The fused time step.  FORM 0: slot i continues particle i (SISR).  FORM 1: slot i continues particle k_i drawn from the
 // first-stage weights.  Thread tid owns the tile's particles 8 tid .. 8 tid + 7 (the scan's ownership), one at a time.
-template <int FORM>
+template <int FORM, bool RS = false>
 __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
 {
     constexpr int NW = kTileNT / 32;
@@ -378,8 +380,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
     double nx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (FORM == 0 && t > 0 && i0 < a.s.N) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nx[q] = a.th_anc[q][i0];
-        nx[4] = a.s.x_anc[i0];
+        for (int q = 0; q < 4; ++q) nx[q] = a.th_in[q][i0];
+        nx[4] = a.x_in[i0];
     }
 #pragma unroll 1
     for (int k = 0; k < kTileL; ++k) {
@@ -389,8 +391,8 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
         for (int q = 0; q < 5; ++q) in[q] = nx[q];
         if (FORM == 0 && t > 0 && k + 1 < kTileL && i + 1 < a.s.N) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) nx[q] = a.th_anc[q][i + 1];
-            nx[4] = a.s.x_anc[i + 1];
+            for (int q = 0; q < 4; ++q) nx[q] = a.th_in[q][i + 1];
+            nx[4] = a.x_in[i + 1];
         }
         if ((k & 3) == 0) {  // state normals: one Philox block per four particles (the blocks of K1 / K3)
             const uint4 rz = philox4x32(make_uint4((uint32_t)(i >> 2), (uint32_t)t, ctr2, ctr3), a.s.rk);
@@ -456,6 +458,10 @@ __global__ void __launch_bounds__(kTileNT, 2) lw_step_kernel(const LwArgs a)
         }
         double v = __fma_rn(-hh, dexp(-x), __fma_rn(-0.5, x, -SSME_DM_HALF_LOG_2PI));
         if (FORM == 1 && t > 0) v = __dsub_rn(v, lfs_k);
+        if (RS && valid) {  // resampling every rs > 1 steps (liu_west_filter.h:1686): the log-weights accumulate in between
+            if (a.s.lw_carry) v = __dadd_rn(a.s.lwacc[i], v);
+            if (a.s.lw_store) a.s.lwacc[i] = v;
+        }
         if (valid) {
             a.s.x_cur[i] = x;
 #pragma unroll

@@ -426,7 +426,8 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     if (rc) return rc;
     SpillState* s = h->spill_state;
     if (s->world != 1) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West filter runs on one GPU");
-    if (h->cfg.resample_every != 1) return fail(SSME_B200_EUNSUPPORTED, "the Liu-West kernels resample at every step (resample_every = 1)");
+    if (h->cfg.resample_every != 1 && form != 0)
+        return fail(SSME_B200_EUNSUPPORTED, "the auxiliary-particle Liu-West form resamples at every step (resample_every = 1); the SISR form takes a schedule");
     if (!s->part) {
         for (int k = 0; k < 4; ++k) {
             SSME_CUDA(cudaMalloc(&s->th_anc[k], s->local * sizeof(double)));
@@ -456,6 +457,7 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     a.s.nextra = 4;
     for (int k = 0; k < 4; ++k) {
         a.th_anc[k] = s->th_anc[k];
+        a.th_in[k] = s->th_anc[k];
         a.th_cur[k] = s->th_cur[k];
         a.s.extra_cur[k] = s->th_cur[k];
         a.s.extra_anc[k] = s->th_anc[k];
@@ -465,7 +467,9 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     a.s.rel = 1;
     a.s.sb = s->sb;
     a.s.world = 1;
-    a.s.prev_resampled = 1;  // the Liu-West filters resample at every step
+    a.s.prev_resampled = 1;
+    a.s.lwacc = s->lwacc;
+    a.x_in = s->x_anc;
     a.part = s->part;
     a.mom = s->mom;
     a.ctr = reinterpret_cast<unsigned int*>(s->mom + 32);
@@ -479,6 +483,9 @@ static int lw_setup(ssme_b200_handle h, int form, const double* lo, const double
     return SSME_B200_OK;
 }
 
+// After step t the particles are resampled when (t + 1) % rs == 0 (the filters' constructor argument, liu_west_filter.h:1686, 1754).
+static bool lw_resamples_after(ssme_b200_handle h, int t) { return (t + 1) % h->cfg.resample_every == 0; }
+
 // One time step of the Liu-West filter (both forms); `a` carries the output pointers and row0.  SISR form with systematic
 // resampling: three launches (fused step, scan of the tile totals, expansion + moments of the next step).
 static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
@@ -488,6 +495,13 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
     cudaStream_t st = h->stream;
     a.s.t = t;
     const bool apf = (form == 1 && t > 0);
+    const bool schedule = h->cfg.resample_every > 1;  // SISR form only (lw_setup)
+    // without resampling after step t-1 its jittered parameters and states are this step's inputs, in place, and its weights carry over
+    a.s.prev_resampled = (t == 0 || lw_resamples_after(h, t - 1)) ? 1 : 0;
+    a.s.lw_carry = a.s.prev_resampled ? 0 : 1;
+    a.s.lw_store = (schedule && !lw_resamples_after(h, t)) ? 1 : 0;
+    for (int k = 0; k < 4; ++k) a.th_in[k] = a.s.prev_resampled ? s->th_anc[k] : s->th_cur[k];
+    a.x_in = a.s.prev_resampled ? s->x_anc : s->x_cur[0];
     if (apf) {
         // first stage: weights of the predicted states, their tile-relative CDF (in lwc[1]) and M2 + log S2
         LwArgs f = a;
@@ -497,6 +511,8 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         launch_tile_scan(s, f.s, st);
         SSME_CUDA(launch_pdl(lw_step_kernel<1>, tiles, kTileNT, st, a));
         count_launch(2);
+    } else if (schedule) {
+        SSME_CUDA(launch_pdl(lw_step_kernel<0, true>, tiles, kTileNT, st, a));
     } else {
         SSME_CUDA(launch_pdl(lw_step_kernel<0>, tiles, kTileNT, st, a));
     }
@@ -506,7 +522,18 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
         SSME_CUDA(launch_pdl(lw_expect_final_kernel, 1, kTileScanNT, st, a));
         count_launch(1);
     }
-    if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
+    if (!lw_resamples_after(h, t)) {
+        // no resampling: the next step jitters THESE parameters around their (unweighted) moments
+        // (update_parameter_proposal_components looks at the particles only, liu_west_filter.h:2346-2360)
+        LwArgs m = a;
+        for (int k = 0; k < 4; ++k) m.th_anc[k] = s->th_cur[k];
+        m.mode = 0;
+        SSME_CUDA(launch_pdl(lw_moments_kernel, tiles, kTileNT, st, m));
+        if (a.s.ancestors) {
+            spill_identity_kernel<<<tiles, kTileNT, 0, st>>>(a.s);
+            count_launch(1);
+        }
+    } else if (h->cfg.resampler == SSME_B200_RESAMP_SYSTEMATIC) {
         SSME_CUDA(launch_pdl(lw_expand_kernel, tiles, kTileNT, st, a));
     } else {
         if (h->cfg.resampler == SSME_B200_RESAMP_SORTED_MULTINOMIAL) {
@@ -523,9 +550,13 @@ static int lw_step(ssme_b200_handle h, LwArgs& a, int form, int t)
 }
 
 // mean of the untransformed parameter particles -> d_mean[4]
-static int lw_means(ssme_b200_handle h, LwArgs& a, double* d_mean)
+// (steps_done: after a step without resampling the current particles are the jittered ones, th_cur)
+static int lw_means(ssme_b200_handle h, LwArgs& a0, double* d_mean, int steps_done)
 {
     SpillState* s = h->spill_state;
+    LwArgs a = a0;
+    if (steps_done > 0 && !lw_resamples_after(h, steps_done - 1))
+        for (int k = 0; k < 4; ++k) a.th_anc[k] = s->th_cur[k];
     a.mode = 1;
     lw_moments_kernel<<<s->nb, kTileNT, 0, h->stream>>>(a);
     SSME_CUDA(cudaMemcpyAsync(d_mean, s->mom + 20, 4 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -549,7 +580,7 @@ static int lw_run(ssme_b200_handle h, int form, const double* lo, const double* 
     const int T = (int)h->T;
     for (int t = 0; t < T; ++t)
         if ((rc = lw_step(h, a, form, t))) return rc;
-    if (T > 0 && d_final_mean && (rc = lw_means(h, a, d_final_mean))) return rc;
+    if (T > 0 && d_final_mean && (rc = lw_means(h, a, d_final_mean, T))) return rc;
     spill_store_kernel<<<1, 1, 0, h->stream>>>(s->scal, d_loglik);
     SSME_CUDA(cudaGetLastError());
     return SSME_B200_OK;
@@ -694,7 +725,7 @@ int ssme_b200_lw_state(ssme_b200_handle h, double* loglik_host, double* param_me
     if (rc) return rc;
     SpillState* s = h->spill_state;
     double out[5] = {0, 0, 0, 0, 0};
-    if (s->lw_t > 0 && param_means_host && (rc = lw_means(h, s->lw_args, s->lw_row + 7))) return rc;
+    if (s->lw_t > 0 && param_means_host && (rc = lw_means(h, s->lw_args, s->lw_row + 7, s->lw_t))) return rc;
     spill_store_kernel<<<1, 1, 0, h->stream>>>(s->scal, s->lw_row + 11);
     SSME_CUDA(cudaGetLastError());
     SSME_CUDA(cudaMemcpyAsync(out, s->lw_row + 7, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
@@ -711,6 +742,8 @@ int ssme_b200_lw_sim_future(ssme_b200_handle h, uint32_t num_steps, double last_
     if (num_steps == 0) return fail(SSME_B200_EINVAL, "num_steps must be positive");
     if (!h->spill || !h->spill_state || h->spill_state->lw_t < 1)
         return fail(SSME_B200_ERUNTIME, "simulate from a streaming Liu-West run that has filtered at least one observation (ssme_b200_lw_begin / _step)");
+    if (h->cfg.resample_every != 1)
+        return fail(SSME_B200_EUNSUPPORTED, "the future-observation simulator starts from a filter that resamples at every step (resample_every = 1)");
     if (int src = check_stream_ids(sim_stream, 1)) return src;
     int rc = set_device(h);
     if (rc) return rc;

@@ -93,6 +93,43 @@ def test_liu_west_degenerate_weights(oracle, gpu_backend_factory, form, resample
     assert got["loglik"] == ref["loglik"] and np.isfinite(got["loglik"])
 
 
+@pytest.mark.parametrize("resampler", [sb.RESAMP_SYSTEMATIC, sb.RESAMP_MULTINOMIAL, sb.RESAMP_SORTED_MULTINOMIAL])
+@pytest.mark.parametrize("N,T,rs", [(10, 7, 2), (5000, 13, 3), (4096 * 2 + 5, 9, 2), (4096, 8, 5)])
+def test_liu_west_resampling_schedule(oracle, gpu_backend_factory, resampler, N, T, rs):
+    """LWFilter2WithCovs(transforms, delta, rs): resample when (t + 1) % rs == 0 (liu_west_filter.h:1686, 1754).  Between resampling
+    steps the log-weights accumulate, log p(y_t | y_{1:t-1}) = (M + log S) - (M_prev + log S_prev) (:1651-1659), and the next
+    step jitters the (unresampled) parameters around their unweighted moments (:2346-2360).  Whole series and streaming."""
+    y = leverage_series(T, seed=N + T + rs)
+    z = np.concatenate([[0.0], y[:-1]])
+    be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, resample_every=rs, seed=6, force_global_memory=1)
+    be.add_observed_data(y)
+    got = be.lw_filter(LO, HI, delta=0.99, stream_id=2, want_ancestors=True)
+    ref = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, seed=6, filter_id=2, rs=rs)
+    assert np.array_equal(got["ancestors"], ref["ancestors"])
+    assert np.array_equal(got["cond_like"], ref["cond_like"])
+    assert np.array_equal(got["theta_bar"], ref["theta_bar"])
+    assert np.array_equal(got["final_mean"], ref["final_mean"])
+    assert got["loglik"] == ref["loglik"]
+    assert sum(np.array_equal(got["ancestors"][t], np.arange(N)) for t in range(T)) >= T - T // rs - 1   # steps without resampling
+    fai = oracle.lw_filter_run(LO, HI, 0.99, y, N, resampler=resampler, arithmetic=oracle.ARITH_FAITHFUL, seed=6, filter_id=2, rs=rs)
+    if np.array_equal(ref["ancestors"], fai["ancestors"]):
+        assert abs(got["loglik"] - fai["loglik"]) <= 1e-9 * abs(fai["loglik"])
+        assert np.allclose(got["final_mean"], fai["final_mean"], rtol=1e-9, atol=1e-12)
+    ex = be.lw_expectations(LO, HI, delta=0.99, stream_id=2)
+    assert np.array_equal(ex["expect"], ref["expect"]) and np.array_equal(ex["cond_like"], ref["cond_like"])
+    be2 = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=N, resampler=resampler, resample_every=rs, seed=6, force_global_memory=1)
+    be2.lw_begin(LO, HI, delta=0.99, stream_id=2)
+    for t in range(T):
+        cl, tb = be2.lw_step(y[t], z[t])
+        assert cl == ref["cond_like"][t] and np.array_equal(tb, ref["theta_bar"][t])
+    stt = be2.lw_state()
+    assert stt["loglik"] == ref["loglik"] and np.array_equal(stt["param_means"], ref["final_mean"])
+    with pytest.raises(RuntimeError):
+        be2.lw_sim_future(2, 0.0)          # the simulator starts from a filter that resamples at every step
+    with pytest.raises(RuntimeError):
+        be.lw_filter(LO, HI, delta=0.99, form="apf")   # the auxiliary form has no schedule
+
+
 def test_liu_west_forms_agree_statistically(gpu_backend_factory):
     y = leverage_series(60, seed=12, sigma=0.05)
     be = gpu_backend_factory(model=sb.MODEL_SV_LEVERAGE, num_particles=1 << 17, resampler=sb.RESAMP_SYSTEMATIC, seed=3)

@@ -92,8 +92,8 @@ def test_spilled_filter_selected_automatically_and_agrees_statistically(sv_serie
 def test_spilled_mode_argument_checks():
     lw = sb.ParticleFilterBackend(sb.FilterConfig(model=sb.MODEL_SV_LEVERAGE, num_particles=10000, resample_every=2))
     lw.add_observed_data(np.ones(4))
-    with pytest.raises(sb.SsmeB200Error):   # the bootstrap filter takes a schedule, the Liu-West kernels do not
-        lw.lw_filter(np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01]))
+    with pytest.raises(sb.SsmeB200Error):   # the bootstrap and the SISR Liu-West filter take a schedule, the auxiliary form does not
+        lw.lw_filter(np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01]), form="apf")
     lw.close()
     with pytest.raises(sb.SsmeB200Error):
         sb.ParticleFilterBackend(sb.FilterConfig(num_particles=10000, rng_mode=sb.RNG_INJECTED))

@@ -392,3 +392,22 @@ def test_future_simulator_restated(oracle):
         assert 0.5 < a["sim"].std() < 2.0 and abs(a["sim"].mean()) < 0.1
         other = ob.lw_sim_future(lo, hi, 0.99, y, 3000, 6, y[-1], sim_stream=10, seed=4, filter_id=1, form=form)
         assert not np.array_equal(other["sim"], a["sim"])
+
+
+def test_lw_resampling_schedule_restated(oracle):
+    """The Liu-West SISR filter with a resampling schedule (rs > 1, liu_west_filter.h:1686, 1754): canonical vs reference-order
+    arithmetic -- same ancestors (identity rows where no resampling happens), log-likelihood and thetaBar to rounding."""
+    ob = oracle
+    lo, hi = np.array([.8, -.1, .01, -.5]), np.array([.99, .1, .1, -.01])
+    y = 0.5 * np.random.default_rng(5).standard_normal(11)
+    for rs in (2, 3):
+        for res in (0, 1, 2):
+            a = ob.lw_filter_run(lo, hi, 0.99, y, 3000, resampler=res, seed=6, filter_id=2, rs=rs)
+            f = ob.lw_filter_run(lo, hi, 0.99, y, 3000, resampler=res, seed=6, filter_id=2, rs=rs, arithmetic=ob.ARITH_FAITHFUL)
+            assert np.array_equal(a["ancestors"], f["ancestors"])
+            assert abs(a["loglik"] - f["loglik"]) <= 1e-12 * abs(f["loglik"])
+            assert np.abs(a["theta_bar"] - f["theta_bar"]).max() < 1e-12
+            ident = [np.array_equal(a["ancestors"][t], np.arange(3000)) for t in range(11)]
+            assert all(ident[t] for t in range(11) if (t + 1) % rs != 0)
+    one = ob.lw_filter_run(lo, hi, 0.99, y, 3000, seed=6, filter_id=2)
+    assert one["loglik"] != ob.lw_filter_run(lo, hi, 0.99, y, 3000, seed=6, filter_id=2, rs=2)["loglik"]
