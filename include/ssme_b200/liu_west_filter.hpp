@@ -52,14 +52,17 @@ public:
     {
         const std::vector<std::string> want{"logit", "null", "log", "twice_fisher"};
         if (transforms != want) throw std::invalid_argument("the device model uses the transforms logit, null, log, twice_fisher");
-        if (rs != 1) throw std::invalid_argument("the GPU Liu-West filter resamples at every step (rs = 1)");
+        // the resampling schedule of the reference's constructors (liu_west_filter.h:1686, 1754): the SISR form takes it, the
+        // auxiliary-particle form resamples at every step
+        if (rs < 1 || (rs != 1 && form != SSME_B200_LW_SISR))
+            throw std::invalid_argument("the auxiliary-particle GPU Liu-West filter resamples at every step (rs = 1)");
         ssme_b200_config c{};
         c.struct_size = (int32_t)sizeof(c);
         c.device = opt.device;
         c.model = SSME_B200_MODEL_SV_LEVERAGE;
         c.num_particles = (int32_t)nparts;
         c.resampler = opt.resampler;
-        c.resample_every = 1;
+        c.resample_every = (int32_t)rs;
         c.dtype = SSME_B200_DTYPE_F64;
         c.rng_mode = SSME_B200_RNG_PHILOX;
         c.seed = opt.seed;

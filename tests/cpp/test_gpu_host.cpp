@@ -179,6 +179,32 @@ int main(int argc, char** argv)
         REQUIRE(std::isfinite(online.getLogCondLike()));
         REQUIRE(std::abs(big.getLogLike() - big2.getLogLike()) < 0.02 * std::abs(big2.getLogLike()));
     }
+    TEST_CASE("Liu-West SISR filter with a resampling schedule (the reference's constructor argument rs)")
+    {
+        using lw_t = ssme_b200::LWFilter2WithCovs_svol<5000, double>;
+        const std::vector<std::string> tr{"logit", "null", "log", "twice_fisher"};
+        const lw_t::psv lo{.8, -.1, .01, -.5}, hi{.99, .1, .3, -.01};
+        std::vector<double> y{0.3, -0.2, 0.5, 0.1, -0.4, 0.2, 0.05, -0.6}, cov(y.size(), 0.0);
+        for (size_t t = 1; t < y.size(); ++t) cov[t] = y[t - 1];
+        lw_t every(tr, .99, lo, hi, 1), second(tr, .99, lo, hi, 2);   // LWFilter2WithCovs(transforms, delta, rs), liu_west_filter.h:2047
+        every.filter_series(y, cov, 3);
+        second.filter_series(y, cov, 3);
+        REQUIRE(std::isfinite(second.getLogLike()));
+        REQUIRE(second.getLogLike() != every.getLogLike());
+        REQUIRE(second.getLogCondLike(0) == every.getLogCondLike(0));   // step 0 is the same draw in both
+        REQUIRE(std::abs(second.getLogLike() - every.getLogLike()) < 0.05 * std::abs(every.getLogLike()));
+        lw_t online(tr, .99, lo, hi, 2);
+        online.set_stream(3);
+        for (size_t t = 0; t < y.size(); ++t) online.filter(y[t], cov[t]);
+        REQUIRE(online.getLogLike() == second.getLogLike());
+        bool threw = false;
+        try {
+            ssme_b200::LWFilterWithCovs_svol<5000, double> apf(tr, .99, lo, hi, 2);   // the auxiliary form has no schedule
+        } catch (const std::invalid_argument&) {
+            threw = true;
+        }
+        REQUIRE(threw);
+    }
     TEST_CASE("covariate-free Liu-West twins: filter(y_t)")
     {
         using lw_t = ssme_b200::LWFilter2_svol<5000, double>;
