@@ -411,3 +411,26 @@ def test_lw_resampling_schedule_restated(oracle):
             assert all(ident[t] for t in range(11) if (t + 1) % rs != 0)
     one = ob.lw_filter_run(lo, hi, 0.99, y, 3000, seed=6, filter_id=2)
     assert one["loglik"] != ob.lw_filter_run(lo, hi, 0.99, y, 3000, seed=6, filter_id=2, rs=2)["loglik"]
+
+
+def test_lw_with_fixed_parameters_is_the_bootstrap_filter(oracle):
+    """delta = 1 (a = 1, h^2 = 0: no jitter) and a prior box that is a point: every particle carries the same parameters, so the
+    Liu-West filter IS the bootstrap filter of the leverage model -- same state streams, same resampling uniforms.  Ties the
+    Liu-West restatement, schedule included, to the bootstrap one, whose schedule logic is pinned to the reference's own
+    LWFilter2::filter compiled here (tests/test_refhdr.py::test_lwfilter2_step_equals_the_faithful_oracle)."""
+    ob = oracle
+    th = np.array([0.9, 0.05, 0.3, -0.3])
+    rng = np.random.default_rng(4)
+    T = 15
+    x, y = np.zeros(T), np.zeros(T)
+    for t in range(T):
+        x[t] = 0.9 * (x[t - 1] if t else 0) + 0.3 * rng.normal()
+        y[t] = np.exp(x[t] / 2) * rng.normal()
+    for rs in (1, 2, 3):
+        for res in (0, 2):
+            for arith, tiled in ((ob.ARITH_FAITHFUL, 0), (ob.ARITH_CANONICAL, 3)):
+                a = ob.lw_filter_run(th, th, 1.0, y, 2000, resampler=res, seed=6, filter_id=2, rs=rs, arithmetic=arith)
+                b = ob.filter_run(th, y, 2000, model=1, resampler=res, rs=rs, L=8, NT=512, tiled=tiled, seed=6, filter_id=2, arithmetic=arith)
+                assert np.array_equal(a["ancestors"], b["ancestors"])
+                assert np.abs(a["cond_like"] - b["cond_like"]).max() < 1e-13
+                assert abs(a["loglik"] - b["loglik"]) <= 1e-14 * abs(b["loglik"])
