@@ -923,7 +923,7 @@ static int lw_filter_impl(const ssme_oracle_cfg* cfg, int32_t form, const double
      * (:1651-1659).  The parameter moments stay unweighted (update_parameter_proposal_components looks at the particles only).
      * SISR form only. */
     const int32_t rs = cfg->resample_every < 1 ? 1 : cfg->resample_every;
-    if (rs > 1 && (form != 0 || st || sim)) return -7;
+    if (rs > 1 && (form != 0 || sim)) return -7;
     int prev_resampled = 1, have_pend = 0;
     double M_prev = 0.0, S_prev = 0.0;
     const int32_t nt = cfg->scan_threads ? cfg->scan_threads : 512;

@@ -263,11 +263,15 @@ int lw_run(Filter& f, const double* y, const double* cov, int T, const double* u
     return 0;
 }
 
+// rs: the resampling schedule.  The test model's constructor does not forward one (test/test_liu_west.cpp:257-263 calls the base
+// with (transforms, delta)), so the base class's member is set directly (test-only access, see the #define above): the filter
+// code that runs is the reference's LWFilter2WithCovs::filter, which resamples when (m_now + 1) % m_resampSched == 0 (:2272, :2340).
 template <size_t N>
 int lw_leverage_form0(const double* lo, const double* hi, double delta, const double* y, const double* cov, int T, const double* u_prior,
-                      const double* z_state, const double* z_jitter, const uint32_t* seeds, const lw_out& o)
+                      const double* z_state, const double* z_jitter, const uint32_t* seeds, const lw_out& o, unsigned rs = 1)
 {
     svol_lw_2_par<N, double> f(delta, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3], 1);
+    f.m_resampSched = rs;
     return lw_run<svol_lw_2_par<N, double>, N>(f, y, cov, T, u_prior, z_state, z_jitter, nullptr, seeds, o);
 }
 
@@ -466,6 +470,25 @@ int ssme_refhdr_lw_leverage(int form, int N, const double* lo, const double* hi,
             return lw_run<svol_lw_1_par<NPARTS, double>, NPARTS>(f, y, cov, T, u_prior, z_state, z_jitter, u_aux, seeds, o);
         }
         throw std::invalid_argument("form");
+    } catch (const std::exception& e) {
+        return fail(e);
+    }
+}
+
+// form 0 with a resampling schedule rs >= 1 (LWFilter2WithCovs(transforms, delta, rs), liu_west_filter.h:2047)
+int ssme_refhdr_lw_leverage_rs(int N, int rs, const double* lo, const double* hi, double delta, const double* y, const double* cov, int T,
+                               const double* u_prior, const double* z_state, const double* z_jitter, const uint32_t* seeds,
+                               double* cond_like, double* theta_bar, double* x_post, double* th_post, double* expect, double* u_resamp)
+{
+    try {
+        if (rs < 1) throw std::invalid_argument("rs");
+        const lw_out o{cond_like, theta_bar, x_post, th_post, expect, u_resamp};
+        switch (N) {
+        case 16: return lw_leverage_form0<16>(lo, hi, delta, y, cov, T, u_prior, z_state, z_jitter, seeds, o, (unsigned)rs);
+        case 100: return lw_leverage_form0<100>(lo, hi, delta, y, cov, T, u_prior, z_state, z_jitter, seeds, o, (unsigned)rs);
+        case 500: return lw_leverage_form0<500>(lo, hi, delta, y, cov, T, u_prior, z_state, z_jitter, seeds, o, (unsigned)rs);
+        default: throw std::invalid_argument("unsupported N");
+        }
     } catch (const std::exception& e) {
         return fail(e);
     }

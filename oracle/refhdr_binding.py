@@ -134,6 +134,26 @@ def lw_leverage(form, N, lo, hi, delta, y, u_prior, z_state, z_jitter, seeds, u_
     return {"cond_like": cl, "theta_bar": tb, "x_post": xp, "th_post": tp, "expect": ex, "u_resamp": ur}
 
 
+def lw_leverage_rs(N, rs, lo, hi, delta, y, u_prior, z_state, z_jitter, seeds, cov=None):
+    """LWFilter2WithCovs::filter on svol_lw_2_par with the resampling schedule rs (m_resampSched set directly)."""
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    T = y.size
+    u_prior = np.ascontiguousarray(u_prior, dtype=np.float64)
+    z_state = np.ascontiguousarray(z_state, dtype=np.float64)
+    z_jitter = np.ascontiguousarray(z_jitter, dtype=np.float64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
+    cl, tb, xp, tp, ex = np.empty(T), np.zeros((T, 4)), np.empty((T, N)), np.empty((T, N, 4)), np.zeros((T, 5))
+    ur = np.empty((T, N + 1))
+    fn = lib().ssme_refhdr_lw_leverage_rs
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 10
+    _check(fn(N, rs, _vp(lo), _vp(hi), delta, _vp(y), _vp(cov), T, _vp(u_prior), _vp(z_state), _vp(z_jitter), _vp(seeds),
+              _vp(cl), _vp(tb), _vp(xp), _vp(tp), _vp(ex), _vp(ur)))
+    return {"cond_like": cl, "theta_bar": tb, "x_post": xp, "th_post": tp, "expect": ex, "u_resamp": ur}
+
+
 def pmmh_chain(start_trans, data, iters, t0, t1, c0, z_prop, u_acc, tmp_dir):
     start_trans = np.ascontiguousarray(start_trans, dtype=np.float64)
     data = np.ascontiguousarray(data, dtype=np.float64)

@@ -168,6 +168,31 @@ def test_liu_west_filters_equal_the_faithful_oracle(form, N, T, delta):
     assert abs(ref["cond_like"].sum() - orc["loglik"]) <= 1e-12 * abs(orc["loglik"])
 
 
+@pytest.mark.parametrize("N,T,rs,delta", [(16, 120, 2, .99), (100, 90, 3, .99), (500, 40, 2, .95), (100, 60, 5, .99)])
+def test_liu_west_resampling_schedule_equals_the_faithful_oracle(N, T, rs, delta):
+    """LWFilter2WithCovs::filter (:2191-2343), unmodified, with the resampling schedule rs of its constructor (:2047; resample when
+    (m_now + 1) % m_resampSched == 0, :2272, :2340): the weights accumulate between resampling steps, log p(y_t | y_{1:t-1}) uses
+    the old weights (:2238-2245), the parameters are jittered around their unweighted moments.  Against the oracle's FAITHFUL
+    Liu-West filter with the same schedule on identical streams: theta-bar bit-identical, cond-likes and expectations <= 1e-12."""
+    rng = np.random.default_rng(17 * N + rs)
+    y = _sv_series(T, seed=N + 3)
+    up, zs, zj = rng.random((N, 4)), rng.standard_normal((T, N)), rng.standard_normal((T, N, 4))
+    seeds = rng.integers(1, 2 ** 31, size=T)
+    ref = rb.lw_leverage_rs(N, rs, LO, HI, delta, y, up, zs, zj, seeds)
+    orc = ob.lw_filter_run(LO, HI, delta, y, N, resampler=1, arithmetic=ob.ARITH_FAITHFUL, rs=rs,
+                           streams=dict(u_prior=up, z_state=zs, z_jitter=zj, u_resamp=ref["u_resamp"], u_aux=np.zeros((T, N))))
+    assert orc["margin"] > 1e-11
+    assert np.array_equal(ref["theta_bar"][1:], orc["theta_bar"][1:])
+    rel = np.abs(ref["cond_like"] - orc["cond_like"]) / np.maximum(np.abs(orc["cond_like"]), 1e-3)
+    assert rel.max() <= 1e-12
+    assert np.abs(ref["expect"] - orc["expect"]).max() <= 1e-12
+    ident = [np.array_equal(orc["ancestors"][t], np.arange(N)) for t in range(T)]
+    assert all(ident[t] for t in range(T) if (t + 1) % rs != 0) and not all(ident)
+    # and the schedule matters: rs = 1 on the same streams is another filter
+    one = rb.lw_leverage_rs(N, 1, LO, HI, delta, y, up, zs, zj, seeds)
+    assert not np.allclose(one["cond_like"], ref["cond_like"])
+
+
 def test_independent_rng_loglik_means_agree(oracle):
     """North star: 'with independent RNG, posterior means agree within Monte Carlo standard error'.  The reference-side
     filters draw from std::mt19937 + std::normal_distribution / std::discrete_distribution (the example's svol_bs on the pf
