@@ -3,18 +3,22 @@
 // THREE launches over tiles of kTile = 4096 particles (512 threads x 8) -- the "tile-relative" order:
 //   K3a spill_step_kernel     x' = f(x_anc, z), lw = log g(y | x'), tile max m_b, w = exp(lw - m_b), tile-local inclusive
 //                             scan cl, tile total T_b                                   (reads 8 B, writes 16 B / particle)
-//   K3d tile_scan_kernel      M = max_b m_b, s_b = exp(m_b - M), scan of T_b s_b -> tile ends E, total S, log p(y_t | y_{1:t-1})
+//   K3d tile scan             M = max_b m_b, s_b = exp(m_b - M), scan of T_b s_b -> tile ends E, total S, log p(y_t | y_{1:t-1});
+//                             one CTA with everything in shared memory up to 1024 tiles (spill_tile_scan_small_kernel), one
+//                             launch of 32 CTAs with two grid barriers beyond 2048 (spill_tile_scan_merged_kernel); the general
+//                             one-CTA and two-launch forms cover the sizes in between and above 2^29 particles
 //   K3e expand / resample     global CDF C_i = E_{b-1} + cl_i s_b; systematic: offspring counts, no search; multinomial: two-level
 //                             descent + gather                                          (reads 16 B, writes 8 B / particle)
 // Weighting every tile relative to ITS OWN maximum removes the global maximum from the per-particle path: the log-weights never
-// travel through HBM (48 -> 32 bytes per particle-step of traffic) and a rank of the multi-GPU form (K5) needs nothing from
+// travel through HBM (64 -> 48 bytes per particle-step of traffic) and a rank of the multi-GPU form (K5) needs nothing from
 // its peers until the tile totals are scanned -- one exchange of (m_b, T_b, max cl) per step.  The Liu-West kernels (K4,
 // lw_kernel.cuh) use the same order, the tile scan, the resamplers and expand_counts() of this file.
 // Same per-particle arithmetic and Philox streams as K1; the scan / search order is the oracle's "tiled"
 // order (oracle/pf_oracle.c: tiled_build / tiled_search), so results are bit-identical to it -- and
 // independent of how many GPUs the tiles are spread over (K5).
-// Reference restated: the same BSFilter::filter step as K1 (liu_west_filter.h:1608-1761 twin); the
-// reference keeps particles in std::array members of the filter object and cannot reach these sizes.
+// Reference restated: the same BSFilter::filter step as K1 (liu_west_filter.h:1608-1761 twin), the resampling schedule rs of its
+// constructor included (log-weights accumulate in lwacc between resampling steps); the reference keeps particles in std::array
+// members of the filter object and cannot reach these sizes.
 #pragma once
 #include "det_math.cuh"
 #include "pf_kernel.cuh"
